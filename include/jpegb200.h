@@ -1,0 +1,168 @@
+/* jpegb200.h -- C ABI of libjpegb200.so, the B200-native (sm_100a) baseline-JPEG
+ * encode path that stands in for the CPU/OpenCL path of
+ * rusty-electron/jpeg-encoder-opencl.
+ *
+ * The reference has no plugin/FFI layer: its boundary is the set of C++ free
+ * functions declared in src/utils.hpp:77-137 and called, in order, by
+ * JpegEncoderHost (src/OpenCLProject_JpegEncoder.cpp:59-225).  Every "staged"
+ * entry point below replaces one of those functions and keeps its data layout
+ * (AoS rgb_pixel_t / rgb_pixel_d_t images, int[rows][64] block arrays); the
+ * citation after each prototype is the reference declaration it replaces.
+ * host/utils_compat.hpp re-declares the reference names on top of this ABI so
+ * the reference driver can be re-linked unchanged.
+ *
+ * Conventions: plain pointers and sizes only; caller owns every in/out buffer;
+ * the library owns device memory, pinned staging and streams inside jb_ctx;
+ * every call returns a jb_status (0 = ok) and never throws; jb_last_error()
+ * gives the message.  One jb_ctx per host thread; any number per GPU.  There is
+ * no CPU fallback: without a CUDA device jb_create fails with JB_E_CUDA.
+ */
+#ifndef JPEGB200_H
+#define JPEGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jb_ctx jb_ctx;
+
+typedef enum {
+    JB_OK = 0,
+    JB_E_INVALID = 1,     /* bad argument                                       */
+    JB_E_CUDA = 2,        /* CUDA runtime error / no device                     */
+    JB_E_NOSPACE = 3,     /* output capacity too small (see jb_required_bytes)  */
+    JB_E_NOMEM = 4,       /* allocation failed                                  */
+    JB_E_UNSUPPORTED = 5, /* e.g. dimension > 65535 without JB_FLAG_CLAMP_SOF   */
+    JB_E_INTERNAL = 6
+} jb_status;
+
+/* Chroma handling. */
+#define JB_SUB_444 0     /* no chroma averaging; 8x8 MCU = Y Cb Cr                               */
+#define JB_SUB_REPL420 1 /* the reference's "4:2:0": 2x2 mean replicated (utils.cpp:113-141),   *
+                          * coded 4:4:4 in the order of HuffmanEncoder (utils.cpp:667-695)      */
+#define JB_SUB_420 2     /* true 4:2:0: 16x16 MCU = Y00 Y01 Y10 Y11 Cb Cr                         */
+
+/* Flags. The three REF_* flags reproduce the reference's defects for verbatim comparisons. */
+#define JB_FLAG_REF_INPLACE_DCT 0x1u /* Q1 utils.cpp:342-345 (staged jb_dct_f64 only)            */
+#define JB_FLAG_REF_TYPO_TABLES 0x2u /* Q2 huffman.hpp:92-98 17-bit luma AC codes 3/4..3/A       */
+#define JB_FLAG_REF_ALWAYS_EOB 0x4u  /* Q3 utils.cpp:607-608 EOB also after a full block         */
+#define JB_FLAG_CLAMP_SOF 0x8u       /* declare min(dim,65535) in SOF0                */
+#define JB_FLAG_NO_TIE_FIXUP 0x10u   /* skip the binary64 replay of near-tie coefficients        */
+
+typedef struct {
+    int32_t subsampling;      /* JB_SUB_*                                                   */
+    int32_t restart_interval; /* MCUs per restart interval, 0 = none (<= 65535)            */
+    uint32_t flags;           /* JB_FLAG_*                                                  */
+    uint32_t qlum[64];        /* row-major [v][u], as quant_mat_lum  (utils.hpp:42-51)      */
+    uint32_t qchrom[64];      /* row-major [v][u], as quant_mat_chrom (utils.hpp:53-62)     */
+} jb_params;
+
+/* Per-stage device times of the last fused call, in microseconds; the first
+ * nine fields mirror CPUTelemetry (utils.hpp:65-75).  In the fused path CSC,
+ * CDS, level shift, DCT, quantisation and zigzag are one kernel: its time is
+ * reported in DCTTime and the others are 0. */
+typedef struct {
+    double CSCTime, CDSTime, levelShiftTime, DCTTime, QuantTime, TotalCopyTime, zigZagTime, RLETime, HuffmanTime;
+    double transform_us; /* fused transform kernel (== DCTTime)                     */
+    double fixup_us;     /* near-tie binary64 replay                                */
+    double entropy_us;   /* all entropy-coder kernels (lengths, scans, pack, stuff) */
+    double h2d_us, d2h_us;
+    uint64_t transform_launches, total_launches; /* kernels launched by the library since jb_reset_counters */
+    uint64_t tie_fixups;                         /* coefficients replayed in binary64 in the last call      */
+} jb_timings;
+
+/* ---- context ------------------------------------------------------------- */
+int jb_create(int device, jb_ctx **ctx);
+void jb_destroy(jb_ctx *ctx);
+const char *jb_last_error(const jb_ctx *ctx);
+int jb_sync(jb_ctx *ctx);
+void *jb_stream(jb_ctx *ctx);                 /* the cudaStream_t kernels are launched on */
+int jb_set_profiling(jb_ctx *ctx, int on);    /* record CUDA events around each kernel    */
+int jb_get_timings(jb_ctx *ctx, jb_timings *t);
+int jb_reset_counters(jb_ctx *ctx);
+int jb_version(void);
+
+/* pinned host memory for the e2e path (replaces the reference's malloc'd buffers, utils.cpp:50) */
+int jb_host_alloc(void **p, size_t bytes);
+int jb_host_free(void *p);
+int jb_device_alloc(jb_ctx *ctx, void **p, size_t bytes);
+int jb_device_free(jb_ctx *ctx, void *p);
+int jb_memcpy_h2d(jb_ctx *ctx, void *dst, const void *src, size_t bytes);
+int jb_memcpy_d2h(jb_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ---- staged entry points: host pointers, synchronous, reference layouts --- */
+int jb_csc_rgb8_aos(jb_ctx *ctx, uint8_t *px, size_t W, size_t H);
+/*      replaces void performCSC(ppm_t*)                                   utils.hpp:81  */
+int jb_cds_aos(jb_ctx *ctx, uint8_t *ycc, size_t W, size_t H);
+/*      replaces void performCDS(ppm_t*)                                   utils.hpp:82  */
+int jb_padded_size(size_t W, size_t H, size_t mult, size_t *nW, size_t *nH);
+/*      replaces void getNearest8x8ImageSize(size_t,size_t,size_t*,size_t*) utils.hpp:98 */
+int jb_pad_mirror_aos(jb_ctx *ctx, const uint8_t *src, size_t W, size_t H, uint8_t *dst, size_t nW, size_t nH);
+/*      replaces copyToLargerImage + addReversedPadding                    utils.hpp:97,99 */
+int jb_u8_to_f64(jb_ctx *ctx, const uint8_t *src, double *dst, size_t n);
+/*      replaces void copyUIntToDoubleImage(ppm_t*, ppm_d_t*)              utils.hpp:94  */
+int jb_levelshift_f64(jb_ctx *ctx, double *img, size_t n, double val);
+/*      replaces void substractfromAll(ppm_d_t*, double)                   utils.hpp:100 */
+int jb_dct_f64(jb_ctx *ctx, double *img, size_t W, size_t H, uint32_t flags);
+/*      replaces void performDCT(ppm_d_t*)                                 utils.hpp:102 */
+int jb_quantize_f64(jb_ctx *ctx, double *img, size_t W, size_t H, const uint32_t qlum[64], const uint32_t qchrom[64]);
+/*      replaces void performQuantization(ppm_d_t*, const unsigned[][8], const unsigned[][8])  utils.hpp:106 */
+int jb_blockify(jb_ctx *ctx, const double *img, size_t W, size_t H, int32_t *linear);
+/*      replaces void everyMCUisnow2DArray(ppm_d_t*, int[][64])            utils.hpp:122 */
+int jb_zigzag(jb_ctx *ctx, const int32_t *linear, int32_t *zz, size_t rows);
+/*      replaces void performZigZag(int[][64], int[][64], int)             utils.hpp:127 */
+int jb_rle(jb_ctx *ctx, const int32_t *zz, size_t rows, uint32_t flags, int32_t *pairs, uint32_t *counts);
+/*      replaces void performRLE(int[][64], vector<vector<int>>&, int)     utils.hpp:132
+ *      pairs: rows x 128 ints (run,value,...); counts[r] = ints used by row r */
+int jb_huffman(jb_ctx *ctx, const int32_t *zz, size_t rows_per_channel, uint32_t flags, uint8_t *bits, size_t cap_bytes,
+               uint64_t *nbits);
+/*      replaces std::string HuffmanEncoder(int[][64], vector<vector<int>>&, int)  utils.hpp:137
+ *      zz = int[3*rows_per_channel][64] (planar by channel); output = the same bit
+ *      sequence packed MSB-first, *nbits bits, no padding/stuffing/markers */
+
+/* ---- fused path ------------------------------------------------------------ */
+int jb_quality_tables(int quality, uint32_t qlum[64], uint32_t qchrom[64]); /* IJG scaling of utils.hpp:42-62 */
+size_t jb_num_mcus(size_t W, size_t H, int subsampling);
+int jb_blocks_per_mcu(int subsampling);
+size_t jb_header_bytes(const jb_params *p);
+size_t jb_required_bytes(jb_ctx *ctx); /* after JB_E_NOSPACE: bytes the last call needed */
+
+/* RGB8 AoS (host) -> quantised zigzag int16 coefficients in scan order
+ * [n_mcu][blocks_per_mcu][64] (host).  One kernel does performCSC .. performZigZag. */
+int jb_transform(jb_ctx *ctx, const uint8_t *rgb, size_t W, size_t H, size_t pitch, const jb_params *p, int16_t *coef);
+/* scan-order coefficients (host) -> entropy segment bytes (host): 1-padding, FF00 stuffing, RSTn */
+int jb_entropy(jb_ctx *ctx, const int16_t *coef, size_t n_mcu, const jb_params *p, uint8_t *out, size_t cap,
+               size_t *out_len);
+/* RGB8 (host) -> complete JFIF file (host) */
+int jb_encode_jfif(jb_ctx *ctx, const uint8_t *rgb, size_t W, size_t H, size_t pitch, const jb_params *p, uint8_t *out,
+                   size_t cap, size_t *out_len);
+/* n_frames equally sized RGB8 frames (host, frame f at rgb + f*frame_stride) -> n_frames JFIF
+ * files packed back to back in out; offsets[f], sizes[f] (host arrays) locate them.
+ * Host<->device copies are pipelined with the kernels over several streams. */
+int jb_encode_batch(jb_ctx *ctx, const uint8_t *rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
+                    size_t frame_stride, const jb_params *p, uint8_t *out, size_t cap, uint64_t *offsets,
+                    uint64_t *sizes);
+/* Same with every buffer resident in HBM (d_* are device pointers); asynchronous on jb_stream(),
+ * complete after jb_sync().  d_total receives the total bytes (1 x uint64). */
+int jb_encode_batch_device(jb_ctx *ctx, const uint8_t *d_rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
+                           size_t frame_stride, const jb_params *p, uint8_t *d_out, size_t cap, uint64_t *d_offsets,
+                           uint64_t *d_sizes, uint64_t *d_total);
+/* One horizontal strip of a large image whose restart intervals are whole MCU rows groups
+ * (multi-GPU: strip s on GPU s).  Produces only entropy bytes (no header, no EOI); RST
+ * numbering starts at first_interval; a RST marker follows the last interval unless
+ * last_strip.  rgb is a device pointer when d_out is (device_io != 0). */
+int jb_encode_strip(jb_ctx *ctx, const uint8_t *rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params *p,
+                    uint64_t first_interval, int last_strip, int device_io, uint8_t *out, size_t cap, size_t *out_len);
+/* JFIF header (SOI..SOS) for a W x H image with these parameters (host) */
+int jb_write_header(const jb_params *p, size_t W, size_t H, uint8_t *out, size_t cap, size_t *out_len);
+
+/* Deterministic synthetic RGB8 image rows [y0, y0+rows) generated on the device */
+int jb_synth_rgb_device(jb_ctx *ctx, uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPEGB200_H */

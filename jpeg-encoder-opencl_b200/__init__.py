@@ -1,0 +1,362 @@
+"""jpegb200 -- Python (ctypes) binding of libjpegb200.so, the B200-native baseline-JPEG
+encode path with the per-stage function surface of rusty-electron/jpeg-encoder-opencl
+(reference: src/utils.hpp:77-137, driver order src/OpenCLProject_JpegEncoder.cpp:59-225).
+
+The directory name contains a hyphen, so import it through `load()` in
+__graft_entry__.py / tests/conftest.py (module name `jpegb200`).  This module is a thin
+binding: all work happens in the CUDA library, and there is no CPU fallback -- a missing
+library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjpegb200.so")
+
+SUB_444, SUB_REPL420, SUB_420 = 0, 1, 2
+FLAG_REF_INPLACE_DCT, FLAG_REF_TYPO_TABLES, FLAG_REF_ALWAYS_EOB = 1, 2, 4
+FLAG_CLAMP_SOF, FLAG_NO_TIE_FIXUP = 8, 16
+OK, E_INVALID, E_CUDA, E_NOSPACE, E_NOMEM, E_UNSUPPORTED, E_INTERNAL = range(7)
+
+# every symbol include/jpegb200.h declares (tests check that the library exports them all)
+SYMBOLS = [
+    "jb_create", "jb_destroy", "jb_last_error", "jb_sync", "jb_stream", "jb_set_profiling", "jb_get_timings",
+    "jb_reset_counters", "jb_version", "jb_host_alloc", "jb_host_free", "jb_device_alloc", "jb_device_free",
+    "jb_memcpy_h2d", "jb_memcpy_d2h", "jb_csc_rgb8_aos", "jb_cds_aos", "jb_padded_size", "jb_pad_mirror_aos",
+    "jb_u8_to_f64", "jb_levelshift_f64", "jb_dct_f64", "jb_quantize_f64", "jb_blockify", "jb_zigzag", "jb_rle",
+    "jb_huffman", "jb_quality_tables", "jb_num_mcus", "jb_blocks_per_mcu", "jb_header_bytes", "jb_required_bytes",
+    "jb_transform", "jb_entropy", "jb_encode_jfif", "jb_encode_batch", "jb_encode_batch_device", "jb_encode_strip",
+    "jb_write_header", "jb_synth_rgb_device",
+]
+
+
+class JbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"jpegb200 error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("subsampling", C.c_int32), ("restart_interval", C.c_int32), ("flags", C.c_uint32),
+                ("qlum", C.c_uint32 * 64), ("qchrom", C.c_uint32 * 64)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("CSCTime", "CDSTime", "levelShiftTime", "DCTTime", "QuantTime",
+                                          "TotalCopyTime", "zigZagTime", "RLETime", "HuffmanTime", "transform_us",
+                                          "fixup_us", "entropy_us", "h2d_us", "d2h_us")] + \
+               [(n, C.c_uint64) for n in ("transform_launches", "total_launches", "tie_fixups")]
+
+
+def build(verbose=False):
+    """Compile libjpegb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", HERE, "-j8"], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libjpegb200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C library (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
+    PP = C.POINTER(Params)
+    L.jb_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.jb_destroy.argtypes = [vp]
+    L.jb_destroy.restype = None
+    L.jb_last_error.argtypes = [vp]
+    L.jb_last_error.restype = C.c_char_p
+    L.jb_sync.argtypes = [vp]
+    L.jb_stream.argtypes = [vp]
+    L.jb_stream.restype = vp
+    L.jb_set_profiling.argtypes = [vp, C.c_int]
+    L.jb_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.jb_reset_counters.argtypes = [vp]
+    L.jb_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.jb_host_free.argtypes = [vp]
+    L.jb_device_alloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.jb_device_free.argtypes = [vp, vp]
+    L.jb_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    L.jb_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.jb_csc_rgb8_aos.argtypes = [vp, vp, sz, sz]
+    L.jb_cds_aos.argtypes = [vp, vp, sz, sz]
+    L.jb_padded_size.argtypes = [sz, sz, sz, C.POINTER(sz), C.POINTER(sz)]
+    L.jb_pad_mirror_aos.argtypes = [vp, vp, sz, sz, vp, sz, sz]
+    L.jb_u8_to_f64.argtypes = [vp, vp, vp, sz]
+    L.jb_levelshift_f64.argtypes = [vp, vp, sz, C.c_double]
+    L.jb_dct_f64.argtypes = [vp, vp, sz, sz, C.c_uint32]
+    L.jb_quantize_f64.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.jb_blockify.argtypes = [vp, vp, sz, sz, vp]
+    L.jb_zigzag.argtypes = [vp, vp, vp, sz]
+    L.jb_rle.argtypes = [vp, vp, sz, C.c_uint32, vp, vp]
+    L.jb_huffman.argtypes = [vp, vp, sz, C.c_uint32, vp, sz, C.POINTER(u64)]
+    L.jb_quality_tables.argtypes = [C.c_int, vp, vp]
+    L.jb_num_mcus.argtypes = [sz, sz, C.c_int]
+    L.jb_num_mcus.restype = sz
+    L.jb_blocks_per_mcu.argtypes = [C.c_int]
+    L.jb_header_bytes.argtypes = [PP]
+    L.jb_header_bytes.restype = sz
+    L.jb_required_bytes.argtypes = [vp]
+    L.jb_required_bytes.restype = sz
+    L.jb_transform.argtypes = [vp, vp, sz, sz, sz, PP, vp]
+    L.jb_entropy.argtypes = [vp, vp, sz, PP, vp, sz, C.POINTER(sz)]
+    L.jb_encode_jfif.argtypes = [vp, vp, sz, sz, sz, PP, vp, sz, C.POINTER(sz)]
+    L.jb_encode_batch.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp]
+    L.jb_encode_batch_device.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, vp]
+    L.jb_encode_strip.argtypes = [vp, vp, sz, sz, sz, PP, u64, C.c_int, C.c_int, vp, sz, C.POINTER(sz)]
+    L.jb_write_header.argtypes = [PP, sz, sz, vp, sz, C.POINTER(sz)]
+    L.jb_synth_rgb_device.argtypes = [vp, u64, sz, sz, sz, sz, vp]
+    _lib = L
+    return L
+
+
+def quality_tables(quality):
+    """IJG-scaled versions of the reference's q50 tables (utils.hpp:42-62)."""
+    ql = np.zeros(64, np.uint32)
+    qc = np.zeros(64, np.uint32)
+    lib().jb_quality_tables(int(quality), ql.ctypes.data, qc.ctypes.data)
+    return ql, qc
+
+
+def make_params(subsampling=SUB_420, quality=None, qlum=None, qchrom=None, restart_interval=0, flags=0):
+    p = Params()
+    p.subsampling, p.restart_interval, p.flags = subsampling, restart_interval, flags
+    if quality is not None:
+        qlum, qchrom = quality_tables(quality)
+    for i in range(64):
+        p.qlum[i] = int(qlum[i])
+        p.qchrom[i] = int(qchrom[i])
+    return p
+
+
+def header_bytes(params):
+    return lib().jb_header_bytes(C.byref(params))
+
+
+def _ptr(a):
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+class Encoder:
+    """One jb_ctx on one GPU.  Methods mirror the reference's stage functions (utils.hpp:81-137)."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.jb_create(device, C.byref(h))
+        if rc != OK:
+            raise JbError(rc, "jb_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.jb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise JbError(rc, self.L.jb_last_error(self.h).decode())
+
+    # ---- staged: the reference's per-stage functions ------------------------------------
+    def performCSC(self, img):
+        """In place on an (H, W, 3) uint8 array; utils.hpp:81."""
+        assert img.dtype == np.uint8 and img.flags.c_contiguous
+        self._ck(self.L.jb_csc_rgb8_aos(self.h, _ptr(img), img.shape[1], img.shape[0]))
+        return img
+
+    def performCDS(self, img):
+        assert img.dtype == np.uint8 and img.flags.c_contiguous
+        self._ck(self.L.jb_cds_aos(self.h, _ptr(img), img.shape[1], img.shape[0]))
+        return img
+
+    def padMirror(self, img, mult=8):
+        H, W, _ = img.shape
+        nW, nH = -(-W // mult) * mult, -(-H // mult) * mult
+        out = np.empty((nH, nW, 3), np.uint8)
+        self._ck(self.L.jb_pad_mirror_aos(self.h, _ptr(np.ascontiguousarray(img)), W, H, _ptr(out), nW, nH))
+        return out
+
+    def copyUIntToDoubleImage(self, img):
+        out = np.empty(img.shape, np.float64)
+        self._ck(self.L.jb_u8_to_f64(self.h, _ptr(np.ascontiguousarray(img)), _ptr(out), img.size))
+        return out
+
+    def substractfromAll(self, imgd, val=128.0):
+        self._ck(self.L.jb_levelshift_f64(self.h, _ptr(imgd), imgd.size, float(val)))
+        return imgd
+
+    def performDCT(self, imgd, flags=0):
+        self._ck(self.L.jb_dct_f64(self.h, _ptr(imgd), imgd.shape[1], imgd.shape[0], flags))
+        return imgd
+
+    def performQuantization(self, imgd, qlum, qchrom):
+        ql = np.ascontiguousarray(qlum, np.uint32)
+        qc = np.ascontiguousarray(qchrom, np.uint32)
+        self._ck(self.L.jb_quantize_f64(self.h, _ptr(imgd), imgd.shape[1], imgd.shape[0], _ptr(ql), _ptr(qc)))
+        return imgd
+
+    def everyMCUisnow2DArray(self, imgd):
+        H, W, _ = imgd.shape
+        out = np.empty((3 * W * H // 64, 64), np.int32)
+        self._ck(self.L.jb_blockify(self.h, _ptr(imgd), W, H, _ptr(out)))
+        return out
+
+    def performZigZag(self, linear):
+        out = np.empty_like(linear)
+        self._ck(self.L.jb_zigzag(self.h, _ptr(np.ascontiguousarray(linear)), _ptr(out), linear.shape[0]))
+        return out
+
+    def performRLE(self, zz, flags=0):
+        """Returns a list of 1-D int32 arrays (run, value, ...) like vector<vector<int>>; utils.hpp:132."""
+        rows = zz.shape[0]
+        pairs = np.empty((rows, 128), np.int32)
+        counts = np.empty(rows, np.uint32)
+        self._ck(self.L.jb_rle(self.h, _ptr(np.ascontiguousarray(zz)), rows, flags, _ptr(pairs), _ptr(counts)))
+        return [pairs[i, :counts[i]].copy() for i in range(rows)]
+
+    def HuffmanEncoder(self, zz, rows_per_channel, flags=0):
+        """Returns (packed MSB-first bytes, nbits): the bit sequence of utils.hpp:137."""
+        cap = zz.shape[0] * 64 * 4 + 64
+        out = np.zeros(cap, np.uint8)
+        nbits = C.c_uint64()
+        self._ck(self.L.jb_huffman(self.h, _ptr(np.ascontiguousarray(zz, np.int32)), rows_per_channel, flags, _ptr(out),
+                                   cap, C.byref(nbits)))
+        return out[: (nbits.value + 7) // 8].copy(), nbits.value
+
+    # ---- fused ---------------------------------------------------------------------------
+    def transform(self, rgb, params):
+        """(H, W, 3) uint8 -> int16 [n_mcu, blocks_per_mcu, 64] zigzag coefficients in scan order."""
+        H, W, _ = rgb.shape
+        rgb = np.ascontiguousarray(rgb)
+        n = self.L.jb_num_mcus(W, H, params.subsampling)
+        out = np.empty((n, self.L.jb_blocks_per_mcu(params.subsampling), 64), np.int16)
+        self._ck(self.L.jb_transform(self.h, _ptr(rgb), W, H, W * 3, C.byref(params), _ptr(out)))
+        return out
+
+    def entropy(self, coef, params):
+        coef = np.ascontiguousarray(coef, np.int16)
+        cap = coef.size * 4 + 4096
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t()
+        self._ck(self.L.jb_entropy(self.h, _ptr(coef), coef.shape[0], C.byref(params), _ptr(out), cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def encode_jfif(self, rgb, params, cap=None):
+        H, W, _ = rgb.shape
+        rgb = np.ascontiguousarray(rgb)
+        cap = cap if cap is not None else W * H * 3 + 65536
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t()
+        self._ck(self.L.jb_encode_jfif(self.h, _ptr(rgb), W, H, W * 3, C.byref(params), _ptr(out), cap, C.byref(n)))
+        return out[: n.value].tobytes()
+
+    def encode_batch(self, frames, params, out=None):
+        """frames: (N, H, W, 3) uint8 (numpy, ideally pinned).  Returns (out, offsets, sizes)."""
+        N, H, W, _ = frames.shape
+        assert frames.flags.c_contiguous
+        if out is None:
+            out = np.empty(N * (W * H + 4096), np.uint8)
+        offs = np.zeros(N, np.uint64)
+        sizes = np.zeros(N, np.uint64)
+        self._ck(self.L.jb_encode_batch(self.h, _ptr(frames), N, W, H, W * 3, W * H * 3, C.byref(params), _ptr(out),
+                                        out.size, _ptr(offs), _ptr(sizes)))
+        return out, offs, sizes
+
+    def encode_batch_ptr(self, rgb_ptr, N, W, H, pitch, frame_stride, params, out_ptr, cap, offs, sizes):
+        self._ck(self.L.jb_encode_batch(self.h, rgb_ptr, N, W, H, pitch, frame_stride, C.byref(params), out_ptr, cap,
+                                        _ptr(offs), _ptr(sizes)))
+
+    def encode_batch_device(self, d_rgb, N, W, H, pitch, frame_stride, params, d_out, cap, d_offs, d_sizes, d_total):
+        """All pointers are device addresses (ints); asynchronous, finish with sync()."""
+        self._ck(self.L.jb_encode_batch_device(self.h, d_rgb, N, W, H, pitch, frame_stride, C.byref(params), d_out, cap,
+                                               d_offs, d_sizes, d_total))
+
+    def encode_strip(self, rgb, params, first_interval, last_strip, W=None, rows=None, pitch=None, device_io=False,
+                     out=None, cap=None):
+        if not device_io:
+            rows, W, _ = rgb.shape
+            rgb = np.ascontiguousarray(rgb)
+            pitch = W * 3
+            cap = W * rows * 3 + 65536
+            out = np.empty(cap, np.uint8)
+        n = C.c_size_t()
+        self._ck(self.L.jb_encode_strip(self.h, _ptr(rgb), W, rows, pitch, C.byref(params), first_interval,
+                                        int(last_strip), int(device_io), _ptr(out), cap, C.byref(n)))
+        return out[: n.value].copy() if not device_io else n.value
+
+    def write_header(self, params, W, H):
+        out = np.empty(1024, np.uint8)
+        n = C.c_size_t()
+        rc = self.L.jb_write_header(C.byref(params), W, H, _ptr(out), 1024, C.byref(n))
+        assert rc == OK
+        return out[: n.value].tobytes()
+
+    def synth_device(self, seed, W, y0, rows, pitch, d_out):
+        self._ck(self.L.jb_synth_rgb_device(self.h, seed, W, y0, rows, pitch, d_out))
+
+    def synth(self, seed, W, H):
+        """Synthetic image generated on the GPU, returned as numpy (tests)."""
+        d = self.device_alloc(W * H * 3)
+        try:
+            self.synth_device(seed, W, 0, H, W * 3, d)
+            out = np.empty((H, W, 3), np.uint8)
+            self._ck(self.L.jb_memcpy_d2h(self.h, _ptr(out), d, out.size))
+        finally:
+            self.device_free(d)
+        return out
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def sync(self):
+        self._ck(self.L.jb_sync(self.h))
+
+    def stream(self):
+        return self.L.jb_stream(self.h)
+
+    def set_profiling(self, on):
+        self._ck(self.L.jb_set_profiling(self.h, int(on)))
+
+    def reset_counters(self):
+        self._ck(self.L.jb_reset_counters(self.h))
+
+    def timings(self):
+        t = Timings()
+        self._ck(self.L.jb_get_timings(self.h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.L.jb_device_alloc(self.h, C.byref(p), nbytes))
+        return p.value
+
+    def device_free(self, p):
+        self._ck(self.L.jb_device_free(self.h, p))
+
+    def h2d(self, dptr, arr):
+        self._ck(self.L.jb_memcpy_h2d(self.h, dptr, _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dptr, nbytes=None):
+        self._ck(self.L.jb_memcpy_d2h(self.h, _ptr(arr), dptr, arr.nbytes if nbytes is None else nbytes))
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array over cudaMallocHost memory (kept alive by the returned array's base)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    if lib().jb_host_alloc(C.byref(p), max(n, 1)) != OK:
+        raise MemoryError("jb_host_alloc failed")
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr

@@ -1,0 +1,1066 @@
+// C ABI of libjpegb200.so (include/jpegb200.h): context, device workspaces,
+// CUDA streams with pinned staging (replacing the reference's OpenCL
+// context/queue/buffer plumbing, src/OpenCLProject_JpegEncoder.cpp:257-315 and
+// its per-stage blocking enqueueWrite/enqueueRead pairs, cpp:336-616), the
+// staged per-function entry points and the fused/batched encode calls.
+// There is no CPU fallback anywhere in this file: every entry point runs CUDA
+// kernels or fails with JB_E_CUDA.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "jb_internal.h"
+
+using namespace jb;
+
+namespace {
+
+constexpr int kSlots = 3;               // in-flight groups of the batched host path
+constexpr size_t kUbufBytesPerBlock = 64;  // unstuffed-buffer budget (typical use: 5-40 B/block)
+
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, used = 0;
+};
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int kind;  // 0 transform, 1 fixup, 2 entropy, 3 h2d, 4 d2h
+};
+
+// One in-flight unit of work: stream + device workspace + pinned result words.
+struct Slot {
+    cudaStream_t st = nullptr;
+    Arena arena;
+    // carved from the arena by plan()
+    uint8_t* d_rgb = nullptr;
+    int16_t* d_coef = nullptr;
+    uint32_t* d_tie_list = nullptr;
+    uint32_t* d_scalars = nullptr;  // [0] tie_count, [1] n_ff_tiles, then status[4] (u64, 8-aligned) at +16 bytes
+    EntropyWork w{};
+    uint8_t* d_out = nullptr;
+    size_t d_out_cap = 0;
+    uint64_t* d_frame_off = nullptr;
+    uint64_t* d_frame_size = nullptr;
+    uint64_t* d_total = nullptr;
+    uint8_t* d_hdr = nullptr;
+    uint32_t tie_cap = 0;
+    // pinned host mirror: [0..3] status, [4] total, [5] tie_count, then frame_off[n], frame_size[n]
+    uint64_t* h_res = nullptr;
+    size_t h_res_cap = 0;
+    cudaEvent_t ev_scalars = nullptr, ev_done = nullptr;
+    bool busy = false;
+    // bookkeeping of the group in flight
+    size_t first_frame = 0, n_frames = 0;
+};
+
+}  // namespace
+
+struct jb_ctx {
+    int device = 0;
+    char err[512] = {0};
+    Slot slot[kSlots];
+    uint32_t* d_ydown = nullptr;
+    double* d_costab = nullptr;
+    double* d_scale = nullptr;
+    HuffDev* d_huff[2] = {nullptr, nullptr};
+    Arena scratch;  // staged entry points
+    bool profiling = false;
+    std::vector<EventPair> events;
+    std::vector<cudaEvent_t> event_pool;
+    jb_timings tm{};
+    uint64_t required = 0;
+    uint64_t pending_status_slot = 0;
+};
+
+namespace {
+
+int fail(jb_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, JB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int arena_reserve(jb_ctx* ctx, Arena& a, size_t bytes) {
+    if (bytes <= a.cap) {
+        a.used = 0;
+        return JB_OK;
+    }
+    if (a.base) CK(cudaFree(a.base));
+    a.base = nullptr;
+    a.cap = 0;
+    size_t want = bytes + bytes / 8 + (1u << 20);
+    cudaError_t e = cudaMalloc(&a.base, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, JB_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    a.cap = want;
+    a.used = 0;
+    return JB_OK;
+}
+
+template <class T>
+T* carve(Arena& a, size_t count) {
+    size_t off = align_up(a.used, 256);
+    a.used = off + count * sizeof(T);
+    return reinterpret_cast<T*>(a.base + off);
+}
+
+struct Plan {
+    Geometry g;
+    size_t n_frames;
+    size_t n_blocks, n_tiles, n_int_total;
+    size_t rgb_bytes;      // 0 when the input is already on the device
+    size_t d_pitch, d_frame_stride;
+    size_t ubuf_cap, chunks_cap, out_cap;  // out_cap 0 when the output is a caller's device buffer
+};
+
+size_t plan_bytes(const Plan& p) {
+    size_t b = 0;
+    auto add = [&](size_t n) { b = align_up(b, 256) + n; };
+    add(p.rgb_bytes);
+    add(p.n_blocks * 128);
+    add(p.n_blocks * 4);                   // tie list
+    add(64);                               // scalars
+    add((p.n_tiles * 256 + 1) * 4);        // blk_prefix
+    add(p.n_tiles * 4);
+    add((p.n_tiles + 1) * 8);
+    add(p.n_int_total * 4);
+    add(p.n_int_total * 8);
+    add((p.n_int_total + 1) * 8);
+    add(p.ubuf_cap);
+    add((p.chunks_cap + 256) * 4);
+    add((p.chunks_cap / 256 + 2) * 4);
+    add((p.chunks_cap / 256 + 3) * 8);
+    add(p.n_int_total * 4);
+    add((p.n_int_total + 1) * 8);
+    add(p.out_cap);
+    add(p.n_frames * 8);
+    add(p.n_frames * 8);
+    add(8);
+    add(1024);
+    return align_up(b, 256) + 4096;
+}
+
+int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
+    int rc = arena_reserve(ctx, s.arena, plan_bytes(p));
+    if (rc) return rc;
+    Arena& a = s.arena;
+    s.d_rgb = carve<uint8_t>(a, p.rgb_bytes);
+    s.d_coef = carve<int16_t>(a, p.n_blocks * 64);
+    s.d_tie_list = carve<uint32_t>(a, p.n_blocks);
+    s.tie_cap = (uint32_t)p.n_blocks;
+    s.d_scalars = carve<uint32_t>(a, 16);
+    s.w.blk_prefix = carve<uint32_t>(a, p.n_tiles * 256 + 1);
+    s.w.tile_bits = carve<uint32_t>(a, p.n_tiles);
+    s.w.tile_base = carve<uint64_t>(a, p.n_tiles + 1);
+    s.w.int_slot = carve<uint32_t>(a, p.n_int_total);
+    s.w.int_bits = carve<uint64_t>(a, p.n_int_total);
+    s.w.int_ubase = carve<uint64_t>(a, p.n_int_total + 1);
+    s.w.ubuf = carve<uint8_t>(a, p.ubuf_cap);
+    s.w.ubuf_cap = p.ubuf_cap;
+    s.w.ff_prefix = carve<uint32_t>(a, p.chunks_cap + 256);
+    s.w.ff_tile = carve<uint32_t>(a, p.chunks_cap / 256 + 2);
+    s.w.ff_tile_base = carve<uint64_t>(a, p.chunks_cap / 256 + 3);
+    s.w.int_osize = carve<uint32_t>(a, p.n_int_total);
+    s.w.int_obase = carve<uint64_t>(a, p.n_int_total + 1);
+    s.d_out = carve<uint8_t>(a, p.out_cap);
+    s.d_out_cap = p.out_cap;
+    s.d_frame_off = carve<uint64_t>(a, p.n_frames);
+    s.d_frame_size = carve<uint64_t>(a, p.n_frames);
+    s.d_total = carve<uint64_t>(a, 1);
+    s.d_hdr = carve<uint8_t>(a, 1024);
+    s.w.n_ff_tiles = s.d_scalars + 1;
+    s.w.status = reinterpret_cast<uint64_t*>(s.d_scalars + 4);
+    // pinned result block: result words, then (last 1 KB) the staging area of the JFIF header
+    size_t need = (8 + 2 * p.n_frames) * sizeof(uint64_t) + 2048;
+    if (need > s.h_res_cap) {
+        if (s.h_res) cudaFreeHost(s.h_res);
+        s.h_res = nullptr;
+        s.h_res_cap = 0;
+        CK(cudaMallocHost(&s.h_res, need * 2));
+        s.h_res_cap = need * 2;
+    }
+    return JB_OK;
+}
+
+int make_plan(jb_ctx* ctx, size_t n_frames, size_t W, size_t H, const jb_params* p, bool host_in, bool host_out,
+              Plan* out) {
+    if (!p || W == 0 || H == 0 || n_frames == 0) return fail(ctx, JB_E_INVALID, "empty image or null parameters");
+    if (p->subsampling < 0 || p->subsampling > 2) return fail(ctx, JB_E_INVALID, "bad subsampling %d", p->subsampling);
+    if (p->restart_interval < 0 || p->restart_interval > 65535)
+        return fail(ctx, JB_E_INVALID, "restart interval %d out of range", p->restart_interval);
+    for (int i = 0; i < 64; ++i)
+        if (p->qlum[i] < 1 || p->qlum[i] > 255 || p->qchrom[i] < 1 || p->qchrom[i] > 255)
+            return fail(ctx, JB_E_INVALID, "quantisation table entries must be 1..255");
+    if ((W > 65535 || H > 65535) && !(p->flags & JB_FLAG_CLAMP_SOF))
+        return fail(ctx, JB_E_UNSUPPORTED, "dimension > 65535 needs JB_FLAG_CLAMP_SOF (SOF0 sizes are 16 bit)");
+    if (W >= (1u << 24) || H >= (1u << 24)) return fail(ctx, JB_E_UNSUPPORTED, "image too large");
+    Plan pl;
+    pl.g = make_geometry(W, H, p->subsampling, p->restart_interval);
+    size_t m = (size_t)pl.g.mcu_px;
+    if ((size_t)pl.g.mcux * m - W > W || (size_t)pl.g.mcuy * m - H > H)
+        return fail(ctx, JB_E_UNSUPPORTED, "image smaller than the mirror padding it needs (utils.cpp:211-233)");
+    pl.n_frames = n_frames;
+    pl.n_blocks = n_frames * (size_t)pl.g.n_mcu * (size_t)pl.g.bpm;
+    if (pl.n_blocks >= (1u << 26))
+        return fail(ctx, JB_E_UNSUPPORTED, "more than 2^26 blocks in one call; split the batch");
+    pl.n_tiles = (pl.n_blocks + 255) / 256;
+    pl.n_int_total = n_frames * (size_t)pl.g.n_int;
+    pl.d_pitch = align_up(W * 3, 16);
+    pl.d_frame_stride = pl.d_pitch * H;
+    pl.rgb_bytes = host_in ? pl.d_frame_stride * n_frames + 64 : 0;
+    pl.ubuf_cap = align_up(pl.n_blocks * kUbufBytesPerBlock + pl.n_int_total * 16, 4096);
+    pl.chunks_cap = pl.ubuf_cap / 16;
+    pl.out_cap = host_out ? pl.ubuf_cap + pl.ubuf_cap / 8 + n_frames * 1024 : 0;
+    *out = pl;
+    return JB_OK;
+}
+
+cudaEvent_t get_event(jb_ctx* ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Timed {
+    jb_ctx* ctx;
+    cudaStream_t st;
+    EventPair ep;
+    bool on;
+    Timed(jb_ctx* c, cudaStream_t s, int kind) : ctx(c), st(s), on(c->profiling) {
+        if (on) {
+            ep.a = get_event(c);
+            ep.b = get_event(c);
+            ep.kind = kind;
+            cudaEventRecord(ep.a, st);
+        }
+    }
+    ~Timed() {
+        if (on) {
+            cudaEventRecord(ep.b, st);
+            ctx->events.push_back(ep);
+        }
+    }
+};
+
+void resolve_events(jb_ctx* ctx) {
+    for (auto& ep : ctx->events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
+            double us = ms * 1000.0;
+            switch (ep.kind) {
+                case 0: ctx->tm.transform_us += us; break;
+                case 1: ctx->tm.fixup_us += us; break;
+                case 2: ctx->tm.entropy_us += us; break;
+                case 3: ctx->tm.h2d_us += us; break;
+                default: ctx->tm.d2h_us += us; break;
+            }
+        }
+        ctx->event_pool.push_back(ep.a);
+        ctx->event_pool.push_back(ep.b);
+    }
+    ctx->events.clear();
+    ctx->tm.DCTTime = ctx->tm.transform_us;
+    ctx->tm.HuffmanTime = ctx->tm.entropy_us;
+    ctx->tm.TotalCopyTime = ctx->tm.h2d_us + ctx->tm.d2h_us;
+}
+
+// Enqueue transform (+fix-up) + entropy coder for frames already in device memory.
+int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, const uint8_t* d_rgb, size_t pitch,
+                   size_t frame_stride, const Framing& fr, size_t W, size_t H, uint8_t* d_out, size_t out_cap,
+                   uint64_t* d_off, uint64_t* d_size, uint64_t* d_total) {
+    CK(cudaMemsetAsync(s.d_scalars, 0, 64, s.st));
+    TransformArgs ta{};
+    ta.rgb = d_rgb;
+    ta.pitch = pitch;
+    ta.frame_stride = frame_stride;
+    ta.n_frames = (int)pl.n_frames;
+    ta.g = pl.g;
+    ta.coef = s.d_coef;
+    ta.ydown = ctx->d_ydown;
+    ta.tie_list = s.d_tie_list;
+    ta.tie_count = s.d_scalars;
+    ta.tie_cap = s.tie_cap;
+    build_quant_const(p->qlum, p->qchrom, &ta.qc);
+    if (p->flags & JB_FLAG_NO_TIE_FIXUP)
+        for (int t = 0; t < 2; ++t)
+            for (int i = 0; i < 64; ++i) ta.qc.band[t][i] = 1.0f;  // never flag
+    {
+        Timed t(ctx, s.st, 0);
+        int n = launch_transform(ta, s.st);
+        ctx->tm.transform_launches += n;
+        ctx->tm.total_launches += n;
+    }
+    if (!(p->flags & JB_FLAG_NO_TIE_FIXUP)) {
+        FixupArgs fa{};
+        fa.rgb = d_rgb;
+        fa.pitch = pitch;
+        fa.frame_stride = frame_stride;
+        fa.g = pl.g;
+        fa.coef = s.d_coef;
+        fa.ydown = ctx->d_ydown;
+        fa.tie_list = s.d_tie_list;
+        fa.tie_count = s.d_scalars;
+        fa.tie_cap = s.tie_cap;
+        fa.costab = ctx->d_costab;
+        fa.scale = ctx->d_scale;
+        memcpy(fa.qt.q[0], p->qlum, sizeof(fa.qt.q[0]));
+        memcpy(fa.qt.q[1], p->qchrom, sizeof(fa.qt.q[1]));
+        Timed t(ctx, s.st, 1);
+        ctx->tm.total_launches += launch_fixup(fa, s.st);
+    }
+    if (!d_out) return JB_OK;  // transform only
+    EntropyArgs ea{};
+    ea.coef = s.d_coef;
+    ea.g = pl.g;
+    ea.n_frames = (int)pl.n_frames;
+    ea.n_blocks = (uint32_t)pl.n_blocks;
+    ea.n_int_total = (uint32_t)pl.n_int_total;
+    ea.huff = ctx->d_huff[(p->flags & JB_FLAG_REF_TYPO_TABLES) ? 1 : 0];
+    ea.always_eob = (p->flags & JB_FLAG_REF_ALWAYS_EOB) ? 1u : 0u;
+    ea.fr = fr;
+    ea.w = s.w;
+    ea.hdr = s.d_hdr;
+    ea.out = d_out;
+    ea.out_cap = out_cap;
+    ea.frame_off = d_off;
+    ea.frame_size = d_size;
+    ea.total_out = d_total;
+    if (fr.hdr_bytes) {
+        // the header travels through the pinned result block so that the copy is truly asynchronous
+        uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024;
+        size_t n = build_header(p, W, H, h);
+        if (n != fr.hdr_bytes) return fail(ctx, JB_E_INTERNAL, "header size mismatch");
+        CK(cudaMemcpyAsync(s.d_hdr, h, n, cudaMemcpyHostToDevice, s.st));
+    }
+    {
+        Timed t(ctx, s.st, 2);
+        ctx->tm.total_launches += launch_entropy(ea, s.st);
+    }
+    CK(cudaGetLastError());
+    return JB_OK;
+}
+
+int status_to_rc(jb_ctx* ctx, const uint64_t* st, uint64_t tie_count, uint32_t tie_cap) {
+    ctx->tm.tie_fixups = tie_count;
+    if (tie_count > tie_cap) return fail(ctx, JB_E_INTERNAL, "near-tie list overflow (%llu > %u)", (unsigned long long)tie_count, tie_cap);
+    if (st[0] & JB_STATUS_UBUF_OVERFLOW) {
+        ctx->required = st[1];
+        return fail(ctx, JB_E_NOSPACE, "entropy workspace too small: need %llu bytes", (unsigned long long)st[1]);
+    }
+    if (st[0] & JB_STATUS_OUT_OVERFLOW) {
+        ctx->required = st[2];
+        return fail(ctx, JB_E_NOSPACE, "output buffer too small: need %llu bytes", (unsigned long long)st[2]);
+    }
+    return JB_OK;
+}
+
+void fill_tables(jb_ctx* ctx, std::vector<uint32_t>& ydown, double* costab, double* scale) {
+    (void)ctx;
+    // Y tie table: bit (r<<8|g) set when the reference's binary64 expression
+    // (utils.cpp:107) lands below the exact integer value 0.299r+0.587g+0.114b.
+    ydown.assign(2048, 0);
+    for (uint32_t r = 0; r < 256; ++r)
+        for (uint32_t g = 0; g < 256; ++g)
+            for (uint32_t b = 0; b < 256; ++b) {
+                uint32_t s = 299 * r + 587 * g + 114 * b;
+                if (s % 1000) continue;
+                volatile double y = 0.299 * r + 0.587 * g + 0.114 * b;
+                if ((uint32_t)(uint8_t)y != s / 1000) ydown[(r << 8 | g) >> 5] |= 1u << ((r << 8 | g) & 31);
+            }
+    // utils.cpp:330-332 and 336: same expressions, same libm
+    for (size_t u = 0; u < 8; ++u)
+        for (size_t x = 0; x < 8; ++x) costab[u * 8 + x] = cos((2 * x + 1) * u * M_PI / 16.0);
+    for (size_t u = 0; u < 8; ++u)
+        for (size_t v = 0; v < 8; ++v) {
+            double alphaU = (u == 0) ? 1.0 / sqrt(2) : 1.0;
+            double alphaV = (v == 0) ? 1.0 / sqrt(2) : 1.0;
+            scale[u * 8 + v] = (alphaU * alphaV / 4.0);
+        }
+}
+
+int scratch(jb_ctx* ctx, size_t bytes) { return arena_reserve(ctx, ctx->scratch, bytes + 4096); }
+
+}  // namespace
+
+// =============================================================== context ====
+extern "C" {
+
+int jb_version(void) { return 100; }
+
+int jb_create(int device, jb_ctx** out) {
+    if (!out) return JB_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return JB_E_CUDA;
+    if (device < 0 || device >= n) return JB_E_INVALID;
+    jb_ctx* ctx = new (std::nothrow) jb_ctx();
+    if (!ctx) return JB_E_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return JB_E_CUDA;
+    }
+    for (auto& s : ctx->slot) {
+        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.ev_scalars, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming) != cudaSuccess) {
+            jb_destroy(ctx);
+            return JB_E_CUDA;
+        }
+    }
+    std::vector<uint32_t> ydown;
+    double costab[64], scale[64];
+    fill_tables(ctx, ydown, costab, scale);
+    HuffDev hd[2];
+    build_huff(false, &hd[0]);
+    build_huff(true, &hd[1]);
+    bool ok = cudaMalloc(&ctx->d_ydown, 2048 * 4) == cudaSuccess && cudaMalloc(&ctx->d_costab, 64 * 8) == cudaSuccess &&
+              cudaMalloc(&ctx->d_scale, 64 * 8) == cudaSuccess && cudaMalloc(&ctx->d_huff[0], sizeof(HuffDev)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_huff[1], sizeof(HuffDev)) == cudaSuccess;
+    ok = ok && cudaMemcpy(ctx->d_ydown, ydown.data(), 2048 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(ctx->d_costab, costab, sizeof(costab), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(ctx->d_scale, scale, sizeof(scale), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(ctx->d_huff[0], &hd[0], sizeof(HuffDev), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(ctx->d_huff[1], &hd[1], sizeof(HuffDev), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        jb_destroy(ctx);
+        return JB_E_CUDA;
+    }
+    *out = ctx;
+    return JB_OK;
+}
+
+void jb_destroy(jb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& s : ctx->slot) {
+        if (s.arena.base) cudaFree(s.arena.base);
+        if (s.h_res) cudaFreeHost(s.h_res);
+        if (s.ev_scalars) cudaEventDestroy(s.ev_scalars);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.st) cudaStreamDestroy(s.st);
+    }
+    if (ctx->scratch.base) cudaFree(ctx->scratch.base);
+    for (auto& ep : ctx->events) {
+        cudaEventDestroy(ep.a);
+        cudaEventDestroy(ep.b);
+    }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    cudaFree(ctx->d_ydown);
+    cudaFree(ctx->d_costab);
+    cudaFree(ctx->d_scale);
+    cudaFree(ctx->d_huff[0]);
+    cudaFree(ctx->d_huff[1]);
+    delete ctx;
+}
+
+const char* jb_last_error(const jb_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+
+void* jb_stream(jb_ctx* ctx) { return ctx ? (void*)ctx->slot[0].st : nullptr; }
+
+int jb_sync(jb_ctx* ctx) {
+    if (!ctx) return JB_E_INVALID;
+    for (auto& s : ctx->slot) CK(cudaStreamSynchronize(s.st));
+    resolve_events(ctx);
+    // device-resident calls report their status here
+    Slot& s = ctx->slot[0];
+    if (s.busy) {
+        s.busy = false;
+        return status_to_rc(ctx, s.h_res, s.h_res[5], s.tie_cap);
+    }
+    return JB_OK;
+}
+
+int jb_set_profiling(jb_ctx* ctx, int on) {
+    if (!ctx) return JB_E_INVALID;
+    ctx->profiling = on != 0;
+    return JB_OK;
+}
+
+int jb_get_timings(jb_ctx* ctx, jb_timings* t) {
+    if (!ctx || !t) return JB_E_INVALID;
+    *t = ctx->tm;
+    return JB_OK;
+}
+
+int jb_reset_counters(jb_ctx* ctx) {
+    if (!ctx) return JB_E_INVALID;
+    ctx->tm = jb_timings{};
+    return JB_OK;
+}
+
+size_t jb_required_bytes(jb_ctx* ctx) { return ctx ? (size_t)ctx->required : 0; }
+
+int jb_host_alloc(void** p, size_t bytes) {
+    if (!p) return JB_E_INVALID;
+    return cudaMallocHost(p, bytes) == cudaSuccess ? JB_OK : JB_E_NOMEM;
+}
+int jb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? JB_OK : JB_E_CUDA; }
+int jb_device_alloc(jb_ctx* ctx, void** p, size_t bytes) {
+    if (!ctx || !p) return JB_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, JB_E_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return JB_OK;
+}
+int jb_device_free(jb_ctx* ctx, void* p) {
+    CK(cudaFree(p));
+    return JB_OK;
+}
+int jb_memcpy_h2d(jb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->slot[0].st));
+    CK(cudaStreamSynchronize(ctx->slot[0].st));
+    return JB_OK;
+}
+int jb_memcpy_d2h(jb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->slot[0].st));
+    CK(cudaStreamSynchronize(ctx->slot[0].st));
+    return JB_OK;
+}
+
+// ================================================================ staged ====
+// Each call: host -> device, one kernel, device -> host, synchronous -- the
+// reference's per-stage protocol (cpp:336-616) with the blocking OpenCL
+// transfers replaced by stream-ordered copies.
+
+#define STAGE_BEGIN(bytes)                           \
+    if (!ctx) return JB_E_INVALID;                   \
+    CK(cudaSetDevice(ctx->device));                  \
+    {                                                \
+        int rc_ = scratch(ctx, (bytes));             \
+        if (rc_) return rc_;                         \
+    }                                                \
+    cudaStream_t st = ctx->slot[0].st;               \
+    Arena& A = ctx->scratch;                         \
+    (void)A;
+
+#define STAGE_END()                   \
+    CK(cudaGetLastError());           \
+    CK(cudaStreamSynchronize(st));    \
+    return JB_OK;
+
+int jb_csc_rgb8_aos(jb_ctx* ctx, uint8_t* px, size_t W, size_t H) {
+    size_t n = W * H;
+    if (!px || n == 0) return fail(ctx, JB_E_INVALID, "empty image");
+    STAGE_BEGIN(n * 3)
+    uint8_t* d = carve<uint8_t>(A, n * 3);
+    CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_csc(d, n, ctx->d_ydown, st);
+    CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_cds_aos(jb_ctx* ctx, uint8_t* px, size_t W, size_t H) {
+    size_t n = W * H;
+    if (!px || n == 0) return fail(ctx, JB_E_INVALID, "empty image");
+    STAGE_BEGIN(n * 3)
+    uint8_t* d = carve<uint8_t>(A, n * 3);
+    CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st));
+    if (W >= 2 && H >= 2) ctx->tm.total_launches += launch_cds(d, W, H, st);
+    CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_padded_size(size_t W, size_t H, size_t mult, size_t* nW, size_t* nH) {
+    if (!nW || !nH || mult == 0) return JB_E_INVALID;
+    *nW = (W + mult - 1) / mult * mult;
+    *nH = (H + mult - 1) / mult * mult;
+    return JB_OK;
+}
+
+int jb_pad_mirror_aos(jb_ctx* ctx, const uint8_t* src, size_t W, size_t H, uint8_t* dst, size_t nW, size_t nH) {
+    if (!src || !dst || W == 0 || H == 0 || nW < W || nH < H) return fail(ctx, JB_E_INVALID, "bad sizes");
+    if (nW - W > W || nH - H > H) return fail(ctx, JB_E_UNSUPPORTED, "padding larger than the image");
+    STAGE_BEGIN(W * H * 3 + nW * nH * 3 + 512)
+    uint8_t* ds = carve<uint8_t>(A, W * H * 3);
+    uint8_t* dd = carve<uint8_t>(A, nW * nH * 3);
+    CK(cudaMemcpyAsync(ds, src, W * H * 3, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_pad(ds, W, H, dd, nW, nH, st);
+    CK(cudaMemcpyAsync(dst, dd, nW * nH * 3, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_u8_to_f64(jb_ctx* ctx, const uint8_t* src, double* dst, size_t n) {
+    if (!src || !dst || n == 0) return fail(ctx, JB_E_INVALID, "empty input");
+    STAGE_BEGIN(n * 9 + 512)
+    double* dd = carve<double>(A, n);
+    uint8_t* ds = carve<uint8_t>(A, n);
+    CK(cudaMemcpyAsync(ds, src, n, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_u8_to_f64(ds, dd, n, st);
+    CK(cudaMemcpyAsync(dst, dd, n * 8, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_levelshift_f64(jb_ctx* ctx, double* img, size_t n, double val) {
+    if (!img || n == 0) return fail(ctx, JB_E_INVALID, "empty input");
+    STAGE_BEGIN(n * 8)
+    double* d = carve<double>(A, n);
+    CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_sub_f64(d, n, val, st);
+    CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_dct_f64(jb_ctx* ctx, double* img, size_t W, size_t H, uint32_t flags) {
+    if (!img || W == 0 || H == 0 || (W & 7) || (H & 7)) return fail(ctx, JB_E_INVALID, "size must be a multiple of 8");
+    size_t n = W * H * 3;
+    STAGE_BEGIN(n * 8)
+    double* d = carve<double>(A, n);
+    CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches +=
+        launch_dct_f64(d, W, H, (flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0, ctx->d_costab, ctx->d_scale, st);
+    CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_quantize_f64(jb_ctx* ctx, double* img, size_t W, size_t H, const uint32_t ql[64], const uint32_t qc[64]) {
+    if (!img || !ql || !qc || W == 0 || H == 0) return fail(ctx, JB_E_INVALID, "bad arguments");
+    size_t n = W * H * 3;
+    STAGE_BEGIN(n * 8)
+    double* d = carve<double>(A, n);
+    QuantTables qt;
+    memcpy(qt.q[0], ql, sizeof(qt.q[0]));
+    memcpy(qt.q[1], qc, sizeof(qt.q[1]));
+    CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_quant_f64(d, W, H, qt, st);
+    CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_blockify(jb_ctx* ctx, const double* img, size_t W, size_t H, int32_t* linear) {
+    if (!img || !linear || W == 0 || H == 0 || (W & 7) || (H & 7)) return fail(ctx, JB_E_INVALID, "bad arguments");
+    size_t n = W * H * 3;
+    STAGE_BEGIN(n * 12 + 512)
+    double* d = carve<double>(A, n);
+    int32_t* o = carve<int32_t>(A, n);
+    CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_blockify(d, W, H, o, st);
+    CK(cudaMemcpyAsync(linear, o, n * 4, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_zigzag(jb_ctx* ctx, const int32_t* linear, int32_t* zz, size_t rows) {
+    if (!linear || !zz || rows == 0) return fail(ctx, JB_E_INVALID, "bad arguments");
+    size_t n = rows * 64;
+    STAGE_BEGIN(n * 8 + 512)
+    int32_t* a = carve<int32_t>(A, n);
+    int32_t* b = carve<int32_t>(A, n);
+    CK(cudaMemcpyAsync(a, linear, n * 4, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_zigzag(a, b, rows, st);
+    CK(cudaMemcpyAsync(zz, b, n * 4, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_rle(jb_ctx* ctx, const int32_t* zz, size_t rows, uint32_t flags, int32_t* pairs, uint32_t* counts) {
+    if (!zz || !pairs || !counts || rows == 0) return fail(ctx, JB_E_INVALID, "bad arguments");
+    STAGE_BEGIN(rows * (256 + 512 + 4) + 1024)
+    int32_t* a = carve<int32_t>(A, rows * 64);
+    int32_t* b = carve<int32_t>(A, rows * 128);
+    uint32_t* c = carve<uint32_t>(A, rows);
+    CK(cudaMemcpyAsync(a, zz, rows * 256, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_rle(a, rows, (flags & JB_FLAG_REF_ALWAYS_EOB) ? 1 : 0, b, c, st);
+    CK(cudaMemcpyAsync(pairs, b, rows * 512, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(counts, c, rows * 4, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+// ================================================================= fused ====
+
+int jb_quality_tables(int quality, uint32_t ql[64], uint32_t qc[64]) {
+    // IJG scaling of the reference's q50 tables (utils.hpp:42-62 = T.81 K.1/K.2)
+    static const uint32_t l50[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                                     14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                                     18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                                     49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+    static const uint32_t c50[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                     24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                                     99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                     99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+    if (!ql || !qc) return JB_E_INVALID;
+    quality = quality < 1 ? 1 : quality > 100 ? 100 : quality;
+    int s = quality < 50 ? 5000 / quality : 200 - 2 * quality;
+    for (int i = 0; i < 64; ++i) {
+        long a = ((long)l50[i] * s + 50) / 100, b = ((long)c50[i] * s + 50) / 100;
+        ql[i] = (uint32_t)(a < 1 ? 1 : a > 255 ? 255 : a);
+        qc[i] = (uint32_t)(b < 1 ? 1 : b > 255 ? 255 : b);
+    }
+    return JB_OK;
+}
+
+size_t jb_num_mcus(size_t W, size_t H, int sub) { return (size_t)make_geometry(W, H, sub, 0).n_mcu; }
+int jb_blocks_per_mcu(int sub) { return sub == JB_SUB_420 ? 6 : 3; }
+
+size_t jb_header_bytes(const jb_params* p) {
+    if (!p) return 0;
+    uint8_t tmp[1024];
+    return build_header(p, 8, 8, tmp);
+}
+
+int jb_write_header(const jb_params* p, size_t W, size_t H, uint8_t* out, size_t cap, size_t* out_len) {
+    if (!p || !out || !out_len) return JB_E_INVALID;
+    uint8_t tmp[1024];
+    size_t n = build_header(p, W, H, tmp);
+    *out_len = n;
+    if (n > cap) return JB_E_NOSPACE;
+    memcpy(out, tmp, n);
+    return JB_OK;
+}
+
+static int upload_frames(jb_ctx* ctx, Slot& s, const Plan& pl, const uint8_t* rgb, size_t W, size_t H, size_t pitch,
+                         size_t frame_stride) {
+    Timed t(ctx, s.st, 3);
+    if (pitch == pl.d_pitch && (frame_stride == pl.d_frame_stride || pl.n_frames == 1)) {
+        CK(cudaMemcpyAsync(s.d_rgb, rgb, pl.d_frame_stride * pl.n_frames, cudaMemcpyHostToDevice, s.st));
+    } else if (frame_stride == pitch * H) {
+        CK(cudaMemcpy2DAsync(s.d_rgb, pl.d_pitch, rgb, pitch, W * 3, H * pl.n_frames, cudaMemcpyHostToDevice, s.st));
+    } else {
+        for (size_t f = 0; f < pl.n_frames; ++f)
+            CK(cudaMemcpy2DAsync(s.d_rgb + f * pl.d_frame_stride, pl.d_pitch, rgb + f * frame_stride, pitch, W * 3, H,
+                                 cudaMemcpyHostToDevice, s.st));
+    }
+    return JB_OK;
+}
+
+int jb_transform(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t H, size_t pitch, const jb_params* p, int16_t* coef) {
+    if (!ctx || !rgb || !coef) return fail(ctx, JB_E_INVALID, "null argument");
+    if (pitch < W * 3) return fail(ctx, JB_E_INVALID, "pitch smaller than a row");
+    CK(cudaSetDevice(ctx->device));
+    Plan pl;
+    int rc = make_plan(ctx, 1, W, H, p, true, false, &pl);
+    if (rc) return rc;
+    Slot& s = ctx->slot[0];
+    if ((rc = slot_prepare(ctx, s, pl))) return rc;
+    if ((rc = upload_frames(ctx, s, pl, rgb, W, H, pitch, pitch * H))) return rc;
+    Framing fr{};
+    if ((rc = enqueue_encode(ctx, s, pl, p, s.d_rgb, pl.d_pitch, pl.d_frame_stride, fr, W, H, nullptr, 0, nullptr,
+                             nullptr, nullptr)))
+        return rc;
+    CK(cudaMemcpyAsync(coef, s.d_coef, pl.n_blocks * 128, cudaMemcpyDeviceToHost, s.st));
+    s.h_res[5] = 0;
+    CK(cudaMemcpyAsync(s.h_res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+    resolve_events(ctx);
+    uint64_t zero[4] = {0, 0, 0, 0};
+    return status_to_rc(ctx, zero, (uint32_t)s.h_res[5], s.tie_cap);
+}
+
+// Entropy-code coefficients that are already in the slot's d_coef.
+static int entropy_from_slot(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, const Framing& fr, uint8_t* out,
+                             size_t cap, size_t* out_len, uint64_t* nbits) {
+    EntropyArgs ea{};
+    ea.coef = s.d_coef;
+    ea.g = pl.g;
+    ea.n_frames = (int)pl.n_frames;
+    ea.n_blocks = (uint32_t)pl.n_blocks;
+    ea.n_int_total = (uint32_t)pl.n_int_total;
+    ea.huff = ctx->d_huff[(p->flags & JB_FLAG_REF_TYPO_TABLES) ? 1 : 0];
+    ea.always_eob = (p->flags & JB_FLAG_REF_ALWAYS_EOB) ? 1u : 0u;
+    ea.fr = fr;
+    ea.w = s.w;
+    ea.hdr = s.d_hdr;
+    ea.out = s.d_out;
+    ea.out_cap = s.d_out_cap;
+    ea.total_out = s.d_total;
+    {
+        Timed t(ctx, s.st, 2);
+        ctx->tm.total_launches += launch_entropy(ea, s.st);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s.h_res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpyAsync(s.h_res + 4, s.d_total, 8, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpyAsync(s.h_res + 6, s.w.int_bits, 8, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+    int rc = status_to_rc(ctx, s.h_res, 0, s.tie_cap);
+    if (rc) return rc;
+    size_t n;
+    const uint8_t* src;
+    if (fr.raw_bits) {
+        if (nbits) *nbits = s.h_res[6];
+        n = (size_t)((s.h_res[6] + 7) >> 3);
+        src = s.w.ubuf;
+    } else {
+        n = (size_t)s.h_res[4];
+        src = s.d_out;
+    }
+    if (out_len) *out_len = n;
+    if (n > cap) {
+        ctx->required = n;
+        return fail(ctx, JB_E_NOSPACE, "output buffer too small: need %zu bytes", n);
+    }
+    CK(cudaMemcpyAsync(out, src, n, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+    resolve_events(ctx);
+    return JB_OK;
+}
+
+int jb_entropy(jb_ctx* ctx, const int16_t* coef, size_t n_mcu, const jb_params* p, uint8_t* out, size_t cap,
+               size_t* out_len) {
+    if (!ctx || !coef || !out || !p || n_mcu == 0) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    // geometry only matters through n_mcu / blocks per MCU / restart interval here
+    size_t m = p->subsampling == JB_SUB_420 ? 16 : 8;
+    Plan pl;
+    int rc = make_plan(ctx, 1, m, m, p, false, true, &pl);
+    if (rc) return rc;
+    if (n_mcu * (size_t)pl.g.bpm >= (1u << 26)) return fail(ctx, JB_E_UNSUPPORTED, "too many blocks");
+    {
+        pl.g.n_mcu = (int)n_mcu;
+        pl.g.ri = p->restart_interval > 0 ? p->restart_interval : (int)n_mcu;
+        pl.g.n_int = (pl.g.n_mcu + pl.g.ri - 1) / pl.g.ri;
+        pl.n_blocks = n_mcu * (size_t)pl.g.bpm;
+        pl.n_tiles = (pl.n_blocks + 255) / 256;
+        pl.n_int_total = (size_t)pl.g.n_int;
+        pl.ubuf_cap = align_up(pl.n_blocks * kUbufBytesPerBlock + pl.n_int_total * 16, 4096);
+        pl.chunks_cap = pl.ubuf_cap / 16;
+        pl.out_cap = pl.ubuf_cap + pl.ubuf_cap / 8 + 1024;
+    }
+    Slot& s = ctx->slot[0];
+    if ((rc = slot_prepare(ctx, s, pl))) return rc;
+    CK(cudaMemsetAsync(s.d_scalars, 0, 64, s.st));
+    CK(cudaMemcpyAsync(s.d_coef, coef, pl.n_blocks * 128, cudaMemcpyHostToDevice, s.st));
+    Framing fr{};
+    return entropy_from_slot(ctx, s, pl, p, fr, out, cap, out_len, nullptr);
+}
+
+int jb_huffman(jb_ctx* ctx, const int32_t* zz, size_t rpc, uint32_t flags, uint8_t* bits, size_t cap, uint64_t* nbits) {
+    if (!ctx || !zz || !bits || rpc == 0) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    jb_params p{};
+    p.subsampling = JB_SUB_REPL420;
+    p.flags = flags;
+    for (int i = 0; i < 64; ++i) p.qlum[i] = p.qchrom[i] = 1;
+    Plan pl;
+    int rc = make_plan(ctx, 1, 8, 8, &p, false, true, &pl);
+    if (rc) return rc;
+    pl.g.n_mcu = (int)rpc;
+    pl.g.ri = (int)rpc;
+    pl.g.n_int = 1;
+    pl.n_blocks = rpc * 3;
+    if (pl.n_blocks >= (1u << 26)) return fail(ctx, JB_E_UNSUPPORTED, "too many blocks");
+    pl.n_tiles = (pl.n_blocks + 255) / 256;
+    pl.n_int_total = 1;
+    pl.ubuf_cap = align_up(pl.n_blocks * 256 + 16, 4096);  // worst case: the bit string is the product here
+    pl.chunks_cap = pl.ubuf_cap / 16;
+    pl.out_cap = 4096;
+    pl.rgb_bytes = rpc * 3 * 64 * 4;  // staging for the int32 planar input
+    Slot& s = ctx->slot[0];
+    if ((rc = slot_prepare(ctx, s, pl))) return rc;
+    CK(cudaMemsetAsync(s.d_scalars, 0, 64, s.st));
+    int32_t* d_zz = reinterpret_cast<int32_t*>(s.d_rgb);
+    CK(cudaMemcpyAsync(d_zz, zz, rpc * 3 * 64 * 4, cudaMemcpyHostToDevice, s.st));
+    ctx->tm.total_launches += launch_planar_to_scan(d_zz, rpc, s.d_coef, s.st);
+    Framing fr{};
+    fr.raw_bits = 1;
+    size_t n = 0;
+    return entropy_from_slot(ctx, s, pl, &p, fr, bits, cap, &n, nbits);
+}
+
+// Harvest a finished group of the batched host path: read its totals, copy its bytes out.
+static int harvest(jb_ctx* ctx, Slot& s, uint8_t* out, size_t cap, uint64_t* offsets, uint64_t* sizes,
+                   uint64_t* running) {
+    CK(cudaEventSynchronize(s.ev_scalars));
+    int rc = status_to_rc(ctx, s.h_res, (uint32_t)s.h_res[5], s.tie_cap);
+    if (rc) return rc;
+    uint64_t total = s.h_res[4];
+    if (*running + total > cap) {
+        ctx->required = *running + total;
+        return fail(ctx, JB_E_NOSPACE, "output buffer too small: need more than %llu bytes",
+                    (unsigned long long)(*running + total));
+    }
+    {
+        Timed t(ctx, s.st, 4);
+        CK(cudaMemcpyAsync(out + *running, s.d_out, total, cudaMemcpyDeviceToHost, s.st));
+    }
+    CK(cudaEventRecord(s.ev_done, s.st));
+    for (size_t f = 0; f < s.n_frames; ++f) {
+        if (offsets) offsets[s.first_frame + f] = *running + s.h_res[6 + f];
+        if (sizes) sizes[s.first_frame + f] = s.h_res[6 + s.n_frames + f];
+    }
+    *running += total;
+    s.busy = false;
+    return JB_OK;
+}
+
+int jb_encode_batch(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
+                    size_t frame_stride, const jb_params* p, uint8_t* out, size_t cap, uint64_t* offsets,
+                    uint64_t* sizes) {
+    if (!ctx || !rgb || !out) return fail(ctx, JB_E_INVALID, "null argument");
+    if (pitch < W * 3 || (n_frames > 1 && frame_stride < pitch * H)) return fail(ctx, JB_E_INVALID, "bad pitch/stride");
+    CK(cudaSetDevice(ctx->device));
+    // group size: about 96 MB of RGB per group, at least one frame
+    size_t frame_bytes = W * H * 3;
+    size_t fpg = std::max<size_t>(1, (96u << 20) / std::max<size_t>(frame_bytes, 1));
+    fpg = std::min(fpg, n_frames);
+    Plan pl;
+    int rc = make_plan(ctx, fpg, W, H, p, true, true, &pl);
+    if (rc) return rc;
+    Framing fr{};
+    fr.hdr_bytes = (uint32_t)jb_header_bytes(p);
+    fr.emit_eoi = 1;
+    size_t n_groups = (n_frames + fpg - 1) / fpg;
+    uint64_t running = 0;
+    size_t harvested = 0;
+    for (auto& s : ctx->slot) s.busy = false;
+    for (size_t gi = 0; gi < n_groups; ++gi) {
+        Slot& s = ctx->slot[gi % kSlots];
+        if (s.busy) {  // the slot still holds group gi - kSlots: drain it first (in order)
+            if ((rc = harvest(ctx, s, out, cap, offsets, sizes, &running))) goto drain;
+            ++harvested;
+        }
+        CK(cudaEventSynchronize(s.ev_done));  // its previous D2H must have left the device buffer
+        {
+            size_t f0 = gi * fpg, nf = std::min(fpg, n_frames - f0);
+            Plan gp = pl;
+            if (nf != fpg && (rc = make_plan(ctx, nf, W, H, p, true, true, &gp))) goto drain;
+            if (s.arena.cap == 0 && (rc = slot_prepare(ctx, s, pl))) goto drain;  // size every slot for a full group
+            if ((rc = slot_prepare(ctx, s, gp))) goto drain;
+            s.first_frame = f0;
+            s.n_frames = nf;
+            if ((rc = upload_frames(ctx, s, gp, rgb + f0 * frame_stride, W, H, pitch, frame_stride))) goto drain;
+            if ((rc = enqueue_encode(ctx, s, gp, p, s.d_rgb, gp.d_pitch, gp.d_frame_stride, fr, W, H, s.d_out,
+                                     s.d_out_cap, s.d_frame_off, s.d_frame_size, s.d_total)))
+                goto drain;
+            CK(cudaMemcpyAsync(s.h_res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
+            CK(cudaMemcpyAsync(s.h_res + 4, s.d_total, 8, cudaMemcpyDeviceToHost, s.st));
+            s.h_res[5] = 0;
+            CK(cudaMemcpyAsync(s.h_res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
+            CK(cudaMemcpyAsync(s.h_res + 6, s.d_frame_off, nf * 8, cudaMemcpyDeviceToHost, s.st));
+            CK(cudaMemcpyAsync(s.h_res + 6 + nf, s.d_frame_size, nf * 8, cudaMemcpyDeviceToHost, s.st));
+            CK(cudaEventRecord(s.ev_scalars, s.st));
+            s.busy = true;
+        }
+    }
+    // drain the remaining groups in submission order
+    for (size_t gi = harvested; gi < n_groups; ++gi) {
+        Slot& s = ctx->slot[gi % kSlots];
+        if (s.busy && (rc = harvest(ctx, s, out, cap, offsets, sizes, &running))) goto drain;
+    }
+    rc = JB_OK;
+drain:
+    for (auto& s : ctx->slot) {
+        cudaStreamSynchronize(s.st);
+        s.busy = false;
+    }
+    resolve_events(ctx);
+    return rc;
+}
+
+int jb_encode_jfif(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t H, size_t pitch, const jb_params* p, uint8_t* out,
+                   size_t cap, size_t* out_len) {
+    uint64_t off = 0, size = 0;
+    int rc = jb_encode_batch(ctx, rgb, 1, W, H, pitch, pitch * H, p, out, cap, &off, &size);
+    if (out_len) *out_len = rc == JB_E_NOSPACE ? (size_t)jb_required_bytes(ctx) : (size_t)size;
+    return rc;
+}
+
+int jb_encode_batch_device(jb_ctx* ctx, const uint8_t* d_rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
+                           size_t frame_stride, const jb_params* p, uint8_t* d_out, size_t cap, uint64_t* d_offsets,
+                           uint64_t* d_sizes, uint64_t* d_total) {
+    if (!ctx || !d_rgb || !d_out) return fail(ctx, JB_E_INVALID, "null argument");
+    if (pitch < W * 3 || (n_frames > 1 && frame_stride < pitch * H)) return fail(ctx, JB_E_INVALID, "bad pitch/stride");
+    CK(cudaSetDevice(ctx->device));
+    Plan pl;
+    int rc = make_plan(ctx, n_frames, W, H, p, false, false, &pl);
+    if (rc) return rc;
+    Slot& s = ctx->slot[0];
+    if (s.arena.cap < plan_bytes(pl)) CK(cudaStreamSynchronize(s.st));  // regrowing frees the arena
+    if ((rc = slot_prepare(ctx, s, pl))) return rc;
+    Framing fr{};
+    fr.hdr_bytes = (uint32_t)jb_header_bytes(p);
+    fr.emit_eoi = 1;
+    if ((rc = enqueue_encode(ctx, s, pl, p, d_rgb, pitch, frame_stride, fr, W, H, d_out, cap, d_offsets, d_sizes,
+                             d_total ? d_total : s.d_total)))
+        return rc;
+    CK(cudaMemcpyAsync(s.h_res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
+    s.h_res[5] = 0;
+    CK(cudaMemcpyAsync(s.h_res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
+    s.busy = true;  // status is examined by jb_sync
+    return JB_OK;
+}
+
+int jb_encode_strip(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params* p,
+                    uint64_t first_interval, int last_strip, int device_io, uint8_t* out, size_t cap, size_t* out_len) {
+    if (!ctx || !rgb || !out || !out_len) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    Plan pl;
+    int rc = make_plan(ctx, 1, W, strip_rows, p, !device_io, !device_io, &pl);
+    if (rc) return rc;
+    if (p->restart_interval <= 0 || pl.g.ri % pl.g.mcux != 0)
+        return fail(ctx, JB_E_INVALID, "strips need a restart interval that is a whole number of MCU rows");
+    if (!last_strip && strip_rows % (size_t)pl.g.mcu_px)
+        return fail(ctx, JB_E_INVALID, "only the last strip may have a partial MCU row");
+    Slot& s = ctx->slot[0];
+    CK(cudaStreamSynchronize(s.st));
+    if ((rc = slot_prepare(ctx, s, pl))) return rc;
+    Framing fr{};
+    fr.final_rst = last_strip ? 0u : 1u;
+    fr.rst_phase = (uint32_t)(first_interval & 7);
+    const uint8_t* d_rgb = rgb;
+    size_t d_pitch = pitch;
+    if (!device_io) {
+        if ((rc = upload_frames(ctx, s, pl, rgb, W, strip_rows, pitch, pitch * strip_rows))) return rc;
+        d_rgb = s.d_rgb;
+        d_pitch = pl.d_pitch;
+    }
+    uint8_t* d_out = device_io ? out : s.d_out;
+    size_t d_cap = device_io ? cap : s.d_out_cap;
+    if ((rc = enqueue_encode(ctx, s, pl, p, d_rgb, d_pitch, d_pitch * strip_rows, fr, W, strip_rows, d_out, d_cap,
+                             nullptr, nullptr, s.d_total)))
+        return rc;
+    CK(cudaMemcpyAsync(s.h_res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpyAsync(s.h_res + 4, s.d_total, 8, cudaMemcpyDeviceToHost, s.st));
+    s.h_res[5] = 0;
+    CK(cudaMemcpyAsync(s.h_res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+    if ((rc = status_to_rc(ctx, s.h_res, (uint32_t)s.h_res[5], s.tie_cap))) return rc;
+    *out_len = (size_t)s.h_res[4];
+    if (!device_io) {
+        if (*out_len > cap) {
+            ctx->required = *out_len;
+            return fail(ctx, JB_E_NOSPACE, "output buffer too small: need %zu bytes", *out_len);
+        }
+        CK(cudaMemcpyAsync(out, s.d_out, *out_len, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaStreamSynchronize(s.st));
+    }
+    resolve_events(ctx);
+    return JB_OK;
+}
+
+int jb_synth_rgb_device(jb_ctx* ctx, uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t* d_out) {
+    if (!ctx || !d_out || pitch < W * 3) return fail(ctx, JB_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.total_launches += launch_synth(seed, W, y0, rows, pitch, d_out, ctx->slot[0].st);
+    CK(cudaGetLastError());
+    return JB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,433 @@
+// GPU entropy coder: RLE + Huffman (utils.cpp:572-698) as a multi-pass parallel
+// coder, plus what the reference lacks for a real JPEG stream: byte packing,
+// 1-padding, 0xFF00 stuffing, RSTn/EOI markers.
+//
+//   k_len       one thread per 8x8 block: code length of the block (DC difference
+//               + run/size symbols); exclusive scan inside each 256-block tile
+//   k_scan      exclusive scan of the tile totals (device-wide bit offsets)
+//   k_intervals bits / reserved bytes of every restart interval
+//   k_scan      byte offset of every interval in the unstuffed buffer
+//   k_zero      clear the used part of the unstuffed buffer
+//   k_pack      one thread per block: re-walk the block and OR its codes into the
+//               unstuffed buffer at its bit offset (+ 1-padding at interval end)
+//   k_ff_count  0xFF bytes per 16-byte chunk, scan inside 256-chunk tiles
+//   k_scan      device-wide 0xFF prefix
+//   k_int_out   output bytes of every interval (data + stuffing + marker + header)
+//   k_scan      output offset of every interval / frame
+//   k_finalize  capacity check, frame table
+//   k_stuff     copy chunks to their final place inserting 0x00 after 0xFF, markers
+//   k_headers   JFIF header in front of every frame
+// Bit order is MSB first; the unstuffed buffer is addressed as big-endian words.
+#include "jb_internal.h"
+
+namespace jb {
+
+constexpr int TILE = 256;
+
+// ------------------------------------------------------------ block walker --
+struct LenSink {
+    uint32_t bits;
+    __device__ __forceinline__ void put(uint32_t, int len) { bits += (uint32_t)len; }
+};
+
+struct BitSink {
+    uint64_t acc;
+    int n;
+    uint32_t* wp;
+    __device__ __forceinline__ void init(uint8_t* base, uint64_t bitpos) {
+        wp = reinterpret_cast<uint32_t*>(base) + (bitpos >> 5);
+        n = (int)(bitpos & 31);
+        acc = 0;
+    }
+    __device__ __forceinline__ void put(uint32_t code, int len) {
+        acc = (acc << len) | code;
+        n += len;
+        if (n >= 32) {
+            n -= 32;
+            atomicOr(wp, __byte_perm((uint32_t)(acc >> n), 0, 0x0123));
+            ++wp;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (n > 0) atomicOr(wp, __byte_perm((uint32_t)(acc << (32 - n)), 0, 0x0123));
+    }
+};
+
+// value bits of v in `cat` bits: v >= 0 -> v, v < 0 -> v + 2^cat - 1 (utils.cpp:630-653)
+__device__ __forceinline__ void cat_bits(int v, int& cat, uint32_t& vb) {
+    cat = 32 - __clz(abs(v));  // utils.cpp:623-627
+    vb = (uint32_t)(v + (v >> 31)) & ((1u << cat) - 1u);
+}
+
+// One block as HuffmanEncoder codes it (utils.cpp:667-694); w = 64 int16 in zigzag order.
+template <class Sink>
+__device__ __forceinline__ void encode_block(const uint32_t (&w)[32], int dc_diff, const uint32_t* s_ac,
+                                             const uint32_t* s_dc, bool always_eob, Sink& s) {
+    int cat;
+    uint32_t vb;
+    cat_bits(dc_diff, cat, vb);
+    uint32_t e = s_dc[cat];
+    s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
+    int run = 0;
+#pragma unroll
+    for (int k = 1; k < 64; ++k) {
+        int v = (k & 1) ? ((int)w[k >> 1] >> 16) : (int)(short)(w[k >> 1] & 0xFFFFu);
+        if (v == 0) {
+            ++run;
+        } else {
+            while (run >= 16) {  // ZRL, utils.cpp:592-597
+                uint32_t z = s_ac[0xF0];
+                s.put(z >> 5, (int)(z & 31u));
+                run -= 16;
+            }
+            cat_bits(v, cat, vb);
+            e = s_ac[(run << 4) | cat];
+            s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
+            run = 0;
+        }
+    }
+    if (run > 0 || always_eob) {  // EOB, utils.cpp:607-608 (Q3 when always_eob)
+        e = s_ac[0];
+        s.put(e >> 5, (int)(e & 31u));
+    }
+}
+
+struct BlockInfo {
+    int comp;          // 0 Y, 1 Cb, 2 Cr
+    int pred;          // DC predictor
+    uint32_t interval; // global restart-interval index
+    bool last_in_interval;
+};
+
+__device__ __forceinline__ BlockInfo block_info(const EntropyArgs& a, uint32_t b) {
+    BlockInfo bi;
+    const uint32_t bpm = (uint32_t)a.g.bpm, bpf = (uint32_t)a.g.n_mcu * bpm, ri = (uint32_t)a.g.ri;
+    uint32_t f = b / bpf, rb = b - f * bpf;
+    uint32_t mcu = rb / bpm, j = rb - mcu * bpm;
+    uint32_t k = mcu / ri;
+    bool first = mcu - k * ri == 0;  // first MCU of its restart interval: predictors are 0
+    bi.interval = f * (uint32_t)a.g.n_int + k;
+    uint32_t mcu_end = min((k + 1) * ri, (uint32_t)a.g.n_mcu);
+    bi.last_in_interval = (mcu == mcu_end - 1) && (j == bpm - 1);
+    uint32_t prev;
+    bool has_prev;
+    if (bpm == 3) {
+        bi.comp = (int)j;
+        has_prev = !first;
+        prev = b - 3;
+    } else {
+        bi.comp = j < 4 ? 0 : (int)j - 3;
+        if (j >= 1 && j <= 3) {
+            has_prev = true;
+            prev = b - 1;
+        } else {
+            has_prev = !first;
+            prev = b - (j == 0 ? 3u : 6u);
+        }
+    }
+    bi.pred = has_prev ? (int)a.coef[(size_t)prev * 64] : 0;  // utils.cpp:669-670
+    return bi;
+}
+
+__device__ __forceinline__ void load_block(const EntropyArgs& a, uint32_t b, uint32_t (&w)[32]) {
+    const uint4* p = reinterpret_cast<const uint4*>(a.coef) + (size_t)b * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint4 q = __ldg(p + i);
+        w[4 * i] = q.x;
+        w[4 * i + 1] = q.y;
+        w[4 * i + 2] = q.z;
+        w[4 * i + 3] = q.w;
+    }
+}
+
+__device__ __forceinline__ void load_tables(const EntropyArgs& a, uint32_t (&s_ac)[2][256], uint32_t (&s_dc)[2][16]) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_ac[0][0])[i] = (&a.huff->ac[0][0])[i];
+    if (threadIdx.x < 32) (&s_dc[0][0])[threadIdx.x] = (&a.huff->dc[0][0])[threadIdx.x];
+    __syncthreads();
+}
+
+// exclusive scan of one value per thread over a 256-thread CTA; total in *total
+__device__ __forceinline__ uint32_t cta_scan_256(uint32_t x, uint32_t* s_warp, uint32_t& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t t = s_warp[i];
+        if (i < wid) base += t;
+        tot += t;
+    }
+    __syncthreads();
+    total = tot;
+    return base + inc - x;
+}
+
+__global__ void __launch_bounds__(TILE) k_len(const __grid_constant__ EntropyArgs a) {
+    __shared__ uint32_t s_ac[2][256], s_dc[2][16], s_warp[8];
+    load_tables(a, s_ac, s_dc);
+    uint32_t b = blockIdx.x * TILE + threadIdx.x;
+    uint32_t bits = 0;
+    if (b < a.n_blocks) {
+        uint32_t w[32];
+        load_block(a, b, w);
+        BlockInfo bi = block_info(a, b);
+        int t = bi.comp ? 1 : 0;
+        LenSink s{0};
+        encode_block(w, (int)(short)(w[0] & 0xFFFFu) - bi.pred, s_ac[t], s_dc[t], a.always_eob != 0, s);
+        bits = s.bits;
+    }
+    uint32_t total;
+    uint32_t ex = cta_scan_256(bits, s_warp, total);
+    a.w.blk_prefix[b] = ex;  // padded to a whole tile
+    if (threadIdx.x == 0) a.w.tile_bits[blockIdx.x] = total;
+}
+
+// Single-CTA exclusive scan: out[i] = sum in[0..i), out[n] = total.
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t n,
+                                               const uint32_t* n_dev) {
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    if (n_dev) n = *n_dev;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 4096) {
+        uint32_t i0 = base + threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = i0 + j < n ? in[i0 + j] : 0u;
+        uint64_t sum = (uint64_t)v[0] + v[1] + v[2] + v[3], inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        uint64_t wbase = 0, tot = 0;
+        for (int i = 0; i < 32; ++i) {
+            uint64_t t = s_warp[i];
+            if (i < wid) wbase += t;
+            tot += t;
+        }
+        uint64_t ex = s_carry + wbase + inc - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < n) out[i0 + j] = ex;
+            ex += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+// bit offset (inside the whole batch) of block x; x may equal n_blocks
+__device__ __forceinline__ uint64_t bit_prefix(const EntropyArgs& a, uint32_t x) {
+    uint64_t g = a.w.tile_base[x >> 8];
+    if (x & 255u) g += a.w.blk_prefix[x];
+    return g;
+}
+
+__device__ __forceinline__ void interval_blocks(const EntropyArgs& a, uint32_t i, uint32_t& s, uint32_t& e) {
+    const uint32_t bpm = (uint32_t)a.g.bpm, bpf = (uint32_t)a.g.n_mcu * bpm, ri = (uint32_t)a.g.ri;
+    uint32_t f = i / (uint32_t)a.g.n_int, k = i - f * (uint32_t)a.g.n_int;
+    s = f * bpf + k * ri * bpm;
+    e = f * bpf + min((k + 1) * ri, (uint32_t)a.g.n_mcu) * bpm;
+}
+
+__global__ void k_intervals(const __grid_constant__ EntropyArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_int_total) return;
+    uint32_t s, e;
+    interval_blocks(a, i, s, e);
+    uint64_t bits = bit_prefix(a, e) - bit_prefix(a, s);
+    a.w.int_bits[i] = bits;
+    uint64_t nb = (bits + 7) >> 3;
+    uint64_t slot = (nb + 15) & ~15ull;
+    if (slot == 0) slot = 16;
+    a.w.int_slot[i] = (uint32_t)slot;
+}
+
+__global__ void k_zero(const __grid_constant__ EntropyArgs a) {
+    uint64_t total = a.w.int_ubase[a.n_int_total];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.w.status[1] = total;
+        if (total > a.w.ubuf_cap) atomicOr((unsigned long long*)&a.w.status[0], JB_STATUS_UBUF_OVERFLOW);
+    }
+    if (total > a.w.ubuf_cap) return;
+    uint4* p = reinterpret_cast<uint4*>(a.w.ubuf);
+    uint64_t n = total >> 4;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(TILE) k_pack(const __grid_constant__ EntropyArgs a) {
+    __shared__ uint32_t s_ac[2][256], s_dc[2][16];
+    load_tables(a, s_ac, s_dc);
+    if (a.w.int_ubase[a.n_int_total] > a.w.ubuf_cap) return;
+    uint32_t b = blockIdx.x * TILE + threadIdx.x;
+    if (b >= a.n_blocks) return;
+    uint32_t w[32];
+    load_block(a, b, w);
+    BlockInfo bi = block_info(a, b);
+    uint32_t s0, e0;
+    interval_blocks(a, bi.interval, s0, e0);
+    uint64_t pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
+    int t = bi.comp ? 1 : 0;
+    BitSink s;
+    s.init(a.w.ubuf, pos);
+    encode_block(w, (int)(short)(w[0] & 0xFFFFu) - bi.pred, s_ac[t], s_dc[t], a.always_eob != 0, s);
+    if (bi.last_in_interval && !a.fr.raw_bits) {  // pad the interval to a byte boundary with 1s (T.81 F.1.2.3)
+        int pad = (int)((8 - (a.w.int_bits[bi.interval] & 7)) & 7);
+        if (pad) s.put((1u << pad) - 1u, pad);
+    }
+    s.finish();
+}
+
+__device__ __forceinline__ uint32_t count_ff(uint4 q) {
+    return (__popc(__vcmpeq4(q.x, 0xFFFFFFFFu)) + __popc(__vcmpeq4(q.y, 0xFFFFFFFFu)) +
+            __popc(__vcmpeq4(q.z, 0xFFFFFFFFu)) + __popc(__vcmpeq4(q.w, 0xFFFFFFFFu))) >> 3;
+}
+
+__global__ void __launch_bounds__(TILE) k_ff_count(const __grid_constant__ EntropyArgs a) {
+    __shared__ uint32_t s_warp[8];
+    uint64_t total = a.w.int_ubase[a.n_int_total];
+    if (total > a.w.ubuf_cap) total = 0;
+    uint64_t n_chunks = total >> 4;
+    uint32_t n_tiles = (uint32_t)((n_chunks + TILE - 1) / TILE);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.w.n_ff_tiles = n_tiles;
+    const uint4* p = reinterpret_cast<const uint4*>(a.w.ubuf);
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint64_t c = (uint64_t)t * TILE + threadIdx.x;
+        uint32_t cnt = c < n_chunks ? count_ff(p[c]) : 0u;
+        uint32_t tot;
+        uint32_t ex = cta_scan_256(cnt, s_warp, tot);
+        a.w.ff_prefix[c] = ex;
+        if (threadIdx.x == 0) a.w.ff_tile[t] = tot;
+    }
+}
+
+__device__ __forceinline__ uint64_t ff_prefix(const EntropyArgs& a, uint64_t c) {
+    uint64_t g = a.w.ff_tile_base[c >> 8];
+    if (c & 255u) g += a.w.ff_prefix[c];
+    return g;
+}
+
+// marker that follows interval k of a frame: 0 = none, else the second marker byte
+__device__ __forceinline__ uint32_t marker_after(const EntropyArgs& a, uint32_t k) {
+    if (k + 1 < (uint32_t)a.g.n_int || a.fr.final_rst) return 0xD0u + ((k + a.fr.rst_phase) & 7u);
+    return a.fr.emit_eoi ? 0xD9u : 0u;
+}
+
+__global__ void k_int_out(const __grid_constant__ EntropyArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_int_total) return;
+    uint32_t k = i % (uint32_t)a.g.n_int;
+    uint64_t ff = ff_prefix(a, a.w.int_ubase[i + 1] >> 4) - ff_prefix(a, a.w.int_ubase[i] >> 4);
+    uint64_t nb = (a.w.int_bits[i] + 7) >> 3;
+    uint64_t sz = nb + ff + (marker_after(a, k) ? 2u : 0u) + (k == 0 ? a.fr.hdr_bytes : 0u);
+    a.w.int_osize[i] = (uint32_t)sz;
+}
+
+__global__ void k_finalize(const __grid_constant__ EntropyArgs a) {
+    uint64_t total = a.w.int_obase[a.n_int_total];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        a.w.status[2] = total;
+        if (total > a.out_cap) atomicOr((unsigned long long*)&a.w.status[0], JB_STATUS_OUT_OVERFLOW);
+        if (a.total_out) *a.total_out = total;
+    }
+    if (i < (uint32_t)a.n_frames) {
+        uint64_t o0 = a.w.int_obase[i * (uint32_t)a.g.n_int], o1 = a.w.int_obase[(i + 1) * (uint32_t)a.g.n_int];
+        if (a.frame_off) a.frame_off[i] = o0;
+        if (a.frame_size) a.frame_size[i] = o1 - o0;
+    }
+}
+
+__global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyArgs a) {
+    uint64_t total = a.w.int_ubase[a.n_int_total];
+    if (total > a.w.ubuf_cap || a.w.int_obase[a.n_int_total] > a.out_cap) return;
+    uint64_t n_chunks = total >> 4;
+    const uint4* p = reinterpret_cast<const uint4*>(a.w.ubuf);
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks;
+         c += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t pos = c << 4;
+        // interval i with int_ubase[i] <= pos < int_ubase[i+1]
+        uint32_t lo = 0, hi = a.n_int_total;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (a.w.int_ubase[mid] <= pos) lo = mid; else hi = mid;
+        }
+        uint32_t i = lo, k = i % (uint32_t)a.g.n_int;
+        uint64_t ub = a.w.int_ubase[i];
+        uint64_t off = pos - ub, nb = (a.w.int_bits[i] + 7) >> 3;
+        uint64_t dst = a.w.int_obase[i] + (k == 0 ? a.fr.hdr_bytes : 0u) + off + (ff_prefix(a, c) - ff_prefix(a, ub >> 4));
+        uint4 q = p[c];
+        uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+        int valid = off >= nb ? 0 : (nb - off < 16 ? (int)(nb - off) : 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < valid) {
+                uint32_t byte = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                a.out[dst++] = (uint8_t)byte;
+                if (byte == 0xFFu) a.out[dst++] = 0;  // T.81 F.1.2.3 byte stuffing
+            }
+        }
+        if (off + 16 >= nb) {  // last chunk of the interval: marker
+            uint32_t m = marker_after(a, k);
+            if (m) {
+                a.out[dst] = 0xFF;
+                a.out[dst + 1] = (uint8_t)m;
+            }
+        }
+    }
+}
+
+__global__ void k_headers(const __grid_constant__ EntropyArgs a) {
+    if (a.w.int_obase[a.n_int_total] > a.out_cap) return;
+    uint32_t n = (uint32_t)a.n_frames * a.fr.hdr_bytes;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        uint32_t f = t / a.fr.hdr_bytes, j = t - f * a.fr.hdr_bytes;
+        a.out[a.w.int_obase[f * (uint32_t)a.g.n_int] + j] = a.hdr[j];
+    }
+}
+
+int launch_entropy(const EntropyArgs& a, cudaStream_t s) {
+    if (a.n_blocks == 0) return 0;
+    int launches = 0;
+    uint32_t n_tiles = (a.n_blocks + TILE - 1) / TILE;
+    uint32_t gi = (a.n_int_total + 255) / 256;
+    k_len<<<n_tiles, TILE, 0, s>>>(a);
+    k_scan<<<1, 1024, 0, s>>>(a.w.tile_bits, a.w.tile_base, n_tiles, nullptr);
+    k_intervals<<<gi, 256, 0, s>>>(a);
+    k_scan<<<1, 1024, 0, s>>>(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr);
+    k_zero<<<592, 256, 0, s>>>(a);
+    k_pack<<<n_tiles, TILE, 0, s>>>(a);
+    launches += 6;
+    if (a.fr.raw_bits) return launches;
+    k_ff_count<<<1184, TILE, 0, s>>>(a);
+    k_scan<<<1, 1024, 0, s>>>(a.w.ff_tile, a.w.ff_tile_base, 0, a.w.n_ff_tiles);
+    k_int_out<<<gi, 256, 0, s>>>(a);
+    k_scan<<<1, 1024, 0, s>>>(a.w.int_osize, a.w.int_obase, a.n_int_total, nullptr);
+    uint32_t gf = ((uint32_t)a.n_frames + 255) / 256;
+    k_finalize<<<gf, 256, 0, s>>>(a);
+    k_stuff<<<1184, TILE, 0, s>>>(a);
+    launches += 6;
+    if (a.fr.hdr_bytes) {
+        k_headers<<<148, 256, 0, s>>>(a);
+        ++launches;
+    }
+    return launches;
+}
+
+}  // namespace jb

@@ -1,0 +1,162 @@
+// Internal declarations shared by the translation units of libjpegb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/jpegb200.h"
+#include "jb_math.h"
+
+namespace jb {
+
+// Geometry of one frame (or one strip) in MCUs / blocks.
+struct Geometry {
+    int W, H;      // source size in pixels (unpadded)
+    int sub;       // JB_SUB_*
+    int mcu_px;    // 8 (444, REPL420) or 16 (420)
+    int mcux, mcuy;
+    int bpm;       // blocks per MCU: 3 or 6
+    int n_mcu;     // per frame
+    int ri;        // restart interval in MCUs (== n_mcu when none)
+    int n_int;     // restart intervals per frame
+};
+
+inline Geometry make_geometry(size_t W, size_t H, int sub, int restart_interval) {
+    Geometry g;
+    g.W = (int)W;
+    g.H = (int)H;
+    g.sub = sub;
+    g.mcu_px = sub == JB_SUB_420 ? 16 : 8;
+    g.mcux = (int)((W + g.mcu_px - 1) / g.mcu_px);
+    g.mcuy = (int)((H + g.mcu_px - 1) / g.mcu_px);
+    g.bpm = sub == JB_SUB_420 ? 6 : 3;
+    g.n_mcu = g.mcux * g.mcuy;
+    g.ri = restart_interval > 0 ? restart_interval : g.n_mcu;
+    g.n_int = (g.n_mcu + g.ri - 1) / g.ri;
+    return g;
+}
+
+// Quantisation constants in natural [v][u] order; table 0 = luma, 1 = chroma.
+struct QuantConst {
+    float mul[2][64];   // alpha(u)alpha(v) / (4 q aan(u) aan(v))
+    float band[2][64];  // 0.5 - JB_DCT_ERR_BOUND * mul
+};
+
+struct QuantTables {
+    uint32_t q[2][64];  // the caller's integer tables, natural order
+};
+
+struct TransformArgs {
+    const uint8_t* rgb;
+    size_t pitch, frame_stride;
+    int n_frames;
+    Geometry g;
+    int16_t* coef;          // [n_frames][n_mcu][bpm][64], zigzag order
+    const uint32_t* ydown;  // 2048 words, see jb_math.h
+    uint32_t* tie_list;     // near-tie coefficient indices (block*64 + zigzag position)
+    uint32_t* tie_count;
+    uint32_t tie_cap;
+    int units_per_row;
+    uint32_t total_units;
+    QuantConst qc;
+};
+
+struct FixupArgs {
+    const uint8_t* rgb;
+    size_t pitch, frame_stride;
+    Geometry g;
+    int16_t* coef;
+    const uint32_t* ydown;
+    const uint32_t* tie_list;
+    const uint32_t* tie_count;
+    uint32_t tie_cap;
+    const double* costab;  // [u][x] = cos((2x+1) u pi / 16), from the host's libm
+    const double* scale;   // [u][v] = alpha(u) alpha(v) / 4.0
+    QuantTables qt;
+};
+
+// Huffman tables as the kernels consume them: (code << 5) | length.
+struct HuffDev {
+    uint32_t ac[2][256];  // [luma/chroma][run<<4 | cat]
+    uint32_t dc[2][16];   // [luma/chroma][cat]
+};
+
+// How entropy segments are framed in the output.
+struct Framing {
+    uint32_t hdr_bytes;   // JFIF header written in front of each frame's first interval (0 = none)
+    uint32_t emit_eoi;    // append FFD9 after each frame's last interval
+    uint32_t final_rst;   // append RSTn after the last interval instead (strips)
+    uint32_t rst_phase;   // index of the first interval (strips)
+    uint32_t raw_bits;    // reference-style bit string: no padding, no stuffing, no markers
+};
+
+// Device work arrays of the entropy coder (all sized by the context).
+struct EntropyWork {
+    uint32_t* blk_prefix;   // [n_blocks] exclusive bit prefix inside its 256-block tile
+    uint32_t* tile_bits;    // [n_tiles]
+    uint64_t* tile_base;    // [n_tiles + 1] exclusive scan of tile_bits
+    uint32_t* int_slot;     // [n_int_total] bytes reserved in the unstuffed buffer (multiple of 16)
+    uint64_t* int_bits;     // [n_int_total]
+    uint64_t* int_ubase;    // [n_int_total + 1] byte offset of each interval in the unstuffed buffer
+    uint8_t* ubuf;          // unstuffed bytes
+    uint64_t ubuf_cap;
+    uint32_t* ff_prefix;    // [ubuf_cap / 16] exclusive 0xFF count inside its chunk tile
+    uint32_t* ff_tile;      // [ubuf_cap / 16 / 256 + 1]
+    uint64_t* ff_tile_base; // same + 1
+    uint32_t* n_ff_tiles;   // device scalar
+    uint32_t* int_osize;    // [n_int_total]
+    uint64_t* int_obase;    // [n_int_total + 1]
+    uint64_t* status;       // [0] error bits, [1] required ubuf bytes, [2] required out bytes, [3] total bits
+};
+
+struct EntropyArgs {
+    const int16_t* coef;
+    Geometry g;
+    int n_frames;
+    uint32_t n_blocks;     // total blocks in the batch
+    uint32_t n_int_total;  // n_frames * g.n_int
+    const HuffDev* huff;
+    uint32_t always_eob;
+    Framing fr;
+    EntropyWork w;
+    const uint8_t* hdr;    // device copy of the JFIF header
+    uint8_t* out;
+    uint64_t out_cap;
+    uint64_t* frame_off;   // [n_frames] (may be null)
+    uint64_t* frame_size;  // [n_frames] (may be null)
+    uint64_t* total_out;   // device scalar (may be null)
+};
+
+#define JB_STATUS_UBUF_OVERFLOW 1ull
+#define JB_STATUS_OUT_OVERFLOW 2ull
+#define JB_STATUS_TIE_OVERFLOW 4ull
+
+// ---- launchers (each returns the number of kernels it launched) -------------
+int launch_transform(const TransformArgs& a, cudaStream_t s);
+int launch_fixup(const FixupArgs& a, cudaStream_t s);
+int launch_entropy(const EntropyArgs& a, cudaStream_t s);
+int launch_synth(uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t* d_out, cudaStream_t s);
+
+// staged kernels (device pointers)
+int launch_csc(uint8_t* px, size_t n, const uint32_t* ydown, cudaStream_t s);
+int launch_cds(uint8_t* px, size_t W, size_t H, cudaStream_t s);
+int launch_pad(const uint8_t* src, size_t W, size_t H, uint8_t* dst, size_t nW, size_t nH, cudaStream_t s);
+int launch_u8_to_f64(const uint8_t* src, double* dst, size_t n, cudaStream_t s);
+int launch_sub_f64(double* img, size_t n, double val, cudaStream_t s);
+int launch_dct_f64(double* img, size_t W, size_t H, int inplace, const double* costab, const double* scale,
+                   cudaStream_t s);
+int launch_quant_f64(double* img, size_t W, size_t H, const QuantTables& qt, cudaStream_t s);
+int launch_blockify(const double* img, size_t W, size_t H, int32_t* linear, cudaStream_t s);
+int launch_zigzag(const int32_t* linear, int32_t* zz, size_t rows, cudaStream_t s);
+int launch_rle(const int32_t* zz, size_t rows, int always_eob, int32_t* pairs, uint32_t* counts, cudaStream_t s);
+int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStream_t s);
+
+// host helpers
+void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out);
+void build_huff(bool typo, HuffDev* out);
+size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* out);  // out >= 1024 bytes
+extern const uint8_t kZigzag[64];  // zigzag position -> natural index
+
+}  // namespace jb

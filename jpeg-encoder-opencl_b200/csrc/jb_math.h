@@ -1,0 +1,156 @@
+// Arithmetic shared by every kernel of the B200 JPEG encode path.
+//
+// Everything here is `__host__ __device__` and written with explicit
+// fmaf/__fmul_rn-style operations (the library is compiled with -fmad=false) so
+// that a host build of this header evaluates bit-for-bit what the GPU
+// evaluates.  tests/ compile it for the host to check the arithmetic against
+// the oracle without a GPU; the product only ever runs it on the device.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define JB_HD __host__ __device__ __forceinline__
+#else
+#include <math.h>
+#define JB_HD static inline
+#endif
+
+namespace jb {
+
+// ---------------------------------------------------------------------------
+// Colour conversion, exact.  Reference: src/utils.cpp:100-109
+//   Y  = (u8)(0.299 r + 0.587 g + 0.114 b)
+//   Cb = (u8)(-0.168736 r - 0.331264 g + 0.5 b + 128)
+//   Cr = (u8)(0.5 r - 0.418688 g - 0.081312 b + 128)          (binary64, truncation)
+// Each channel is evaluated as a 8.24 fixed-point number T whose top byte is the
+// exact floor of the real-valued expression: the coefficients are rounded so
+// that the fixed-point error e satisfies 0 <= e < 1/1000 (Y) resp. 1/31250
+// (Cb, Cr), which is the spacing of the attainable fractional parts.  The only
+// inputs on which the reference's binary64 evaluation can differ from the exact
+// floor are those whose exact value is an integer ("ties"): T & JB_*_TIE_MASK
+// == 0 identifies exactly those (checked over all 2^24 colours in
+// tests/test_math_host.py).  For Cb and Cr binary64 never lands below the
+// integer (0 of 32768 ties each); for Y it does on 3464 of 16774 ties, which
+// are looked up in a 65536-bit table indexed by (r,g) (b is determined by
+// (r,g) on a tie) that the host fills by evaluating the binary64 expression.
+// ---------------------------------------------------------------------------
+constexpr uint32_t KY_R = 5016388u, KY_G = 9848226u, KY_B = 1912603u;  // ceil(c * 2^24)
+constexpr uint32_t KCB_R = 2830920u, KCB_G = 5557687u;                 // floor(c * 2^24)
+constexpr uint32_t KCR_G = 7024419u, KCR_B = 1364188u;                 // floor(c * 2^24)
+constexpr uint32_t Y_TIE_MASK = 0x00FFFC00u;                           // frac < 1024/2^24
+constexpr uint32_t C_TIE_MASK = 0x00FFFE00u;                           // frac <  512/2^24
+
+JB_HD uint32_t csc_ty(uint32_t r, uint32_t g, uint32_t b) { return KY_R * r + KY_G * g + KY_B * b; }
+JB_HD uint32_t csc_tcb(uint32_t r, uint32_t g, uint32_t b) {
+    return 0x80000000u + (b << 23) - KCB_R * r - KCB_G * g;
+}
+JB_HD uint32_t csc_tcr(uint32_t r, uint32_t g, uint32_t b) {
+    return 0x80000000u + (r << 23) - KCR_G * g - KCR_B * b;
+}
+// ydown: 2048 words; bit (r<<8|g) set when the reference's Y lands one below the exact value.
+JB_HD uint32_t csc_y(uint32_t r, uint32_t g, uint32_t b, const uint32_t* ydown) {
+    uint32_t t = csc_ty(r, g, b);
+    uint32_t y = t >> 24;
+    if ((t & Y_TIE_MASK) == 0) {
+        uint32_t i = (r << 8) | g;
+        y -= (ydown[i >> 5] >> (i & 31)) & 1u;
+    }
+    return y;
+}
+JB_HD uint32_t csc_cb(uint32_t r, uint32_t g, uint32_t b) { return csc_tcb(r, g, b) >> 24; }
+JB_HD uint32_t csc_cr(uint32_t r, uint32_t g, uint32_t b) { return csc_tcr(r, g, b) >> 24; }
+
+// ---------------------------------------------------------------------------
+// 8-point forward DCT, Arai-Agui-Nakajima factorisation (5 multiplies, all
+// folded into FMAs where an add follows).  Output k is the orthonormal-free
+// DCT-II sum  sum_x v[x] cos((2x+1)k pi/16)  multiplied by AAN_SCALE[k]
+// (see aan_scale below).
+// The scale is folded into the quantisation multiplier.
+// ---------------------------------------------------------------------------
+JB_HD float jb_fmaf(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+
+#define JB_C4 0.70710678118654752440f   // cos(4pi/16)
+#define JB_C6 0.38268343236508977173f   // cos(6pi/16)
+#define JB_Q 0.54119610014619698440f    // cos(2pi/16) - cos(6pi/16)
+#define JB_R 1.30656296487637652785f    // cos(2pi/16) + cos(6pi/16)
+
+JB_HD void fdct8(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7) {
+    float s07 = d0 + d7, m07 = d0 - d7;
+    float s16 = d1 + d6, m16 = d1 - d6;
+    float s25 = d2 + d5, m25 = d2 - d5;
+    float s34 = d3 + d4, m34 = d3 - d4;
+    // even half
+    float e0 = s07 + s34, e3 = s07 - s34;
+    float e1 = s16 + s25, e2 = s16 - s25;
+    d0 = e0 + e1;
+    d4 = e0 - e1;
+    float w = e2 + e3;
+    d2 = jb_fmaf(w, JB_C4, e3);
+    d6 = jb_fmaf(w, -JB_C4, e3);
+    // odd half
+    float o0 = m34 + m25, o1 = m25 + m16, o2 = m16 + m07;
+    float z5 = (o0 - o2) * JB_C6;
+    float z2 = jb_fmaf(o0, JB_Q, z5);
+    float z4 = jb_fmaf(o2, JB_R, z5);
+    float z11 = jb_fmaf(o1, JB_C4, m07);
+    float z13 = jb_fmaf(o1, -JB_C4, m07);
+    d5 = z13 + z2;
+    d3 = z13 - z2;
+    d1 = z11 + z4;
+    d7 = z11 - z4;
+}
+
+// fdct8 output k equals aan_scale(k) * sum_x v[x] cos((2x+1) k pi/16):
+// aan_scale(0) = 1, aan_scale(k) = 2 cos(k pi/16).
+JB_HD double aan_scale(int k) {
+    const double s[8] = {1.0,
+                         2.0 * 0.98078528040323044913,
+                         2.0 * 0.92387953251128675613,
+                         2.0 * 0.83146961230254523708,
+                         2.0 * 0.70710678118654752440,
+                         2.0 * 0.55557023301960222474,
+                         2.0 * 0.38268343236508977173,
+                         2.0 * 0.19509032201612826785};
+    return s[k];
+}
+
+// ---------------------------------------------------------------------------
+// Quantisation of one AAN-scaled coefficient.
+//   t = a * mul,  mul = alpha(u) alpha(v) / (4 q aan_scale(u) aan_scale(v))
+// so t approximates F/q of src/utils.cpp:454-467.  The result is rounded to
+// nearest with the 1.5*2^23 trick.  `near_tie` is set when t is within `band`
+// of a half-integer, i.e. when binary32 error could change the rounding the
+// reference makes in binary64: those coefficients are recomputed exactly (same
+// binary64 operation order as the reference) by the fix-up kernel.
+// ---------------------------------------------------------------------------
+#define JB_ROUND_MAGIC 12582912.0f  // 1.5 * 2^23
+
+// Returns the bit pattern of (1.5*2^23 + round(a*mul)): its low 16 bits are the
+// two's-complement int16 coefficient (0x4B400000 has a zero low half).
+JB_HD uint32_t quantize_bits(float a, float mul, float band, bool& near_tie) {
+    float r = jb_fmaf(a, mul, JB_ROUND_MAGIC);  // integer nearest to a*mul, one rounding
+    float ri = r - JB_ROUND_MAGIC;              // exact
+    float d = jb_fmaf(a, mul, -ri);             // a*mul - ri, in [-0.5, 0.5]
+    near_tie = fabsf(d) > band;                 // band = 0.5 - delta
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(r);
+#else
+    union { float f; uint32_t i; } u;
+    u.f = r;
+    return u.i;
+#endif
+}
+
+// Error budget of fdct8 applied to rows then columns of integer samples in
+// [-128,127], in units of the AAN-scaled output, plus the relative error of the
+// final multiply (|a| <= 2^15).  Measured maximum over 4e5 adversarial blocks is
+// 1.2e-3; the analytic worst case (tests/test_math_host.py) is below 1.2e-2.
+#define JB_DCT_ERR_BOUND 0.015625  // 2^-6
+
+}  // namespace jb

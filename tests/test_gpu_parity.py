@@ -1,0 +1,435 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle, and -- where
+oracle/_ref was built -- with the reference's own code.  Everything here needs a GPU.
+
+Bars (BASELINE.json north_star): quantised coefficients bit-exact (the binary64 tie
+fix-up removes even the <=1-LSB tolerance the spec allows), entropy stream byte-exact,
+decoded PSNR identical.
+"""
+import hashlib
+import io
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import noise_image
+
+pytestmark = pytest.mark.gpu
+
+sha = lambda b: hashlib.sha256(bytes(b)).hexdigest()
+SUBS = [ol.SUB_444, ol.SUB_REPL420, ol.SUB_420]
+SUBNAME = {0: "444", 1: "repl420", 2: "420"}
+
+
+def mismatch_report(got, want):
+    d = np.flatnonzero(got.reshape(-1) != want.reshape(-1))
+    if d.size == 0:
+        return "equal"
+    g, w = got.reshape(-1), want.reshape(-1)
+    head = ", ".join(f"[{i}] got {g[i]} want {w[i]}" for i in d[:8])
+    return f"{d.size} of {g.size} differ (max abs {np.abs(g[d].astype(np.int64) - w[d]).max()}): {head}"
+
+
+# ------------------------------------------------------------------ staged ------------
+
+def test_csc_full_colour_cube(enc, golden):
+    """performCSC over all 2^24 colours == the reference (sha256 pinned in tests/golden)."""
+    h = hashlib.sha256()
+    L = ol.oracle()
+    for r in range(0, 256, 16):
+        cube = np.zeros((16, 256, 256, 3), np.uint8)
+        cube[..., 0] = np.arange(r, r + 16)[:, None, None]
+        cube[..., 1] = np.arange(256)[None, :, None]
+        cube[..., 2] = np.arange(256)[None, None, :]
+        want = cube.copy().reshape(-1)
+        L.orc_csc(want, want.size // 3)
+        got = enc.performCSC(cube.reshape(16 * 256, 256, 3))
+        assert np.array_equal(got.reshape(-1), want), mismatch_report(got, want)
+        h.update(got.tobytes())
+    assert h.hexdigest() == golden["csc_cube_sha256"]
+
+
+@pytest.mark.parametrize("shape", [(254, 253), (64, 64), (17, 33), (2, 2), (1, 9)])
+def test_cds_pad(enc, shape):
+    H, W = shape
+    img = noise_image(1, W, H)
+    L = ol.oracle()
+    want = img.copy()
+    L.orc_cds(want.reshape(-1), W, H)
+    got = enc.performCDS(img.copy())
+    assert np.array_equal(got, want), mismatch_report(got, want)
+    if W >= 8 and H >= 8:
+        nW, nH = -(-W // 8) * 8, -(-H // 8) * 8
+        wantp = np.zeros((nH, nW, 3), np.uint8)
+        assert L.orc_pad_mirror(np.ascontiguousarray(want), W, H, wantp, nW, nH) == 0
+        gotp = enc.padMirror(got, 8)
+        assert np.array_equal(gotp, wantp), mismatch_report(gotp, wantp)
+
+
+@pytest.mark.parametrize("inplace", [0, 1])
+def test_staged_f64_pipeline_bit_exact(enc, jb, fruit, golden, inplace):
+    """copyUIntToDoubleImage .. HuffmanEncoder on fruit.ppm: every stage equals the oracle
+    bit for bit (binary64 included), and the digests equal the reference's."""
+    L = ol.oracle()
+    ql, qc = ol.q50()
+    ycc = ol.ycc_padded(fruit, ol.SUB_REPL420)
+    # the GPU's own CSC/CDS/pad of the source must give the same padded image
+    g = enc.padMirror(enc.performCDS(enc.performCSC(fruit.copy())), 8)
+    assert np.array_equal(g, ycc)
+    nH, nW, _ = ycc.shape
+    want = np.zeros(ycc.size, np.float64)
+    L.orc_u8_to_double(ycc.reshape(-1), want, ycc.size)
+    got = enc.copyUIntToDoubleImage(ycc)
+    assert np.array_equal(got.reshape(-1), want)
+    L.orc_subtract(want, want.size, 128.0)
+    enc.substractfromAll(got, 128.0)
+    assert np.array_equal(got.reshape(-1), want)
+    L.orc_dct_image(want, nW, nH, inplace)
+    enc.performDCT(got, jb.FLAG_REF_INPLACE_DCT if inplace else 0)
+    assert np.array_equal(got.reshape(-1).view(np.uint64), want.view(np.uint64)), \
+        f"binary64 DCT differs: max abs {np.abs(got.reshape(-1) - want).max()}"
+    L.orc_quantize_image(want, nW, nH, ql, qc)
+    enc.performQuantization(got, ql, qc)
+    assert np.array_equal(got.reshape(-1), want)
+    rpc = nW * nH // 64
+    lin_w = np.zeros((3 * rpc, 64), np.int32)
+    zz_w = np.zeros_like(lin_w)
+    L.orc_blockify(want, nW, nH, lin_w)
+    L.orc_zigzag(lin_w, zz_w, 3 * rpc)
+    lin = enc.everyMCUisnow2DArray(got)
+    assert np.array_equal(lin, lin_w)
+    zz = enc.performZigZag(lin)
+    assert np.array_equal(zz, zz_w)
+    key = "as_written" if inplace else "dct_from_copy"
+    assert sha(zz.tobytes()) == golden["fruit"][key]["zigzag_sha256"]
+    # RLE (always-EOB as in the reference) and Huffman with the reference's quirks
+    flags = jb.FLAG_REF_ALWAYS_EOB | jb.FLAG_REF_TYPO_TABLES
+    rle = enc.performRLE(zz, flags)
+    pairs = np.zeros(130, np.int32)
+    for i in range(0, 3 * rpc, 7):
+        n = L.orc_rle_block(np.ascontiguousarray(zz_w[i]), pairs, 1)
+        assert np.array_equal(rle[i], pairs[:n]), f"RLE row {i}"
+    packed, nbits = enc.HuffmanEncoder(zz, rpc, flags)
+    assert nbits == golden["fruit"][key]["nbits"]
+    assert sha(ol.bits_to_ascii(packed, nbits)) == golden["fruit"][key]["bits_sha256"]
+    # conformant tables / EOB rule vs the oracle
+    packed2, nbits2 = enc.HuffmanEncoder(zz, rpc, 0)
+    wantp = np.zeros(zz.size * 4, np.uint8)
+    nb = L.orc_huffman_ref(zz_w, rpc, 0, wantp, wantp.size)
+    assert nbits2 == nb and np.array_equal(packed2, wantp[: (nb + 7) // 8])
+
+
+def test_huffman_typo_codes_exercised(enc, jb):
+    """Blocks built to hit luma AC 3/4..3/A (Q2) and full blocks (Q3): reference-exact bits."""
+    rpc = 40
+    rng = np.random.default_rng(5)
+    zz = np.zeros((3 * rpc, 64), np.int32)
+    for b in range(3 * rpc):
+        zz[b, 0] = rng.integers(-1000, 1000)
+        pos = 1
+        while pos < 64:
+            pos += int(rng.choice([0, 1, 3, 3, 3, 17, 35]))
+            if pos >= 64:
+                break
+            mag = int(rng.choice([1, 2, 9, 17, 40, 100, 300, 700, 1023]))
+            zz[b, pos] = mag if rng.random() < 0.5 else -mag
+            pos += 1
+        if b % 5 == 0:
+            zz[b, 63] = 3
+    L = ol.oracle()
+    for flags in (0, ol.Q2, ol.Q3, ol.Q2 | ol.Q3):
+        want = np.zeros(zz.size * 4, np.uint8)
+        nb = L.orc_huffman_ref(zz, rpc, flags, want, want.size)
+        got, nbits = enc.HuffmanEncoder(zz, rpc, flags)
+        assert nbits == nb, f"flags {flags}: {nbits} vs {nb} bits"
+        assert np.array_equal(got, want[: (nb + 7) // 8]), f"flags {flags}"
+    R = ol.ref()
+    if R is not None:  # the reference's own HuffmanEncoder, as written
+        bits = np.zeros(zz.size * 28, np.uint8)
+        n = R.ref_HuffmanEncoder(zz.copy(), rpc, bits.ctypes.data, bits.size)
+        got, nbits = enc.HuffmanEncoder(zz, rpc, ol.Q2 | ol.Q3)
+        assert nbits == n and ol.bits_to_ascii(got, nbits) == bits[:n].tobytes()
+
+
+# ------------------------------------------------------------------- fused ------------
+
+def _params(jb, sub, q, ri=0, flags=0):
+    ql, qc = ol.quality_tables(q)
+    return jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri, flags=flags), ql, qc
+
+
+@pytest.mark.parametrize("sub", SUBS)
+@pytest.mark.parametrize("q", [50, 75, 90])
+def test_transform_fruit_bit_exact(enc, jb, fruit, sub, q):
+    """Config #1: fruit.ppm coefficients == the binary64 reference formula, every coefficient."""
+    p, ql, qc = _params(jb, sub, q)
+    got = enc.transform(fruit, p)
+    want = ol.transform(fruit, sub, ql, qc)
+    assert np.array_equal(got, want), mismatch_report(got, want)
+    t = enc.timings()
+    assert t["tie_fixups"] > 0  # the near-tie replay did run (DC ties occur in ~1/64 of the blocks)
+
+
+def test_transform_fruit_matches_reference_digest(enc, jb, fruit, golden):
+    """REPLICATED_420 at the reference's q50: zigzag array digest of SURVEY 8c (DCT from a copy)."""
+    p, ql, qc = _params(jb, ol.SUB_REPL420, 50)
+    coef = enc.transform(fruit, p)
+    planar = np.concatenate([coef[:, c, :] for c in range(3)]).astype(np.int32)
+    assert sha(planar.tobytes()) == golden["fruit"]["dct_from_copy"]["zigzag_sha256"]
+
+
+@pytest.mark.parametrize("sub", SUBS)
+@pytest.mark.parametrize("shape", [(16, 16), (8, 24), (33, 47), (100, 300), (131, 253), (64, 1040), (255, 511)])
+def test_transform_shapes(enc, jb, sub, shape):
+    """Odd sizes, partial units, mirror padding, the odd-edge chroma rule; noise and smooth content."""
+    H, W = shape
+    m = 16 if sub == ol.SUB_420 else 8
+    if (-W) % m > W or (-H) % m > H:
+        pytest.skip("padding larger than the image (the reference would read out of bounds)")
+    for img in (noise_image(W * 1000 + H, W, H), ol.synth(7, W, H)):
+        for q in (75, 100):
+            p, ql, qc = _params(jb, sub, q)
+            got = enc.transform(img, p)
+            want = ol.transform(img, sub, ql, qc)
+            assert np.array_equal(got, want), f"{SUBNAME[sub]} {W}x{H} q{q}: " + mismatch_report(got, want)
+
+
+def test_transform_grey_and_flat(enc, jb):
+    """Grey pixels make every Y a CSC tie (table look-up path) and flat blocks make exact DC ties."""
+    H, W = 64, 96
+    g = np.repeat(np.random.default_rng(3).integers(0, 256, (H, W, 1), dtype=np.uint8), 3, axis=2)
+    flat = np.zeros((H, W, 3), np.uint8)
+    for by in range(H // 8):
+        for bx in range(W // 8):
+            flat[by * 8:(by + 1) * 8, bx * 8:(bx + 1) * 8] = (by * 12 + bx * 7) % 256
+    for img in (g, flat):
+        for sub in SUBS:
+            p, ql, qc = _params(jb, sub, 50)
+            got = enc.transform(img, p)
+            want = ol.transform(img, sub, ql, qc)
+            assert np.array_equal(got, want), mismatch_report(got, want)
+
+
+def test_no_fixup_stays_within_one_lsb_at_ties(enc, jb, fruit):
+    """Without the replay the binary32 path may differ by one LSB, and only where the kernel flags a near-tie."""
+    p, ql, qc = _params(jb, ol.SUB_420, 75, flags=jb.FLAG_NO_TIE_FIXUP)
+    got = enc.transform(fruit, p).astype(np.int32)
+    want = ol.transform(fruit, ol.SUB_420, ql, qc).astype(np.int32)
+    assert np.abs(got - want).max() <= 1
+    assert (got != want).mean() < 1e-3
+
+
+@pytest.mark.parametrize("sub", SUBS)
+@pytest.mark.parametrize("ri", [0, 1, 3, 16, 1000])
+def test_entropy_bytes_given_identical_coefficients(enc, jb, sub, ri):
+    img = noise_image(11, 200, 120) // 2 + ol.synth(3, 200, 120) // 2
+    for q in (30, 75, 95):
+        p, ql, qc = _params(jb, sub, q, ri)
+        coef = ol.transform(img, sub, ql, qc)
+        want, _ = ol.entropy(coef, sub, ri)
+        got = enc.entropy(coef, p)
+        assert len(got) == len(want) and np.array_equal(got, want), \
+            f"{SUBNAME[sub]} ri={ri} q{q}: {len(got)} vs {len(want)} bytes; " + \
+            (mismatch_report(got, want) if len(got) == len(want) else "")
+
+
+def test_entropy_stuffing_heavy(enc, jb):
+    """Coefficients chosen to produce long runs of 1 bits (many 0xFF bytes) and tiny intervals."""
+    rng = np.random.default_rng(9)
+    n_mcu = 300
+    coef = np.zeros((n_mcu, 3, 64), np.int16)
+    coef[:, :, 0] = rng.integers(-2040, 2040, (n_mcu, 3))
+    coef[:, :, 1:] = np.where(rng.random((n_mcu, 3, 63)) < 0.3, -1 * rng.integers(1, 1024, (n_mcu, 3, 63)), 0)
+    coef[::7, :, 63] = 1023
+    for ri in (0, 1, 2, 50):
+        p = jb.make_params(ol.SUB_444, quality=75, restart_interval=ri)
+        want, _ = ol.entropy(coef, ol.SUB_444, ri)
+        got = enc.entropy(coef, p)
+        assert (want == 0xFF).sum() > 100
+        assert len(got) == len(want) and np.array_equal(got, want), f"ri={ri}"
+
+
+@pytest.mark.parametrize("sub", SUBS)
+def test_jfif_fruit_byte_exact_and_decodes(enc, jb, fruit, sub):
+    """Config #1: whole file == the oracle's, decodes in PIL and OpenCV with identical PSNR."""
+    from PIL import Image
+    import cv2
+    for q, ri in ((75, 0), (75, 16), (50, 0), (90, 4)):
+        p, ql, qc = _params(jb, sub, q, ri)
+        got = enc.encode_jfif(fruit, p)
+        want = ol.encode_jfif(fruit, sub, ql, qc, ri)
+        assert got == want, f"{SUBNAME[sub]} q{q} ri={ri}: {len(got)} vs {len(want)} bytes"
+        a = np.array(Image.open(io.BytesIO(got)).convert("RGB"))
+        b = cv2.imdecode(np.frombuffer(got, np.uint8), cv2.IMREAD_COLOR)[:, :, ::-1]
+        assert a.shape == fruit.shape and b.shape == fruit.shape
+        psnr = lambda x: 10 * np.log10(255.0 ** 2 / np.mean((x.astype(np.float64) - fruit) ** 2))
+        assert abs(psnr(a) - psnr(b)) < 0.01
+    # REPLICATED_420 q50 without restarts is 17 006 bytes and decodes to 18.86 dB
+    if sub == ol.SUB_REPL420:
+        p, ql, qc = _params(jb, sub, 50)
+        jf = enc.encode_jfif(fruit, p)
+        assert len(jf) == 17006
+        a = np.array(Image.open(io.BytesIO(jf)).convert("RGB")).astype(np.float64)
+        assert abs(10 * np.log10(255.0 ** 2 / np.mean((a - fruit) ** 2)) - 18.862) < 0.01
+
+
+def test_batch_equals_single_frames(enc, jb):
+    N, H, W = 7, 72, 104
+    frames = np.stack([ol.synth(100 + i, W, H) for i in range(N)])
+    frames[3] = noise_image(4, W, H)
+    p, ql, qc = _params(jb, ol.SUB_420, 75, 7)
+    out, offs, sizes = enc.encode_batch(frames, p)
+    assert offs[0] == 0 and np.all(offs[1:] == np.cumsum(sizes)[:-1])
+    for i in range(N):
+        want = ol.encode_jfif(frames[i], ol.SUB_420, ql, qc, 7)
+        got = out[int(offs[i]): int(offs[i] + sizes[i])].tobytes()
+        assert got == want, f"frame {i}: {len(got)} vs {len(want)}"
+
+
+def test_batch_many_groups_pipelined(enc, jb):
+    """More groups than pipeline slots (frames of ~0.4 MB -> several 96 MB groups would need thousands of
+    frames; shrink by using large frames)."""
+    N, H, W = 10, 2160, 3840  # 24.9 MB per frame -> 3 frames per group -> 4 groups > 3 slots
+    base = ol.synth(1, W, 256)
+    frames = np.empty((N, H, W, 3), np.uint8)
+    for i in range(N):
+        frames[i] = np.roll(np.tile(base, (H // 256 + 1, 1, 1))[:H], i * 37, axis=0)
+    p, ql, qc = _params(jb, ol.SUB_420, 75, 240)
+    out, offs, sizes = enc.encode_batch(frames, p)
+    single = [enc.encode_jfif(frames[i], p) for i in range(N)]
+    for i in range(N):
+        assert out[int(offs[i]): int(offs[i] + sizes[i])].tobytes() == single[i], f"frame {i}"
+    # one MCU row (= one restart interval) of frame 2 against the oracle, via the strip identity
+    strip = frames[2][16 * 10: 16 * 11]
+    coef = ol.transform(strip, ol.SUB_420, ql, qc)
+    want, _ = ol.entropy(coef, ol.SUB_420, 240)
+    hdr = jb.header_bytes(p)
+    body = np.frombuffer(single[2], np.uint8)[hdr:-2]
+    marks = np.flatnonzero((body[:-1] == 0xFF) & (body[1:] >= 0xD0) & (body[1:] <= 0xD7))
+    seg = body[marks[9] + 2: marks[10]]
+    assert np.array_equal(seg, want), f"interval 10: {len(seg)} vs {len(want)}"
+
+
+def test_device_resident_api(enc, jb):
+    N, H, W = 3, 48, 80
+    frames = np.stack([ol.synth(50 + i, W, H) for i in range(N)])
+    p, ql, qc = _params(jb, ol.SUB_420, 75)
+    d_rgb = enc.device_alloc(frames.nbytes)
+    cap = 1 << 20
+    d_out = enc.device_alloc(cap)
+    d_tab = enc.device_alloc(8 * (2 * N + 1))
+    try:
+        enc.h2d(d_rgb, frames)
+        enc.encode_batch_device(d_rgb, N, W, H, W * 3, W * H * 3, p, d_out, cap, d_tab, d_tab + 8 * N, d_tab + 16 * N)
+        enc.sync()
+        tab = np.zeros(2 * N + 1, np.uint64)
+        enc.d2h(tab, d_tab)
+        out = np.zeros(int(tab[2 * N]), np.uint8)
+        enc.d2h(out, d_out)
+        for i in range(N):
+            want = ol.encode_jfif(frames[i], ol.SUB_420, ql, qc, 0)
+            assert out[int(tab[i]): int(tab[i] + tab[N + i])].tobytes() == want
+        # too small an output buffer is reported, not overrun
+        enc.encode_batch_device(d_rgb, N, W, H, W * 3, W * H * 3, p, d_out, 100, d_tab, d_tab + 8 * N, d_tab + 16 * N)
+        with pytest.raises(jb.JbError) as ei:
+            enc.sync()
+        assert ei.value.code == jb.E_NOSPACE
+    finally:
+        for d in (d_rgb, d_out, d_tab):
+            enc.device_free(d)
+
+
+def test_strips_concatenate_to_whole_image(enc, jb):
+    """RST strips (multi-GPU split of one image): header + strips + EOI == whole-image encode with DRI."""
+    H, W = 200, 176
+    img = ol.synth(77, W, H)
+    mcux = W // 16
+    p, ql, qc = _params(jb, ol.SUB_420, 75, mcux)  # one restart interval per MCU row
+    whole = ol.encode_jfif(img, ol.SUB_420, ql, qc, mcux)
+    assert enc.encode_jfif(img, p) == whole
+    rows = [0, 64, 112, 200]
+    parts = [enc.write_header(p, W, H)]
+    for s in range(3):
+        strip = img[rows[s]: rows[s + 1]]
+        parts.append(enc.encode_strip(strip, p, first_interval=rows[s] // 16, last_strip=(s == 2)).tobytes())
+    parts.append(b"\xff\xd9")
+    assert b"".join(parts) == whole
+
+
+def test_synth_generator_matches_oracle(enc):
+    for seed, W, H in ((0x4B3840, 200, 50), (0xF000, 97, 61), (1, 1920, 8)):
+        assert np.array_equal(enc.synth(seed, W, H), ol.synth(seed, W, H))
+
+
+def test_error_paths(enc, jb):
+    img = noise_image(1, 32, 32)
+    p = jb.make_params(ol.SUB_420, quality=75)
+    with pytest.raises(jb.JbError) as e:
+        enc.encode_jfif(img, p, cap=64)
+    assert e.value.code == jb.E_NOSPACE
+    bad = jb.make_params(ol.SUB_420, quality=75)
+    bad.qlum[5] = 0
+    with pytest.raises(jb.JbError) as e:
+        enc.encode_jfif(img, bad)
+    assert e.value.code == jb.E_INVALID
+    with pytest.raises(jb.JbError) as e:  # 4 px wide cannot be mirror-padded to 16 (utils.cpp:211-233)
+        enc.encode_jfif(noise_image(1, 4, 32), p)
+    assert e.value.code == jb.E_UNSUPPORTED
+
+
+# ------------------------------------------------------- BASELINE.json full sizes -----
+
+def _decode_psnr(jf, rgb):
+    import cv2
+    dec = cv2.imdecode(np.frombuffer(jf, np.uint8), cv2.IMREAD_COLOR)[:, :, ::-1]
+    assert dec.shape == rgb.shape
+    return 10 * np.log10(255.0 ** 2 / np.mean((dec.astype(np.float32) - rgb) ** 2))
+
+
+def _interval_segments(jf, hdr):
+    body = np.frombuffer(jf, np.uint8)[hdr:-2]
+    marks = np.flatnonzero((body[:-1] == 0xFF) & (body[1:] >= 0xD0) & (body[1:] <= 0xD7))
+    assert np.all((body[marks + 1] - 0xD0) == np.arange(len(marks)) % 8)  # RSTn count modulo 8
+    bounds = np.concatenate([[0], marks + 2, [len(body) + 2]])
+    return body, marks, bounds
+
+
+def test_config2_4k_444_q90(enc, jb):
+    """Config #2: synthetic 3840x2160 4:4:4 q90.  Size-independent checks: decodes, sane PSNR, and
+    sampled MCU rows equal the oracle through the restart-interval identity."""
+    W, H = 3840, 2160
+    img = enc.synth(0x4B3840, W, H)
+    assert np.array_equal(img[1000:1008], ol.synth(0x4B3840, W, 8, 1000))
+    mcux = W // 8
+    p, ql, qc = _params(jb, ol.SUB_444, 90, mcux)
+    jf = enc.encode_jfif(img, p)
+    assert _decode_psnr(jf, img) > 35
+    body, marks, bounds = _interval_segments(jf, jb.header_bytes(p))
+    assert len(marks) == H // 8 - 1
+    for row in (0, 133, 269):
+        coef = ol.transform(img[row * 8: row * 8 + 8], ol.SUB_444, ql, qc)
+        want, _ = ol.entropy(coef, ol.SUB_444, mcux)
+        seg = body[bounds[row]: bounds[row + 1] - 2]
+        assert np.array_equal(seg, want), f"MCU row {row}"
+    # the same image without restart markers: same coefficients -> same decoded pixels
+    p0, _, _ = _params(jb, ol.SUB_444, 90, 0)
+    import cv2
+    a = cv2.imdecode(np.frombuffer(jf, np.uint8), cv2.IMREAD_COLOR)
+    b = cv2.imdecode(np.frombuffer(enc.encode_jfif(img, p0), np.uint8), cv2.IMREAD_COLOR)
+    assert np.array_equal(a, b)
+
+
+def test_config3_8k_420_q75_restart(enc, jb):
+    """Config #3: synthetic 7680x4320 4:2:0 q75, DRI = one MCU row (480 MCUs)."""
+    W, H = 7680, 4320
+    img = enc.synth(0x4B7680, W, H)
+    p, ql, qc = _params(jb, ol.SUB_420, 75, 480)
+    jf = enc.encode_jfif(img, p, cap=W * H)
+    assert _decode_psnr(jf, img) > 30
+    body, marks, bounds = _interval_segments(jf, jb.header_bytes(p))
+    assert len(marks) == H // 16 - 1
+    for row in (0, 100, 269):
+        coef = ol.transform(img[row * 16: row * 16 + 16], ol.SUB_420, ql, qc)
+        want, _ = ol.entropy(coef, ol.SUB_420, 480)
+        seg = body[bounds[row]: bounds[row + 1] - 2]
+        assert np.array_equal(seg, want), f"MCU row {row}"
