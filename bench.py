@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200 JPEG encode path (BASELINE.json metric:
+"encode megapixels/sec (4:2:0, q75) at 1/2/4/8 B200; fused-kernel HBM GB/s").
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch of synthetic frames.  Default workload:
+BASELINE.json config #4 sharded by image, weak scaling: every GPU encodes --frames
+1920x1080 frames, 4:2:0, q75 (at 8 GPUs x 512 frames this is exactly the 4096-frame batch).
+`value` is device-resident (RGB already in HBM, JFIF bytes left in HBM); `e2e` is the same
+work through the public host API jb_encode_batch (pinned host RGB in, pinned host JFIF out,
+H2D/D2H inside the timed region).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "encode megapixels/sec (4:2:0, q75)"
+WORKLOADS = {
+    # name: (W, H, subsampling, quality, restart interval in MCUs, default frames per GPU)
+    "batch1080p": (1920, 1080, "420", 75, 0, 512),
+    "8k": (7680, 4320, "420", 75, 480, 8),
+    "4k444": (3840, 2160, "444", 90, 0, 32),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="batch1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (0 = workload default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------
+# CPU reference arm: the reference's own src/utils.cpp (oracle/_ref, compiled unmodified),
+# driven in the order of JpegEncoderHost, one process per host core on distinct frames.
+# ----------------------------------------------------------------------------------------
+
+def _ref_worker(args):
+    seed, W, H, o0 = args
+    import numpy as np  # noqa: F401
+    import oracle_lib as ol
+    rgb = ol.synth(seed, W, H)
+    kind = "reference" if ol.have_ref() else "port"
+    t0 = time.perf_counter()
+    if kind == "reference":
+        ol.ref_pipeline(rgb, 0, o0=o0)  # as written: CSC, CDS, pad, shift, DCT, quant, zigzag, RLE, Huffman
+    else:
+        ql, qc = ol.q50()
+        ol.entropy(ol.transform(rgb, ol.SUB_REPL420, ql, qc, ol.AS_WRITTEN), ol.SUB_REPL420, 0, ol.AS_WRITTEN, True)
+    return time.perf_counter() - t0, kind
+
+
+def cpu_reference_pass(W, H, frames_per_core, cores, pool, seed0=0xF000):
+    """One bounded sample: cores x frames_per_core frames through the reference CPU path.
+    Returns (MP/s over all cores, wall seconds, kind)."""
+    jobs = [(seed0 + i, W, H, False) for i in range(cores * frames_per_core)]
+    t0 = time.perf_counter()
+    res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    return len(jobs) * W * H / 1e6 / wall, wall, res[0][1]
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    import multiprocessing as mp
+    W, H, sub, q, ri, _ = WORKLOADS[a.workload]
+    cores = os.cpu_count() or 1
+    # a 1080p frame costs the reference ~3.5 s on one core: one frame per core per step
+    sw, sh = (W, H) if W * H <= 1920 * 1080 else (W, 64)
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(max(a.warmup, 0)):
+            cpu_reference_pass(sw, sh, 1, cores, pool)
+        walls, kind = [], "reference"
+        for _ in range(a.steps):
+            _, wall, kind = cpu_reference_pass(sw, sh, 1, cores, pool)
+            walls.append(wall)
+    ms = 1000.0 * sum(walls) / len(walls)
+    value = cores * sw * sh / 1e6 / (ms / 1000.0)
+    sample = (f"{cores} frames of {sw}x{sh} per step (one per core), reference CPU path as written "
+              f"(its only mode: replicated 4:2:0 coded 4:4:4, q50 tables, -O2)"
+              + ("" if (sw, sh) == (W, H) else f"; strip of the {W}x{H} image, full-image figure is extrapolated"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "MP/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a, 0), "note": "CPU arm: rank 0 only, host cores, no GPU"},
+        "cpu_baseline": {"value": round(value, 4), "unit": "MP/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(a, frames):
+    W, H, sub, q, ri, dflt = WORKLOADS[a.workload]
+    f = frames or a.frames or dflt
+    return (f"{a.workload}: {f} synthetic {W}x{H} RGB8 frames per GPU, {sub}, q{q}, "
+            f"restart interval {ri} MCUs, sharded by image")
+
+
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        try:
+            sm = [float(r[0]) for r in rows]
+            mx = max(float(r[1]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
+                    "power_w_max": max(float(r[2]) for r in rows)}
+        except Exception:
+            return None
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    jb = entry.load()
+    enc = jb.Encoder(local_rank)  # raises if the CUDA library or a GPU is missing: no fallback
+
+    W, H, subname, q, ri, dflt = WORKLOADS[a.workload]
+    F = a.frames or dflt
+    sub = {"420": jb.SUB_420, "444": jb.SUB_444}[subname]
+    params = jb.make_params(sub, quality=q, restart_interval=ri)
+    pitch, fstride = W * 3, W * H * 3
+    px_per_step = W * H * F  # per GPU
+
+    # inputs: generated on the device (identical to the oracle's generator), copied once to pinned host
+    d_rgb = torch.empty(F * fstride, dtype=torch.uint8, device="cuda")
+    for f in range(F):
+        enc.synth_device(0xF000 + rank * F + f, W, 0, H, pitch, d_rgb.data_ptr() + f * fstride)
+    enc.sync()
+    cap = F * (W * H // 2 + 4096)
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_tab = torch.zeros(2 * F + 1, dtype=torch.int64, device="cuda")
+    ext = torch.cuda.ExternalStream(enc.stream())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        enc.encode_batch_device(d_rgb.data_ptr(), F, W, H, pitch, fstride, params, d_out.data_ptr(), cap,
+                                d_tab.data_ptr(), d_tab.data_ptr() + 8 * F, d_tab.data_ptr() + 16 * F)
+
+    # ---- device-resident timed region ------------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    enc.sync()
+    enc.set_profiling(True)
+    enc.reset_counters()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(ext)
+    for _ in range(a.steps):
+        step_device()
+    ev1.record(ext)
+    enc.sync()
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_total = ev0.elapsed_time(ev1)
+    tm = enc.timings()
+    enc.set_profiling(False)
+    total_bytes = int(d_tab[2 * F].item())
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = float(t_ms.item()) / a.steps
+    value = world * px_per_step / 1e6 / (ms_step / 1e3)
+
+    # ---- roofline of the fused transform kernel (CUDA events on its own stream, timed region) ----
+    peak, peak_src = peaks()
+    g_mcu = 16 if sub == jb.SUB_420 else 8
+    padded = (-(-W // g_mcu) * g_mcu) * (-(-H // g_mcu) * g_mcu)
+    samples_per_px = 1.5 if sub == jb.SUB_420 else 3.0
+    alg_bytes = F * (3 * W * H + 2 * samples_per_px * padded)  # read RGB8 + write int16 coefficients
+    k_us = tm["transform_us"] / max(tm["transform_launches"], 1)
+    achieved = alg_bytes / (k_us * 1e-6) / 1e9
+    traffic = None
+    try:  # per-launch DRAM bytes from the committed ncu capture of the same command, if present
+        with open(os.path.join(ROOT, "profiles", "r01_transform_ncu_summary.json")) as f:
+            prof = json.load(f)
+        if prof.get("workload") == a.workload and prof.get("frames") == F:
+            traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "k_transform (fused CSC+subsample+shift+FDCT+quant+zigzag)", "bound": "hbm",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "kernel_us_per_launch": round(k_us, 2),
+                "step_breakdown_us": {"transform": round(tm["transform_us"] / a.steps, 1),
+                                      "tie_fixup": round(tm["fixup_us"] / a.steps, 1),
+                                      "entropy": round(tm["entropy_us"] / a.steps, 1)}}
+    launches_device = int(tm["total_launches"])
+
+    # ---- end to end through the public host API: pinned host in, pinned host out ----------------
+    e2e = None
+    if not a.no_e2e:
+        h_rgb = jb.pinned_empty((F, H, W, 3))
+        enc.d2h(h_rgb, d_rgb.data_ptr())
+        h_out = jb.pinned_empty((cap,))
+        offs = np.zeros(F, np.uint64)
+        sizes = np.zeros(F, np.uint64)
+
+        def step_host():
+            enc.encode_batch_ptr(h_rgb.ctypes.data, F, W, H, pitch, fstride, params, h_out.ctypes.data, cap, offs, sizes)
+
+        for _ in range(max(a.warmup, 3)):
+            step_host()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(a.steps):
+            step_host()
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        barrier()
+        e_ms = torch.tensor([(w1 - w0) * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        e_step = float(e_ms.item()) / a.steps
+        out_bytes = int(sizes.sum())
+        assert out_bytes == total_bytes, (out_bytes, total_bytes)  # host path == device path
+        e2e = {"value": round(world * px_per_step / 1e6 / (e_step / 1e3), 1), "unit": "MP/s",
+               "ms_per_step": round(e_step, 3), "h2d_bytes_per_step": int(F * fstride),
+               "d2h_bytes_per_step": int(out_bytes + 16 * F + 48),
+               "api": "jb_encode_batch (pinned host RGB -> pinned host JFIF, 3 streams, 96 MB groups)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's own code on the host cores ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        # in a fresh process (no fork after CUDA initialisation): one bounded sample of the reference arm
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                "--warmup", "0", "--workload", a.workload], capture_output=True, text=True, timeout=600)
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:  # the GPU numbers stand on their own; say why the baseline is missing
+            cpu = {"value": None, "unit": "MP/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a, F), "frames_per_gpu": F, "width": W, "height": H,
+                       "subsampling": subname, "quality": q, "restart_interval": ri,
+                       "l2": "inputs per step (%.2f GB) far exceed the 126 MB L2" % (F * fstride / 1e9),
+                       "bits_per_pixel": round(8.0 * total_bytes / px_per_step, 4),
+                       "tie_fixups_per_step": int(tm["tie_fixups"])},
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": launches_device,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

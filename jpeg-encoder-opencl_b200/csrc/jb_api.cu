@@ -138,7 +138,7 @@ size_t plan_bytes(const Plan& p) {
     auto add = [&](size_t n) { b = align_up(b, 256) + n; };
     add(p.rgb_bytes);
     add(p.n_blocks * 128);
-    add(p.n_blocks * 4);                   // tie list
+    add(p.n_blocks * 64 * 4);              // tie list: every coefficient may be flagged (never overflows)
     add(64);                               // scalars
     add((p.n_tiles * 256 + 1) * 4);        // blk_prefix
     add(p.n_tiles * 4);
@@ -166,8 +166,8 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     Arena& a = s.arena;
     s.d_rgb = carve<uint8_t>(a, p.rgb_bytes);
     s.d_coef = carve<int16_t>(a, p.n_blocks * 64);
-    s.d_tie_list = carve<uint32_t>(a, p.n_blocks);
-    s.tie_cap = (uint32_t)p.n_blocks;
+    s.d_tie_list = carve<uint32_t>(a, p.n_blocks * 64);
+    s.tie_cap = (uint32_t)(p.n_blocks * 64);
     s.d_scalars = carve<uint32_t>(a, 16);
     s.w.blk_prefix = carve<uint32_t>(a, p.n_tiles * 256 + 1);
     s.w.tile_bits = carve<uint32_t>(a, p.n_tiles);
