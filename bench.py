@@ -260,6 +260,7 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                 "kernel_us_per_launch": round(k_us, 2),
                 "step_breakdown_us": {"transform": round(tm["transform_us"] / a.steps, 1),
+                                      "edge_mcus": round(tm["edge_us"] / a.steps, 1),
                                       "tie_fixup": round(tm["fixup_us"] / a.steps, 1),
                                       "entropy": round(tm["entropy_us"] / a.steps, 1)}}
     launches_device = int(tm["total_launches"])

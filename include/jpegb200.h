@@ -70,6 +70,7 @@ typedef struct {
     double fixup_us;     /* near-tie binary64 replay                                */
     double entropy_us;   /* all entropy-coder kernels (lengths, scans, pack, stuff) */
     double h2d_us, d2h_us;
+    double edge_us;      /* generic kernel for MCUs that need mirror padding            */
     uint64_t transform_launches, total_launches; /* kernels launched by the library since jb_reset_counters */
     uint64_t tie_fixups;                         /* coefficients replayed in binary64 in the last call      */
 } jb_timings;

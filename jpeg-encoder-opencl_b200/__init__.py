@@ -47,7 +47,7 @@ class Params(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("CSCTime", "CDSTime", "levelShiftTime", "DCTTime", "QuantTime",
                                           "TotalCopyTime", "zigZagTime", "RLETime", "HuffmanTime", "transform_us",
-                                          "fixup_us", "entropy_us", "h2d_us", "d2h_us")] + \
+                                          "fixup_us", "entropy_us", "h2d_us", "d2h_us", "edge_us")] + \
                [(n, C.c_uint64) for n in ("transform_launches", "total_launches", "tie_fixups")]
 
 

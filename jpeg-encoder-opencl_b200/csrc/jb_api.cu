@@ -29,7 +29,7 @@ struct Arena {
 
 struct EventPair {
     cudaEvent_t a, b;
-    int kind;  // 0 transform, 1 fixup, 2 entropy, 3 h2d, 4 d2h
+    int kind;  // 0 transform, 1 fixup, 2 entropy, 3 h2d, 4 d2h, 5 edge MCUs
 };
 
 // One in-flight unit of work: stream + device workspace + pinned result words.
@@ -277,6 +277,7 @@ void resolve_events(jb_ctx* ctx) {
                 case 1: ctx->tm.fixup_us += us; break;
                 case 2: ctx->tm.entropy_us += us; break;
                 case 3: ctx->tm.h2d_us += us; break;
+                case 5: ctx->tm.edge_us += us; break;
                 default: ctx->tm.d2h_us += us; break;
             }
         }
@@ -314,6 +315,10 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         int n = launch_transform(ta, s.st);
         ctx->tm.transform_launches += n;
         ctx->tm.total_launches += n;
+    }
+    {
+        Timed t(ctx, s.st, 5);
+        ctx->tm.total_launches += launch_transform_edge(ta, s.st);
     }
     if (!(p->flags & JB_FLAG_NO_TIE_FIXUP)) {
         FixupArgs fa{};

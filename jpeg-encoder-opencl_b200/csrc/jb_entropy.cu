@@ -15,8 +15,8 @@
 //   k_int_out   output bytes of every interval (data + stuffing + marker + header)
 //   k_scan      output offset of every interval / frame
 //   k_finalize  capacity check, frame table
-//   k_stuff     copy chunks to their final place inserting 0x00 after 0xFF, markers
-//   k_headers   JFIF header in front of every frame
+//   k_stuff     assemble the final bytes per 4 KB tile in shared memory (0x00 after 0xFF,
+//               markers, JFIF headers) and store them with coalesced 128-bit stores
 // Bit order is MSB first; the unstuffed buffer is addressed as big-endian words.
 #include "jb_internal.h"
 
@@ -354,51 +354,87 @@ __global__ void k_finalize(const __grid_constant__ EntropyArgs a) {
     }
 }
 
+// Final placement.  One CTA per tile of 256 chunks (4 KB of unstuffed bytes).  The output
+// stream is partitioned among chunks -- a chunk owns its data bytes with their stuffing
+// zeros, the marker after its interval if it is the interval's last chunk, and the JFIF
+// header if it is the first chunk of a frame -- so a tile owns one contiguous byte range
+// [g0, g1) of the output.  The tile is assembled in shared memory (placed so that shared and
+// global addresses agree modulo 16) and then stored with 128-bit coalesced stores; a tile
+// whose range does not fit the window (pathological: thousands of tiny frames) writes bytes
+// straight to global memory.
+constexpr int STUFF_WIN = 12288;
+
 __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyArgs a) {
+    __shared__ __align__(16) uint8_t win[STUFF_WIN + 32];
+    __shared__ uint64_t s_g0, s_g1;
     uint64_t total = a.w.int_ubase[a.n_int_total];
     if (total > a.w.ubuf_cap || a.w.int_obase[a.n_int_total] > a.out_cap) return;
-    uint64_t n_chunks = total >> 4;
+    const uint64_t n_chunks = total >> 4;
+    const uint32_t n_tiles = (uint32_t)((n_chunks + TILE - 1) / TILE);
     const uint4* p = reinterpret_cast<const uint4*>(a.w.ubuf);
-    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks;
-         c += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t pos = c << 4;
-        // interval i with int_ubase[i] <= pos < int_ubase[i+1]
-        uint32_t lo = 0, hi = a.n_int_total;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (a.w.int_ubase[mid] <= pos) lo = mid; else hi = mid;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t c = (uint64_t)tile * TILE + threadIdx.x;
+        const bool have = c < n_chunks;
+        uint64_t dst = 0, start = 0, end = 0;
+        uint32_t wds[4] = {0, 0, 0, 0}, marker = 0;
+        int valid = 0;
+        bool hdr = false;
+        if (have) {
+            uint64_t pos = c << 4;
+            uint32_t lo = 0, hi = a.n_int_total;  // interval i with int_ubase[i] <= pos < int_ubase[i+1]
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (a.w.int_ubase[mid] <= pos) lo = mid; else hi = mid;
+            }
+            uint32_t i = lo, k = i % (uint32_t)a.g.n_int;
+            uint64_t ub = a.w.int_ubase[i];
+            uint64_t off = pos - ub, nb = (a.w.int_bits[i] + 7) >> 3;
+            hdr = k == 0 && off == 0 && a.fr.hdr_bytes != 0;
+            start = a.w.int_obase[i] + (k == 0 && off != 0 ? a.fr.hdr_bytes : 0u) + off +
+                    (ff_prefix(a, c) - ff_prefix(a, ub >> 4));
+            dst = start + (hdr ? a.fr.hdr_bytes : 0u);
+            uint4 q = p[c];
+            wds[0] = q.x; wds[1] = q.y; wds[2] = q.z; wds[3] = q.w;
+            valid = off >= nb ? 0 : (nb - off < 16 ? (int)(nb - off) : 16);
+            if (off + 16 >= nb) marker = marker_after(a, k);  // last chunk of the interval
+            end = dst + (uint64_t)valid + count_ff(q) + (marker ? 2u : 0u);
         }
-        uint32_t i = lo, k = i % (uint32_t)a.g.n_int;
-        uint64_t ub = a.w.int_ubase[i];
-        uint64_t off = pos - ub, nb = (a.w.int_bits[i] + 7) >> 3;
-        uint64_t dst = a.w.int_obase[i] + (k == 0 ? a.fr.hdr_bytes : 0u) + off + (ff_prefix(a, c) - ff_prefix(a, ub >> 4));
-        uint4 q = p[c];
-        uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-        int valid = off >= nb ? 0 : (nb - off < 16 ? (int)(nb - off) : 16);
+        if (threadIdx.x == 0) s_g0 = start;
+        if (have && (threadIdx.x == TILE - 1 || c + 1 == n_chunks)) s_g1 = end;
+        __syncthreads();
+        const uint64_t g0 = s_g0, g1 = s_g1;
+        const uintptr_t P0 = reinterpret_cast<uintptr_t>(a.out) + g0;
+        const uint32_t base = (uint32_t)(P0 & 15);
+        const bool fits = g1 - g0 <= STUFF_WIN;
+        uint8_t* o = fits ? win + base - g0 : a.out;  // o[pos] addresses output byte pos either way
+        if (have) {
+            if (hdr)
+                for (uint32_t j = 0; j < a.fr.hdr_bytes; ++j) o[start + j] = a.hdr[j];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (j < valid) {
-                uint32_t byte = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-                a.out[dst++] = (uint8_t)byte;
-                if (byte == 0xFFu) a.out[dst++] = 0;  // T.81 F.1.2.3 byte stuffing
+            for (int j = 0; j < 16; ++j) {
+                if (j < valid) {
+                    uint32_t byte = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                    o[dst++] = (uint8_t)byte;
+                    if (byte == 0xFFu) o[dst++] = 0;  // T.81 F.1.2.3 byte stuffing
+                }
+            }
+            if (marker) {
+                o[dst] = 0xFF;
+                o[dst + 1] = (uint8_t)marker;
             }
         }
-        if (off + 16 >= nb) {  // last chunk of the interval: marker
-            uint32_t m = marker_after(a, k);
-            if (m) {
-                a.out[dst] = 0xFF;
-                a.out[dst + 1] = (uint8_t)m;
-            }
+        __syncthreads();
+        if (fits) {
+            const uint32_t n = (uint32_t)(g1 - g0);
+            const uint32_t head = min(n, (16u - base) & 15u);          // bytes before the first 16-byte boundary
+            const uint32_t n16 = (n - head) >> 4, tail = (n - head) & 15u;
+            if (threadIdx.x < head) a.out[g0 + threadIdx.x] = win[base + threadIdx.x];
+            uint4* gdst = reinterpret_cast<uint4*>(a.out + g0 + head);
+            const uint4* ssrc = reinterpret_cast<const uint4*>(win + base + head);
+            for (uint32_t j = threadIdx.x; j < n16; j += TILE) gdst[j] = ssrc[j];
+            if (threadIdx.x < tail) a.out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = win[base + head + 16 * n16 + threadIdx.x];
         }
-    }
-}
-
-__global__ void k_headers(const __grid_constant__ EntropyArgs a) {
-    if (a.w.int_obase[a.n_int_total] > a.out_cap) return;
-    uint32_t n = (uint32_t)a.n_frames * a.fr.hdr_bytes;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        uint32_t f = t / a.fr.hdr_bytes, j = t - f * a.fr.hdr_bytes;
-        a.out[a.w.int_obase[f * (uint32_t)a.g.n_int] + j] = a.hdr[j];
+        __syncthreads();
     }
 }
 
@@ -423,10 +459,6 @@ int launch_entropy(const EntropyArgs& a, cudaStream_t s) {
     k_finalize<<<gf, 256, 0, s>>>(a);
     k_stuff<<<1184, TILE, 0, s>>>(a);
     launches += 6;
-    if (a.fr.hdr_bytes) {
-        k_headers<<<148, 256, 0, s>>>(a);
-        ++launches;
-    }
     return launches;
 }
 

@@ -40,8 +40,11 @@ inline Geometry make_geometry(size_t W, size_t H, int sub, int restart_interval)
 
 // Quantisation constants in natural [v][u] order; table 0 = luma, 1 = chroma.
 struct QuantConst {
-    float mul[2][64];   // alpha(u)alpha(v) / (4 q aan(u) aan(v))
-    float band[2][64];  // 0.5 - JB_DCT_ERR_BOUND * mul
+    float mul[2][64];    // alpha(u)alpha(v) / (4 q aan(u) aan(v))
+    float band[2][64];   // 0.5 - (worst-case binary32 error of coefficient n, in quotient units)
+    uint32_t dc_d[2];    // 8 q[0]: the DC coefficient is S / dc_d with S the exact integer sample sum
+    uint32_t dc_m[2];    // ceil(2^32 / (2 dc_d))
+    uint32_t dc_exact;   // 1 when "ties go towards zero" reproduces the reference's binary64 DC for every S
 };
 
 struct QuantTables {
@@ -60,6 +63,7 @@ struct TransformArgs {
     uint32_t tie_cap;
     int units_per_row;
     uint32_t total_units;
+    int fast_mcux, fast_mcuy;  // MCUs per row / column that lie completely inside the image
     QuantConst qc;
 };
 
@@ -134,7 +138,8 @@ struct EntropyArgs {
 #define JB_STATUS_TIE_OVERFLOW 4ull
 
 // ---- launchers (each returns the number of kernels it launched) -------------
-int launch_transform(const TransformArgs& a, cudaStream_t s);
+int launch_transform(const TransformArgs& a, cudaStream_t s);       // MCUs inside the image (hot kernel)
+int launch_transform_edge(const TransformArgs& a, cudaStream_t s);  // MCUs that need mirror padding
 int launch_fixup(const FixupArgs& a, cudaStream_t s);
 int launch_entropy(const EntropyArgs& a, cudaStream_t s);
 int launch_synth(uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t* d_out, cudaStream_t s);
@@ -155,6 +160,7 @@ int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStre
 
 // host helpers
 void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out);
+void aan_error_bound(double err[64], double amax[64]);  // worst-case |binary32 - exact| per AAN output
 void build_huff(bool typo, HuffDev* out);
 size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* out);  // out >= 1024 bytes
 extern const uint8_t kZigzag[64];  // zigzag position -> natural index

@@ -82,7 +82,70 @@ void build_huff(bool typo, HuffDev* out) {
     }
 }
 
+// ---- worst-case error of the binary32 AAN transform -------------------------------
+// Forward error analysis of fdct8 (jb_math.h) applied to rows, then columns, of
+// integer samples |x| <= 128: every node carries (max |value|, bound on |computed -
+// exact|).  Additions of integers below 2^24 are exact; every other operation adds
+// the unit round-off u = 2^-24 times its result magnitude, and every irrational
+// constant its representation error.  The result bounds |a - a_exact| for each of
+// the 64 AAN-scaled outputs; tests/test_math_host.py checks measured errors against it.
+namespace {
+struct Bnd {
+    double m, e;
+    bool isint;
+};
+const double kU = 5.9604644775390625e-08;  // 2^-24
+Bnd b_add(Bnd a, Bnd b) {
+    Bnd r;
+    r.m = a.m + b.m;
+    r.isint = a.isint && b.isint && r.m < 16777216.0;
+    r.e = a.e + b.e + (r.isint ? 0.0 : kU * (r.m + a.e + b.e));
+    return r;
+}
+Bnd b_fma(Bnd w, double c, Bnd x) {
+    Bnd r;
+    c = fabs(c);
+    r.m = w.m * c + x.m;
+    r.isint = false;
+    double e = w.e * c + w.m * c * kU + x.e;
+    r.e = e + kU * (r.m + e);
+    return r;
+}
+void b_fdct8(Bnd* d) {
+    const Bnd zero{0, 0, true};
+    Bnd s07 = b_add(d[0], d[7]), s16 = b_add(d[1], d[6]), s25 = b_add(d[2], d[5]), s34 = b_add(d[3], d[4]);
+    Bnd e0 = b_add(s07, s34), e1 = b_add(s16, s25);  // differences have the same bounds as sums
+    Bnd o[8];
+    o[0] = o[4] = b_add(e0, e1);
+    Bnd w = b_add(e1, e0);
+    o[2] = o[6] = b_fma(w, JB_C4, e0);
+    Bnd o0 = b_add(s34, s25), o1 = b_add(s25, s16), o2 = b_add(s16, s07);
+    Bnd z5 = b_fma(b_add(o0, o2), JB_C6, zero);
+    Bnd z2 = b_fma(o0, JB_Q, z5), z4 = b_fma(o2, JB_R, z5), z11 = b_fma(o1, JB_C4, s07);
+    o[5] = o[3] = b_add(z11, z2);
+    o[1] = o[7] = b_add(z11, z4);
+    for (int i = 0; i < 8; ++i) d[i] = o[i];
+}
+}  // namespace
+
+void aan_error_bound(double err[64], double amax[64]) {
+    Bnd row[8];
+    for (int i = 0; i < 8; ++i) row[i] = Bnd{128.0, 0.0, true};
+    b_fdct8(row);
+    for (int u = 0; u < 8; ++u) {
+        Bnd col[8];
+        for (int i = 0; i < 8; ++i) col[i] = row[u];
+        b_fdct8(col);
+        for (int v = 0; v < 8; ++v) {
+            err[v * 8 + u] = col[v].e;
+            amax[v * 8 + u] = col[v].m;
+        }
+    }
+}
+
 void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out) {
+    double err[64], amax[64];
+    aan_error_bound(err, amax);
     for (int t = 0; t < 2; ++t) {
         const uint32_t* q = t ? qc : ql;
         for (int v = 0; v < 8; ++v)
@@ -91,11 +154,35 @@ void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst*
                 double alpha = (u == 0 ? M_SQRT1_2 : 1.0) * (v == 0 ? M_SQRT1_2 : 1.0);
                 double mul = alpha / (4.0 * (double)q[n] * aan_scale(u) * aan_scale(v));
                 out->mul[t][n] = (float)mul;
-                // round the band towards "more ties": float(0.5 - delta) may round up, so shave one ulp
-                float band = (float)(0.5 - JB_DCT_ERR_BOUND * mul);
-                out->band[t][n] = nextafterf(band, 0.0f);
+                // error of a*mul: transform error, the multiplier's own rounding, and the two roundings
+                // inside quantize_bits; 25 % margin on top of the worst case.
+                double delta = 1.25 * ((err[n] + 2.0 * kU * amax[n]) * mul) + 1e-6;
+                float band = (float)(0.5 - delta);
+                out->band[t][n] = nextafterf(band, 0.0f);  // float(0.5 - delta) may have rounded up
             }
+        // DC in integers: S / (8 q) with exact ties going towards zero.  Check the rule against the
+        // reference's binary64 expression (utils.cpp:336, 460) for every possible sample sum S.
+        uint32_t D = 8 * q[0];
+        out->dc_d[t] = D;
+        out->dc_m[t] = (uint32_t)((0x100000000ull + 2 * D - 1) / (2 * D));
     }
+    double a0 = 1.0 / sqrt(2);
+    volatile double scale00 = (a0 * a0 / 4.0);
+    bool ok = true;
+    for (int t = 0; t < 2 && ok; ++t) {
+        uint32_t D = out->dc_d[t];
+        double q = (double)(t ? qc : ql)[0];
+        for (int S = -8192; S <= 8192 && ok; ++S) {
+            volatile double F = (double)S * scale00;
+            volatile double quo = F / q;
+            int want = (int)round(quo);
+            uint32_t A = (uint32_t)(S < 0 ? -S : S);
+            uint32_t m = (uint32_t)(((uint64_t)(2 * A + D - 1) * out->dc_m[t]) >> 32);
+            int got = S < 0 ? -(int)m : (int)m;
+            ok = got == want;
+        }
+    }
+    out->dc_exact = ok ? 1u : 0u;
 }
 
 static void put16(uint8_t* p, unsigned v) {

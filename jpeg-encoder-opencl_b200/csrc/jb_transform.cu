@@ -10,11 +10,15 @@
 //
 // Work decomposition: one warp owns a "unit" (16 MCUs of 16x16 px in 4:2:0, 32
 // MCUs of 8x8 px otherwise); one thread keeps a whole 8x8 block in registers, so
-// both DCT passes, quantisation and the zigzag permutation need no shuffles and
-// no shared memory.  Results are staged through a per-warp, XOR-swizzled 4 KB
-// shared-memory tile so that the HBM stores are coalesced 128-bit stores of
-// whole 128-byte blocks.  Algorithmic HBM traffic: 3 B/px read + 2 B/sample
-// written = 6 B/px (4:2:0) or 9 B/px (4:4:4, replicated 4:2:0).
+// both DCT passes, quantisation and the zigzag permutation need no shuffles.
+// Results are staged through a per-warp, XOR-swizzled 4 KB shared-memory tile so
+// that the HBM stores are coalesced 128-bit stores of whole 128-byte blocks.
+// k_transform handles MCUs that lie completely inside the image; the few MCUs
+// that need mirror padding (last MCU column/row of an image whose size is not a
+// multiple of the MCU) go through k_transform_edge, a small generic kernel, which
+// keeps the hot kernel free of the padding code (instruction-cache footprint).
+// Algorithmic HBM traffic: 3 B/px read + 2 B/sample written = 6 B/px (4:2:0) or
+// 9 B/px (4:4:4, replicated 4:2:0).
 #include "jb_pixels.cuh"
 
 namespace jb {
@@ -29,6 +33,19 @@ __device__ __forceinline__ void fdct2d(float (&v)[64]) {
         fdct8(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
 }
 
+// DC coefficient in exact integer arithmetic.  v[0] is the exact integer sum S of
+// the 64 level-shifted samples (the AAN DC path only adds), F = S/8, and the
+// reference rounds S*c/q with c = fl(fl(1/sqrt2)^2/4) slightly below 1/8, i.e. an
+// exact tie goes towards zero; the host checks this rule against the binary64
+// expression for every S before enabling it (QuantConst::dc_exact).
+template <int TAB>
+__device__ __forceinline__ uint32_t quantize_dc(float s, const TransformArgs& a) {
+    int S = __float2int_rn(s);
+    uint32_t A = (uint32_t)abs(S);
+    uint32_t m = __umulhi(2u * A + a.qc.dc_d[TAB] - 1u, a.qc.dc_m[TAB]);  // floor((2A + D - 1) / 2D)
+    return (uint32_t)(S < 0 ? -(int)m : (int)m);
+}
+
 // Quantise the block in v (natural order), permute to zigzag, pack to int16 and
 // write the 128 bytes to this lane's row of the warp's swizzled staging tile.
 template <int TAB>
@@ -39,7 +56,13 @@ __device__ __forceinline__ void quant_stage(const float (&v)[64], const Transfor
     for (int j = 0; j < 32; ++j) {
         const int n0 = zz_nat(2 * j), n1 = zz_nat(2 * j + 1);
         bool t0, t1;
-        uint32_t b0 = quantize_bits(v[n0], a.qc.mul[TAB][n0], a.qc.band[TAB][n0], t0);
+        uint32_t b0;
+        if (j == 0 && a.qc.dc_exact) {
+            b0 = quantize_dc<TAB>(v[0], a);
+            t0 = false;
+        } else {
+            b0 = quantize_bits(v[n0], a.qc.mul[TAB][n0], a.qc.band[TAB][n0], t0);
+        }
         uint32_t b1 = quantize_bits(v[n1], a.qc.mul[TAB][n1], a.qc.band[TAB][n1], t1);
         if (j < 16) {
             if (t0) tie_lo |= 1u << (2 * j);
@@ -55,7 +78,8 @@ __device__ __forceinline__ void quant_stage(const float (&v)[64], const Transfor
         st[lane * 8 + (p ^ (lane & 7))] = make_uint4(wd[4 * p], wd[4 * p + 1], wd[4 * p + 2], wd[4 * p + 3]);
 }
 
-__device__ __forceinline__ void append_ties(const TransformArgs& a, uint32_t gblock, uint32_t lo, uint32_t hi) {
+__device__ __noinline__ void append_ties(uint32_t* list, uint32_t* count, uint32_t cap, uint32_t gblock, uint32_t lo,
+                                         uint32_t hi) {
     while (lo | hi) {
         int k;
         if (lo) {
@@ -65,8 +89,8 @@ __device__ __forceinline__ void append_ties(const TransformArgs& a, uint32_t gbl
             k = 31 + __ffs(hi);
             hi &= hi - 1;
         }
-        uint32_t idx = atomicAdd(a.tie_count, 1u);
-        if (idx < a.tie_cap) a.tie_list[idx] = gblock * 64u + (uint32_t)k;
+        uint32_t idx = atomicAdd(count, 1u);
+        if (idx < cap) list[idx] = gblock * 64u + (uint32_t)k;
     }
 }
 
@@ -85,125 +109,130 @@ __device__ __forceinline__ void copy_out(const uint4* st, uint4* coef4, size_t m
     }
 }
 
-__device__ __forceinline__ uint32_t pack_s8(uint32_t acc, int val, int pos) {
-    return acc | (((uint32_t)val & 0xFFu) << (8 * pos));
+// ---- colour conversion of one row of 8 pixels (24 bytes in w) ----------------
+// T values are the 8.24 fixed-point numbers of jb_math.h; the three multiply-adds
+// per channel are written as PTX so that they stay three IMADs.
+__device__ __forceinline__ uint32_t mad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
-__device__ __forceinline__ float unpack_s8(uint32_t w, int pos) { return (float)(int)(int8_t)(w >> (8 * pos)); }
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_perm(w, 0, 0x4440 + k); }
 
-// ------------------------------------------------------------------ 4:2:0 --
-// Lane = one 8-pixel-wide, 16-row half of a 16x16 MCU: two luma blocks, then
-// (after exchanging chroma halves with the partner lane) one chroma block.
-template <int ALIGN>
-__device__ __forceinline__ void load_half_420(const Image& im, int px, int py, int h, bool interior, float (&v)[64],
-                                              uint32_t (&cbq)[8], uint32_t (&crq)[8]) {
-    uint32_t pcb[4], pcr[4];
-    if (interior) {
-        const uint8_t* row = im.base + (size_t)(py + h * 8) * im.pitch + (size_t)px * 3;
+struct Row8 {
+    int y[8];         // level-shifted luma
+    uint32_t cb[8];   // T_cb, T_cr: the chroma byte is the top byte
+    uint32_t cr[8];
+};
+
+__device__ __forceinline__ void csc_row8(const uint32_t (&w)[6], const uint32_t* __restrict__ ydown, Row8& o) {
+    uint32_t ty[8], tmin = 0xFFFFFFFFu;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            uint32_t w[6];
-            load24<ALIGN>(row + (size_t)r * im.pitch, w);
-            uint32_t hcb[4], hcr[4];
+    for (int i = 0; i < 8; ++i) {
+        const int k = 3 * i;
+        uint32_t R = byte_of(w[k >> 2], k & 3), G = byte_of(w[(k + 1) >> 2], (k + 1) & 3),
+                 B = byte_of(w[(k + 2) >> 2], (k + 2) & 3);
+        ty[i] = mad(B, KY_B, mad(G, KY_G, mad(R, KY_R, 0x80000000u)));  // T_y - 128.0
+        o.cb[i] = mad(B, 0x00800000u, mad(G, 0u - KCB_G, mad(R, 0u - KCB_R, 0x80000000u)));
+        o.cr[i] = mad(R, 0x00800000u, mad(B, 0u - KCR_B, mad(G, 0u - KCR_G, 0x80000000u)));
+        tmin = min(tmin, ty[i] & Y_TIE_MASK);
+        o.y[i] = (int)ty[i] >> 24;
+    }
+    if (tmin == 0) {  // some pixel of the row is a CSC tie (exact integer luma): consult the table
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint32_t R = byte24(w, 3 * i), G = byte24(w, 3 * i + 1), B = byte24(w, 3 * i + 2);
-                v[r * 8 + i] = (float)((int)csc_y(R, G, B, im.ydown) - 128);
-                uint32_t cb = csc_cb(R, G, B), cr = csc_cr(R, G, B);
-                if (i & 1) {
-                    hcb[i >> 1] += cb;
-                    hcr[i >> 1] += cr;
-                } else {
-                    hcb[i >> 1] = cb;
-                    hcr[i >> 1] = cr;
-                }
-            }
-            if (r & 1) {
-                uint32_t qb = 0, qr = 0;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    qb = pack_s8(qb, (int)((pcb[c] + hcb[c]) >> 2) - 128, c);
-                    qr = pack_s8(qr, (int)((pcr[c] + hcr[c]) >> 2) - 128, c);
-                }
-                cbq[h * 4 + (r >> 1)] = qb;
-                crq[h * 4 + (r >> 1)] = qr;
-            } else {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    pcb[c] = hcb[c];
-                    pcr[c] = hcr[c];
-                }
-            }
-        }
-    } else {
-        // fully unrolled so that v[] keeps static indices (stays in registers)
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            uint32_t qb = 0, qr = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint32_t Y, Cb, Cr;
-                ycc_at<true>(im, px + i, py + h * 8 + r, Y, Cb, Cr);
-                v[r * 8 + i] = (float)((int)Y - 128);
-                // chroma sample (ci, cj) of the 4:2:0 planes = replicated plane at (2ci, 2cj)
-                if ((r & 1) == 0 && (i & 1) == 0) {
-                    qb = pack_s8(qb, (int)Cb - 128, i >> 1);
-                    qr = pack_s8(qr, (int)Cr - 128, i >> 1);
-                }
-            }
-            if ((r & 1) == 0) {
-                cbq[h * 4 + (r >> 1)] = qb;
-                crq[h * 4 + (r >> 1)] = qr;
+        for (int i = 0; i < 8; ++i) {
+            if ((ty[i] & Y_TIE_MASK) == 0) {
+                const int k = 3 * i;
+                uint32_t idx = (byte_of(w[k >> 2], k & 3) << 8) | byte_of(w[(k + 1) >> 2], (k + 1) & 3);
+                o.y[i] -= (int)((__ldg(ydown + (idx >> 5)) >> (idx & 31)) & 1u);
             }
         }
     }
 }
 
+// ------------------------------------------------------------------ 4:2:0 --
+// Lane = one 8-pixel-wide, 16-row half of a 16x16 MCU: two luma blocks, then one
+// chroma block (left lane Cb, right lane Cr).  Chroma samples are parked as
+// floats in shared memory: word address m*136 + ch*68 + row*8 + col (the pads
+// make both the 128-bit writes and the 128-bit reads bank-conflict free).
+constexpr int CH_MCU_STRIDE = 136, CH_BLK_STRIDE = 68, CH_WARP_WORDS = 16 * CH_MCU_STRIDE;
+
 template <int ALIGN>
-__device__ __forceinline__ void unit_420(const TransformArgs& a, const Image& im, size_t mcu_g0, int mcu_x0, int my,
-                                         uint4* st, int lane) {
+__device__ __forceinline__ void unit_420(const TransformArgs& a, const Image& im, size_t mcu_g0, int mcu_x0,
+                                         int mcus_valid, int my, uint4* st, float* ch, int lane) {
     const int m = lane >> 1, half = lane & 1;
-    const int mcus_valid = min(16, a.g.mcux - mcu_x0);
     const bool valid = m < mcus_valid;
-    const int px = (mcu_x0 + m) * 16 + half * 8, py = my * 16;
-    const bool interior = px + 8 <= a.g.W && py + 16 <= a.g.H;
     const uint32_t gb0 = (uint32_t)(mcu_g0 + m) * 6u;
     uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
     float v[64];
-    uint32_t cbq[8], crq[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cbq[j] = crq[j] = 0;
+    const uint8_t* col0 = im.base + (size_t)((mcu_x0 + m) * 16 + half * 8) * 3;
 
-#pragma unroll
+#pragma unroll 1
     for (int h = 0; h < 2; ++h) {
         if (valid) {
-            load_half_420<ALIGN>(im, px, py, h, interior, v, cbq, crq);
+            // rows below an (even) image height are mirrored (utils.cpp:223-232); with H even the mirrored
+            // row pair is again a complete 2x2-cell pair, so the chroma means are the reference's
+            uint32_t w[8][6];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                load24<ALIGN>(col0 + (size_t)mirror(my * 16 + h * 8 + r, im.H) * im.pitch, w[r]);
+            uint32_t pb[4], pr[4];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                Row8 o;
+                csc_row8(w[r], im.ydown, o);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[r * 8 + i] = (float)o.y[i];
+                uint32_t sb[4], sr[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    sb[c] = (o.cb[2 * c] >> 24) + (o.cb[2 * c + 1] >> 24);
+                    sr[c] = (o.cr[2 * c] >> 24) + (o.cr[2 * c + 1] >> 24);
+                }
+                if (r & 1) {  // utils.cpp:126-127: truncated mean of the 2x2 cell, then level shift
+                    float4 fb, fr;
+                    fb.x = (float)((int)((pb[0] + sb[0]) >> 2) - 128);
+                    fb.y = (float)((int)((pb[1] + sb[1]) >> 2) - 128);
+                    fb.z = (float)((int)((pb[2] + sb[2]) >> 2) - 128);
+                    fb.w = (float)((int)((pb[3] + sb[3]) >> 2) - 128);
+                    fr.x = (float)((int)((pr[0] + sr[0]) >> 2) - 128);
+                    fr.y = (float)((int)((pr[1] + sr[1]) >> 2) - 128);
+                    fr.z = (float)((int)((pr[2] + sr[2]) >> 2) - 128);
+                    fr.w = (float)((int)((pr[3] + sr[3]) >> 2) - 128);
+                    float* dst = ch + m * CH_MCU_STRIDE + (h * 4 + (r >> 1)) * 8 + half * 4;
+                    *reinterpret_cast<float4*>(dst) = fb;
+                    *reinterpret_cast<float4*>(dst + CH_BLK_STRIDE) = fr;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        pb[c] = sb[c];
+                        pr[c] = sr[c];
+                    }
+                }
+            }
             fdct2d(v);
             uint32_t tl = 0, th = 0;
             quant_stage<0>(v, a, st, lane, tl, th);
-            if (tl | th) append_ties(a, gb0 + 2 * h + half, tl, th);
+            if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 2 * h + half, tl, th);
         }
         __syncwarp();
         copy_out<6>(st, coef4, mcu_g0, mcus_valid, 2 * h, lane);
         __syncwarp();
     }
-    // exchange chroma halves: the left lane builds Cb, the right lane builds Cr
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        uint32_t send = half ? cbq[j] : crq[j];
-        uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-        uint32_t lo = half ? recv : cbq[j];
-        uint32_t hi = half ? crq[j] : recv;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            v[j * 8 + i] = unpack_s8(lo, i);
-            v[j * 8 + 4 + i] = unpack_s8(hi, i);
-        }
-    }
     if (valid) {
+        const float* src = ch + m * CH_MCU_STRIDE + half * CH_BLK_STRIDE;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float4 f = *reinterpret_cast<const float4*>(src + j * 4);
+            v[4 * j] = f.x;
+            v[4 * j + 1] = f.y;
+            v[4 * j + 2] = f.z;
+            v[4 * j + 3] = f.w;
+        }
         fdct2d(v);
         uint32_t tl = 0, th = 0;
         quant_stage<1>(v, a, st, lane, tl, th);
-        if (tl | th) append_ties(a, gb0 + 4 + half, tl, th);
+        if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 4 + half, tl, th);
     }
     __syncwarp();
     copy_out<6>(st, coef4, mcu_g0, mcus_valid, 4, lane);
@@ -212,105 +241,90 @@ __device__ __forceinline__ void unit_420(const TransformArgs& a, const Image& im
 
 // ------------------------------------------------- 4:4:4 / replicated 4:2:0 --
 // Lane = one 8x8 MCU: Y, Cb, Cr blocks in turn; chroma is parked as packed bytes.
-template <int ALIGN, bool CDS>
-__device__ __forceinline__ void load_mcu_444(const Image& im, int px, int py, bool interior, float (&v)[64],
-                                             uint32_t (&cq)[2][8][2]) {
-    if (interior) {
-        const uint8_t* row = im.base + (size_t)py * im.pitch + (size_t)px * 3;
-        uint32_t pcb[4], pcr[4];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            uint32_t w[6];
-            load24<ALIGN>(row + (size_t)r * im.pitch, w);
-            uint32_t cb[8], cr[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint32_t R = byte24(w, 3 * i), G = byte24(w, 3 * i + 1), B = byte24(w, 3 * i + 2);
-                v[r * 8 + i] = (float)((int)csc_y(R, G, B, im.ydown) - 128);
-                cb[i] = csc_cb(R, G, B);
-                cr[i] = csc_cr(R, G, B);
-            }
-            if (!CDS) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if ((i & 3) == 0) cq[0][r][i >> 2] = cq[1][r][i >> 2] = 0;
-                    cq[0][r][i >> 2] = pack_s8(cq[0][r][i >> 2], (int)cb[i] - 128, i & 3);
-                    cq[1][r][i >> 2] = pack_s8(cq[1][r][i >> 2], (int)cr[i] - 128, i & 3);
-                }
-            } else if ((r & 1) == 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    pcb[c] = cb[2 * c] + cb[2 * c + 1];
-                    pcr[c] = cr[2 * c] + cr[2 * c + 1];
-                }
-            } else {
-                uint32_t qb[2] = {0, 0}, qr[2] = {0, 0};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    int mb = (int)((pcb[c] + cb[2 * c] + cb[2 * c + 1]) >> 2) - 128;
-                    int mr = (int)((pcr[c] + cr[2 * c] + cr[2 * c + 1]) >> 2) - 128;
-                    qb[c >> 1] = pack_s8(pack_s8(qb[c >> 1], mb, (2 * c) & 3), mb, (2 * c + 1) & 3);
-                    qr[c >> 1] = pack_s8(pack_s8(qr[c >> 1], mr, (2 * c) & 3), mr, (2 * c + 1) & 3);
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    cq[0][r - 1][k] = cq[0][r][k] = qb[k];
-                    cq[1][r - 1][k] = cq[1][r][k] = qr[k];
-                }
-            }
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            uint32_t qb[2] = {0, 0}, qr[2] = {0, 0};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint32_t Y, Cb, Cr;
-                ycc_at<CDS>(im, px + i, py + r, Y, Cb, Cr);
-                v[r * 8 + i] = (float)((int)Y - 128);
-                qb[i >> 2] = pack_s8(qb[i >> 2], (int)Cb - 128, i & 3);
-                qr[i >> 2] = pack_s8(qr[i >> 2], (int)Cr - 128, i & 3);
-            }
-            cq[0][r][0] = qb[0];
-            cq[0][r][1] = qb[1];
-            cq[1][r][0] = qr[0];
-            cq[1][r][1] = qr[1];
-        }
-    }
+__device__ __forceinline__ uint32_t pack_s8(uint32_t acc, int val, int pos) {
+    return acc | (((uint32_t)val & 0xFFu) << (8 * pos));
 }
+__device__ __forceinline__ float unpack_s8(uint32_t w, int pos) { return (float)(int)(int8_t)(w >> (8 * pos)); }
 
 template <int ALIGN, bool CDS>
-__device__ __forceinline__ void unit_444(const TransformArgs& a, const Image& im, size_t mcu_g0, int mcu_x0, int my,
-                                         uint4* st, int lane) {
-    const int mcus_valid = min(32, a.g.mcux - mcu_x0);
+__device__ __forceinline__ void unit_444(const TransformArgs& a, const Image& im, size_t mcu_g0, int mcu_x0,
+                                         int mcus_valid, int my, uint4* st, int lane) {
     const bool valid = lane < mcus_valid;
-    const int px = (mcu_x0 + lane) * 8, py = my * 8;
-    const bool interior = px + 8 <= a.g.W && py + 8 <= a.g.H;
     const uint32_t gb0 = (uint32_t)(mcu_g0 + lane) * 3u;
     uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
     float v[64];
     uint32_t cq[2][8][2];
     if (valid) {
-        load_mcu_444<ALIGN, CDS>(im, px, py, interior, v, cq);
+        const uint8_t* col0 = im.base + (size_t)((mcu_x0 + lane) * 8) * 3;
+        uint32_t pb[4], pr[4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            uint32_t w[6];
+            load24<ALIGN>(col0 + (size_t)mirror(my * 8 + r, im.H) * im.pitch, w);  // mirrored below the image
+            Row8 o;
+            csc_row8(w, im.ydown, o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[r * 8 + i] = (float)o.y[i];
+            if (!CDS) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    uint32_t qb = 0, qr = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        qb = pack_s8(qb, (int)(o.cb[4 * k + i] >> 24) - 128, i);
+                        qr = pack_s8(qr, (int)(o.cr[4 * k + i] >> 24) - 128, i);
+                    }
+                    cq[0][r][k] = qb;
+                    cq[1][r][k] = qr;
+                }
+            } else {
+                uint32_t sb[4], sr[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    sb[c] = (o.cb[2 * c] >> 24) + (o.cb[2 * c + 1] >> 24);
+                    sr[c] = (o.cr[2 * c] >> 24) + (o.cr[2 * c + 1] >> 24);
+                }
+                if (r & 1) {  // the truncated 2x2 mean is written back to all four pixels (utils.cpp:130-138)
+                    uint32_t qb[2] = {0, 0}, qr[2] = {0, 0};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        int mb = (int)((pb[c] + sb[c]) >> 2) - 128, mr = (int)((pr[c] + sr[c]) >> 2) - 128;
+                        qb[c >> 1] = pack_s8(pack_s8(qb[c >> 1], mb, (2 * c) & 3), mb, (2 * c + 1) & 3);
+                        qr[c >> 1] = pack_s8(pack_s8(qr[c >> 1], mr, (2 * c) & 3), mr, (2 * c + 1) & 3);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        cq[0][r - 1][k] = cq[0][r][k] = qb[k];
+                        cq[1][r - 1][k] = cq[1][r][k] = qr[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        pb[c] = sb[c];
+                        pr[c] = sr[c];
+                    }
+                }
+            }
+        }
         fdct2d(v);
         uint32_t tl = 0, th = 0;
         quant_stage<0>(v, a, st, lane, tl, th);
-        if (tl | th) append_ties(a, gb0, tl, th);
+        if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0, tl, th);
     }
     __syncwarp();
     copy_out<3>(st, coef4, mcu_g0, mcus_valid, 0, lane);
     __syncwarp();
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         if (valid) {
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[r * 8 + i] = unpack_s8(cq[c][r][i >> 2], i & 3);
+                for (int i = 0; i < 8; ++i) v[r * 8 + i] = unpack_s8(c ? cq[1][r][i >> 2] : cq[0][r][i >> 2], i & 3);
             fdct2d(v);
             uint32_t tl = 0, th = 0;
             quant_stage<1>(v, a, st, lane, tl, th);
-            if (tl | th) append_ties(a, gb0 + 1 + c, tl, th);
+            if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 1 + c, tl, th);
         }
         __syncwarp();
         copy_out<3>(st, coef4, mcu_g0, mcus_valid, 1 + c, lane);
@@ -320,40 +334,129 @@ __device__ __forceinline__ void unit_444(const TransformArgs& a, const Image& im
 
 template <int SUB, int ALIGN>
 __global__ void __launch_bounds__(128, 4) k_transform(const __grid_constant__ TransformArgs a) {
-    __shared__ uint4 stage[4][256];
+    // dynamic shared memory: 4 staging tiles of 4 KB, then (4:2:0 only) 4 chroma parking areas
+    extern __shared__ uint4 smem[];
+    float* chroma = reinterpret_cast<float*>(smem + 4 * 256);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4* st = stage[warp];
-    const uint32_t units_per_frame = (uint32_t)a.units_per_row * (uint32_t)a.g.mcuy;
+    uint4* st = smem + warp * 256;
+    const uint32_t units_per_frame = (uint32_t)a.units_per_row * (uint32_t)a.fast_mcuy;
     const int mcus_per_unit = SUB == JB_SUB_420 ? 16 : 32;
     for (uint32_t unit = blockIdx.x * 4 + warp; unit < a.total_units; unit += gridDim.x * 4) {
         uint32_t f = unit / units_per_frame, rem = unit - f * units_per_frame;
         int my = (int)(rem / (uint32_t)a.units_per_row), ux = (int)(rem - (uint32_t)my * (uint32_t)a.units_per_row);
         Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
         int mcu_x0 = ux * mcus_per_unit;
+        int mcus_valid = min(mcus_per_unit, a.fast_mcux - mcu_x0);
         size_t mcu_g0 = (size_t)f * (size_t)a.g.n_mcu + (size_t)my * (size_t)a.g.mcux + (size_t)mcu_x0;
         if (SUB == JB_SUB_420)
-            unit_420<ALIGN>(a, im, mcu_g0, mcu_x0, my, st, lane);
+            unit_420<ALIGN>(a, im, mcu_g0, mcu_x0, mcus_valid, my, st, chroma + warp * CH_WARP_WORDS, lane);
         else
-            unit_444<ALIGN, SUB == JB_SUB_REPL420>(a, im, mcu_g0, mcu_x0, my, st, lane);
+            unit_444<ALIGN, SUB == JB_SUB_REPL420>(a, im, mcu_g0, mcu_x0, mcus_valid, my, st, lane);
     }
+}
+
+// ---------------------------------------------------------------- edge MCUs --
+// One thread per block of an MCU that reaches into the mirror padding.  Samples
+// come from ycc_at (the reference's CSC -> CDS -> pad order at any coordinate);
+// the DCT / quantisation arithmetic is the same binary32 code as the hot kernel.
+__global__ void __launch_bounds__(64) k_transform_edge(const __grid_constant__ TransformArgs a) {
+    const int bpm = a.g.bpm;
+    const uint32_t col_mcus = a.fast_mcux < a.g.mcux ? (uint32_t)a.g.mcuy : 0u;   // the last MCU column
+    const uint32_t row_mcus = a.fast_mcuy < a.g.mcuy ? (uint32_t)a.fast_mcux : 0u; // the last MCU row (minus the corner)
+    const uint32_t per_frame = (col_mcus + row_mcus) * (uint32_t)bpm;
+    const uint32_t total = per_frame * (uint32_t)a.n_frames;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        uint32_t f = t / per_frame, r = t - f * per_frame;
+        uint32_t e = r / (uint32_t)bpm, blk = r - e * (uint32_t)bpm;
+        int mx, my;
+        if (e < col_mcus) {
+            mx = a.g.mcux - 1;
+            my = (int)e;
+        } else {
+            mx = (int)(e - col_mcus);
+            my = a.g.mcuy - 1;
+        }
+        int comp, x0, y0, step;
+        if (a.g.sub == JB_SUB_420) {
+            comp = blk < 4 ? 0 : (int)blk - 3;
+            x0 = mx * 16 + (blk < 4 ? (int)(blk & 1) * 8 : 0);
+            y0 = my * 16 + (blk < 4 ? (int)(blk >> 1) * 8 : 0);
+            step = blk < 4 ? 1 : 2;  // chroma sample (i,j) = replicated plane at (2i,2j)
+        } else {
+            comp = (int)blk;
+            x0 = mx * 8;
+            y0 = my * 8;
+            step = 1;
+        }
+        Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
+        float v[64];
+        for (int y = 0; y < 8; ++y)
+            for (int x = 0; x < 8; ++x) {
+                uint32_t Y, Cb, Cr;
+                if (a.g.sub == JB_SUB_444)
+                    ycc_at<false>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
+                else
+                    ycc_at<true>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
+                v[y * 8 + x] = (float)((int)(comp == 0 ? Y : comp == 1 ? Cb : Cr) - 128);
+            }
+        for (int i = 0; i < 8; ++i)
+            fdct8(v[i * 8], v[i * 8 + 1], v[i * 8 + 2], v[i * 8 + 3], v[i * 8 + 4], v[i * 8 + 5], v[i * 8 + 6], v[i * 8 + 7]);
+        for (int i = 0; i < 8; ++i)
+            fdct8(v[i], v[8 + i], v[16 + i], v[24 + i], v[32 + i], v[40 + i], v[48 + i], v[56 + i]);
+        const int tab = comp ? 1 : 0;
+        uint32_t gblock = (uint32_t)(((size_t)f * a.g.n_mcu + (size_t)my * a.g.mcux + mx) * bpm + blk);
+        int16_t* out = a.coef + (size_t)gblock * 64;
+        for (int k = 0; k < 64; ++k) {
+            int n = c_zz[k];
+            bool tie = false;
+            uint32_t bits;
+            if (k == 0 && a.qc.dc_exact)
+                bits = tab ? quantize_dc<1>(v[0], a) : quantize_dc<0>(v[0], a);
+            else
+                bits = quantize_bits(v[n], a.qc.mul[tab][n], a.qc.band[tab][n], tie);
+            out[k] = (int16_t)(bits & 0xFFFFu);
+            if (tie) {
+                uint32_t idx = atomicAdd(a.tie_count, 1u);
+                if (idx < a.tie_cap) a.tie_list[idx] = gblock * 64u + (uint32_t)k;
+            }
+        }
+    }
+}
+
+template <int SUB, int ALIGN>
+static void launch_one(const TransformArgs& a, int grid, cudaStream_t s) {
+    const int smem = 4 * 256 * 16 + (SUB == JB_SUB_420 ? 4 * CH_WARP_WORDS * 4 : 0);
+    // > 48 KB of dynamic shared memory needs the opt-in (per device, so set it on every launch: ~1 us)
+    cudaFuncSetAttribute(k_transform<SUB, ALIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_transform<SUB, ALIGN><<<grid, 128, smem, s>>>(a);
 }
 
 template <int SUB>
 static void launch_sub(const TransformArgs& a, int align, int grid, cudaStream_t s) {
     if (align == 8)
-        k_transform<SUB, 8><<<grid, 128, 0, s>>>(a);
+        launch_one<SUB, 8>(a, grid, s);
     else if (align == 4)
-        k_transform<SUB, 4><<<grid, 128, 0, s>>>(a);
+        launch_one<SUB, 4>(a, grid, s);
     else
-        k_transform<SUB, 1><<<grid, 128, 0, s>>>(a);
+        launch_one<SUB, 1>(a, grid, s);
+}
+
+// MCUs the hot kernel can take: all whose 8/16-pixel columns lie inside the image, and rows
+// below the image only when row mirroring reproduces the reference (no chroma cells, or an
+// even height so that a mirrored row pair is again a complete 2x2 cell pair).
+static void plan_fast(TransformArgs& a) {
+    const int mcus_per_unit = a.g.sub == JB_SUB_420 ? 16 : 32;
+    const bool rows_ok = a.g.sub == JB_SUB_444 || (a.g.H % 2 == 0);
+    a.fast_mcux = a.g.W % a.g.mcu_px ? a.g.mcux - 1 : a.g.mcux;
+    a.fast_mcuy = (a.g.H % a.g.mcu_px) && !rows_ok ? a.g.mcuy - 1 : a.g.mcuy;
+    a.units_per_row = (a.fast_mcux + mcus_per_unit - 1) / mcus_per_unit;
+    a.total_units = (uint32_t)a.units_per_row * (uint32_t)a.fast_mcuy * (uint32_t)a.n_frames;
 }
 
 int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     TransformArgs a = a_in;
-    const int mcus_per_unit = a.g.sub == JB_SUB_420 ? 16 : 32;
-    a.units_per_row = (a.g.mcux + mcus_per_unit - 1) / mcus_per_unit;
-    a.total_units = (uint32_t)a.units_per_row * (uint32_t)a.g.mcuy * (uint32_t)a.n_frames;
-    if (a.total_units == 0) return 0;
+    plan_fast(a);
+    if (!a.total_units) return 0;
     uintptr_t bits = (uintptr_t)a.rgb | (uintptr_t)a.pitch | (uintptr_t)a.frame_stride;
     int align = (bits & 7) == 0 ? 8 : (bits & 3) == 0 ? 4 : 1;
     int sms = 148;
@@ -369,14 +472,28 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     return 1;
 }
 
+int launch_transform_edge(const TransformArgs& a_in, cudaStream_t s) {
+    TransformArgs a = a_in;
+    plan_fast(a);
+    size_t edge = ((a.fast_mcux < a.g.mcux ? (size_t)a.g.mcuy : 0) + (a.fast_mcuy < a.g.mcuy ? (size_t)a.fast_mcux : 0)) *
+                  (size_t)a.g.bpm * (size_t)a.n_frames;
+    if (!edge) return 0;
+    size_t g = (edge + 63) / 64;
+    k_transform_edge<<<(int)(g > 148 * 32 ? 148 * 32 : g), 64, 0, s>>>(a);
+    return 1;
+}
+
 // ---------------------------------------------------------------- fix-up ----
-// One thread per listed coefficient: the reference's formula in the reference's
-// operation order (utils.cpp:314-347 with the block read from a copy, then
-// utils.cpp:454-467), in binary64 with unfused multiplies and adds.
-__global__ void k_fixup(const __grid_constant__ FixupArgs a) {
+// One warp per listed coefficient: the 64 samples are produced by the lanes in
+// parallel (two each); lane 0 then adds the 64 terms in the reference's order
+// (utils.cpp:314-347 with the block read from a copy, then utils.cpp:454-467),
+// in binary64 with unfused multiplies and adds.
+__global__ void __launch_bounds__(128) k_fixup(const __grid_constant__ FixupArgs a) {
     uint32_t n = *a.tie_count;
     if (n > a.tie_cap) n = a.tie_cap;
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
         uint32_t entry = a.tie_list[e];
         uint32_t gblock = entry >> 6, k = entry & 63;
         uint32_t bpf = (uint32_t)a.g.n_mcu * (uint32_t)a.g.bpm;
@@ -385,17 +502,10 @@ __global__ void k_fixup(const __grid_constant__ FixupArgs a) {
         int my = (int)(mcu / (uint32_t)a.g.mcux), mx = (int)(mcu - (uint32_t)my * (uint32_t)a.g.mcux);
         int comp, x0, y0, step;
         if (a.g.sub == JB_SUB_420) {
-            if (blk < 4) {
-                comp = 0;
-                x0 = mx * 16 + (int)(blk & 1) * 8;
-                y0 = my * 16 + (int)(blk >> 1) * 8;
-                step = 1;
-            } else {
-                comp = (int)blk - 3;
-                x0 = mx * 16;
-                y0 = my * 16;
-                step = 2;
-            }
+            comp = blk < 4 ? 0 : (int)blk - 3;
+            x0 = mx * 16 + (blk < 4 ? (int)(blk & 1) * 8 : 0);
+            y0 = my * 16 + (blk < 4 ? (int)(blk >> 1) * 8 : 0);
+            step = blk < 4 ? 1 : 2;
         } else {
             comp = (int)blk;
             x0 = mx * 8;
@@ -403,29 +513,36 @@ __global__ void k_fixup(const __grid_constant__ FixupArgs a) {
             step = 1;
         }
         Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
-        int nat = c_zz[k], v = nat >> 3, u = nat & 7;
-        double sum = 0.0;
-        for (int y = 0; y < 8; ++y)
-            for (int x = 0; x < 8; ++x) {
-                uint32_t Y, Cb, Cr;
-                if (a.g.sub == JB_SUB_444)
-                    ycc_at<false>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
-                else
-                    ycc_at<true>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
-                double smp = (double)(comp == 0 ? Y : comp == 1 ? Cb : Cr);  // utils.cpp:236
-                smp = __dsub_rn(smp, 128.0);                                   // utils.cpp:190
-                double t = __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), a.costab[v * 8 + y]);
-                sum = __dadd_rn(sum, t);                                       // utils.cpp:330
-            }
-        sum = __dmul_rn(sum, a.scale[u * 8 + v]);                              // utils.cpp:336
-        double q = (double)a.qt.q[comp ? 1 : 0][nat];
-        double r = round(__ddiv_rn(sum, q));                                   // utils.cpp:460
-        a.coef[(size_t)gblock * 64 + k] = (int16_t)(int)r;                     // utils.cpp:490
+        const int nat = c_zz[k], v = nat >> 3, u = nat & 7;
+        double term[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            int i = lane + 32 * j, x = i & 7, y = i >> 3;
+            uint32_t Y, Cb, Cr;
+            if (a.g.sub == JB_SUB_444)
+                ycc_at<false>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
+            else
+                ycc_at<true>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
+            double smp = (double)(comp == 0 ? Y : comp == 1 ? Cb : Cr);                          // utils.cpp:236
+            smp = __dsub_rn(smp, 128.0);                                                          // utils.cpp:190
+            term[j] = __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), a.costab[v * 8 + y]);        // utils.cpp:330
+        }
+        double sum = 0.0;  // y outer, x inner = index order 0..63
+        for (int i = 0; i < 64; ++i) {
+            double t = __shfl_sync(0xffffffffu, i < 32 ? term[0] : term[1], i & 31);
+            sum = __dadd_rn(sum, t);
+        }
+        if (lane == 0) {
+            sum = __dmul_rn(sum, a.scale[u * 8 + v]);                                             // utils.cpp:336
+            double q = (double)a.qt.q[comp ? 1 : 0][nat];
+            double r = round(__ddiv_rn(sum, q));                                                  // utils.cpp:460
+            a.coef[(size_t)gblock * 64 + k] = (int16_t)(int)r;                                    // utils.cpp:490
+        }
     }
 }
 
 int launch_fixup(const FixupArgs& a, cudaStream_t s) {
-    k_fixup<<<296, 128, 0, s>>>(a);
+    k_fixup<<<148 * 8, 128, 0, s>>>(a);
     return 1;
 }
 
