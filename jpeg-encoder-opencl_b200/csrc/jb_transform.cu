@@ -160,8 +160,11 @@ constexpr int CH_MCU_STRIDE = 136, CH_BLK_STRIDE = 68, CH_WARP_WORDS = 16 * CH_M
 template <int ALIGN>
 __device__ __forceinline__ void unit_420(const TransformArgs& a, const Image& im, size_t mcu_g0, int mcu_x0,
                                          int mcus_valid, int my, uint4* st, float* ch, int lane) {
-    const int m = lane >> 1, half = lane & 1;
-    const bool valid = m < mcus_valid;
+    const int half = lane & 1;
+    const bool valid = (lane >> 1) < mcus_valid;
+    // lanes without an MCU of their own redo the last valid one (no stores): the code stays
+    // convergent, which lets the CTA-wide barriers sit anywhere
+    const int m = valid ? lane >> 1 : max(mcus_valid - 1, 0);
     const uint32_t gb0 = (uint32_t)(mcu_g0 + m) * 6u;
     uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
     float v[64];
@@ -169,7 +172,8 @@ __device__ __forceinline__ void unit_420(const TransformArgs& a, const Image& im
 
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
-        if (valid) {
+        __syncthreads();  // keep the CTA's warps in step (instruction cache), see TW
+        {
             // rows below an (even) image height are mirrored (utils.cpp:223-232); with H even the mirrored
             // row pair is again a complete 2x2-cell pair, so the chroma means are the reference's
             uint32_t w[8][6];
@@ -213,13 +217,14 @@ __device__ __forceinline__ void unit_420(const TransformArgs& a, const Image& im
             fdct2d(v);
             uint32_t tl = 0, th = 0;
             quant_stage<0>(v, a, st, lane, tl, th);
-            if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 2 * h + half, tl, th);
+            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 2 * h + half, tl, th);
         }
         __syncwarp();
         copy_out<6>(st, coef4, mcu_g0, mcus_valid, 2 * h, lane);
         __syncwarp();
     }
-    if (valid) {
+    __syncthreads();
+    {
         const float* src = ch + m * CH_MCU_STRIDE + half * CH_BLK_STRIDE;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -232,7 +237,7 @@ __device__ __forceinline__ void unit_420(const TransformArgs& a, const Image& im
         fdct2d(v);
         uint32_t tl = 0, th = 0;
         quant_stage<1>(v, a, st, lane, tl, th);
-        if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 4 + half, tl, th);
+        if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 4 + half, tl, th);
     }
     __syncwarp();
     copy_out<6>(st, coef4, mcu_g0, mcus_valid, 4, lane);
@@ -250,12 +255,13 @@ template <int ALIGN, bool CDS>
 __device__ __forceinline__ void unit_444(const TransformArgs& a, const Image& im, size_t mcu_g0, int mcu_x0,
                                          int mcus_valid, int my, uint4* st, int lane) {
     const bool valid = lane < mcus_valid;
-    const uint32_t gb0 = (uint32_t)(mcu_g0 + lane) * 3u;
+    const int ml = valid ? lane : max(mcus_valid - 1, 0);  // convergent code: see unit_420
+    const uint32_t gb0 = (uint32_t)(mcu_g0 + ml) * 3u;
     uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
     float v[64];
     uint32_t cq[2][8][2];
-    if (valid) {
-        const uint8_t* col0 = im.base + (size_t)((mcu_x0 + lane) * 8) * 3;
+    {
+        const uint8_t* col0 = im.base + (size_t)((mcu_x0 + ml) * 8) * 3;
         uint32_t pb[4], pr[4];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -309,14 +315,15 @@ __device__ __forceinline__ void unit_444(const TransformArgs& a, const Image& im
         fdct2d(v);
         uint32_t tl = 0, th = 0;
         quant_stage<0>(v, a, st, lane, tl, th);
-        if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0, tl, th);
+        if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0, tl, th);
     }
     __syncwarp();
     copy_out<3>(st, coef4, mcu_g0, mcus_valid, 0, lane);
     __syncwarp();
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-        if (valid) {
+        __syncthreads();
+        {
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -324,7 +331,7 @@ __device__ __forceinline__ void unit_444(const TransformArgs& a, const Image& im
             fdct2d(v);
             uint32_t tl = 0, th = 0;
             quant_stage<1>(v, a, st, lane, tl, th);
-            if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 1 + c, tl, th);
+            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 1 + c, tl, th);
         }
         __syncwarp();
         copy_out<3>(st, coef4, mcu_g0, mcus_valid, 1 + c, lane);
@@ -332,21 +339,28 @@ __device__ __forceinline__ void unit_444(const TransformArgs& a, const Image& im
     }
 }
 
+// TW warps per CTA.  One CTA of 16 warps per SM, with CTA-wide barriers at the stage boundaries,
+// keeps all resident warps within a short window of the (long, fully unrolled) instruction
+// stream, so that they share instruction-cache fetches instead of thrashing it.
+constexpr int TW = 16;
+
 template <int SUB, int ALIGN>
-__global__ void __launch_bounds__(128, 4) k_transform(const __grid_constant__ TransformArgs a) {
+__global__ void __launch_bounds__(TW * 32, 16 / TW) k_transform(const __grid_constant__ TransformArgs a) {
     // dynamic shared memory: 4 staging tiles of 4 KB, then (4:2:0 only) 4 chroma parking areas
     extern __shared__ uint4 smem[];
-    float* chroma = reinterpret_cast<float*>(smem + 4 * 256);
+    float* chroma = reinterpret_cast<float*>(smem + TW * 256);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* st = smem + warp * 256;
     const uint32_t units_per_frame = (uint32_t)a.units_per_row * (uint32_t)a.fast_mcuy;
     const int mcus_per_unit = SUB == JB_SUB_420 ? 16 : 32;
-    for (uint32_t unit = blockIdx.x * 4 + warp; unit < a.total_units; unit += gridDim.x * 4) {
+    for (uint32_t base = blockIdx.x * TW; base < a.total_units; base += gridDim.x * TW) {
+        const bool active = base + warp < a.total_units;  // uniform trip count: every warp reaches the barriers
+        const uint32_t unit = active ? base + warp : base;
         uint32_t f = unit / units_per_frame, rem = unit - f * units_per_frame;
         int my = (int)(rem / (uint32_t)a.units_per_row), ux = (int)(rem - (uint32_t)my * (uint32_t)a.units_per_row);
         Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
         int mcu_x0 = ux * mcus_per_unit;
-        int mcus_valid = min(mcus_per_unit, a.fast_mcux - mcu_x0);
+        int mcus_valid = active ? min(mcus_per_unit, a.fast_mcux - mcu_x0) : 0;
         size_t mcu_g0 = (size_t)f * (size_t)a.g.n_mcu + (size_t)my * (size_t)a.g.mcux + (size_t)mcu_x0;
         if (SUB == JB_SUB_420)
             unit_420<ALIGN>(a, im, mcu_g0, mcu_x0, mcus_valid, my, st, chroma + warp * CH_WARP_WORDS, lane);
@@ -425,10 +439,10 @@ __global__ void __launch_bounds__(64) k_transform_edge(const __grid_constant__ T
 
 template <int SUB, int ALIGN>
 static void launch_one(const TransformArgs& a, int grid, cudaStream_t s) {
-    const int smem = 4 * 256 * 16 + (SUB == JB_SUB_420 ? 4 * CH_WARP_WORDS * 4 : 0);
+    const int smem = TW * 256 * 16 + (SUB == JB_SUB_420 ? TW * CH_WARP_WORDS * 4 : 0);
     // > 48 KB of dynamic shared memory needs the opt-in (per device, so set it on every launch: ~1 us)
     cudaFuncSetAttribute(k_transform<SUB, ALIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    k_transform<SUB, ALIGN><<<grid, 128, smem, s>>>(a);
+    k_transform<SUB, ALIGN><<<grid, TW * 32, smem, s>>>(a);
 }
 
 template <int SUB>
@@ -461,8 +475,8 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     int align = (bits & 7) == 0 ? 8 : (bits & 3) == 0 ? 4 : 1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    int need = (int)((a.total_units + 3) / 4);
-    int grid = need < sms * 16 ? need : sms * 16;
+    int need = (int)((a.total_units + TW - 1) / TW);
+    int grid = need < sms * (16 / TW) ? need : sms * (16 / TW);
     if (a.g.sub == JB_SUB_420)
         launch_sub<JB_SUB_420>(a, align, grid, s);
     else if (a.g.sub == JB_SUB_REPL420)
