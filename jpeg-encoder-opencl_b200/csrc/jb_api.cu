@@ -141,6 +141,8 @@ size_t plan_bytes(const Plan& p) {
     add(p.n_blocks * 64 * 4);              // tie list: every coefficient may be flagged (never overflows)
     add(64);                               // scalars
     add((p.n_tiles * 256 + 1) * 4);        // blk_prefix
+    add(p.n_tiles * 256 * 4);              // blk_len
+    add(p.n_tiles * 256 * 16);             // slots
     add(p.n_tiles * 4);
     add((p.n_tiles + 1) * 8);
     add(p.n_int_total * 4);
@@ -170,6 +172,8 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.tie_cap = (uint32_t)(p.n_blocks * 64);
     s.d_scalars = carve<uint32_t>(a, 16);
     s.w.blk_prefix = carve<uint32_t>(a, p.n_tiles * 256 + 1);
+    s.w.blk_len = carve<uint32_t>(a, p.n_tiles * 256);
+    s.w.slots = carve<uint4>(a, p.n_tiles * 256);
     s.w.tile_bits = carve<uint32_t>(a, p.n_tiles);
     s.w.tile_base = carve<uint64_t>(a, p.n_tiles + 1);
     s.w.int_slot = carve<uint32_t>(a, p.n_int_total);
@@ -384,30 +388,6 @@ int status_to_rc(jb_ctx* ctx, const uint64_t* st, uint64_t tie_count, uint32_t t
     return JB_OK;
 }
 
-void fill_tables(jb_ctx* ctx, std::vector<uint32_t>& ydown, double* costab, double* scale) {
-    (void)ctx;
-    // Y tie table: bit (r<<8|g) set when the reference's binary64 expression
-    // (utils.cpp:107) lands below the exact integer value 0.299r+0.587g+0.114b.
-    ydown.assign(2048, 0);
-    for (uint32_t r = 0; r < 256; ++r)
-        for (uint32_t g = 0; g < 256; ++g)
-            for (uint32_t b = 0; b < 256; ++b) {
-                uint32_t s = 299 * r + 587 * g + 114 * b;
-                if (s % 1000) continue;
-                volatile double y = 0.299 * r + 0.587 * g + 0.114 * b;
-                if ((uint32_t)(uint8_t)y != s / 1000) ydown[(r << 8 | g) >> 5] |= 1u << ((r << 8 | g) & 31);
-            }
-    // utils.cpp:330-332 and 336: same expressions, same libm
-    for (size_t u = 0; u < 8; ++u)
-        for (size_t x = 0; x < 8; ++x) costab[u * 8 + x] = cos((2 * x + 1) * u * M_PI / 16.0);
-    for (size_t u = 0; u < 8; ++u)
-        for (size_t v = 0; v < 8; ++v) {
-            double alphaU = (u == 0) ? 1.0 / sqrt(2) : 1.0;
-            double alphaV = (v == 0) ? 1.0 / sqrt(2) : 1.0;
-            scale[u * 8 + v] = (alphaU * alphaV / 4.0);
-        }
-}
-
 int scratch(jb_ctx* ctx, size_t bytes) { return arena_reserve(ctx, ctx->scratch, bytes + 4096); }
 
 }  // namespace
@@ -438,9 +418,10 @@ int jb_create(int device, jb_ctx** out) {
             return JB_E_CUDA;
         }
     }
-    std::vector<uint32_t> ydown;
+    std::vector<uint32_t> ydown(2048);
     double costab[64], scale[64];
-    fill_tables(ctx, ydown, costab, scale);
+    build_ydown(ydown.data());
+    build_dct_tables(costab, scale);
     HuffDev hd[2];
     build_huff(false, &hd[0]);
     build_huff(true, &hd[1]);
@@ -699,27 +680,6 @@ int jb_rle(jb_ctx* ctx, const int32_t* zz, size_t rows, uint32_t flags, int32_t*
 }
 
 // ================================================================= fused ====
-
-int jb_quality_tables(int quality, uint32_t ql[64], uint32_t qc[64]) {
-    // IJG scaling of the reference's q50 tables (utils.hpp:42-62 = T.81 K.1/K.2)
-    static const uint32_t l50[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
-                                     14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
-                                     18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
-                                     49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
-    static const uint32_t c50[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
-                                     24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
-                                     99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
-                                     99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
-    if (!ql || !qc) return JB_E_INVALID;
-    quality = quality < 1 ? 1 : quality > 100 ? 100 : quality;
-    int s = quality < 50 ? 5000 / quality : 200 - 2 * quality;
-    for (int i = 0; i < 64; ++i) {
-        long a = ((long)l50[i] * s + 50) / 100, b = ((long)c50[i] * s + 50) / 100;
-        ql[i] = (uint32_t)(a < 1 ? 1 : a > 255 ? 255 : a);
-        qc[i] = (uint32_t)(b < 1 ? 1 : b > 255 ? 255 : b);
-    }
-    return JB_OK;
-}
 
 size_t jb_num_mcus(size_t W, size_t H, int sub) { return (size_t)make_geometry(W, H, sub, 0).n_mcu; }
 int jb_blocks_per_mcu(int sub) { return sub == JB_SUB_420 ? 6 : 3; }

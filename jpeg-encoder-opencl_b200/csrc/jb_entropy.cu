@@ -2,14 +2,15 @@
 // coder, plus what the reference lacks for a real JPEG stream: byte packing,
 // 1-padding, 0xFF00 stuffing, RSTn/EOI markers.
 //
-//   k_len       one thread per 8x8 block: code length of the block (DC difference
-//               + run/size symbols); exclusive scan inside each 256-block tile
+//   k_encode    one thread per 8x8 block (tile of 256 blocks staged in shared memory): non-zero
+//               mask, sparse walk of the run/size symbols, first 128 code bits kept in a slot,
+//               code length; exclusive scan of the lengths inside each 256-block tile
 //   k_scan      exclusive scan of the tile totals (device-wide bit offsets)
 //   k_intervals bits / reserved bytes of every restart interval
 //   k_scan      byte offset of every interval in the unstuffed buffer
 //   k_zero      clear the used part of the unstuffed buffer
-//   k_pack      one thread per block: re-walk the block and OR its codes into the
-//               unstuffed buffer at its bit offset (+ 1-padding at interval end)
+//   k_pack      one thread per block: shift the slot to the block's bit offset and OR it into
+//               the unstuffed buffer (+ 1-padding at interval end; longer blocks are re-walked)
 //   k_ff_count  0xFF bytes per 16-byte chunk, scan inside 256-chunk tiles
 //   k_scan      device-wide 0xFF prefix
 //   k_int_out   output bytes of every interval (data + stuffing + marker + header)
@@ -25,11 +26,6 @@ namespace jb {
 constexpr int TILE = 256;
 
 // ------------------------------------------------------------ block walker --
-struct LenSink {
-    uint32_t bits;
-    __device__ __forceinline__ void put(uint32_t, int len) { bits += (uint32_t)len; }
-};
-
 struct BitSink {
     uint64_t acc;
     int n;
@@ -59,42 +55,10 @@ __device__ __forceinline__ void cat_bits(int v, int& cat, uint32_t& vb) {
     vb = (uint32_t)(v + (v >> 31)) & ((1u << cat) - 1u);
 }
 
-// One block as HuffmanEncoder codes it (utils.cpp:667-694); w = 64 int16 in zigzag order.
-template <class Sink>
-__device__ __forceinline__ void encode_block(const uint32_t (&w)[32], int dc_diff, const uint32_t* s_ac,
-                                             const uint32_t* s_dc, bool always_eob, Sink& s) {
-    int cat;
-    uint32_t vb;
-    cat_bits(dc_diff, cat, vb);
-    uint32_t e = s_dc[cat];
-    s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
-    int run = 0;
-#pragma unroll
-    for (int k = 1; k < 64; ++k) {
-        int v = (k & 1) ? ((int)w[k >> 1] >> 16) : (int)(short)(w[k >> 1] & 0xFFFFu);
-        if (v == 0) {
-            ++run;
-        } else {
-            while (run >= 16) {  // ZRL, utils.cpp:592-597
-                uint32_t z = s_ac[0xF0];
-                s.put(z >> 5, (int)(z & 31u));
-                run -= 16;
-            }
-            cat_bits(v, cat, vb);
-            e = s_ac[(run << 4) | cat];
-            s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
-            run = 0;
-        }
-    }
-    if (run > 0 || always_eob) {  // EOB, utils.cpp:607-608 (Q3 when always_eob)
-        e = s_ac[0];
-        s.put(e >> 5, (int)(e & 31u));
-    }
-}
-
 struct BlockInfo {
     int comp;          // 0 Y, 1 Cb, 2 Cr
-    int pred;          // DC predictor
+    uint32_t prev;     // block whose DC is the predictor (valid when has_prev)
+    bool has_prev;     // false at the start of a restart interval: predictor 0
     uint32_t interval; // global restart-interval index
     bool last_in_interval;
 };
@@ -109,36 +73,21 @@ __device__ __forceinline__ BlockInfo block_info(const EntropyArgs& a, uint32_t b
     bi.interval = f * (uint32_t)a.g.n_int + k;
     uint32_t mcu_end = min((k + 1) * ri, (uint32_t)a.g.n_mcu);
     bi.last_in_interval = (mcu == mcu_end - 1) && (j == bpm - 1);
-    uint32_t prev;
-    bool has_prev;
     if (bpm == 3) {
         bi.comp = (int)j;
-        has_prev = !first;
-        prev = b - 3;
+        bi.has_prev = !first;
+        bi.prev = b - 3;
     } else {
         bi.comp = j < 4 ? 0 : (int)j - 3;
         if (j >= 1 && j <= 3) {
-            has_prev = true;
-            prev = b - 1;
+            bi.has_prev = true;
+            bi.prev = b - 1;
         } else {
-            has_prev = !first;
-            prev = b - (j == 0 ? 3u : 6u);
+            bi.has_prev = !first;
+            bi.prev = b - (j == 0 ? 3u : 6u);
         }
     }
-    bi.pred = has_prev ? (int)a.coef[(size_t)prev * 64] : 0;  // utils.cpp:669-670
     return bi;
-}
-
-__device__ __forceinline__ void load_block(const EntropyArgs& a, uint32_t b, uint32_t (&w)[32]) {
-    const uint4* p = reinterpret_cast<const uint4*>(a.coef) + (size_t)b * 8;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        uint4 q = __ldg(p + i);
-        w[4 * i] = q.x;
-        w[4 * i + 1] = q.y;
-        w[4 * i + 2] = q.z;
-        w[4 * i + 3] = q.w;
-    }
 }
 
 __device__ __forceinline__ void load_tables(const EntropyArgs& a, uint32_t (&s_ac)[2][256], uint32_t (&s_dc)[2][16]) {
@@ -170,19 +119,123 @@ __device__ __forceinline__ uint32_t cta_scan_256(uint32_t x, uint32_t* s_warp, u
     return base + inc - x;
 }
 
-__global__ void __launch_bounds__(TILE) k_len(const __grid_constant__ EntropyArgs a) {
+// ---- sparse block walk ---------------------------------------------------------------
+// 2 bits per 32-bit word: which of its two int16 halves are non-zero
+__device__ __forceinline__ uint32_t nz2(uint32_t w) {
+    return ((w & 0xFFFFu) ? 1u : 0u) | ((w >> 16) ? 2u : 0u);
+}
+
+// Sink that keeps the first 128 bits of a block's code left-aligned in a 4-word slot (MSB
+// first) and counts all bits.  Blocks longer than 128 bits are re-walked by k_pack.
+struct SlotSink {
+    uint64_t acc;
+    int n;
+    uint32_t bits;
+    uint32_t* slot;  // 4 words (shared memory)
+    int wi;
+    __device__ __forceinline__ void init(uint32_t* s) {
+        slot = s;
+        acc = 0;
+        n = 0;
+        bits = 0;
+        wi = 0;
+        s[0] = s[1] = s[2] = s[3] = 0;
+    }
+    __device__ __forceinline__ void put(uint32_t code, int len) {
+        bits += (uint32_t)len;
+        acc = (acc << len) | code;
+        n += len;
+        if (n >= 32) {
+            n -= 32;
+            if (wi < 4) slot[wi] = (uint32_t)(acc >> n);
+            ++wi;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (n > 0 && wi < 4) slot[wi] = (uint32_t)(acc << (32 - n));
+    }
+};
+
+// The block as HuffmanEncoder codes it (utils.cpp:667-694), visiting only the non-zero AC
+// coefficients: mask bit k = coefficient k != 0, value(k) fetches coefficient k.
+template <class Sink, class Fetch>
+__device__ __forceinline__ void encode_sparse(uint64_t mask, Fetch value, int dc_diff, const uint32_t* s_ac,
+                                              const uint32_t* s_dc, bool always_eob, Sink& s) {
+    int cat;
+    uint32_t vb;
+    cat_bits(dc_diff, cat, vb);
+    uint32_t e = s_dc[cat];
+    s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
+    uint64_t m = mask & ~1ull;
+    int cur = 1;  // next AC position to account for
+    while (m) {
+        int pos = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        int run = pos - cur;
+        cur = pos + 1;
+        while (run >= 16) {  // ZRL, utils.cpp:592-597
+            uint32_t z = s_ac[0xF0];
+            s.put(z >> 5, (int)(z & 31u));
+            run -= 16;
+        }
+        cat_bits(value(pos), cat, vb);
+        e = s_ac[(run << 4) | cat];
+        s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
+    }
+    if (cur < 64 || always_eob) {  // EOB, utils.cpp:607-608 (Q3 when always_eob)
+        e = s_ac[0];
+        s.put(e >> 5, (int)(e & 31u));
+    }
+}
+
+// One thread per block.  The tile's coefficients (256 blocks, 32 KB) are staged in shared
+// memory with coalesced 128-bit loads (XOR swizzle: piece p of block t at t*8 + (p ^ (t&7))).
+// Each thread builds the non-zero mask of its block, walks the non-zero coefficients, keeps
+// the first 128 code bits in a slot and the total length; lengths are scanned per tile.
+__global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ EntropyArgs a) {
+    __shared__ uint4 s_coef[TILE * 8];
+    __shared__ __align__(16) uint32_t s_slot[TILE * 4];
     __shared__ uint32_t s_ac[2][256], s_dc[2][16], s_warp[8];
-    load_tables(a, s_ac, s_dc);
-    uint32_t b = blockIdx.x * TILE + threadIdx.x;
+    const uint32_t t = threadIdx.x, b0 = blockIdx.x * TILE, b = b0 + t;
+    const uint4* src = reinterpret_cast<const uint4*>(a.coef) + (size_t)b0 * 8;
+    const uint32_t n_here = min((uint32_t)TILE, a.n_blocks - b0) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t g = i * TILE + t, blk = g >> 3, pc = g & 7;
+        if (g < n_here) s_coef[blk * 8 + (pc ^ (blk & 7))] = __ldg(src + g);
+    }
+    load_tables(a, s_ac, s_dc);  // ends with __syncthreads()
     uint32_t bits = 0;
     if (b < a.n_blocks) {
-        uint32_t w[32];
-        load_block(a, b, w);
+        uint64_t mask = 0;
+        int dc = 0;
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {
+            uint4 q = s_coef[t * 8 + (pc ^ (t & 7))];
+            if (pc == 0) dc = (int)(short)(q.x & 0xFFFFu);
+            uint64_t m8 = nz2(q.x) | (nz2(q.y) << 2) | (nz2(q.z) << 4) | (nz2(q.w) << 6);
+            mask |= m8 << (8 * pc);
+        }
         BlockInfo bi = block_info(a, b);
-        int t = bi.comp ? 1 : 0;
-        LenSink s{0};
-        encode_block(w, (int)(short)(w[0] & 0xFFFFu) - bi.pred, s_ac[t], s_dc[t], a.always_eob != 0, s);
+        const int tab = bi.comp ? 1 : 0;
+        const short* mine = reinterpret_cast<const short*>(s_coef);
+        auto value = [&](int pos) { return (int)mine[(t * 8 + ((pos >> 3) ^ (t & 7))) * 8 + (pos & 7)]; };
+        int pred = 0;  // DC of the previous block of the component (utils.cpp:669-670)
+        if (bi.has_prev) {
+            if (bi.prev >= b0) {
+                uint32_t pt = bi.prev - b0;
+                pred = (int)mine[(pt * 8 + (pt & 7)) * 8];  // piece 0 of block pt sits at pt*8 + (0 ^ (pt&7))
+            } else {
+                pred = (int)a.coef[(size_t)bi.prev * 64];
+            }
+        }
+        SlotSink s;
+        s.init(s_slot + t * 4);
+        encode_sparse(mask, value, dc - pred, s_ac[tab], s_dc[tab], a.always_eob != 0, s);
+        s.finish();
         bits = s.bits;
+        a.w.blk_len[b] = bits;
+        a.w.slots[b] = *reinterpret_cast<const uint4*>(s_slot + t * 4);
     }
     uint32_t total;
     uint32_t ex = cta_scan_256(bits, s_warp, total);
@@ -271,27 +324,67 @@ __global__ void k_zero(const __grid_constant__ EntropyArgs a) {
         p[i] = make_uint4(0, 0, 0, 0);
 }
 
+// One thread per block: shift the pre-encoded slot to the block's bit offset and OR it into
+// the unstuffed buffer (big-endian words); 1-padding after the last block of an interval.
+// Blocks longer than a slot are left to k_pack_long.
 __global__ void __launch_bounds__(TILE) k_pack(const __grid_constant__ EntropyArgs a) {
-    __shared__ uint32_t s_ac[2][256], s_dc[2][16];
-    load_tables(a, s_ac, s_dc);
     if (a.w.int_ubase[a.n_int_total] > a.w.ubuf_cap) return;
     uint32_t b = blockIdx.x * TILE + threadIdx.x;
     if (b >= a.n_blocks) return;
-    uint32_t w[32];
-    load_block(a, b, w);
     BlockInfo bi = block_info(a, b);
     uint32_t s0, e0;
     interval_blocks(a, bi.interval, s0, e0);
-    uint64_t pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
-    int t = bi.comp ? 1 : 0;
-    BitSink s;
-    s.init(a.w.ubuf, pos);
-    encode_block(w, (int)(short)(w[0] & 0xFFFFu) - bi.pred, s_ac[t], s_dc[t], a.always_eob != 0, s);
-    if (bi.last_in_interval && !a.fr.raw_bits) {  // pad the interval to a byte boundary with 1s (T.81 F.1.2.3)
-        int pad = (int)((8 - (a.w.int_bits[bi.interval] & 7)) & 7);
-        if (pad) s.put((1u << pad) - 1u, pad);
+    const uint64_t pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
+    const uint32_t len = a.w.blk_len[b];
+    uint32_t* words = reinterpret_cast<uint32_t*>(a.w.ubuf);
+    if (len <= 128) {
+        const uint4 q = a.w.slots[b];
+        const uint32_t w[6] = {0u, q.x, q.y, q.z, q.w, 0u};
+        const uint32_t sh = (uint32_t)(pos & 31);
+        const uint64_t wi = pos >> 5;
+        const uint32_t nw = (sh + len + 31) >> 5;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            if ((uint32_t)j < nw) {
+                uint32_t o = __funnelshift_r(w[j + 1], w[j], sh);  // bits of (w[j]:w[j+1]) >> sh
+                if (o) atomicOr(words + wi + j, __byte_perm(o, 0, 0x0123));
+            }
+        }
     }
-    s.finish();
+    if (bi.last_in_interval && !a.fr.raw_bits) {  // pad the interval to a byte boundary with 1s (T.81 F.1.2.3)
+        uint32_t pad = (uint32_t)((8 - (a.w.int_bits[bi.interval] & 7)) & 7);
+        if (pad) {
+            uint64_t pp = pos + len;
+            uint32_t o = ((1u << pad) - 1u) << (32 - (uint32_t)(pp & 31) - pad);
+            atomicOr(words + (pp >> 5), __byte_perm(o, 0, 0x0123));
+        }
+    }
+}
+
+// Blocks whose code is longer than a slot (rare at usual qualities): re-walk the
+// coefficients and OR the codes straight into the unstuffed buffer.
+__global__ void __launch_bounds__(TILE) k_pack_long(const __grid_constant__ EntropyArgs a) {
+    __shared__ uint32_t s_ac[2][256], s_dc[2][16];
+    load_tables(a, s_ac, s_dc);
+    if (a.w.int_ubase[a.n_int_total] > a.w.ubuf_cap) return;
+    for (uint32_t b = blockIdx.x * TILE + threadIdx.x; b < a.n_blocks; b += gridDim.x * TILE) {
+        if (a.w.blk_len[b] <= 128) continue;
+        BlockInfo bi = block_info(a, b);
+        uint32_t s0, e0;
+        interval_blocks(a, bi.interval, s0, e0);
+        const uint64_t pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
+        const short* c = reinterpret_cast<const short*>(a.coef) + (size_t)b * 64;
+        uint64_t mask = 0;
+        for (int k = 0; k < 64; ++k)
+            if (c[k] != 0) mask |= 1ull << k;
+        auto value = [&](int p) { return (int)c[p]; };
+        const int pred = bi.has_prev ? (int)a.coef[(size_t)bi.prev * 64] : 0;
+        const int tab = bi.comp ? 1 : 0;
+        BitSink s;
+        s.init(a.w.ubuf, pos);
+        encode_sparse(mask, value, (int)c[0] - pred, s_ac[tab], s_dc[tab], a.always_eob != 0, s);
+        s.finish();
+    }
 }
 
 __device__ __forceinline__ uint32_t count_ff(uint4 q) {
@@ -443,13 +536,14 @@ int launch_entropy(const EntropyArgs& a, cudaStream_t s) {
     int launches = 0;
     uint32_t n_tiles = (a.n_blocks + TILE - 1) / TILE;
     uint32_t gi = (a.n_int_total + 255) / 256;
-    k_len<<<n_tiles, TILE, 0, s>>>(a);
+    k_encode<<<n_tiles, TILE, 0, s>>>(a);
     k_scan<<<1, 1024, 0, s>>>(a.w.tile_bits, a.w.tile_base, n_tiles, nullptr);
     k_intervals<<<gi, 256, 0, s>>>(a);
     k_scan<<<1, 1024, 0, s>>>(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr);
     k_zero<<<592, 256, 0, s>>>(a);
     k_pack<<<n_tiles, TILE, 0, s>>>(a);
-    launches += 6;
+    k_pack_long<<<1184, TILE, 0, s>>>(a);
+    launches += 7;
     if (a.fr.raw_bits) return launches;
     k_ff_count<<<1184, TILE, 0, s>>>(a);
     k_scan<<<1, 1024, 0, s>>>(a.w.ff_tile, a.w.ff_tile_base, 0, a.w.n_ff_tiles);

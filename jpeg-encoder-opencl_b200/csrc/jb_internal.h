@@ -99,6 +99,8 @@ struct Framing {
 // Device work arrays of the entropy coder (all sized by the context).
 struct EntropyWork {
     uint32_t* blk_prefix;   // [n_blocks] exclusive bit prefix inside its 256-block tile
+    uint32_t* blk_len;      // [n_blocks] code length of every block in bits
+    uint4* slots;           // [n_blocks] first 128 code bits of every block, left aligned, MSB first
     uint32_t* tile_bits;    // [n_tiles]
     uint64_t* tile_base;    // [n_tiles + 1] exclusive scan of tile_bits
     uint32_t* int_slot;     // [n_int_total] bytes reserved in the unstuffed buffer (multiple of 16)
@@ -162,6 +164,8 @@ int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStre
 void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out);
 void aan_error_bound(double err[64], double amax[64]);  // worst-case |binary32 - exact| per AAN output
 void build_huff(bool typo, HuffDev* out);
+void build_ydown(uint32_t ydown[2048]);
+void build_dct_tables(double costab[64], double scale[64]);
 size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* out);  // out >= 1024 bytes
 extern const uint8_t kZigzag[64];  // zigzag position -> natural index
 

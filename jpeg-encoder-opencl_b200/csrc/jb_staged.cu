@@ -162,7 +162,7 @@ __global__ void k_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef) {
     }
 }
 
-// Synthetic image of SURVEY.md section 8d (integer only; same as oracle/jpeg_oracle.c orc_synth_rgb)
+// Synthetic image of SURVEY.md section 8d (integer only, so that the CPU checker can regenerate it bit for bit)
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;

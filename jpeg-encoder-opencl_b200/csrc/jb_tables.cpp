@@ -185,6 +185,33 @@ void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst*
     out->dc_exact = ok ? 1u : 0u;
 }
 
+// Y tie table (jb_math.h): bit (r<<8|g) set when the reference's binary64 expression
+// (utils.cpp:107) lands below the exact integer value of 0.299r + 0.587g + 0.114b.
+void build_ydown(uint32_t ydown[2048]) {
+    memset(ydown, 0, 2048 * sizeof(uint32_t));
+    for (uint32_t r = 0; r < 256; ++r)
+        for (uint32_t g = 0; g < 256; ++g)
+            for (uint32_t b = 0; b < 256; ++b) {
+                uint32_t s = 299 * r + 587 * g + 114 * b;
+                if (s % 1000) continue;
+                volatile double y = 0.299 * r + 0.587 * g + 0.114 * b;
+                if ((uint32_t)(uint8_t)y != s / 1000) ydown[(r << 8 | g) >> 5] |= 1u << ((r << 8 | g) & 31);
+            }
+}
+
+// The cosine and scale factors of the binary64 replay, formed exactly as the reference forms
+// them (utils.cpp:330-332 and 317-318, 336) with the same libm.
+void build_dct_tables(double costab[64], double scale[64]) {
+    for (size_t u = 0; u < 8; ++u)
+        for (size_t x = 0; x < 8; ++x) costab[u * 8 + x] = cos((2 * x + 1) * u * M_PI / 16.0);
+    for (size_t u = 0; u < 8; ++u)
+        for (size_t v = 0; v < 8; ++v) {
+            double alphaU = (u == 0) ? 1.0 / sqrt(2) : 1.0;
+            double alphaV = (v == 0) ? 1.0 / sqrt(2) : 1.0;
+            scale[u * 8 + v] = (alphaU * alphaV / 4.0);
+        }
+}
+
 static void put16(uint8_t* p, unsigned v) {
     p[0] = (uint8_t)(v >> 8);
     p[1] = (uint8_t)v;
@@ -226,3 +253,25 @@ size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* h) {
 }
 
 }  // namespace jb
+
+// ---- host-only entry points of the C ABI (no device needed) ---------------------------
+extern "C" int jb_quality_tables(int quality, uint32_t ql[64], uint32_t qc[64]) {
+    // IJG scaling of the reference's q50 tables (utils.hpp:42-62 = T.81 K.1/K.2)
+    static const uint32_t l50[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                                     14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                                     18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                                     49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+    static const uint32_t c50[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                     24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                                     99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                     99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+    if (!ql || !qc) return JB_E_INVALID;
+    quality = quality < 1 ? 1 : quality > 100 ? 100 : quality;
+    int s = quality < 50 ? 5000 / quality : 200 - 2 * quality;
+    for (int i = 0; i < 64; ++i) {
+        long a = ((long)l50[i] * s + 50) / 100, b = ((long)c50[i] * s + 50) / 100;
+        ql[i] = (uint32_t)(a < 1 ? 1 : a > 255 ? 255 : a);
+        qc[i] = (uint32_t)(b < 1 ? 1 : b > 255 ? 255 : b);
+    }
+    return JB_OK;
+}

@@ -45,8 +45,10 @@ def main():
     g["huffman_tables"] = tabs
     import ctypes as C
     buf = C.create_string_buffer(64)
-    g["value_kat"] = {str(v): [R.ref_getValueCategory(v), buf.raw[: R.ref_valueToBitString(v, buf)].decode()]
-                      for v in list(range(-40, 41)) + [-2047, -1024, -1023, -512, -255, 255, 511, 1023, 1024, 2047]}
+    g["value_kat"] = {}
+    for v in list(range(-40, 41)) + [-2047, -1024, -1023, -512, -255, 255, 511, 1023, 1024, 2047]:
+        n = R.ref_valueToBitString(v, buf)  # fill the buffer first, then read it
+        g["value_kat"][str(v)] = [R.ref_getValueCategory(v), buf.raw[:n].decode()]
     # CSC over the whole colour cube, r major / b minor, through the reference's performCSC
     h = hashlib.sha256()
     ydown = 0

@@ -1,0 +1,141 @@
+// TEST-ONLY host harness (compiled by tests/test_math_host.py with g++, no GPU needed).
+// jb_math.h and jb_tables.cpp are written so that the host evaluates bit-for-bit the
+// arithmetic the kernels evaluate; this program checks that arithmetic against the
+// reference's formulas (restated here in binary64, utils.cpp:100-109, 314-347, 454-467):
+//   1. colour conversion over all 2^24 colours (fixed point + tie table == binary64 + truncation)
+//   2. the analytic error bound of the binary32 AAN transform against measured errors
+//   3. the block pipeline (DCT -> quantise with near-tie flags): every coefficient the fast
+//      path does NOT flag equals the binary64 result; flagged ones are the only candidates
+//   4. the integer DC rule for every quantiser value
+// It prints one JSON object.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "jb_internal.h"
+
+using namespace jb;
+
+static double cs[8][8];
+
+static void ref_dct_quant(const int* smp, const uint32_t* q, int* out /* natural order */) {
+    for (size_t u = 0; u < 8; ++u)
+        for (size_t v = 0; v < 8; ++v) {
+            double au = (u == 0) ? 1.0 / std::sqrt(2) : 1.0, av = (v == 0) ? 1.0 / std::sqrt(2) : 1.0;
+            double s = 0.0;
+            for (size_t y = 0; y < 8; ++y)
+                for (size_t x = 0; x < 8; ++x) s += (double)smp[y * 8 + x] * cs[u][x] * cs[v][y];
+            s *= (au * av / 4.0);
+            out[v * 8 + u] = (int)std::round(s / q[v * 8 + u]);
+        }
+}
+
+int main() {
+    for (size_t u = 0; u < 8; ++u)
+        for (size_t x = 0; x < 8; ++x) cs[u][x] = std::cos((2 * x + 1) * u * M_PI / 16.0);
+
+    // ---- 1. colour conversion ---------------------------------------------------------
+    std::vector<uint32_t> ydown(2048);
+    build_ydown(ydown.data());
+    long csc_bad = 0, y_ties = 0, y_down = 0;
+    for (uint32_t r = 0; r < 256; ++r)
+        for (uint32_t g = 0; g < 256; ++g)
+            for (uint32_t b = 0; b < 256; ++b) {
+                uint8_t y = (uint8_t)(0.299 * r + 0.587 * g + 0.114 * b);
+                uint8_t cb = (uint8_t)(-0.168736 * r - 0.331264 * g + 0.5 * b + 128);
+                uint8_t cr = (uint8_t)(0.5 * r - 0.418688 * g - 0.081312 * b + 128);
+                if (csc_y(r, g, b, ydown.data()) != y || csc_cb(r, g, b) != cb || csc_cr(r, g, b) != cr) ++csc_bad;
+                if ((csc_ty(r, g, b) & Y_TIE_MASK) == 0) {
+                    ++y_ties;
+                    if ((csc_ty(r, g, b) >> 24) != y) ++y_down;
+                }
+            }
+
+    // ---- 2./3. transform error and near-tie logic ---------------------------------------
+    double err[64], amax[64];
+    aan_error_bound(err, amax);
+    double worst_ratio = 0, max_err = 0, max_bound = 0;
+    long coefs = 0, flagged = 0, unflagged_wrong = 0, flagged_differ = 0, max_lsb = 0;
+    srand(12345);
+    const int qualities[4] = {50, 75, 90, 100};
+    for (int trial = 0; trial < 60000; ++trial) {
+        int smp[64];
+        int mode = trial % 6;
+        for (int i = 0; i < 64; ++i) {
+            int v;
+            if (mode == 0) v = rand() % 256 - 128;
+            else if (mode == 1) v = (rand() & 1) ? 127 : -128;
+            else if (mode == 2) v = ((i * 7 + trial) % 3 == 0) ? 127 : -128;
+            else if (mode == 3) v = (rand() % 9 - 4) + (i % 8) * 16 - 60;
+            else if (mode == 4) v = (trial / 6) % 256 - 128;  // flat blocks: exact DC ties
+            else v = (rand() & 3) ? -128 : 127;
+            smp[i] = v;
+        }
+        float a[64];
+        for (int i = 0; i < 64; ++i) a[i] = (float)smp[i];
+        for (int r = 0; r < 8; ++r)
+            fdct8(a[r * 8], a[r * 8 + 1], a[r * 8 + 2], a[r * 8 + 3], a[r * 8 + 4], a[r * 8 + 5], a[r * 8 + 6], a[r * 8 + 7]);
+        for (int c = 0; c < 8; ++c) fdct8(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c]);
+        for (int v = 0; v < 8; ++v)
+            for (int u = 0; u < 8; ++u) {
+                double s = 0;
+                for (int y = 0; y < 8; ++y)
+                    for (int x = 0; x < 8; ++x) s += smp[y * 8 + x] * cs[u][x] * cs[v][y];
+                double e = std::fabs((double)a[v * 8 + u] - s * aan_scale(u) * aan_scale(v));
+                if (e > max_err) max_err = e;
+                if (err[v * 8 + u] > 0 && e / err[v * 8 + u] > worst_ratio) worst_ratio = e / err[v * 8 + u];
+                // outputs that only add integers must be exact (up to the binary64 noise of this check)
+                if (err[v * 8 + u] == 0 && e > 1e-9) worst_ratio = 1e9;
+            }
+        // quantise with the tables of one quality (IJG scaling of the reference's q50 tables)
+        uint32_t ql[64], qc[64];
+        jb_quality_tables(qualities[trial % 4], ql, qc);
+        QuantConst k;
+        build_quant_const(ql, qc, &k);
+        int want[64];
+        ref_dct_quant(smp, ql, want);
+        for (int n = 0; n < 64; ++n) {
+            bool tie = false;
+            int got;
+            if (n == 0 && k.dc_exact) {
+                int S = (int)lrintf(a[0]);
+                uint32_t A = (uint32_t)std::abs(S);
+                uint32_t m = (uint32_t)(((uint64_t)(2 * A + k.dc_d[0] - 1) * k.dc_m[0]) >> 32);
+                got = S < 0 ? -(int)m : (int)m;
+            } else {
+                uint32_t bits = quantize_bits(a[n], k.mul[0][n], k.band[0][n], tie);
+                got = (int)(int16_t)(bits & 0xFFFF);
+            }
+            ++coefs;
+            if (tie) {
+                ++flagged;
+                if (got != want[n]) ++flagged_differ;
+            } else if (got != want[n]) {
+                ++unflagged_wrong;
+            }
+            long d = std::labs((long)got - want[n]);
+            if (d > max_lsb) max_lsb = d;
+        }
+    }
+    for (int n = 0; n < 64; ++n)
+        if (err[n] > max_bound) max_bound = err[n];
+
+    // ---- 4. integer DC rule for every quantiser value ------------------------------------
+    int dc_rule_failures = 0;
+    for (uint32_t q = 1; q <= 255; ++q) {
+        uint32_t ql[64], qc[64];
+        for (int i = 0; i < 64; ++i) ql[i] = qc[i] = q;
+        QuantConst k;
+        build_quant_const(ql, qc, &k);
+        if (!k.dc_exact) ++dc_rule_failures;
+    }
+
+    printf("{\"csc_mismatches\": %ld, \"y_ties\": %ld, \"y_ties_down\": %ld, \"max_err\": %.6e, \"max_bound\": %.6e, "
+           "\"worst_err_over_bound\": %.4f, \"coefs\": %ld, \"flagged\": %ld, \"unflagged_wrong\": %ld, "
+           "\"flagged_differ\": %ld, \"max_lsb\": %ld, \"dc_rule_failures\": %d}\n",
+           csc_bad, y_ties, y_down, max_err, max_bound, worst_ratio, coefs, flagged, unflagged_wrong, flagged_differ,
+           max_lsb, dc_rule_failures);
+    return 0;
+}

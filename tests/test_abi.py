@@ -1,0 +1,80 @@
+"""CPU tests of the drop-in boundary: libjpegb200.so loads, exports every symbol that
+include/jpegb200.h declares, its host-only entry points agree with the oracle, and without a
+GPU the product fails loudly instead of falling back to anything."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "jpegb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(jb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(jb):
+    L = jb.lib()
+    names = declared_symbols()
+    assert len(names) >= 38
+    for n in names:
+        assert hasattr(L, n), f"{n} is declared in include/jpegb200.h but not exported"
+    assert sorted(jb.SYMBOLS) == names  # the Python binding covers the whole header
+
+
+def test_no_oracle_in_product(jb):
+    """The shipped library must not link or reference the test-only oracle."""
+    blob = open(jb.LIB_PATH, "rb").read()
+    assert b"orc_" not in blob and b"liboracle" not in blob and b"libjpegref" not in blob
+    for root, _, files in os.walk(os.path.join(ROOT, "jpeg-encoder-opencl_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cpp", ".h", ".cuh", ".hpp", ".py")):
+                text = open(os.path.join(root, f)).read()
+                assert "oracle_lib" not in text and "jpeg_oracle" not in text, f
+
+
+def test_host_only_entry_points_match_oracle(jb):
+    L = jb.lib()
+    for q in (1, 10, 50, 75, 90, 100):
+        a, b = jb.quality_tables(q)
+        c, d = ol.quality_tables(q)
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+    nW, nH = C.c_size_t(), C.c_size_t()
+    assert L.jb_padded_size(253, 254, 8, C.byref(nW), C.byref(nH)) == 0 and (nW.value, nH.value) == (256, 256)
+    assert L.jb_padded_size(1920, 1080, 16, C.byref(nW), C.byref(nH)) == 0 and (nW.value, nH.value) == (1920, 1088)
+    for sub in (0, 1, 2):
+        assert L.jb_blocks_per_mcu(sub) == ol.oracle().orc_blocks_per_mcu(sub)
+        assert L.jb_num_mcus(253, 254, sub) == ol.oracle().orc_num_mcus(253, 254, sub)
+        for ri in (0, 7):
+            ql, qc = ol.quality_tables(75)
+            p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri)
+            out = np.zeros(1024, np.uint8)
+            n = C.c_size_t()
+            assert L.jb_write_header(C.byref(p), 253, 254, out.ctypes.data, 1024, C.byref(n)) == 0
+            want = ol.jfif_header(253, 254, sub, ql, qc, ri)
+            assert n.value == len(want) == jb.header_bytes(p) and np.array_equal(out[: n.value], want)
+
+
+def test_fails_loudly_without_gpu(jb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(jb.JbError) as e:
+        jb.Encoder(0)
+    assert e.value.code == jb.E_CUDA
+
+
+def test_compat_header_covers_the_reference_surface():
+    """utils_compat.hpp re-declares the reference's stage functions (utils.hpp:81-137) by name."""
+    text = open(os.path.join(ROOT, "jpeg-encoder-opencl_b200", "host", "utils_compat.hpp")).read()
+    for name in ("performCSC", "performCDS", "getNearest8x8ImageSize", "copyToLargerImage", "addReversedPadding",
+                 "copyUIntToDoubleImage", "substractfromAll", "performDCT", "performQuantization",
+                 "everyMCUisnow2DArray", "performZigZag", "performRLE", "HuffmanEncoder", "readPPMImage",
+                 "writePPMImage", "quant_mat_lum", "quant_mat_chrom"):
+        assert re.search(rf"\b{name}\b", text), name

@@ -1,0 +1,51 @@
+"""CPU test of the kernels' arithmetic: jb_math.h + jb_tables.cpp compiled for the host
+(tests/host_math.cpp) evaluate bit-for-bit what the GPU evaluates (explicit fmaf, -fmad=false),
+so the exactness arguments of DESIGN.md can be checked without a GPU."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def report():
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "host_math")
+    csrc = os.path.join(ROOT, "jpeg-encoder-opencl_b200", "csrc")
+    inc = "/usr/local/cuda/include"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", f"-I{inc}", f"-I{csrc}",
+                    os.path.join(ROOT, "tests", "host_math.cpp"), os.path.join(csrc, "jb_tables.cpp"), "-o", exe],
+                   check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, check=True, timeout=600)
+    return json.loads(r.stdout)
+
+
+def test_colour_conversion_exact_over_all_colours(report):
+    """Fixed-point CSC + Y tie table == the reference's binary64 expressions (utils.cpp:107-109)."""
+    assert report["csc_mismatches"] == 0
+    assert report["y_ties"] == 16774 and report["y_ties_down"] == 3464
+
+
+def test_transform_error_within_analytic_bound(report):
+    """Measured |binary32 AAN - exact| never exceeds aan_error_bound(); the bound stays below 2^-6."""
+    assert report["worst_err_over_bound"] <= 1.0
+    assert report["max_bound"] < 0.015625
+    assert report["max_err"] < report["max_bound"]
+
+
+def test_unflagged_coefficients_equal_binary64_reference(report):
+    """Quantised coefficients differ from the binary64 formula only where the fast path raised its
+    near-tie flag (those are replayed in binary64 by k_fixup), and then by one LSB at most."""
+    assert report["coefs"] > 3_000_000
+    assert report["unflagged_wrong"] == 0
+    assert report["max_lsb"] <= 1
+    assert report["flagged_differ"] <= report["flagged"]
+    assert report["flagged"] / report["coefs"] < 0.01
+
+
+def test_integer_dc_rule_holds_for_every_quantiser(report):
+    assert report["dc_rule_failures"] == 0
