@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tensor-dct", type=int, default=0, help="1: tcgen05 variant of the transform kernel (4:2:0)")
     return ap.parse_args()
 
 
@@ -187,7 +188,8 @@ def main():
     W, H, subname, q, ri, dflt = WORKLOADS[a.workload]
     F = a.frames or dflt
     sub = {"420": jb.SUB_420, "444": jb.SUB_444}[subname]
-    params = jb.make_params(sub, quality=q, restart_interval=ri)
+    params = jb.make_params(sub, quality=q, restart_interval=ri,
+                            flags=jb.FLAG_TENSOR_DCT if (a.tensor_dct and sub == jb.SUB_420) else 0)
     pitch, fstride = W * 3, W * H * 3
     px_per_step = W * H * F  # per GPU
 
@@ -317,7 +319,8 @@ def main():
                        "subsampling": subname, "quality": q, "restart_interval": ri,
                        "l2": "inputs per step (%.2f GB) far exceed the 126 MB L2" % (F * fstride / 1e9),
                        "bits_per_pixel": round(8.0 * total_bytes / px_per_step, 4),
-                       "tie_fixups_per_step": int(tm["tie_fixups"])},
+                       "tie_fixups_per_step": int(tm["tie_fixups"]),
+                       "transform_kernel": "k_transform_tc (tcgen05)" if (a.tensor_dct and sub == jb.SUB_420) else "k_transform (FMA pipe)"},
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": launches_device,
         }

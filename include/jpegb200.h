@@ -51,6 +51,8 @@ typedef enum {
 #define JB_FLAG_REF_ALWAYS_EOB 0x4u  /* Q3 utils.cpp:607-608 EOB also after a full block         */
 #define JB_FLAG_CLAMP_SOF 0x8u       /* declare min(dim,65535) in SOF0                */
 #define JB_FLAG_NO_TIE_FIXUP 0x10u   /* skip the binary64 replay of near-tie coefficients        */
+#define JB_FLAG_TENSOR_DCT 0x20u     /* 4:2:0 only: FDCT+quantiser scale+zigzag as one tcgen05   *
+                                      * contraction per block (bf16x3 split, fp32 in TMEM)       */
 
 typedef struct {
     int32_t subsampling;      /* JB_SUB_*                                                   */

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -48,6 +49,7 @@ struct Slot {
     uint64_t* d_frame_size = nullptr;
     uint64_t* d_total = nullptr;
     uint8_t* d_hdr = nullptr;
+    uint8_t* d_tc = nullptr;  // tensor-core variant: the six bf16 matrices
     uint32_t tie_cap = 0;
     // pinned host mirror: [0..3] status, [4] total, [5] tie_count, then frame_off[n], frame_size[n]
     uint64_t* h_res = nullptr;
@@ -159,6 +161,7 @@ size_t plan_bytes(const Plan& p) {
     add(p.n_frames * 8);
     add(8);
     add(1024);
+    add(49152);
     return align_up(b, 256) + 4096;
 }
 
@@ -192,10 +195,11 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.d_frame_size = carve<uint64_t>(a, p.n_frames);
     s.d_total = carve<uint64_t>(a, 1);
     s.d_hdr = carve<uint8_t>(a, 1024);
+    s.d_tc = carve<uint8_t>(a, 49152);
     s.w.n_ff_tiles = s.d_scalars + 1;
     s.w.status = reinterpret_cast<uint64_t*>(s.d_scalars + 4);
     // pinned result block: result words, then (last 1 KB) the staging area of the JFIF header
-    size_t need = (8 + 2 * p.n_frames) * sizeof(uint64_t) + 2048;
+    size_t need = (8 + 2 * p.n_frames) * sizeof(uint64_t) + 2048 + 49152;
     if (need > s.h_res_cap) {
         if (s.h_res) cudaFreeHost(s.h_res);
         s.h_res = nullptr;
@@ -311,9 +315,17 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ta.tie_count = s.d_scalars;
     ta.tie_cap = s.tie_cap;
     build_quant_const(p->qlum, p->qchrom, &ta.qc);
+    if ((p->flags & JB_FLAG_TENSOR_DCT) && pl.g.sub == JB_SUB_420) {
+        // the six W matrices travel through the pinned result block (asynchronous copy)
+        uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024 - 49152;
+        const char* e = getenv("JB_TC_ERR_SCALE");
+        build_tc_matrices(p->qlum, p->qchrom, e ? atof(e) : JB_TC_ERR_SCALE, h, ta.tband);
+        CK(cudaMemcpyAsync(s.d_tc, h, 49152, cudaMemcpyHostToDevice, s.st));
+        ta.tc_mat = s.d_tc;
+    }
     if (p->flags & JB_FLAG_NO_TIE_FIXUP)
         for (int t = 0; t < 2; ++t)
-            for (int i = 0; i < 64; ++i) ta.qc.band[t][i] = 1.0f;  // never flag
+            for (int i = 0; i < 64; ++i) ta.qc.band[t][i] = ta.tband[t][i] = 1.0f;  // never flag
     {
         Timed t(ctx, s.st, 0);
         int n = launch_transform(ta, s.st);

@@ -64,6 +64,8 @@ struct TransformArgs {
     int units_per_row;
     uint32_t total_units;
     int fast_mcux, fast_mcuy;  // MCUs per row / column that lie completely inside the image
+    const uint8_t* tc_mat;     // tensor-core variant: 6 pre-swizzled bf16 matrices (null = FMA kernel)
+    float tband[2][64];        // tensor-core variant: near-tie bands in zigzag order
     QuantConst qc;
 };
 
@@ -162,7 +164,9 @@ int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStre
 
 // host helpers
 void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out);
-void aan_error_bound(double err[64], double amax[64]);  // worst-case |binary32 - exact| per AAN output
+void aan_error_bound(double err[64], double amax[64]);
+void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, uint8_t* out /* 49152 B */,
+                       float tband[2][64]);  // worst-case |binary32 - exact| per AAN output
 void build_huff(bool typo, HuffDev* out);
 void build_ydown(uint32_t ydown[2048]);
 void build_dct_tables(double costab[64], double scale[64]);

@@ -153,4 +153,9 @@ JB_HD uint32_t quantize_bits(float a, float mul, float band, bool& near_tie) {
 // 1.2e-3; the analytic worst case (tests/test_math_host.py) is below 1.2e-2.
 #define JB_DCT_ERR_BOUND 0.015625  // 2^-6
 
+// Tensor-core variant: bound on |t_mma - t_exact| relative to the largest possible partial sum
+// P = 128 * sum|W|: 192 fp32 accumulation steps of at most one ulp of P each (2^-23), plus the
+// 2^-24 residual of the three-way bf16 split.
+#define JB_TC_ERR_SCALE 2.3e-5
+
 }  // namespace jb

@@ -19,6 +19,8 @@
 // keeps the hot kernel free of the padding code (instruction-cache footprint).
 // Algorithmic HBM traffic: 3 B/px read + 2 B/sample written = 6 B/px (4:2:0) or
 // 9 B/px (4:4:4, replicated 4:2:0).
+#include <cuda_bf16.h>
+
 #include "jb_pixels.cuh"
 
 namespace jb {
@@ -437,6 +439,238 @@ __global__ void __launch_bounds__(64) k_transform_edge(const __grid_constant__ T
     }
 }
 
+// ================================================================ tensor-core variant ==
+// 4:2:0 only.  The block transform (FDCT + quantiser scale + zigzag) is one 64x64 contraction
+// per block: D[128 blocks][64 coefficients] = A[128 blocks][64 samples] x W^T on the 5th-gen
+// tensor cores (tcgen05.mma, kind::f16, bf16 operands, fp32 accumulators in TMEM).  The 8-bit
+// level-shifted samples are exact in bf16; W is split into hi+mid+lo bf16 matrices (24
+// mantissa bits), so one tile costs 3 x 4 MMAs of M128 N64 K16.  A group of 128 threads owns
+// one M=128 tile: thread i writes the 64 samples of its block as row i of the A tile (one
+// 128-bit store per image row, 128-byte swizzle), so no register array of samples exists and
+// the row loop stays rolled (small code: no instruction-cache pressure).  After the MMAs the
+// thread reads row i of D back (tcgen05.ld 32x32b.x64): its own 64 scaled coefficients, already
+// in zigzag order, for rounding, near-tie flagging and packing as in the FMA kernel.
+constexpr int TC_GROUPS = 4;                       // 128-thread groups (M tiles) per CTA, one CTA per SM
+constexpr int TC_B_BYTES = 6 * 8192;               // [table][split] 64x64 bf16
+constexpr int TC_TILE_BYTES = 128 * 128;           // one A tile
+constexpr int TC_SMEM = TC_B_BYTES + TC_GROUPS * 2 * TC_TILE_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {  // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
+        "r"(accumulate));
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, "
+        "%46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t bf16x2(int lo, int hi) {  // two small integers -> packed bf16 (exact)
+    __nv_bfloat162 v = __floats2bfloat162_rn((float)lo, (float)hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Round the 64 scaled coefficients t (zigzag order) of one block, flag near ties, pack, stage.
+template <int TAB>
+__device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const TransformArgs& a, uint4* st, int lane,
+                                               uint32_t& tie_lo, uint32_t& tie_hi) {
+    uint32_t wd[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        uint32_t b[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = 2 * j + e;
+            float x = __uint_as_float(t[k]);
+            if (k == 0 && a.qc.dc_exact) {
+                // x ~ S/(8q): recover the exact integer sample sum S, then the integer DC rule
+                b[e] = quantize_dc<TAB>(x * (float)a.qc.dc_d[TAB], a);
+            } else {
+                float r = x + JB_ROUND_MAGIC, ri = r - JB_ROUND_MAGIC;
+                bool tie = fabsf(x - ri) > a.tband[TAB][k];
+                if (tie) {
+                    if (k < 32) tie_lo |= 1u << k; else tie_hi |= 1u << (k - 32);
+                }
+                b[e] = __float_as_uint(r);
+            }
+        }
+        wd[j] = __byte_perm(b[0], b[1], 0x5410);
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+        st[lane * 8 + (p ^ (lane & 7))] = make_uint4(wd[4 * p], wd[4 * p + 1], wd[4 * p + 2], wd[4 * p + 3]);
+}
+
+template <int ALIGN>
+__global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __grid_constant__ TransformArgs a) {
+    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar[TC_GROUPS];
+    __shared__ uint32_t s_tmem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, wg = gt >> 5, lane = tid & 31;
+    uint8_t* sB = smem;
+    uint8_t* sAy = smem + TC_B_BYTES + g * 2 * TC_TILE_BYTES;  // luma tile, reused as the output staging tile
+    uint8_t* sAc = sAy + TC_TILE_BYTES;                        // chroma tile
+    // ---- one-time setup: W matrices, tensor memory, barriers ---------------------------------------
+    for (int i = tid; i < TC_B_BYTES / 16; i += TC_GROUPS * 128)
+        reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.tc_mat) + i);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "n"(TC_GROUPS * 64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid < TC_GROUPS) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[tid])));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem + (uint32_t)(g * 64);
+    const uint32_t tmem_ld = tmem_d + ((uint32_t)(wg * 32) << 16);
+    const uint32_t mbar = smem_u32(&s_mbar[g]);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 17) | (8u << 24);  // f32 += bf16 x bf16, N=64, M=128
+    uint32_t phase = 0;
+    uint4* st = reinterpret_cast<uint4*>(sAy) + wg * 256;  // this warp's 32 rows of the tile = its staging tile
+    uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
+    const int half = lane & 1;
+    const uint32_t row_sw = (uint32_t)(gt & 7);           // swizzle key of this thread's A row
+    const uint32_t units_per_frame = (uint32_t)a.units_per_row * (uint32_t)a.fast_mcuy;
+    const uint32_t groups_total = gridDim.x * TC_GROUPS;
+
+    // issue the 12 MMAs of one tile (one thread), completion arrives on the group's mbarrier
+    auto issue = [&](const uint8_t* tile, int tab) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint64_t da = umma_desc(smem_u32(tile));
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+            uint64_t db = umma_desc(smem_u32(sB + (tab * 3 + s3) * 8192));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s3 | k) ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+    };
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+
+    for (uint32_t base = (blockIdx.x * TC_GROUPS + g) * 4; base < a.total_units; base += groups_total * 4) {
+        const bool active = base + wg < a.total_units;  // every warp of the group runs the same control flow
+        const uint32_t unit = active ? base + wg : base;
+        uint32_t f = unit / units_per_frame, rem = unit - f * units_per_frame;
+        int my = (int)(rem / (uint32_t)a.units_per_row), ux = (int)(rem - (uint32_t)my * (uint32_t)a.units_per_row);
+        Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
+        const int mcu_x0 = ux * 16;
+        const int mcus_valid = active ? min(16, a.fast_mcux - mcu_x0) : 0;
+        const size_t mcu_g0 = (size_t)f * (size_t)a.g.n_mcu + (size_t)my * (size_t)a.g.mcux + (size_t)mcu_x0;
+        const bool valid = (lane >> 1) < mcus_valid;
+        const int m = valid ? lane >> 1 : max(mcus_valid - 1, 0);
+        const uint32_t gb0 = (uint32_t)(mcu_g0 + m) * 6u;
+        const uint8_t* col0 = im.base + (size_t)((mcu_x0 + m) * 16 + half * 8) * 3;
+        // A-tile rows that receive this lane's chroma: Cb -> row of the even lane, Cr -> row of the odd lane
+        const int row_cb = gt & ~1, row_cr = gt | 1;
+
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            uint32_t pb[4], pr[4];
+#pragma unroll 1
+            for (int r = 0; r < 8; ++r) {
+                uint32_t w[6];
+                load24<ALIGN>(col0 + (size_t)mirror(my * 16 + h * 8 + r, im.H) * im.pitch, w);
+                Row8 o;
+                csc_row8(w, im.ydown, o);
+                uint4 ys = make_uint4(bf16x2(o.y[0], o.y[1]), bf16x2(o.y[2], o.y[3]), bf16x2(o.y[4], o.y[5]),
+                                      bf16x2(o.y[6], o.y[7]));
+                *reinterpret_cast<uint4*>(sAy + gt * 128 + (((uint32_t)r ^ row_sw) << 4)) = ys;
+                uint32_t sb[4], sr[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    sb[c] = (o.cb[2 * c] >> 24) + (o.cb[2 * c + 1] >> 24);
+                    sr[c] = (o.cr[2 * c] >> 24) + (o.cr[2 * c + 1] >> 24);
+                }
+                if (r & 1) {  // utils.cpp:126-127: truncated mean of the 2x2 cell, then level shift
+                    const uint32_t crow = (uint32_t)(h * 4 + (r >> 1));  // chroma row = K chunk
+                    uint2 vb = make_uint2(bf16x2((int)((pb[0] + sb[0]) >> 2) - 128, (int)((pb[1] + sb[1]) >> 2) - 128),
+                                          bf16x2((int)((pb[2] + sb[2]) >> 2) - 128, (int)((pb[3] + sb[3]) >> 2) - 128));
+                    uint2 vr = make_uint2(bf16x2((int)((pr[0] + sr[0]) >> 2) - 128, (int)((pr[1] + sr[1]) >> 2) - 128),
+                                          bf16x2((int)((pr[2] + sr[2]) >> 2) - 128, (int)((pr[3] + sr[3]) >> 2) - 128));
+                    *reinterpret_cast<uint2*>(sAc + row_cb * 128 + ((crow ^ (uint32_t)(row_cb & 7)) << 4) + half * 8) = vb;
+                    *reinterpret_cast<uint2*>(sAc + row_cr * 128 + ((crow ^ (uint32_t)(row_cr & 7)) << 4) + half * 8) = vr;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        pb[c] = sb[c];
+                        pr[c] = sr[c];
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            group_sync();
+            if (gt == 0) issue(sAy, 0);
+            mbar_wait(mbar, phase);
+            phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t t[64];
+            tmem_ld64(tmem_ld, t);
+            uint32_t tl = 0, th = 0;
+            tc_quant_stage<0>(t, a, st, lane, tl, th);
+            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 2 * h + half, tl, th);
+            __syncwarp();
+            copy_out<6>(st, coef4, mcu_g0, mcus_valid, 2 * h, lane);
+            __syncwarp();
+        }
+        // chroma tile (complete after both halves)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        group_sync();
+        if (gt == 0) issue(sAc, 1);
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            uint32_t t[64];
+            tmem_ld64(tmem_ld, t);
+            uint32_t tl = 0, th = 0;
+            tc_quant_stage<1>(t, a, st, lane, tl, th);
+            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 4 + half, tl, th);
+            __syncwarp();
+            copy_out<6>(st, coef4, mcu_g0, mcus_valid, 4, lane);
+            __syncwarp();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_GROUPS * 64));
+}
+
 template <int SUB, int ALIGN>
 static void launch_one(const TransformArgs& a, int grid, cudaStream_t s) {
     const int smem = TW * 256 * 16 + (SUB == JB_SUB_420 ? TW * CH_WARP_WORDS * 4 : 0);
@@ -475,6 +709,18 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     int align = (bits & 7) == 0 ? 8 : (bits & 3) == 0 ? 4 : 1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (a.tc_mat && a.g.sub == JB_SUB_420 && align >= 4) {  // tensor-core variant
+        int needg = (int)((a.total_units + 4 * TC_GROUPS - 1) / (4 * TC_GROUPS));
+        int gridg = needg < sms ? needg : sms;
+        if (align == 8) {
+            cudaFuncSetAttribute(k_transform_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+            k_transform_tc<8><<<gridg, TC_GROUPS * 128, TC_SMEM, s>>>(a);
+        } else {
+            cudaFuncSetAttribute(k_transform_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+            k_transform_tc<4><<<gridg, TC_GROUPS * 128, TC_SMEM, s>>>(a);
+        }
+        return 1;
+    }
     int need = (int)((a.total_units + TW - 1) / TW);
     int grid = need < sms * (16 / TW) ? need : sms * (16 / TW);
     if (a.g.sub == JB_SUB_420)

@@ -433,3 +433,36 @@ def test_config3_8k_420_q75_restart(enc, jb):
         want, _ = ol.entropy(coef, ol.SUB_420, 480)
         seg = body[bounds[row]: bounds[row + 1] - 2]
         assert np.array_equal(seg, want), f"MCU row {row}"
+
+
+# ------------------------------------------------ tensor-core variant of the fused kernel ------------
+
+@pytest.mark.parametrize("q", [50, 75, 90, 100])
+def test_tensor_core_transform_bit_exact(enc, jb, fruit, q):
+    """JB_FLAG_TENSOR_DCT: tcgen05 contraction (bf16x3 split) + binary64 replay == the oracle, bit for bit."""
+    ql, qc = ol.quality_tables(q)
+    for img in (fruit, ol.synth(21, 1920, 128), noise_image(3, 200, 120)):
+        p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, flags=jb.FLAG_TENSOR_DCT)
+        got = enc.transform(img, p)
+        want = ol.transform(img, ol.SUB_420, ql, qc)
+        assert np.array_equal(got, want), f"q{q} {img.shape}: " + mismatch_report(got, want)
+
+
+def test_tensor_core_raw_error_is_small(enc, jb, fruit):
+    """Without the replay the tensor-core path may differ by one LSB at (near) ties only."""
+    ql, qc = ol.quality_tables(75)
+    p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, flags=jb.FLAG_TENSOR_DCT | jb.FLAG_NO_TIE_FIXUP)
+    img = ol.synth(5, 1920, 256)
+    got = enc.transform(img, p).astype(np.int32)
+    want = ol.transform(img, ol.SUB_420, ql, qc).astype(np.int32)
+    assert np.abs(got - want).max() <= 1
+    assert (got != want).mean() < 2e-3
+
+
+def test_tensor_core_jfif_equals_fma_path(enc, jb):
+    frames = np.stack([ol.synth(300 + i, 640, 360) for i in range(4)])
+    a = jb.make_params(ol.SUB_420, quality=75, restart_interval=40)
+    b = jb.make_params(ol.SUB_420, quality=75, restart_interval=40, flags=jb.FLAG_TENSOR_DCT)
+    oa, offa, sza = enc.encode_batch(frames, a)
+    ob, offb, szb = enc.encode_batch(frames, b)
+    assert np.array_equal(sza, szb) and np.array_equal(oa[: int(sza.sum())], ob[: int(szb.sum())])
