@@ -145,6 +145,7 @@ size_t plan_bytes(const Plan& p) {
     add((p.n_tiles * 256 + 1) * 4);        // blk_prefix
     add(p.n_tiles * 256 * 4);              // blk_len
     add(p.n_tiles * 256 * 16);             // slots
+    add(p.n_tiles * 256 * 4);              // long_list
     add(p.n_tiles * 4);
     add((p.n_tiles + 1) * 8);
     add(p.n_int_total * 4);
@@ -161,7 +162,7 @@ size_t plan_bytes(const Plan& p) {
     add(p.n_frames * 8);
     add(8);
     add(1024);
-    add(49152);
+    add(32768);
     return align_up(b, 256) + 4096;
 }
 
@@ -177,6 +178,7 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.w.blk_prefix = carve<uint32_t>(a, p.n_tiles * 256 + 1);
     s.w.blk_len = carve<uint32_t>(a, p.n_tiles * 256);
     s.w.slots = carve<uint4>(a, p.n_tiles * 256);
+    s.w.long_list = carve<uint32_t>(a, p.n_tiles * 256);
     s.w.tile_bits = carve<uint32_t>(a, p.n_tiles);
     s.w.tile_base = carve<uint64_t>(a, p.n_tiles + 1);
     s.w.int_slot = carve<uint32_t>(a, p.n_int_total);
@@ -195,11 +197,12 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.d_frame_size = carve<uint64_t>(a, p.n_frames);
     s.d_total = carve<uint64_t>(a, 1);
     s.d_hdr = carve<uint8_t>(a, 1024);
-    s.d_tc = carve<uint8_t>(a, 49152);
+    s.d_tc = carve<uint8_t>(a, 32768);
     s.w.n_ff_tiles = s.d_scalars + 1;
+    s.w.n_long = s.d_scalars + 2;
     s.w.status = reinterpret_cast<uint64_t*>(s.d_scalars + 4);
     // pinned result block: result words, then (last 1 KB) the staging area of the JFIF header
-    size_t need = (8 + 2 * p.n_frames) * sizeof(uint64_t) + 2048 + 49152;
+    size_t need = (8 + 2 * p.n_frames) * sizeof(uint64_t) + 2048 + 32768;
     if (need > s.h_res_cap) {
         if (s.h_res) cudaFreeHost(s.h_res);
         s.h_res = nullptr;
@@ -317,10 +320,10 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     build_quant_const(p->qlum, p->qchrom, &ta.qc);
     if ((p->flags & JB_FLAG_TENSOR_DCT) && pl.g.sub == JB_SUB_420) {
         // the six W matrices travel through the pinned result block (asynchronous copy)
-        uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024 - 49152;
+        uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024 - 32768;
         const char* e = getenv("JB_TC_ERR_SCALE");
         build_tc_matrices(p->qlum, p->qchrom, e ? atof(e) : JB_TC_ERR_SCALE, h, ta.tband);
-        CK(cudaMemcpyAsync(s.d_tc, h, 49152, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemcpyAsync(s.d_tc, h, 32768, cudaMemcpyHostToDevice, s.st));
         ta.tc_mat = s.d_tc;
     }
     if (p->flags & JB_FLAG_NO_TIE_FIXUP)

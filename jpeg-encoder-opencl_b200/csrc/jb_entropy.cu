@@ -195,45 +195,81 @@ __device__ __forceinline__ void encode_sparse(uint64_t mask, Fetch value, int dc
 __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ EntropyArgs a) {
     __shared__ uint4 s_coef[TILE * 8];
     __shared__ __align__(16) uint32_t s_slot[TILE * 4];
+    __shared__ uint64_t s_mask[TILE];
     __shared__ uint32_t s_ac[2][256], s_dc[2][16], s_warp[8];
+    __shared__ uint32_t s_len[TILE];
+    __shared__ uint32_t s_hist[64], s_start[64];
+    __shared__ uint16_t s_perm[TILE];
     const uint32_t t = threadIdx.x, b0 = blockIdx.x * TILE, b = b0 + t;
     const uint4* src = reinterpret_cast<const uint4*>(a.coef) + (size_t)b0 * 8;
-    const uint32_t n_here = min((uint32_t)TILE, a.n_blocks - b0) * 8;
+    const uint32_t n_blk = min((uint32_t)TILE, a.n_blocks - b0), n_here = n_blk * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         uint32_t g = i * TILE + t, blk = g >> 3, pc = g & 7;
         if (g < n_here) s_coef[blk * 8 + (pc ^ (blk & 7))] = __ldg(src + g);
     }
+    if (t < 64) s_hist[t] = 0;
     load_tables(a, s_ac, s_dc);  // ends with __syncthreads()
-    uint32_t bits = 0;
-    if (b < a.n_blocks) {
+    // ---- non-zero mask of this thread's block, then a counting sort of the tile's blocks by
+    // their number of non-zero AC coefficients: the walk below costs one loop iteration per
+    // non-zero, so warps made of similar blocks do not wait for their busiest lane.
+    uint32_t cnt = 0;
+    if (t < n_blk) {
         uint64_t mask = 0;
-        int dc = 0;
 #pragma unroll
         for (int pc = 0; pc < 8; ++pc) {
             uint4 q = s_coef[t * 8 + (pc ^ (t & 7))];
-            if (pc == 0) dc = (int)(short)(q.x & 0xFFFFu);
             uint64_t m8 = nz2(q.x) | (nz2(q.y) << 2) | (nz2(q.z) << 4) | (nz2(q.w) << 6);
             mask |= m8 << (8 * pc);
         }
-        BlockInfo bi = block_info(a, b);
+        s_mask[t] = mask;
+        cnt = (uint32_t)__popcll(mask & ~1ull);
+        atomicAdd(&s_hist[cnt], 1u);
+    }
+    __syncthreads();
+    if (t < 32) {  // exclusive scan of the 64 bins, busiest blocks first
+        uint32_t h0 = s_hist[63 - 2 * t], h1 = s_hist[62 - 2 * t], inc = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (t >= (uint32_t)o) inc += y;
+        }
+        s_start[63 - 2 * t] = inc - h0 - h1;
+        s_start[62 - 2 * t] = inc - h1;
+    }
+    __syncthreads();
+    if (t < n_blk) s_perm[atomicAdd(&s_start[cnt], 1u)] = (uint16_t)t;
+    __syncthreads();
+    // ---- encode block s_perm[t] ------------------------------------------------------------
+    if (t < n_blk) {
+        const uint32_t k = s_perm[t], bk = b0 + k;
+        const short* cf = reinterpret_cast<const short*>(s_coef);
+        auto value = [&](int pos) { return (int)cf[(k * 8 + ((pos >> 3) ^ (k & 7))) * 8 + (pos & 7)]; };
+        BlockInfo bi = block_info(a, bk);
         const int tab = bi.comp ? 1 : 0;
-        const short* mine = reinterpret_cast<const short*>(s_coef);
-        auto value = [&](int pos) { return (int)mine[(t * 8 + ((pos >> 3) ^ (t & 7))) * 8 + (pos & 7)]; };
         int pred = 0;  // DC of the previous block of the component (utils.cpp:669-670)
         if (bi.has_prev) {
             if (bi.prev >= b0) {
                 uint32_t pt = bi.prev - b0;
-                pred = (int)mine[(pt * 8 + (pt & 7)) * 8];  // piece 0 of block pt sits at pt*8 + (0 ^ (pt&7))
+                pred = (int)cf[(pt * 8 + (pt & 7)) * 8];  // piece 0 of block pt sits at pt*8 + (0 ^ (pt&7))
             } else {
                 pred = (int)a.coef[(size_t)bi.prev * 64];
             }
         }
         SlotSink s;
-        s.init(s_slot + t * 4);
-        encode_sparse(mask, value, dc - pred, s_ac[tab], s_dc[tab], a.always_eob != 0, s);
+        s.init(s_slot + k * 4);
+        encode_sparse(s_mask[k], value, value(0) - pred, s_ac[tab], s_dc[tab], a.always_eob != 0, s);
         s.finish();
-        bits = s.bits;
+        s_len[k] = s.bits;
+        if (s.bits > 128) {  // too long for a slot: k_pack_long re-walks it
+            uint32_t idx = atomicAdd(a.w.n_long, 1u);
+            a.w.long_list[idx] = bk;
+        }
+    }
+    __syncthreads();
+    uint32_t bits = 0;
+    if (t < n_blk) {
+        bits = s_len[t];
         a.w.blk_len[b] = bits;
         a.w.slots[b] = *reinterpret_cast<const uint4*>(s_slot + t * 4);
     }
@@ -367,8 +403,9 @@ __global__ void __launch_bounds__(TILE) k_pack_long(const __grid_constant__ Entr
     __shared__ uint32_t s_ac[2][256], s_dc[2][16];
     load_tables(a, s_ac, s_dc);
     if (a.w.int_ubase[a.n_int_total] > a.w.ubuf_cap) return;
-    for (uint32_t b = blockIdx.x * TILE + threadIdx.x; b < a.n_blocks; b += gridDim.x * TILE) {
-        if (a.w.blk_len[b] <= 128) continue;
+    const uint32_t n_long = *a.w.n_long;
+    for (uint32_t i = blockIdx.x * TILE + threadIdx.x; i < n_long; i += gridDim.x * TILE) {
+        const uint32_t b = a.w.long_list[i];
         BlockInfo bi = block_info(a, b);
         uint32_t s0, e0;
         interval_blocks(a, bi.interval, s0, e0);
@@ -542,7 +579,7 @@ int launch_entropy(const EntropyArgs& a, cudaStream_t s) {
     k_scan<<<1, 1024, 0, s>>>(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr);
     k_zero<<<592, 256, 0, s>>>(a);
     k_pack<<<n_tiles, TILE, 0, s>>>(a);
-    k_pack_long<<<1184, TILE, 0, s>>>(a);
+    k_pack_long<<<296, TILE, 0, s>>>(a);
     launches += 7;
     if (a.fr.raw_bits) return launches;
     k_ff_count<<<1184, TILE, 0, s>>>(a);

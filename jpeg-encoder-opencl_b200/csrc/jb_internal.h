@@ -103,6 +103,8 @@ struct EntropyWork {
     uint32_t* blk_prefix;   // [n_blocks] exclusive bit prefix inside its 256-block tile
     uint32_t* blk_len;      // [n_blocks] code length of every block in bits
     uint4* slots;           // [n_blocks] first 128 code bits of every block, left aligned, MSB first
+    uint32_t* long_list;    // [n_blocks] blocks whose code does not fit a slot
+    uint32_t* n_long;       // device scalar
     uint32_t* tile_bits;    // [n_tiles]
     uint64_t* tile_base;    // [n_tiles + 1] exclusive scan of tile_bits
     uint32_t* int_slot;     // [n_int_total] bytes reserved in the unstuffed buffer (multiple of 16)
@@ -165,7 +167,7 @@ int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStre
 // host helpers
 void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out);
 void aan_error_bound(double err[64], double amax[64]);
-void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, uint8_t* out /* 49152 B */,
+void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, uint8_t* out /* 32768 B */,
                        float tband[2][64]);  // worst-case |binary32 - exact| per AAN output
 void build_huff(bool typo, HuffDev* out);
 void build_ydown(uint32_t ydown[2048]);

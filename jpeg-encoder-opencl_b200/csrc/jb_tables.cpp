@@ -255,21 +255,30 @@ size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* h) {
 // ---- tensor-core variant: the whole block transform as one 64x64 contraction -----------
 // t[n] = sum_k x[k] * W[n][k], k = y*8+x (sample), n = zigzag position, with
 //   W[n][k] = alpha(u)alpha(v)/4 * cos((2x+1)u pi/16) cos((2y+1)v pi/16) / q[v][u],  (v,u) = zigzag(n)
-// i.e. FDCT, quantiser scale and zigzag permutation in a single matrix.  Each W is split into
-// three bf16 matrices (hi + mid + lo carry 24 mantissa bits; the 8-bit samples are exact in
-// bf16) laid out as UMMA B operands: 64 rows (n) x 128 bytes (k), K-major, 128-byte swizzle
-// (16-byte chunk c of row n at n*128 + ((c ^ (n&7)) << 4)).  out = [table][split] x 8192 bytes.
+// i.e. FDCT, quantiser scale and zigzag permutation in a single matrix.  W is scaled by 2^10
+// (undone for free by the FMA that rounds) and split into two fp16 matrices, hi + lo = 22
+// significand bits; the 8-bit samples are exact in fp16.  Layout = UMMA B operand: 64 rows
+// (n) x 128 bytes (k), K-major, 128-byte swizzle (16-byte chunk c of row n at
+// n*128 + ((c ^ (n&7)) << 4)).  out = [table][split] x 8192 bytes.
 // tband[t][n] = 0.5 - err_scale * P(n), P(n) = 128 * sum_k |W[n][k]| the largest possible partial sum.
-static uint16_t to_bf16(double x, double* back) {
-    float f = (float)x;
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);  // round to nearest even on the upper 16 bits
-    uint16_t h = (uint16_t)(r >> 16);
-    uint32_t b = (uint32_t)h << 16;
-    float fb;
-    memcpy(&fb, &b, 4);
-    *back = (double)fb;
+static uint16_t to_fp16(double x, double* back) {
+    // round to nearest even into IEEE binary16 (values here are far from overflow)
+    if (x == 0.0) { *back = 0.0; return 0; }
+    int sign = x < 0; double ax = fabs(x);
+    int e; double m = frexp(ax, &e);          // ax = m * 2^e, m in [0.5,1)
+    int E = e - 1;                             // ax = (2m) * 2^E, 2m in [1,2)
+    uint16_t h;
+    if (E < -14) {                             // subnormal: units of 2^-24
+        double q = nearbyint(ax * 16777216.0);
+        h = (uint16_t)q;
+        *back = q / 16777216.0;
+    } else {
+        double q = nearbyint((2.0 * m - 1.0) * 1024.0);  // 10 fraction bits
+        if (q == 1024.0) { q = 0; ++E; }
+        h = (uint16_t)(((E + 15) << 10) | (int)q);
+        *back = ldexp(1.0 + q / 1024.0, E);
+    }
+    if (sign) { h |= 0x8000; *back = -*back; }
     return h;
 }
 
@@ -285,11 +294,11 @@ void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_
                 int y = k >> 3, x = k & 7;
                 double w = alpha * cos((2 * x + 1) * u * pi / 16.0) * cos((2 * y + 1) * v * pi / 16.0) / (double)q[nat];
                 P += fabs(w) * 128.0;
-                double b0, b1, b2;
-                uint16_t h0 = to_bf16(w, &b0), h1 = to_bf16(w - b0, &b1), h2 = to_bf16(w - b0 - b1, &b2);
+                double b0, b1;
+                uint16_t h0 = to_fp16(w * JB_TC_W_SCALE, &b0), h1 = to_fp16(w * JB_TC_W_SCALE - b0, &b1);
                 size_t off = (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
-                const uint16_t hs[3] = {h0, h1, h2};
-                for (int s = 0; s < 3; ++s) memcpy(out + ((size_t)t * 3 + s) * 8192 + off, &hs[s], 2);
+                memcpy(out + ((size_t)t * 2 + 0) * 8192 + off, &h0, 2);
+                memcpy(out + ((size_t)t * 2 + 1) * 8192 + off, &h1, 2);
             }
             float band = (float)(0.5 - err_scale * P - 1e-6);
             tband[t][n] = nextafterf(band, 0.0f);

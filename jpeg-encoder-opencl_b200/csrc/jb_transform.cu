@@ -19,7 +19,7 @@
 // keeps the hot kernel free of the padding code (instruction-cache footprint).
 // Algorithmic HBM traffic: 3 B/px read + 2 B/sample written = 6 B/px (4:2:0) or
 // 9 B/px (4:4:4, replicated 4:2:0).
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "jb_pixels.cuh"
 
@@ -442,18 +442,19 @@ __global__ void __launch_bounds__(64) k_transform_edge(const __grid_constant__ T
 // ================================================================ tensor-core variant ==
 // 4:2:0 only.  The block transform (FDCT + quantiser scale + zigzag) is one 64x64 contraction
 // per block: D[128 blocks][64 coefficients] = A[128 blocks][64 samples] x W^T on the 5th-gen
-// tensor cores (tcgen05.mma, kind::f16, bf16 operands, fp32 accumulators in TMEM).  The 8-bit
-// level-shifted samples are exact in bf16; W is split into hi+mid+lo bf16 matrices (24
-// mantissa bits), so one tile costs 3 x 4 MMAs of M128 N64 K16.  A group of 128 threads owns
+// tensor cores (tcgen05.mma, kind::f16, fp16 operands, fp32 accumulators in TMEM).  The 8-bit
+// level-shifted samples are exact in fp16; W (times 2^10) is split into hi+lo fp16 matrices (22
+// significand bits), so one tile costs 2 x 4 MMAs of M128 N64 K16.  A group of 128 threads owns
 // one M=128 tile: thread i writes the 64 samples of its block as row i of the A tile (one
 // 128-bit store per image row, 128-byte swizzle), so no register array of samples exists and
 // the row loop stays rolled (small code: no instruction-cache pressure).  After the MMAs the
 // thread reads row i of D back (tcgen05.ld 32x32b.x64): its own 64 scaled coefficients, already
 // in zigzag order, for rounding, near-tie flagging and packing as in the FMA kernel.
 constexpr int TC_GROUPS = 4;                       // 128-thread groups (M tiles) per CTA, one CTA per SM
-constexpr int TC_B_BYTES = 6 * 8192;               // [table][split] 64x64 bf16
+constexpr int TC_TMEM_COLS = 512;                  // 2 accumulators x 64 columns per group, power of two
+constexpr int TC_B_BYTES = 4 * 8192;               // [table][split] 64x64 fp16
 constexpr int TC_TILE_BYTES = 128 * 128;           // one A tile
-constexpr int TC_SMEM = TC_B_BYTES + TC_GROUPS * 2 * TC_TILE_BYTES + 1024;
+constexpr int TC_SMEM = TC_B_BYTES + TC_GROUPS * 3 * TC_TILE_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -496,8 +497,8 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint32_t bf16x2(int lo, int hi) {  // two small integers -> packed bf16 (exact)
-    __nv_bfloat162 v = __floats2bfloat162_rn((float)lo, (float)hi);
+__device__ __forceinline__ uint32_t bf16x2(int lo, int hi) {  // two small integers -> packed fp16 (exact)
+    __half2 v = __floats2half2_rn((float)lo, (float)hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -513,12 +514,13 @@ __device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const Tr
         for (int e = 0; e < 2; ++e) {
             const int k = 2 * j + e;
             float x = __uint_as_float(t[k]);
+            const float inv = (float)(1.0 / JB_TC_W_SCALE);
             if (k == 0 && a.qc.dc_exact) {
-                // x ~ S/(8q): recover the exact integer sample sum S, then the integer DC rule
-                b[e] = quantize_dc<TAB>(x * (float)a.qc.dc_d[TAB], a);
+                // x ~ 2^10 S/(8q): recover the exact integer sample sum S, then the integer DC rule
+                b[e] = quantize_dc<TAB>(x * (inv * (float)a.qc.dc_d[TAB]), a);
             } else {
-                float r = x + JB_ROUND_MAGIC, ri = r - JB_ROUND_MAGIC;
-                bool tie = fabsf(x - ri) > a.tband[TAB][k];
+                float r = jb_fmaf(x, inv, JB_ROUND_MAGIC), ri = r - JB_ROUND_MAGIC;
+                bool tie = fabsf(jb_fmaf(x, inv, -ri)) > a.tband[TAB][k];
                 if (tie) {
                     if (k < 32) tie_lo |= 1u << k; else tie_hi |= 1u << (k - 32);
                 }
@@ -532,54 +534,72 @@ __device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const Tr
         st[lane * 8 + (p ^ (lane & 7))] = make_uint4(wd[4 * p], wd[4 * p + 1], wd[4 * p + 2], wd[4 * p + 3]);
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
 template <int ALIGN>
 __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __grid_constant__ TransformArgs a) {
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
-    __shared__ __align__(8) uint64_t s_mbar[TC_GROUPS];
+    __shared__ __align__(8) uint64_t s_mbar[TC_GROUPS][2];
     __shared__ uint32_t s_tmem;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // keep the address arithmetic on the shared-space pointer (1024-byte alignment for the 128B swizzle)
+    uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, wg = gt >> 5, lane = tid & 31;
     uint8_t* sB = smem;
-    uint8_t* sAy = smem + TC_B_BYTES + g * 2 * TC_TILE_BYTES;  // luma tile, reused as the output staging tile
-    uint8_t* sAc = sAy + TC_TILE_BYTES;                        // chroma tile
+    uint8_t* tile0 = smem + TC_B_BYTES + g * 3 * TC_TILE_BYTES;  // luma rows 0-7   (then staging of Y00/Y01, Cb/Cr)
+    uint8_t* tile1 = tile0 + TC_TILE_BYTES;                      // luma rows 8-15  (then staging of Y10/Y11)
+    uint8_t* tileC = tile1 + TC_TILE_BYTES;                      // chroma
     // ---- one-time setup: W matrices, tensor memory, barriers ---------------------------------------
     for (int i = tid; i < TC_B_BYTES / 16; i += TC_GROUPS * 128)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.tc_mat) + i);
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "n"(TC_GROUPS * 64));
+                     "n"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (tid < TC_GROUPS) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[tid])));
+    if (tid < TC_GROUPS * 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[0][0]) + 8 * tid));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = s_tmem + (uint32_t)(g * 64);
-    const uint32_t tmem_ld = tmem_d + ((uint32_t)(wg * 32) << 16);
-    const uint32_t mbar = smem_u32(&s_mbar[g]);
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 17) | (8u << 24);  // f32 += bf16 x bf16, N=64, M=128
-    uint32_t phase = 0;
-    uint4* st = reinterpret_cast<uint4*>(sAy) + wg * 256;  // this warp's 32 rows of the tile = its staging tile
+    const uint32_t tmem_d0 = s_tmem + (uint32_t)(g * 128), tmem_d1 = tmem_d0 + 64;  // two accumulators per group
+    const uint32_t lane_off = (uint32_t)(wg * 32) << 16;
+    const uint32_t mbar0 = smem_u32(&s_mbar[g][0]), mbar1 = smem_u32(&s_mbar[g][1]);
+    const uint32_t idesc = (1u << 4) | (8u << 17) | (8u << 24);  // f32 += fp16 x fp16 (formats 0), N=64, M=128
+    uint32_t phase0 = 0, phase1 = 0;
     uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
     const int half = lane & 1;
-    const uint32_t row_sw = (uint32_t)(gt & 7);           // swizzle key of this thread's A row
     const uint32_t units_per_frame = (uint32_t)a.units_per_row * (uint32_t)a.fast_mcuy;
     const uint32_t groups_total = gridDim.x * TC_GROUPS;
+    // shared addresses of this thread's A rows: own row (luma), and the rows that take its chroma
+    const uint32_t sw_own = (uint32_t)(gt & 7);
+    const uint32_t a0_row = smem_u32(tile0) + gt * 128, a1_row = smem_u32(tile1) + gt * 128;
+    const int row_cb = gt & ~1, row_cr = gt | 1;
+    const uint32_t ac_cb = smem_u32(tileC) + row_cb * 128 + half * 8, ac_cr = smem_u32(tileC) + row_cr * 128 + half * 8;
+    const uint32_t sw_cb = (uint32_t)(row_cb & 7), sw_cr = (uint32_t)(row_cr & 7);
 
-    // issue the 12 MMAs of one tile (one thread), completion arrives on the group's mbarrier
-    auto issue = [&](const uint8_t* tile, int tab) {
+    // the 8 MMAs of one tile (issued by one thread); completion arrives on `mbar`
+    auto issue = [&](const uint8_t* tile, int tab, uint32_t tmem_d, uint32_t mbar) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint64_t da = umma_desc(smem_u32(tile));
 #pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3) {
-            uint64_t db = umma_desc(smem_u32(sB + (tab * 3 + s3) * 8192));
+        for (int s2 = 0; s2 < 2; ++s2) {
+            uint64_t db = umma_desc(smem_u32(sB + (tab * 2 + s2) * 8192));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s3 | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
     };
-    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    // writes of this thread to the tiles become visible to the tensor core, all threads of the group arrive
+    auto publish = [&]() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    };
 
     for (uint32_t base = (blockIdx.x * TC_GROUPS + g) * 4; base < a.total_units; base += groups_total * 4) {
         const bool active = base + wg < a.total_units;  // every warp of the group runs the same control flow
@@ -594,81 +614,85 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         const int m = valid ? lane >> 1 : max(mcus_valid - 1, 0);
         const uint32_t gb0 = (uint32_t)(mcu_g0 + m) * 6u;
         const uint8_t* col0 = im.base + (size_t)((mcu_x0 + m) * 16 + half * 8) * 3;
-        // A-tile rows that receive this lane's chroma: Cb -> row of the even lane, Cr -> row of the odd lane
-        const int row_cb = gt & ~1, row_cr = gt | 1;
 
+        // colour-convert 8 image rows (4 row pairs) into luma tile `arow` and chroma rows crow0..crow0+3
+        auto convert_half = [&](int h, uint32_t arow) {
+            // software pipeline: the loads of row pair rp+1 are in flight while pair rp is converted
+            uint32_t n0[6], n1[6];
+            const int ybase = my * 16 + h * 8;
+            load24<ALIGN>(col0 + (size_t)mirror(ybase, im.H) * im.pitch, n0);
+            load24<ALIGN>(col0 + (size_t)mirror(ybase + 1, im.H) * im.pitch, n1);
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            uint32_t pb[4], pr[4];
-#pragma unroll 1
-            for (int r = 0; r < 8; ++r) {
-                uint32_t w[6];
-                load24<ALIGN>(col0 + (size_t)mirror(my * 16 + h * 8 + r, im.H) * im.pitch, w);
-                Row8 o;
-                csc_row8(w, im.ydown, o);
-                uint4 ys = make_uint4(bf16x2(o.y[0], o.y[1]), bf16x2(o.y[2], o.y[3]), bf16x2(o.y[4], o.y[5]),
-                                      bf16x2(o.y[6], o.y[7]));
-                *reinterpret_cast<uint4*>(sAy + gt * 128 + (((uint32_t)r ^ row_sw) << 4)) = ys;
-                uint32_t sb[4], sr[4];
+            for (int rp = 0; rp < 4; ++rp) {
+                uint32_t w0[6], w1[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    w0[j] = n0[j];
+                    w1[j] = n1[j];
+                }
+                {
+                    const int yn = min(ybase + 2 * rp + 2, my * 16 + 15);  // last iteration: harmless re-load
+                    load24<ALIGN>(col0 + (size_t)mirror(yn, im.H) * im.pitch, n0);
+                    load24<ALIGN>(col0 + (size_t)mirror(min(yn + 1, my * 16 + 15), im.H) * im.pitch, n1);
+                }
+                Row8 o0, o1;
+                csc_row8(w0, im.ydown, o0);
+                csc_row8(w1, im.ydown, o1);
+                sts128(arow + (((uint32_t)(2 * rp) ^ sw_own) << 4),
+                       make_uint4(bf16x2(o0.y[0], o0.y[1]), bf16x2(o0.y[2], o0.y[3]), bf16x2(o0.y[4], o0.y[5]),
+                                  bf16x2(o0.y[6], o0.y[7])));
+                sts128(arow + (((uint32_t)(2 * rp + 1) ^ sw_own) << 4),
+                       make_uint4(bf16x2(o1.y[0], o1.y[1]), bf16x2(o1.y[2], o1.y[3]), bf16x2(o1.y[4], o1.y[5]),
+                                  bf16x2(o1.y[6], o1.y[7])));
+                int cb[4], cr[4];  // utils.cpp:126-127: truncated mean of the 2x2 cell, then level shift
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    sb[c] = (o.cb[2 * c] >> 24) + (o.cb[2 * c + 1] >> 24);
-                    sr[c] = (o.cr[2 * c] >> 24) + (o.cr[2 * c + 1] >> 24);
+                    cb[c] = (int)(((o0.cb[2 * c] >> 24) + (o0.cb[2 * c + 1] >> 24) + (o1.cb[2 * c] >> 24) + (o1.cb[2 * c + 1] >> 24)) >> 2) - 128;
+                    cr[c] = (int)(((o0.cr[2 * c] >> 24) + (o0.cr[2 * c + 1] >> 24) + (o1.cr[2 * c] >> 24) + (o1.cr[2 * c + 1] >> 24)) >> 2) - 128;
                 }
-                if (r & 1) {  // utils.cpp:126-127: truncated mean of the 2x2 cell, then level shift
-                    const uint32_t crow = (uint32_t)(h * 4 + (r >> 1));  // chroma row = K chunk
-                    uint2 vb = make_uint2(bf16x2((int)((pb[0] + sb[0]) >> 2) - 128, (int)((pb[1] + sb[1]) >> 2) - 128),
-                                          bf16x2((int)((pb[2] + sb[2]) >> 2) - 128, (int)((pb[3] + sb[3]) >> 2) - 128));
-                    uint2 vr = make_uint2(bf16x2((int)((pr[0] + sr[0]) >> 2) - 128, (int)((pr[1] + sr[1]) >> 2) - 128),
-                                          bf16x2((int)((pr[2] + sr[2]) >> 2) - 128, (int)((pr[3] + sr[3]) >> 2) - 128));
-                    *reinterpret_cast<uint2*>(sAc + row_cb * 128 + ((crow ^ (uint32_t)(row_cb & 7)) << 4) + half * 8) = vb;
-                    *reinterpret_cast<uint2*>(sAc + row_cr * 128 + ((crow ^ (uint32_t)(row_cr & 7)) << 4) + half * 8) = vr;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        pb[c] = sb[c];
-                        pr[c] = sr[c];
-                    }
-                }
+                const uint32_t crow = (uint32_t)(h * 4 + rp);  // chroma row = K chunk of the chroma tile
+                sts64(ac_cb + ((crow ^ sw_cb) << 4), make_uint2(bf16x2(cb[0], cb[1]), bf16x2(cb[2], cb[3])));
+                sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(bf16x2(cr[0], cr[1]), bf16x2(cr[2], cr[3])));
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            group_sync();
-            if (gt == 0) issue(sAy, 0);
-            mbar_wait(mbar, phase);
-            phase ^= 1;
+        };
+        // read this thread's row of the accumulator, round / flag / pack, stage in `tile`, store blocks blk, blk+1
+        auto finish = [&](uint32_t tmem_d, uint8_t* tile, int tab, int blk) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t t[64];
-            tmem_ld64(tmem_ld, t);
+            tmem_ld64(tmem_d + lane_off, t);
+            uint4* st = reinterpret_cast<uint4*>(tile) + wg * 256;  // this warp's 32 rows of the tile
             uint32_t tl = 0, th = 0;
-            tc_quant_stage<0>(t, a, st, lane, tl, th);
-            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 2 * h + half, tl, th);
+            if (tab == 0)
+                tc_quant_stage<0>(t, a, st, lane, tl, th);
+            else
+                tc_quant_stage<1>(t, a, st, lane, tl, th);
+            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + blk + half, tl, th);
             __syncwarp();
-            copy_out<6>(st, coef4, mcu_g0, mcus_valid, 2 * h, lane);
+            copy_out<6>(st, coef4, mcu_g0, mcus_valid, blk, lane);
             __syncwarp();
-        }
-        // chroma tile (complete after both halves)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        group_sync();
-        if (gt == 0) issue(sAc, 1);
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
-            uint32_t t[64];
-            tmem_ld64(tmem_ld, t);
-            uint32_t tl = 0, th = 0;
-            tc_quant_stage<1>(t, a, st, lane, tl, th);
-            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 4 + half, tl, th);
-            __syncwarp();
-            copy_out<6>(st, coef4, mcu_g0, mcus_valid, 4, lane);
-            __syncwarp();
-        }
+        };
+
+        convert_half(0, a0_row);
+        publish();
+        if (gt == 0) issue(tile0, 0, tmem_d0, mbar0);
+        convert_half(1, a1_row);
+        publish();
+        if (gt == 0) issue(tile1, 0, tmem_d1, mbar1);
+        mbar_wait(mbar0, phase0);
+        phase0 ^= 1;
+        finish(tmem_d0, tile0, 0, 0);   // Y00 / Y01
+        publish();                      // every thread has read accumulator 0: it can take the chroma tile
+        if (gt == 0) issue(tileC, 1, tmem_d0, mbar0);
+        mbar_wait(mbar1, phase1);
+        phase1 ^= 1;
+        finish(tmem_d1, tile1, 0, 2);   // Y10 / Y11
+        mbar_wait(mbar0, phase0);
+        phase0 ^= 1;
+        finish(tmem_d0, tile0, 1, 4);   // Cb / Cr
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_GROUPS * 64));
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_TMEM_COLS));
 }
 
 template <int SUB, int ALIGN>
