@@ -1,0 +1,88 @@
+"""Turn the round's ncu captures (gpurun_out/) into the committed summaries under profiles/.
+
+  python profiles/summarize.py r01
+reads  gpurun_out/<r>_launches.csv        (ncu --metrics gpu__time_duration.sum launch list)
+       gpurun_out/<r>_prof_full.ncu-rep   (ncu --set full of the step's main kernels)
+       gpurun_out/<r>_prof_tc.ncu-rep     (ncu --set full of the tensor-core transform variant)
+writes profiles/<r>_launches.md, profiles/<r>_kernels.md, profiles/<r>_transform_ncu_summary.json
+"""
+import csv, json, os, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+OUT = os.path.join(ROOT, "gpurun_out")
+
+def launches():
+    rows = [r for r in csv.reader(open(os.path.join(OUT, f"{R}_launches.csv"))) if len(r) > 5]
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[hi]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    vals = [(r[ki], float(r[vi].replace(",", ""))) for r in rows[hi + 1:] if len(r) > vi]
+    starts = [i for i, (k, _) in enumerate(vals) if "k_transform" in k]
+    step = vals[starts[-2]:starts[-1]]  # one complete step
+    tot = sum(v for _, v in step)
+    lines = ["# Launch list of one bench step (512 x 1920x1080, 4:2:0, q75), ncu gpu__time_duration.sum",
+             "", "Cold-cache, serialised launches (compare shares, not absolutes).", "",
+             "| kernel | us | share |", "|---|---:|---:|"]
+    for k, v in step:
+        lines.append(f"| `{k.split('(')[0]}` | {v/1000:.1f} | {100*v/tot:.1f} % |")
+    lines.append(f"| **total** | {tot/1000:.1f} | |")
+    open(os.path.join(ROOT, "profiles", f"{R}_launches.md"), "w").write("\n".join(lines) + "\n")
+    return step
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+        ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
+        ("launch__registers_per_thread", "regs/thread"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+        ("smsp__inst_executed.sum", "warp instructions"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
+        ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+        ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe %"),
+        ("sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "tensor (hmma) pipe %"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard"),
+        ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe_throttle"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait")]
+
+def kernels():
+    md = ["# ncu --set full summaries (round 1)", "",
+          "Workload: `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline` (512 x 1920x1080, 4:2:0, q75).",
+          "Numbers taken under the profiler are diagnostics only; bench values come from CUDA events.", ""]
+    summary = {}
+    for rep in (f"{R}_prof_full.ncu-rep", f"{R}_prof_tc.ncu-rep"):
+        if not os.path.exists(os.path.join(OUT, rep)):
+            continue
+        hdr, units, rows = raw(rep)
+        ki = hdr.index("Kernel Name")
+        for r in rows:
+            name = r[ki].split("(")[0]
+            md += [f"## `{name}`  ({rep})", "", "| metric | value |", "|---|---:|"]
+            rec = {}
+            for key, label in WANT:
+                if key in hdr:
+                    v = r[hdr.index(key)]; u = units[hdr.index(key)]
+                    md.append(f"| {label} | {v} {u} |")
+                    rec[label] = (v, u)
+            md.append("")
+            summary[name] = rec
+    open(os.path.join(ROOT, "profiles", f"{R}_kernels.md"), "w").write("\n".join(md) + "\n")
+    return summary
+
+def to_bytes(v, u):
+    f = float(v.replace(",", ""))
+    return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+
+if __name__ == "__main__":
+    step = launches()
+    summ = kernels()
+    t = next(v for k, v in summ.items() if k.startswith("void k_transform<") or k.startswith("k_transform<"))
+    traffic = to_bytes(*t["dram read"]) + to_bytes(*t["dram write"])
+    json.dump({"round": R, "workload": "batch1080p", "frames": 512, "kernel": "k_transform<2, 8>",
+               "dram_bytes_per_launch": int(traffic), "dram_read": t["dram read"], "dram_write": t["dram write"],
+               "duration_under_ncu": t["duration"], "source": f"gpurun_out/{R}_prof_full.ncu-rep (ncu --set full --clock-control none)"},
+              open(os.path.join(ROOT, "profiles", f"{R}_transform_ncu_summary.json"), "w"), indent=1)
+    print("ok", traffic)
