@@ -146,6 +146,7 @@ size_t plan_bytes(const Plan& p) {
     add(p.n_tiles * 256 * 4);              // blk_len
     add(p.n_tiles * 256 * 16);             // slots
     add(p.n_tiles * 256 * 4);              // long_list
+    add(((p.n_tiles + p.n_int_total + p.chunks_cap / 256) / 4096 + 8) * 2 * 8);  // scan_tmp
     add(p.n_tiles * 4);
     add((p.n_tiles + 1) * 8);
     add(p.n_int_total * 4);
@@ -179,6 +180,7 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.w.blk_len = carve<uint32_t>(a, p.n_tiles * 256);
     s.w.slots = carve<uint4>(a, p.n_tiles * 256);
     s.w.long_list = carve<uint32_t>(a, p.n_tiles * 256);
+    s.w.scan_tmp = carve<uint64_t>(a, ((p.n_tiles + p.n_int_total + p.chunks_cap / 256) / 4096 + 8) * 2);
     s.w.tile_bits = carve<uint32_t>(a, p.n_tiles);
     s.w.tile_base = carve<uint64_t>(a, p.n_tiles + 1);
     s.w.int_slot = carve<uint32_t>(a, p.n_int_total);

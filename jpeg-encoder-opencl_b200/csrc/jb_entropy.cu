@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
 }
 
 // Single-CTA exclusive scan: out[i] = sum in[0..i), out[n] = total.
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t n,
+template <class T>
+__global__ void __launch_bounds__(1024) k_scan(const T* __restrict__ in, uint64_t* __restrict__ out, uint32_t n,
                                                const uint32_t* n_dev) {
     __shared__ uint64_t s_warp[32];
     __shared__ uint64_t s_carry;
@@ -290,10 +291,10 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ in, 
     __syncthreads();
     for (uint32_t base = 0; base < n; base += 4096) {
         uint32_t i0 = base + threadIdx.x * 4;
-        uint32_t v[4];
+        uint64_t v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = i0 + j < n ? in[i0 + j] : 0u;
-        uint64_t sum = (uint64_t)v[0] + v[1] + v[2] + v[3], inc = sum;
+        for (int j = 0; j < 4; ++j) v[j] = i0 + j < n ? (uint64_t)in[i0 + j] : 0ull;
+        uint64_t sum = v[0] + v[1] + v[2] + v[3], inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint64_t y = __shfl_up_sync(0xffffffffu, inc, o);
@@ -318,6 +319,81 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ in, 
         __syncthreads();
     }
     if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+// Device-wide exclusive scan for long arrays: per-chunk sums (k_scan_partial), single-CTA scan of
+// the chunk sums (k_scan<uint64_t>), then every chunk rescans itself from its base (k_scan_apply).
+constexpr uint32_t SCAN_CHUNK = 4096;
+
+__device__ __forceinline__ uint64_t cta_scan_256_u64(uint64_t x, uint64_t* s_warp, uint64_t& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint64_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint64_t t = s_warp[i];
+        if (i < wid) base += t;
+        tot += t;
+    }
+    __syncthreads();
+    total = tot;
+    return base + inc - x;
+}
+
+__global__ void __launch_bounds__(256) k_scan_partial(const uint32_t* __restrict__ in, uint64_t* __restrict__ partial,
+                                                      uint32_t n, const uint32_t* n_dev) {
+    __shared__ uint64_t s_warp[8];
+    if (n_dev) n = *n_dev;
+    const uint32_t i0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * 16;
+    uint64_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sum += i0 + j < n ? (uint64_t)in[i0 + j] : 0ull;
+    uint64_t total;
+    cta_scan_256_u64(sum, s_warp, total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                    const uint64_t* __restrict__ chunk_base, uint32_t n,
+                                                    const uint32_t* n_dev) {
+    __shared__ uint64_t s_warp[8];
+    if (n_dev) n = *n_dev;
+    const uint32_t i0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * 16;
+    uint32_t v[16];
+    uint64_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        v[j] = i0 + j < n ? in[i0 + j] : 0u;
+        sum += v[j];
+    }
+    uint64_t total;
+    uint64_t ex = chunk_base[blockIdx.x] + cta_scan_256_u64(sum, s_warp, total);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (i0 + j <= n) out[i0 + j] = ex;  // index n receives the grand total
+        ex += v[j];
+    }
+}
+
+// out[0..n] = exclusive scan of in[0..n); n is known on the host or read from *n_dev (then n_cap bounds it)
+static int scan_u32(const uint32_t* in, uint64_t* out, uint32_t n_cap, const uint32_t* n_dev, uint64_t* tmp,
+                    cudaStream_t s) {
+    if (n_cap <= 4 * SCAN_CHUNK) {
+        k_scan<uint32_t><<<1, 1024, 0, s>>>(in, out, n_dev ? 0u : n_cap, n_dev);
+        return 1;
+    }
+    const uint32_t chunks = n_cap / SCAN_CHUNK + 1;  // covers index n itself
+    k_scan_partial<<<chunks, 256, 0, s>>>(in, tmp, n_dev ? 0u : n_cap, n_dev);
+    k_scan<uint64_t><<<1, 1024, 0, s>>>(tmp, tmp + chunks + 1, chunks, nullptr);
+    k_scan_apply<<<chunks, 256, 0, s>>>(in, out, tmp + chunks + 1, n_dev ? 0u : n_cap, n_dev);
+    return 3;
 }
 
 // bit offset (inside the whole batch) of block x; x may equal n_blocks
@@ -574,22 +650,23 @@ int launch_entropy(const EntropyArgs& a, cudaStream_t s) {
     uint32_t n_tiles = (a.n_blocks + TILE - 1) / TILE;
     uint32_t gi = (a.n_int_total + 255) / 256;
     k_encode<<<n_tiles, TILE, 0, s>>>(a);
-    k_scan<<<1, 1024, 0, s>>>(a.w.tile_bits, a.w.tile_base, n_tiles, nullptr);
+    launches += scan_u32(a.w.tile_bits, a.w.tile_base, n_tiles, nullptr, a.w.scan_tmp, s);
     k_intervals<<<gi, 256, 0, s>>>(a);
-    k_scan<<<1, 1024, 0, s>>>(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr);
+    launches += scan_u32(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr, a.w.scan_tmp, s);
     k_zero<<<592, 256, 0, s>>>(a);
     k_pack<<<n_tiles, TILE, 0, s>>>(a);
     k_pack_long<<<296, TILE, 0, s>>>(a);
-    launches += 7;
+    launches += 5;
     if (a.fr.raw_bits) return launches;
     k_ff_count<<<1184, TILE, 0, s>>>(a);
-    k_scan<<<1, 1024, 0, s>>>(a.w.ff_tile, a.w.ff_tile_base, 0, a.w.n_ff_tiles);
+    launches += scan_u32(a.w.ff_tile, a.w.ff_tile_base, (uint32_t)(a.w.ubuf_cap / 16 / TILE + 1), a.w.n_ff_tiles,
+                         a.w.scan_tmp, s);
     k_int_out<<<gi, 256, 0, s>>>(a);
-    k_scan<<<1, 1024, 0, s>>>(a.w.int_osize, a.w.int_obase, a.n_int_total, nullptr);
+    launches += scan_u32(a.w.int_osize, a.w.int_obase, a.n_int_total, nullptr, a.w.scan_tmp, s);
     uint32_t gf = ((uint32_t)a.n_frames + 255) / 256;
     k_finalize<<<gf, 256, 0, s>>>(a);
     k_stuff<<<1184, TILE, 0, s>>>(a);
-    launches += 6;
+    launches += 4;
     return launches;
 }
 

@@ -118,6 +118,7 @@ struct EntropyWork {
     uint32_t* n_ff_tiles;   // device scalar
     uint32_t* int_osize;    // [n_int_total]
     uint64_t* int_obase;    // [n_int_total + 1]
+    uint64_t* scan_tmp;     // scratch of the multi-CTA scans
     uint64_t* status;       // [0] error bits, [1] required ubuf bytes, [2] required out bytes, [3] total bits
 };
 
