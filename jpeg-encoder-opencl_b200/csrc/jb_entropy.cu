@@ -63,12 +63,17 @@ struct BlockInfo {
     bool last_in_interval;
 };
 
+// x / d for x, d < 2^26 with the host-computed magic m = ceil(2^52 / d): exact because x * d < 2^52
+__device__ __forceinline__ uint32_t div_magic(uint32_t x, uint64_t m) {
+    return (uint32_t)__umul64hi((uint64_t)x << 12, m);
+}
+
 __device__ __forceinline__ BlockInfo block_info(const EntropyArgs& a, uint32_t b) {
     BlockInfo bi;
     const uint32_t bpm = (uint32_t)a.g.bpm, bpf = (uint32_t)a.g.n_mcu * bpm, ri = (uint32_t)a.g.ri;
-    uint32_t f = b / bpf, rb = b - f * bpf;
-    uint32_t mcu = rb / bpm, j = rb - mcu * bpm;
-    uint32_t k = mcu / ri;
+    uint32_t f = div_magic(b, a.m_bpf), rb = b - f * bpf;
+    uint32_t mcu = __umulhi(rb, 0xAAAAAAABu) >> (bpm == 3 ? 1 : 2), j = rb - mcu * bpm;  // bpm is 3 or 6
+    uint32_t k = div_magic(mcu, a.m_ri);
     bool first = mcu - k * ri == 0;  // first MCU of its restart interval: predictors are 0
     bi.interval = f * (uint32_t)a.g.n_int + k;
     uint32_t mcu_end = min((k + 1) * ri, (uint32_t)a.g.n_mcu);
@@ -157,30 +162,41 @@ struct SlotSink {
 };
 
 // The block as HuffmanEncoder codes it (utils.cpp:667-694), visiting only the non-zero AC
-// coefficients: mask bit k = coefficient k != 0, value(k) fetches coefficient k.
-template <class Sink, class Fetch>
+// coefficients: mask bit k = coefficient k != 0, value(k) fetches coefficient k.  s_small (may
+// be null) maps (run <= 15, |v| <= 15) straight to code + value bits: the common case is one
+// look-up instead of category, value bits and code assembly.
+template <bool SMALL, class Sink, class Fetch>
 __device__ __forceinline__ void encode_sparse(uint64_t mask, Fetch value, int dc_diff, const uint32_t* s_ac,
-                                              const uint32_t* s_dc, bool always_eob, Sink& s) {
+                                              const uint32_t* s_dc, const uint32_t* s_small, bool always_eob, Sink& s) {
     int cat;
     uint32_t vb;
     cat_bits(dc_diff, cat, vb);
     uint32_t e = s_dc[cat];
     s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
-    uint64_t m = mask & ~1ull;
     int cur = 1;  // next AC position to account for
-    while (m) {
-        int pos = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        int run = pos - cur;
-        cur = pos + 1;
-        while (run >= 16) {  // ZRL, utils.cpp:592-597
-            uint32_t z = s_ac[0xF0];
-            s.put(z >> 5, (int)(z & 31u));
-            run -= 16;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {  // positions 1..31, then 32..63: 32-bit mask arithmetic
+        uint32_t m = half ? (uint32_t)(mask >> 32) : ((uint32_t)mask & ~1u);
+        while (m) {
+            int pos = __ffs((int)m) - 1 + 32 * half;
+            m &= m - 1;
+            int run = pos - cur;
+            cur = pos + 1;
+            int v = value(pos);
+            if (SMALL && run < 16 && (uint32_t)(v + 15) <= 30u) {
+                e = s_small[(run << 5) | (v & 31)];
+                s.put(e >> 5, (int)(e & 31u));
+                continue;
+            }
+            while (run >= 16) {  // ZRL, utils.cpp:592-597
+                uint32_t z = s_ac[0xF0];
+                s.put(z >> 5, (int)(z & 31u));
+                run -= 16;
+            }
+            cat_bits(v, cat, vb);
+            e = s_ac[(run << 4) | cat];
+            s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
         }
-        cat_bits(value(pos), cat, vb);
-        e = s_ac[(run << 4) | cat];
-        s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
     }
     if (cur < 64 || always_eob) {  // EOB, utils.cpp:607-608 (Q3 when always_eob)
         e = s_ac[0];
@@ -197,6 +213,7 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
     __shared__ __align__(16) uint32_t s_slot[TILE * 4];
     __shared__ uint64_t s_mask[TILE];
     __shared__ uint32_t s_ac[2][256], s_dc[2][16], s_warp[8];
+    __shared__ uint32_t s_small[2][512];
     __shared__ uint32_t s_len[TILE];
     __shared__ uint32_t s_hist[64], s_start[64];
     __shared__ uint16_t s_perm[TILE];
@@ -209,6 +226,8 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
         if (g < n_here) s_coef[blk * 8 + (pc ^ (blk & 7))] = __ldg(src + g);
     }
     if (t < 64) s_hist[t] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) (&s_small[0][0])[i * TILE + t] = (&a.huff->small[0][0])[i * TILE + t];
     load_tables(a, s_ac, s_dc);  // ends with __syncthreads()
     // ---- non-zero mask of this thread's block, then a counting sort of the tile's blocks by
     // their number of non-zero AC coefficients: the walk below costs one loop iteration per
@@ -258,7 +277,7 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
         }
         SlotSink s;
         s.init(s_slot + k * 4);
-        encode_sparse(s_mask[k], value, value(0) - pred, s_ac[tab], s_dc[tab], a.always_eob != 0, s);
+        encode_sparse<true>(s_mask[k], value, value(0) - pred, s_ac[tab], s_dc[tab], s_small[tab], a.always_eob != 0, s);
         s.finish();
         s_len[k] = s.bits;
         if (s.bits > 128) {  // too long for a slot: k_pack_long re-walks it
@@ -495,7 +514,7 @@ __global__ void __launch_bounds__(TILE) k_pack_long(const __grid_constant__ Entr
         const int tab = bi.comp ? 1 : 0;
         BitSink s;
         s.init(a.w.ubuf, pos);
-        encode_sparse(mask, value, (int)c[0] - pred, s_ac[tab], s_dc[tab], a.always_eob != 0, s);
+        encode_sparse<false>(mask, value, (int)c[0] - pred, s_ac[tab], s_dc[tab], nullptr, a.always_eob != 0, s);
         s.finish();
     }
 }
@@ -644,8 +663,13 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
     }
 }
 
-int launch_entropy(const EntropyArgs& a, cudaStream_t s) {
-    if (a.n_blocks == 0) return 0;
+static uint64_t magic52(uint64_t d) { return ((1ull << 52) + d - 1) / d; }
+
+int launch_entropy(const EntropyArgs& a_in, cudaStream_t s) {
+    if (a_in.n_blocks == 0) return 0;
+    EntropyArgs a = a_in;
+    a.m_bpf = magic52((uint64_t)a.g.n_mcu * (uint64_t)a.g.bpm);
+    a.m_ri = magic52((uint64_t)a.g.ri);
     int launches = 0;
     uint32_t n_tiles = (a.n_blocks + TILE - 1) / TILE;
     uint32_t gi = (a.n_int_total + 255) / 256;

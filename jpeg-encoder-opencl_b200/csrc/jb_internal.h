@@ -87,6 +87,7 @@ struct FixupArgs {
 struct HuffDev {
     uint32_t ac[2][256];  // [luma/chroma][run<<4 | cat]
     uint32_t dc[2][16];   // [luma/chroma][cat]
+    uint32_t small[2][512];  // [luma/chroma][run<<5 | (v & 31)], |v| <= 15: (code + value bits) << 5 | total length
 };
 
 // How entropy segments are framed in the output.
@@ -129,6 +130,7 @@ struct EntropyArgs {
     uint32_t n_blocks;     // total blocks in the batch
     uint32_t n_int_total;  // n_frames * g.n_int
     const HuffDev* huff;
+    uint64_t m_bpf, m_ri;  // ceil(2^52 / blocks per frame), ceil(2^52 / restart interval): see div_magic
     uint32_t always_eob;
     Framing fr;
     EntropyWork w;

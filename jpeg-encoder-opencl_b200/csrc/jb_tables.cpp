@@ -80,6 +80,17 @@ void build_huff(bool typo, HuffDev* out) {
             out->ac[0][(3 << 4) | cat] = (code << 5) | 17u;
         }
     }
+    // run/size code and value bits of small coefficients in one entry (utils.cpp:623-653, 683-691)
+    for (int t = 0; t < 2; ++t)
+        for (int run = 0; run < 16; ++run)
+            for (int v = -15; v <= 15; ++v) {
+                if (v == 0) continue;
+                int a = v < 0 ? -v : v, cat = 0;
+                while (a >> cat) ++cat;
+                uint32_t vb = (uint32_t)(v < 0 ? v + (1 << cat) - 1 : v);
+                uint32_t e = out->ac[t][(run << 4) | cat];
+                out->small[t][(run << 5) | (v & 31)] = ((((e >> 5) << cat) | vb) << 5) | ((e & 31u) + (uint32_t)cat);
+            }
 }
 
 // ---- worst-case error of the binary32 AAN transform -------------------------------
