@@ -19,6 +19,8 @@
 //   k_stuff     assemble the final bytes per 4 KB tile in shared memory (0x00 after 0xFF,
 //               markers, JFIF headers) and store them with coalesced 128-bit stores
 // Bit order is MSB first; the unstuffed buffer is addressed as big-endian words.
+#include <cuda_fp16.h>
+
 #include "jb_internal.h"
 
 namespace jb {
@@ -125,9 +127,19 @@ __device__ __forceinline__ uint32_t cta_scan_256(uint32_t x, uint32_t* s_warp, u
 }
 
 // ---- sparse block walk ---------------------------------------------------------------
-// 2 bits per 32-bit word: which of its two int16 halves are non-zero
-__device__ __forceinline__ uint32_t nz2(uint32_t w) {
-    return ((w & 0xFFFFu) ? 1u : 0u) | ((w >> 16) ? 2u : 0u);
+// 0xFFFF in each half of the result whose int16 half of w is non-zero
+__device__ __forceinline__ uint32_t nz_flags(uint32_t w) {
+    const __half2 z = __half2half2(__ushort_as_half((unsigned short)0));
+    return __hneu2_mask(*reinterpret_cast<const __half2*>(&w), z);
+}
+// bits 0..15 of x -> even bits, bits 16..31 -> odd bits of the result
+__device__ __forceinline__ uint32_t interleave16(uint32_t x) {
+    uint32_t e = x & 0xFFFFu, o = x >> 16;
+    e = (e | (e << 8)) & 0x00FF00FFu; o = (o | (o << 8)) & 0x00FF00FFu;
+    e = (e | (e << 4)) & 0x0F0F0F0Fu; o = (o | (o << 4)) & 0x0F0F0F0Fu;
+    e = (e | (e << 2)) & 0x33333333u; o = (o | (o << 2)) & 0x33333333u;
+    e = (e | (e << 1)) & 0x55555555u; o = (o | (o << 1)) & 0x55555555u;
+    return e | (o << 1);
 }
 
 // Sink that keeps the first 128 bits of a block's code left-aligned in a 4-word slot (MSB
@@ -234,13 +246,22 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
     // non-zero, so warps made of similar blocks do not wait for their busiest lane.
     uint32_t cnt = 0;
     if (t < n_blk) {
-        uint64_t mask = 0;
+        // One half2 "not equal (unordered) to zero" compare flags both int16 halves of a word
+        // (every non-zero coefficient |c| <= 2047 is a non-zero, possibly subnormal or NaN,
+        // binary16 pattern); word j of a 16-word half drops its two flags at bits j and 16+j,
+        // and the even/odd bit planes are interleaved back into zigzag order afterwards.
+        uint32_t eo[2] = {0u, 0u};
 #pragma unroll
         for (int pc = 0; pc < 8; ++pc) {
-            uint4 q = s_coef[t * 8 + (pc ^ (t & 7))];
-            uint64_t m8 = nz2(q.x) | (nz2(q.y) << 2) | (nz2(q.z) << 4) | (nz2(q.w) << 6);
-            mask |= m8 << (8 * pc);
+            const uint4 q = s_coef[t * 8 + (pc ^ (t & 7))];
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = pc * 4 + i, jj = j & 15;
+                eo[j >> 4] |= nz_flags(w[i]) & ((1u << jj) | (1u << (16 + jj)));
+            }
         }
+        const uint64_t mask = (uint64_t)interleave16(eo[0]) | ((uint64_t)interleave16(eo[1]) << 32);
         s_mask[t] = mask;
         cnt = (uint32_t)__popcll(mask & ~1ull);
         atomicAdd(&s_hist[cnt], 1u);
