@@ -58,13 +58,7 @@ __device__ __forceinline__ void quant_stage(const float (&v)[64], const Transfor
     for (int j = 0; j < 32; ++j) {
         const int n0 = zz_nat(2 * j), n1 = zz_nat(2 * j + 1);
         bool t0, t1;
-        uint32_t b0;
-        if (j == 0 && a.qc.dc_exact) {
-            b0 = quantize_dc<TAB>(v[0], a);
-            t0 = false;
-        } else {
-            b0 = quantize_bits(v[n0], a.qc.mul[TAB][n0], a.qc.band[TAB][n0], t0);
-        }
+        uint32_t b0 = quantize_bits(v[n0], a.qc.mul[TAB][n0], a.qc.band[TAB][n0], t0);
         uint32_t b1 = quantize_bits(v[n1], a.qc.mul[TAB][n1], a.qc.band[TAB][n1], t1);
         if (j < 16) {
             if (t0) tie_lo |= 1u << (2 * j);
@@ -74,6 +68,10 @@ __device__ __forceinline__ void quant_stage(const float (&v)[64], const Transfor
             if (t1) tie_hi |= 1u << (2 * j - 31);
         }
         wd[j] = __byte_perm(b0, b1, 0x5410);
+    }
+    if (a.qc.dc_exact) {  // one uniform branch, outside the unrolled loop: DC in exact integer arithmetic
+        wd[0] = __byte_perm(quantize_dc<TAB>(v[0], a), wd[0], 0x7610);
+        tie_lo &= ~1u;
     }
 #pragma unroll
     for (int p = 0; p < 8; ++p)
@@ -507,6 +505,7 @@ template <int TAB>
 __device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const TransformArgs& a, uint4* st, int lane,
                                                uint32_t& tie_lo, uint32_t& tie_hi) {
     uint32_t wd[32];
+    const float inv = (float)(1.0 / JB_TC_W_SCALE);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         uint32_t b[2];
@@ -514,20 +513,20 @@ __device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const Tr
         for (int e = 0; e < 2; ++e) {
             const int k = 2 * j + e;
             float x = __uint_as_float(t[k]);
-            const float inv = (float)(1.0 / JB_TC_W_SCALE);
-            if (k == 0 && a.qc.dc_exact) {
-                // x ~ 2^10 S/(8q): recover the exact integer sample sum S, then the integer DC rule
-                b[e] = quantize_dc<TAB>(x * (inv * (float)a.qc.dc_d[TAB]), a);
-            } else {
-                float r = jb_fmaf(x, inv, JB_ROUND_MAGIC), ri = r - JB_ROUND_MAGIC;
-                bool tie = fabsf(jb_fmaf(x, inv, -ri)) > a.tband[TAB][k];
-                if (tie) {
-                    if (k < 32) tie_lo |= 1u << k; else tie_hi |= 1u << (k - 32);
-                }
-                b[e] = __float_as_uint(r);
+            float r = jb_fmaf(x, inv, JB_ROUND_MAGIC), ri = r - JB_ROUND_MAGIC;
+            bool tie = fabsf(jb_fmaf(x, inv, -ri)) > a.tband[TAB][k];
+            if (tie) {
+                if (k < 32) tie_lo |= 1u << k; else tie_hi |= 1u << (k - 32);
             }
+            b[e] = __float_as_uint(r);
         }
         wd[j] = __byte_perm(b[0], b[1], 0x5410);
+    }
+    if (a.qc.dc_exact) {  // one uniform branch, outside the unrolled loop
+        // t[0] ~ 2^10 S/(8q): recover the exact integer sample sum S, then the integer DC rule
+        uint32_t dc = quantize_dc<TAB>(__uint_as_float(t[0]) * (inv * (float)a.qc.dc_d[TAB]), a);
+        wd[0] = __byte_perm(dc, wd[0], 0x7610);
+        tie_lo &= ~1u;
     }
 #pragma unroll
     for (int p = 0; p < 8; ++p)
