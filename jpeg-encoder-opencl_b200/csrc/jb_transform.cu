@@ -452,7 +452,9 @@ constexpr int TC_GROUPS = 4;                       // 128-thread groups (M tiles
 constexpr int TC_TMEM_COLS = 512;                  // 2 accumulators x 64 columns per group, power of two
 constexpr int TC_B_BYTES = 4 * 8192;               // [table][split] 64x64 fp16
 constexpr int TC_TILE_BYTES = 128 * 128;           // one A tile
-constexpr int TC_SMEM = TC_B_BYTES + TC_GROUPS * 3 * TC_TILE_BYTES + 1024;
+constexpr int TC_ROW_BYTES = 16 * 16 * 3;          // one image row of a warp's unit (16 MCUs of RGB)
+constexpr int TC_RING_BYTES = 2 * 2 * 4 * TC_ROW_BYTES;  // raw-pixel ring of a group: [slot][row of the pair][warp]
+constexpr int TC_SMEM = TC_B_BYTES + TC_GROUPS * (2 * TC_TILE_BYTES + TC_RING_BYTES) + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -503,7 +505,7 @@ __device__ __forceinline__ uint32_t bf16x2(int lo, int hi) {  // two small integ
 // Round the 64 scaled coefficients t (zigzag order) of one block, flag near ties, pack, stage.
 template <int TAB>
 __device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const TransformArgs& a, uint4* st, int lane,
-                                               uint32_t& tie_lo, uint32_t& tie_hi) {
+                                               uint32_t& tie_lo, uint32_t& tie_hi, uint32_t wait_mbar, uint32_t wait_parity) {
     uint32_t wd[32];
     const float inv = (float)(1.0 / JB_TC_W_SCALE);
 #pragma unroll
@@ -528,6 +530,7 @@ __device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const Tr
         wd[0] = __byte_perm(dc, wd[0], 0x7610);
         tie_lo &= ~1u;
     }
+    if (wait_mbar) mbar_wait(wait_mbar, wait_parity);  // the staging area is still an MMA operand until then
 #pragma unroll
     for (int p = 0; p < 8; ++p)
         st[lane * 8 + (p ^ (lane & 7))] = make_uint4(wd[4 * p], wd[4 * p + 1], wd[4 * p + 2], wd[4 * p + 3]);
@@ -540,6 +543,44 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const uint8_t* src) {
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+
+// One warp's unit of 16 MCUs (a 256-pixel wide, 16-row strip of one frame).
+struct TcUnit {
+    const uint8_t* row0;  // first byte of the strip in image row 0
+    int y0;               // first image row
+    int bytes_valid;      // 48 per MCU that exists
+    size_t mcu_g0;        // global index of the first MCU
+};
+
+// Asynchronous copy of one 768-byte strip row into the ring.  16-byte aligned images are copied
+// warp-cooperatively (48 chunks of 16 bytes), others by each lane for itself (its own 24 bytes).
+template <int ALIGN>
+__device__ __forceinline__ void tc_async_row(uint32_t dst, const uint8_t* src, int lane, int bytes_valid) {
+    if (ALIGN == 16) {
+        const int o0 = lane * 16, o1 = 512 + lane * 16;
+        if (o0 < bytes_valid) cp_async<16>(dst + o0, src + o0);
+        if (lane < 16 && o1 < bytes_valid) cp_async<16>(dst + o1, src + o1);
+    } else {
+        const int o = lane * 24;
+        if (o < bytes_valid) {
+#pragma unroll
+            for (int j = 0; j < 24 / ALIGN; ++j) cp_async<ALIGN>(dst + o + j * ALIGN, src + o + j * ALIGN);
+        }
+    }
+}
+
 template <int ALIGN>
 __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __grid_constant__ TransformArgs a) {
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
@@ -549,9 +590,10 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, wg = gt >> 5, lane = tid & 31;
     uint8_t* sB = smem;
-    uint8_t* tile0 = smem + TC_B_BYTES + g * 3 * TC_TILE_BYTES;  // luma rows 0-7   (then staging of Y00/Y01, Cb/Cr)
-    uint8_t* tile1 = tile0 + TC_TILE_BYTES;                      // luma rows 8-15  (then staging of Y10/Y11)
-    uint8_t* tileC = tile1 + TC_TILE_BYTES;                      // chroma
+    uint8_t* tileA = smem + TC_B_BYTES + g * 2 * TC_TILE_BYTES;  // luma rows 0-7, then 8-15; staging between
+    uint8_t* tileC = tileA + TC_TILE_BYTES;                      // chroma
+    // ring of raw pixels: address of this warp's row `r` (0/1) of slot `sl` (0/1)
+    const uint32_t ring = smem_u32(smem + TC_B_BYTES + TC_GROUPS * 2 * TC_TILE_BYTES + g * TC_RING_BYTES) + wg * TC_ROW_BYTES;
     // ---- one-time setup: W matrices, tensor memory, barriers ---------------------------------------
     for (int i = tid; i < TC_B_BYTES / 16; i += TC_GROUPS * 128)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.tc_mat) + i);
@@ -573,10 +615,10 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
     const int half = lane & 1;
     const uint32_t units_per_frame = (uint32_t)a.units_per_row * (uint32_t)a.fast_mcuy;
-    const uint32_t groups_total = gridDim.x * TC_GROUPS;
+    const uint32_t stride = gridDim.x * TC_GROUPS * 4;
     // shared addresses of this thread's A rows: own row (luma), and the rows that take its chroma
     const uint32_t sw_own = (uint32_t)(gt & 7);
-    const uint32_t a0_row = smem_u32(tile0) + gt * 128, a1_row = smem_u32(tile1) + gt * 128;
+    const uint32_t a_row = smem_u32(tileA) + gt * 128;
     const int row_cb = gt & ~1, row_cr = gt | 1;
     const uint32_t ac_cb = smem_u32(tileC) + row_cb * 128 + half * 8, ac_cr = smem_u32(tileC) + row_cr * 128 + half * 8;
     const uint32_t sw_cb = (uint32_t)(row_cb & 7), sw_cr = (uint32_t)(row_cr & 7);
@@ -599,96 +641,123 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
     };
-
-    for (uint32_t base = (blockIdx.x * TC_GROUPS + g) * 4; base < a.total_units; base += groups_total * 4) {
-        const bool active = base + wg < a.total_units;  // every warp of the group runs the same control flow
-        const uint32_t unit = active ? base + wg : base;
+    // every warp of the group runs the same control flow; a warp past the end gets an empty unit
+    auto decode = [&](uint32_t unit_base) {
+        const bool active = unit_base + wg < a.total_units;
+        const uint32_t unit = active ? unit_base + wg : unit_base;
         uint32_t f = unit / units_per_frame, rem = unit - f * units_per_frame;
         int my = (int)(rem / (uint32_t)a.units_per_row), ux = (int)(rem - (uint32_t)my * (uint32_t)a.units_per_row);
-        Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
-        const int mcu_x0 = ux * 16;
-        const int mcus_valid = active ? min(16, a.fast_mcux - mcu_x0) : 0;
-        const size_t mcu_g0 = (size_t)f * (size_t)a.g.n_mcu + (size_t)my * (size_t)a.g.mcux + (size_t)mcu_x0;
-        const bool valid = (lane >> 1) < mcus_valid;
-        const int m = valid ? lane >> 1 : max(mcus_valid - 1, 0);
-        const uint32_t gb0 = (uint32_t)(mcu_g0 + m) * 6u;
-        const uint8_t* col0 = im.base + (size_t)((mcu_x0 + m) * 16 + half * 8) * 3;
+        TcUnit u;
+        u.row0 = a.rgb + (size_t)f * a.frame_stride + (size_t)ux * TC_ROW_BYTES;
+        u.y0 = my * 16;
+        u.bytes_valid = active ? min(16, a.fast_mcux - ux * 16) * 48 : 0;
+        u.mcu_g0 = (size_t)f * (size_t)a.g.n_mcu + (size_t)my * (size_t)a.g.mcux + (size_t)ux * 16;
+        return u;
+    };
+    // start the copy of row pair `rp` (image rows 2rp, 2rp+1 of the strip) into ring slot `sl`; one commit group
+    auto fetch_pair = [&](const TcUnit& u, int rp, int sl) {
+        const uint32_t dst = ring + (uint32_t)sl * (2 * 4 * TC_ROW_BYTES);
+        tc_async_row<ALIGN>(dst, u.row0 + (size_t)mirror(u.y0 + 2 * rp, a.g.H) * a.pitch, lane, u.bytes_valid);
+        tc_async_row<ALIGN>(dst + 4 * TC_ROW_BYTES, u.row0 + (size_t)mirror(u.y0 + 2 * rp + 1, a.g.H) * a.pitch, lane,
+                            u.bytes_valid);
+    };
 
-        // colour-convert 8 image rows (4 row pairs) into luma tile `arow` and chroma rows crow0..crow0+3
-        auto convert_half = [&](int h, uint32_t arow) {
-            // software pipeline: the loads of row pair rp+1 are in flight while pair rp is converted
-            uint32_t n0[6], n1[6];
-            const int ybase = my * 16 + h * 8;
-            load24<ALIGN>(col0 + (size_t)mirror(ybase, im.H) * im.pitch, n0);
-            load24<ALIGN>(col0 + (size_t)mirror(ybase + 1, im.H) * im.pitch, n1);
+    uint32_t base = (blockIdx.x * TC_GROUPS + g) * 4;
+    TcUnit cur = decode(base);
+    if (base < a.total_units) {
+        fetch_pair(cur, 0, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        fetch_pair(cur, 1, 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (; base < a.total_units; base += stride) {
+        const bool has_next = base + stride < a.total_units;
+        const TcUnit nxt = decode(has_next ? base + stride : base);
+        const int mcus_valid = cur.bytes_valid / 48;
+        const size_t mcu_g0 = cur.mcu_g0;
+        const bool valid = (lane >> 1) < mcus_valid;
+        const uint32_t gb0 = (uint32_t)(mcu_g0 + (valid ? lane >> 1 : 0)) * 6u;
+
+        // ---- 16 image rows = 8 row pairs: ring -> registers -> colour conversion -> A tiles -----------
+        // The ring holds two pairs; the refill of a slot (the pair after next, possibly of the next unit)
+        // is issued right after the slot has been read, two pairs of work ahead of its use.
 #pragma unroll 1
-            for (int rp = 0; rp < 4; ++rp) {
-                uint32_t w0[6], w1[6];
+        for (int it = 0; it < 8; ++it) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            if (ALIGN == 16) __syncwarp();  // lanes read bytes that other lanes copied
+            const uint32_t src = ring + (uint32_t)(it & 1) * (2 * 4 * TC_ROW_BYTES) + lane * 24;
+            uint32_t w0[6], w1[6];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    w0[j] = n0[j];
-                    w1[j] = n1[j];
-                }
-                {
-                    const int yn = min(ybase + 2 * rp + 2, my * 16 + 15);  // last iteration: harmless re-load
-                    load24<ALIGN>(col0 + (size_t)mirror(yn, im.H) * im.pitch, n0);
-                    load24<ALIGN>(col0 + (size_t)mirror(min(yn + 1, my * 16 + 15), im.H) * im.pitch, n1);
-                }
-                Row8 o0, o1;
-                csc_row8(w0, im.ydown, o0);
-                csc_row8(w1, im.ydown, o1);
-                sts128(arow + (((uint32_t)(2 * rp) ^ sw_own) << 4),
-                       make_uint4(bf16x2(o0.y[0], o0.y[1]), bf16x2(o0.y[2], o0.y[3]), bf16x2(o0.y[4], o0.y[5]),
-                                  bf16x2(o0.y[6], o0.y[7])));
-                sts128(arow + (((uint32_t)(2 * rp + 1) ^ sw_own) << 4),
-                       make_uint4(bf16x2(o1.y[0], o1.y[1]), bf16x2(o1.y[2], o1.y[3]), bf16x2(o1.y[4], o1.y[5]),
-                                  bf16x2(o1.y[6], o1.y[7])));
-                int cb[4], cr[4];  // utils.cpp:126-127: truncated mean of the 2x2 cell, then level shift
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    cb[c] = (int)(((o0.cb[2 * c] >> 24) + (o0.cb[2 * c + 1] >> 24) + (o1.cb[2 * c] >> 24) + (o1.cb[2 * c + 1] >> 24)) >> 2) - 128;
-                    cr[c] = (int)(((o0.cr[2 * c] >> 24) + (o0.cr[2 * c + 1] >> 24) + (o1.cr[2 * c] >> 24) + (o1.cr[2 * c + 1] >> 24)) >> 2) - 128;
-                }
-                const uint32_t crow = (uint32_t)(h * 4 + rp);  // chroma row = K chunk of the chroma tile
-                sts64(ac_cb + ((crow ^ sw_cb) << 4), make_uint2(bf16x2(cb[0], cb[1]), bf16x2(cb[2], cb[3])));
-                sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(bf16x2(cr[0], cr[1]), bf16x2(cr[2], cr[3])));
+            for (int j = 0; j < 3; ++j) {
+                uint2 v0 = lds64(src + 8 * j), v1 = lds64(src + 4 * TC_ROW_BYTES + 8 * j);
+                w0[2 * j] = v0.x;
+                w0[2 * j + 1] = v0.y;
+                w1[2 * j] = v1.x;
+                w1[2 * j + 1] = v1.y;
             }
-        };
-        // read this thread's row of the accumulator, round / flag / pack, stage in `tile`, store blocks blk, blk+1
-        auto finish = [&](uint32_t tmem_d, uint8_t* tile, int tab, int blk) {
+            if (ALIGN == 16) __syncwarp();  // every lane has read the slot before anyone refills it
+            if (it < 6)
+                fetch_pair(cur, it + 2, it & 1);
+            else if (has_next)
+                fetch_pair(nxt, it - 6, it & 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (it == 4) mbar_wait(mbar0, phase0);  // the MMAs of rows 0-7 have consumed the tile: overwrite it
+
+            Row8 o0, o1;
+            csc_row8(w0, a.ydown, o0);
+            csc_row8(w1, a.ydown, o1);
+            const uint32_t rp = (uint32_t)(it & 3);
+            sts128(a_row + (((2 * rp) ^ sw_own) << 4),
+                   make_uint4(bf16x2(o0.y[0], o0.y[1]), bf16x2(o0.y[2], o0.y[3]), bf16x2(o0.y[4], o0.y[5]),
+                              bf16x2(o0.y[6], o0.y[7])));
+            sts128(a_row + (((2 * rp + 1) ^ sw_own) << 4),
+                   make_uint4(bf16x2(o1.y[0], o1.y[1]), bf16x2(o1.y[2], o1.y[3]), bf16x2(o1.y[4], o1.y[5]),
+                              bf16x2(o1.y[6], o1.y[7])));
+            int cb[4], cr[4];  // utils.cpp:126-127: truncated mean of the 2x2 cell, then level shift
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                cb[c] = (int)(((o0.cb[2 * c] >> 24) + (o0.cb[2 * c + 1] >> 24) + (o1.cb[2 * c] >> 24) + (o1.cb[2 * c + 1] >> 24)) >> 2) - 128;
+                cr[c] = (int)(((o0.cr[2 * c] >> 24) + (o0.cr[2 * c + 1] >> 24) + (o1.cr[2 * c] >> 24) + (o1.cr[2 * c + 1] >> 24)) >> 2) - 128;
+            }
+            const uint32_t crow = (uint32_t)it;  // chroma row = K chunk of the chroma tile
+            sts64(ac_cb + ((crow ^ sw_cb) << 4), make_uint2(bf16x2(cb[0], cb[1]), bf16x2(cb[2], cb[3])));
+            sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(bf16x2(cr[0], cr[1]), bf16x2(cr[2], cr[3])));
+            if (it == 3) {
+                publish();
+                if (gt == 0) issue(tileA, 0, tmem_d0, mbar0);
+            }
+        }
+        publish();
+        if (gt == 0) issue(tileA, 0, tmem_d1, mbar1);
+
+        // read this thread's row of the accumulator, round / flag / pack, stage in tileA, store blocks blk, blk+1
+        auto finish = [&](uint32_t tmem_d, int tab, int blk, uint32_t wait_mbar, uint32_t wait_parity) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t t[64];
             tmem_ld64(tmem_d + lane_off, t);
-            uint4* st = reinterpret_cast<uint4*>(tile) + wg * 256;  // this warp's 32 rows of the tile
+            uint4* st = reinterpret_cast<uint4*>(tileA) + wg * 256;  // this warp's 32 rows of the tile
             uint32_t tl = 0, th = 0;
             if (tab == 0)
-                tc_quant_stage<0>(t, a, st, lane, tl, th);
+                tc_quant_stage<0>(t, a, st, lane, tl, th, wait_mbar, wait_parity);
             else
-                tc_quant_stage<1>(t, a, st, lane, tl, th);
+                tc_quant_stage<1>(t, a, st, lane, tl, th, wait_mbar, wait_parity);
             if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + blk + half, tl, th);
             __syncwarp();
             copy_out<6>(st, coef4, mcu_g0, mcus_valid, blk, lane);
             __syncwarp();
         };
-
-        convert_half(0, a0_row);
-        publish();
-        if (gt == 0) issue(tile0, 0, tmem_d0, mbar0);
-        convert_half(1, a1_row);
-        publish();
-        if (gt == 0) issue(tile1, 0, tmem_d1, mbar1);
-        mbar_wait(mbar0, phase0);
-        phase0 ^= 1;
-        finish(tmem_d0, tile0, 0, 0);   // Y00 / Y01
-        publish();                      // every thread has read accumulator 0: it can take the chroma tile
-        if (gt == 0) issue(tileC, 1, tmem_d0, mbar0);
-        mbar_wait(mbar1, phase1);
+        phase0 ^= 1;                                  // (rows 0-7: completion already observed at it == 4)
+        finish(tmem_d0, 0, 0, mbar1, phase1);         // Y00 / Y01; staging waits for the MMAs of rows 8-15
         phase1 ^= 1;
-        finish(tmem_d1, tile1, 0, 2);   // Y10 / Y11
+        publish();                                    // every thread has read accumulator 0: it takes the chroma tile
+        if (gt == 0) issue(tileC, 1, tmem_d0, mbar0);
+        finish(tmem_d1, 0, 2, 0, 0);                  // Y10 / Y11
         mbar_wait(mbar0, phase0);
         phase0 ^= 1;
-        finish(tmem_d0, tile0, 1, 4);   // Cb / Cr
+        finish(tmem_d0, 1, 4, 0, 0);                  // Cb / Cr
+        cur = nxt;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_TMEM_COLS));
@@ -735,7 +804,10 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     if (a.tc_mat && a.g.sub == JB_SUB_420 && align >= 4) {  // tensor-core variant
         int needg = (int)((a.total_units + 4 * TC_GROUPS - 1) / (4 * TC_GROUPS));
         int gridg = needg < sms ? needg : sms;
-        if (align == 8) {
+        if ((bits & 15) == 0) {
+            cudaFuncSetAttribute(k_transform_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+            k_transform_tc<16><<<gridg, TC_GROUPS * 128, TC_SMEM, s>>>(a);
+        } else if (align == 8) {
             cudaFuncSetAttribute(k_transform_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
             k_transform_tc<8><<<gridg, TC_GROUPS * 128, TC_SMEM, s>>>(a);
         } else {
