@@ -502,6 +502,55 @@ __device__ __forceinline__ uint32_t bf16x2(int lo, int hi) {  // two small integ
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Colour conversion of one row of 8 pixels for the tensor-core kernel: the three T values (8.24
+// fixed point, jb_math.h) per pixel, luma already corrected on CSC ties (top byte = Y).
+struct Row8T {
+    uint32_t y[8], cb[8], cr[8];
+};
+__device__ __forceinline__ void csc_row8_t(const uint32_t (&w)[6], const uint32_t* __restrict__ ydown, Row8T& o) {
+    uint32_t tmin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = 3 * i;
+        uint32_t R = byte_of(w[k >> 2], k & 3), G = byte_of(w[(k + 1) >> 2], (k + 1) & 3),
+                 B = byte_of(w[(k + 2) >> 2], (k + 2) & 3);
+        o.y[i] = mad(B, KY_B, mad(G, KY_G, R * KY_R));
+        o.cb[i] = mad(B, 0x00800000u, mad(G, 0u - KCB_G, mad(R, 0u - KCB_R, 0x80000000u)));
+        o.cr[i] = mad(R, 0x00800000u, mad(B, 0u - KCR_B, mad(G, 0u - KCR_G, 0x80000000u)));
+        tmin = min(tmin, o.y[i] & Y_TIE_MASK);
+    }
+    if (tmin == 0) {  // some pixel of the row is a CSC tie (exact integer luma): consult the table
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if ((o.y[i] & Y_TIE_MASK) == 0) {
+                const int k = 3 * i;
+                uint32_t idx = (byte_of(w[k >> 2], k & 3) << 8) | byte_of(w[(k + 1) >> 2], (k + 1) & 3);
+                o.y[i] -= ((__ldg(ydown + (idx >> 5)) >> (idx & 31)) & 1u) << 24;  // the fraction is tiny: top byte - 1
+            }
+        }
+    }
+}
+// fp16 pair (Y0 - 128, Y1 - 128) from the top bytes of two T values: 0x6400 | n is the fp16 number
+// 1024 + n, and subtracting 1152 is exact.
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t m, uint32_t c) {  // (x & m) | c as ONE LOP3
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(m), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t luma_h2(uint32_t t0, uint32_t t1) {
+    uint32_t bits = and_or(__byte_perm(t0, t1, 0x7773), 0x00FF00FFu, 0x64006400u);
+    __half2 h = __hsub2(*reinterpret_cast<__half2*>(&bits), __floats2half2_rn(1152.0f, 1152.0f));
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// fp16 pair (floor(s0/4) - 128, floor(s1/4) - 128) from two sums of four chroma bytes (s < 1024):
+// 0x6400 | (s & ~3) is 1024 + 4 floor(s/4); one exact FMA does the rest (utils.cpp:126-127).
+__device__ __forceinline__ uint32_t chroma_h2(uint32_t s0, uint32_t s1) {
+    uint32_t bits = and_or(__byte_perm(s0, s1, 0x5410), 0x03FC03FCu, 0x64006400u);
+    __half2 h = __hfma2(*reinterpret_cast<__half2*>(&bits), __floats2half2_rn(0.25f, 0.25f),
+                        __floats2half2_rn(-384.0f, -384.0f));
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // Round the 64 scaled coefficients t (zigzag order) of one block, flag near ties, pack, stage.
 template <int TAB>
 __device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const TransformArgs& a, uint4* st, int lane,
@@ -564,20 +613,18 @@ struct TcUnit {
     size_t mcu_g0;        // global index of the first MCU
 };
 
-// Asynchronous copy of one 768-byte strip row into the ring.  16-byte aligned images are copied
-// warp-cooperatively (48 chunks of 16 bytes), others by each lane for itself (its own 24 bytes).
+// Asynchronous copy of this lane's share of one 768-byte strip row into the ring (dst and src
+// already include the lane's offset).  16-byte aligned images are copied warp-cooperatively
+// (48 chunks of 16 bytes: lane, and lane + 32 for the first 16 lanes), others by each lane for
+// itself (its own 24 bytes).
 template <int ALIGN>
-__device__ __forceinline__ void tc_async_row(uint32_t dst, const uint8_t* src, int lane, int bytes_valid) {
+__device__ __forceinline__ void tc_async_row(uint32_t dst, const uint8_t* src, bool p0, bool p1) {
     if (ALIGN == 16) {
-        const int o0 = lane * 16, o1 = 512 + lane * 16;
-        if (o0 < bytes_valid) cp_async<16>(dst + o0, src + o0);
-        if (lane < 16 && o1 < bytes_valid) cp_async<16>(dst + o1, src + o1);
-    } else {
-        const int o = lane * 24;
-        if (o < bytes_valid) {
+        if (p0) cp_async<16>(dst, src);
+        if (p1) cp_async<16>(dst + 512, src + 512);
+    } else if (p0) {
 #pragma unroll
-            for (int j = 0; j < 24 / ALIGN; ++j) cp_async<ALIGN>(dst + o + j * ALIGN, src + o + j * ALIGN);
-        }
+        for (int j = 0; j < 24 / ALIGN; ++j) cp_async<ALIGN>(dst + j * ALIGN, src + j * ALIGN);
     }
 }
 
@@ -636,6 +683,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
     };
     // writes of this thread to the tiles become visible to the tensor core, all threads of the group arrive
+    // (a full group barrier: arrive/wait for the non-issuing warps and CTA-wide barriers both measured slower)
     auto publish = [&]() {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -654,25 +702,39 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         u.mcu_g0 = (size_t)f * (size_t)a.g.n_mcu + (size_t)my * (size_t)a.g.mcux + (size_t)ux * 16;
         return u;
     };
-    // start the copy of row pair `rp` (image rows 2rp, 2rp+1 of the strip) into ring slot `sl`; one commit group
-    auto fetch_pair = [&](const TcUnit& u, int rp, int sl) {
-        const uint32_t dst = ring + (uint32_t)sl * (2 * 4 * TC_ROW_BYTES);
-        tc_async_row<ALIGN>(dst, u.row0 + (size_t)mirror(u.y0 + 2 * rp, a.g.H) * a.pitch, lane, u.bytes_valid);
-        tc_async_row<ALIGN>(dst + 4 * TC_ROW_BYTES, u.row0 + (size_t)mirror(u.y0 + 2 * rp + 1, a.g.H) * a.pitch, lane,
-                            u.bytes_valid);
+    // fetch cursor: the strip whose rows are being copied into the ring, this lane's share folded in
+    const uint32_t lane_share = (uint32_t)lane * (ALIGN == 16 ? 16u : 24u);
+    const uint32_t ring_wr = ring + lane_share, ring_rd = ring + (uint32_t)lane * 24u;
+    const uint32_t pitch32 = (uint32_t)a.pitch;
+    const uint8_t* fc_src = nullptr;
+    int fc_y0 = 0;
+    bool fc_p0 = false, fc_p1 = false;
+    auto aim = [&](const TcUnit& u) {
+        fc_src = u.row0 + lane_share;
+        fc_y0 = u.y0;
+        fc_p0 = (int)lane_share < u.bytes_valid;
+        fc_p1 = ALIGN == 16 && lane < 16 && (int)lane_share + 512 < u.bytes_valid;
+    };
+    // start the copy of row pair `rp` (image rows 2rp, 2rp+1 of the strip) into ring slot `sl`: one commit group
+    auto fetch_pair = [&](int rp, int sl) {
+        const uint32_t dst = ring_wr + (uint32_t)sl * (2 * 4 * TC_ROW_BYTES);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t y = (uint32_t)mirror(fc_y0 + 2 * rp + r, a.g.H);
+            tc_async_row<ALIGN>(dst + r * 4 * TC_ROW_BYTES, fc_src + (uint64_t)y * pitch32, fc_p0, fc_p1);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     uint32_t base = (blockIdx.x * TC_GROUPS + g) * 4;
     TcUnit cur = decode(base);
     if (base < a.total_units) {
-        fetch_pair(cur, 0, 0);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        fetch_pair(cur, 1, 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        aim(cur);
+        fetch_pair(0, 0);
+        fetch_pair(1, 1);
     }
     for (; base < a.total_units; base += stride) {
-        const bool has_next = base + stride < a.total_units;
-        const TcUnit nxt = decode(has_next ? base + stride : base);
+        const TcUnit nxt = decode(base + stride);  // past the end: an empty unit, nothing is fetched
         const int mcus_valid = cur.bytes_valid / 48;
         const size_t mcu_g0 = cur.mcu_g0;
         const bool valid = (lane >> 1) < mcus_valid;
@@ -685,7 +747,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         for (int it = 0; it < 8; ++it) {
             asm volatile("cp.async.wait_group 1;" ::: "memory");
             if (ALIGN == 16) __syncwarp();  // lanes read bytes that other lanes copied
-            const uint32_t src = ring + (uint32_t)(it & 1) * (2 * 4 * TC_ROW_BYTES) + lane * 24;
+            const uint32_t src = ring_rd + (uint32_t)(it & 1) * (2 * 4 * TC_ROW_BYTES);
             uint32_t w0[6], w1[6];
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -696,32 +758,27 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
                 w1[2 * j + 1] = v1.y;
             }
             if (ALIGN == 16) __syncwarp();  // every lane has read the slot before anyone refills it
-            if (it < 6)
-                fetch_pair(cur, it + 2, it & 1);
-            else if (has_next)
-                fetch_pair(nxt, it - 6, it & 1);
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (it == 6) aim(nxt);
+            fetch_pair((it + 2) & 7, it & 1);
             if (it == 4) mbar_wait(mbar0, phase0);  // the MMAs of rows 0-7 have consumed the tile: overwrite it
 
-            Row8 o0, o1;
-            csc_row8(w0, a.ydown, o0);
-            csc_row8(w1, a.ydown, o1);
+            Row8T o0, o1;
+            csc_row8_t(w0, a.ydown, o0);
+            csc_row8_t(w1, a.ydown, o1);
             const uint32_t rp = (uint32_t)(it & 3);
-            sts128(a_row + (((2 * rp) ^ sw_own) << 4),
-                   make_uint4(bf16x2(o0.y[0], o0.y[1]), bf16x2(o0.y[2], o0.y[3]), bf16x2(o0.y[4], o0.y[5]),
-                              bf16x2(o0.y[6], o0.y[7])));
-            sts128(a_row + (((2 * rp + 1) ^ sw_own) << 4),
-                   make_uint4(bf16x2(o1.y[0], o1.y[1]), bf16x2(o1.y[2], o1.y[3]), bf16x2(o1.y[4], o1.y[5]),
-                              bf16x2(o1.y[6], o1.y[7])));
-            int cb[4], cr[4];  // utils.cpp:126-127: truncated mean of the 2x2 cell, then level shift
+            sts128(a_row + (((2 * rp) ^ sw_own) << 4), make_uint4(luma_h2(o0.y[0], o0.y[1]), luma_h2(o0.y[2], o0.y[3]),
+                                                                  luma_h2(o0.y[4], o0.y[5]), luma_h2(o0.y[6], o0.y[7])));
+            sts128(a_row + (((2 * rp + 1) ^ sw_own) << 4), make_uint4(luma_h2(o1.y[0], o1.y[1]), luma_h2(o1.y[2], o1.y[3]),
+                                                                      luma_h2(o1.y[4], o1.y[5]), luma_h2(o1.y[6], o1.y[7])));
+            uint32_t sb[4], sr[4];  // sums of the four chroma bytes of each 2x2 cell
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                cb[c] = (int)(((o0.cb[2 * c] >> 24) + (o0.cb[2 * c + 1] >> 24) + (o1.cb[2 * c] >> 24) + (o1.cb[2 * c + 1] >> 24)) >> 2) - 128;
-                cr[c] = (int)(((o0.cr[2 * c] >> 24) + (o0.cr[2 * c + 1] >> 24) + (o1.cr[2 * c] >> 24) + (o1.cr[2 * c + 1] >> 24)) >> 2) - 128;
+                sb[c] = (o0.cb[2 * c] >> 24) + (o0.cb[2 * c + 1] >> 24) + (o1.cb[2 * c] >> 24) + (o1.cb[2 * c + 1] >> 24);
+                sr[c] = (o0.cr[2 * c] >> 24) + (o0.cr[2 * c + 1] >> 24) + (o1.cr[2 * c] >> 24) + (o1.cr[2 * c + 1] >> 24);
             }
             const uint32_t crow = (uint32_t)it;  // chroma row = K chunk of the chroma tile
-            sts64(ac_cb + ((crow ^ sw_cb) << 4), make_uint2(bf16x2(cb[0], cb[1]), bf16x2(cb[2], cb[3])));
-            sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(bf16x2(cr[0], cr[1]), bf16x2(cr[2], cr[3])));
+            sts64(ac_cb + ((crow ^ sw_cb) << 4), make_uint2(chroma_h2(sb[0], sb[1]), chroma_h2(sb[2], sb[3])));
+            sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(chroma_h2(sr[0], sr[1]), chroma_h2(sr[2], sr[3])));
             if (it == 3) {
                 publish();
                 if (gt == 0) issue(tileA, 0, tmem_d0, mbar0);
