@@ -551,27 +551,41 @@ __device__ __forceinline__ uint32_t chroma_h2(uint32_t s0, uint32_t s1) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    return ((uint64_t)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // Round the 64 scaled coefficients t (zigzag order) of one block, flag near ties, pack, stage.
 template <int TAB>
 __device__ __forceinline__ void tc_quant_stage(const uint32_t (&t)[64], const TransformArgs& a, uint4* st, int lane,
                                                uint32_t& tie_lo, uint32_t& tie_hi, uint32_t wait_mbar, uint32_t wait_parity) {
     uint32_t wd[32];
     const float inv = (float)(1.0 / JB_TC_W_SCALE);
+    // two coefficients per instruction (packed fp32 FFMA2 / FADD2 of sm_100): r = x inv + 1.5 2^23 rounds to
+    // the nearest integer, d = x inv - (r - 1.5 2^23) is the distance from it
+    const uint64_t inv2 = pack_f32x2(inv, inv), magic2 = pack_f32x2(JB_ROUND_MAGIC, JB_ROUND_MAGIC);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        uint32_t b[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int k = 2 * j + e;
-            float x = __uint_as_float(t[k]);
-            float r = jb_fmaf(x, inv, JB_ROUND_MAGIC), ri = r - JB_ROUND_MAGIC;
-            bool tie = fabsf(jb_fmaf(x, inv, -ri)) > a.tband[TAB][k];
-            if (tie) {
-                if (k < 32) tie_lo |= 1u << k; else tie_hi |= 1u << (k - 32);
-            }
-            b[e] = __float_as_uint(r);
+        const uint64_t x2 = ((uint64_t)t[2 * j + 1] << 32) | t[2 * j];
+        const uint64_t r2 = fma_f32x2(x2, inv2, magic2);
+        const uint64_t d2 = fma_f32x2(x2, inv2, sub_f32x2(magic2, r2));
+        if (fabsf(__uint_as_float((uint32_t)d2)) > a.tband[TAB][2 * j]) {
+            if (j < 16) tie_lo |= 1u << (2 * j); else tie_hi |= 1u << (2 * j - 32);
         }
-        wd[j] = __byte_perm(b[0], b[1], 0x5410);
+        if (fabsf(__uint_as_float((uint32_t)(d2 >> 32))) > a.tband[TAB][2 * j + 1]) {
+            if (j < 16) tie_lo |= 1u << (2 * j + 1); else tie_hi |= 1u << (2 * j - 31);
+        }
+        wd[j] = __byte_perm((uint32_t)r2, (uint32_t)(r2 >> 32), 0x5410);
     }
     if (a.qc.dc_exact) {  // one uniform branch, outside the unrolled loop
         // t[0] ~ 2^10 S/(8q): recover the exact integer sample sum S, then the integer DC rule
