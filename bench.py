@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--tensor-dct", type=int, default=0, help="1: tcgen05 variant of the transform kernel (4:2:0)")
+    ap.add_argument("--tensor-dct", type=int, default=1,
+                    help="4:2:0 transform kernel: 1 = tcgen05 (library default), 0 = CUDA-core FMA kernel (JB_FLAG_FMA_DCT)")
     return ap.parse_args()
 
 
@@ -265,7 +266,7 @@ def main():
     F = a.frames or dflt
     sub = {"420": jb.SUB_420, "444": jb.SUB_444}[subname]
     params = jb.make_params(sub, quality=q, restart_interval=ri,
-                            flags=jb.FLAG_TENSOR_DCT if (a.tensor_dct and sub == jb.SUB_420) else 0)
+                            flags=0 if a.tensor_dct else jb.FLAG_FMA_DCT)
     pitch, fstride = W * 3, W * H * 3
     px_per_step = W * H * F  # per GPU
 
@@ -325,15 +326,18 @@ def main():
     alg_bytes = F * (3 * W * H + 2 * samples_per_px * padded)  # read RGB8 + write int16 coefficients
     k_us = tm["transform_us"] / max(tm["transform_launches"], 1)
     achieved = alg_bytes / (k_us * 1e-6) / 1e9
+    use_tc = bool(a.tensor_dct) and sub == jb.SUB_420
+    kname = "k_transform_tc" if use_tc else "k_transform"
     traffic = None
     try:  # per-launch DRAM bytes from the committed ncu capture of the same command, if present
         with open(os.path.join(ROOT, "profiles", "r01_transform_ncu_summary.json")) as f:
             prof = json.load(f)
         if prof.get("workload") == a.workload and prof.get("frames") == F:
-            traffic = prof.get("dram_bytes_per_launch")
+            traffic = prof.get("kernels", {}).get(kname, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "k_transform (fused CSC+subsample+shift+FDCT+quant+zigzag)", "bound": "hbm",
+    roofline = {"kernel": kname + (" (fused CSC+subsample+shift, tcgen05 FDCT+quant+zigzag)" if use_tc else
+                                   " (fused CSC+subsample+shift+FDCT+quant+zigzag, CUDA cores)"), "bound": "hbm",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                 "kernel_us_per_launch": round(k_us, 2),
@@ -396,7 +400,7 @@ def main():
                        "l2": "inputs per step (%.2f GB) far exceed the 126 MB L2" % (F * fstride / 1e9),
                        "bits_per_pixel": round(8.0 * total_bytes / px_per_step, 4),
                        "tie_fixups_per_step": int(tm["tie_fixups"]),
-                       "transform_kernel": "k_transform_tc (tcgen05)" if (a.tensor_dct and sub == jb.SUB_420) else "k_transform (FMA pipe)"},
+                       "transform_kernel": "k_transform_tc (tcgen05)" if use_tc else "k_transform (FMA pipe)"},
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": launches_device,
         }

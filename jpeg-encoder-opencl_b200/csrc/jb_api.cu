@@ -320,7 +320,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ta.tie_count = s.d_scalars;
     ta.tie_cap = s.tie_cap;
     build_quant_const(p->qlum, p->qchrom, &ta.qc);
-    if ((p->flags & JB_FLAG_TENSOR_DCT) && pl.g.sub == JB_SUB_420) {
+    if (!(p->flags & JB_FLAG_FMA_DCT) && pl.g.sub == JB_SUB_420) {  // tcgen05 transform (launch falls back if unaligned)
         // the six W matrices travel through the pinned result block (asynchronous copy)
         uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024 - 32768;
         const char* e = getenv("JB_TC_ERR_SCALE");

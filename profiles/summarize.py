@@ -79,10 +79,15 @@ def to_bytes(v, u):
 if __name__ == "__main__":
     step = launches()
     summ = kernels()
-    t = next(v for k, v in summ.items() if k.startswith("void k_transform<") or k.startswith("k_transform<"))
-    traffic = to_bytes(*t["dram read"]) + to_bytes(*t["dram write"])
-    json.dump({"round": R, "workload": "batch1080p", "frames": 512, "kernel": "k_transform<2, 8>",
-               "dram_bytes_per_launch": int(traffic), "dram_read": t["dram read"], "dram_write": t["dram write"],
-               "duration_under_ncu": t["duration"], "source": f"gpurun_out/{R}_prof_full.ncu-rep (ncu --set full --clock-control none)"},
+    ks = {}
+    for key, pred in (("k_transform_tc", lambda k: "k_transform_tc" in k),
+                      ("k_transform", lambda k: "k_transform<" in k and "k_transform_tc" not in k)):
+        t = next((v for k, v in summ.items() if pred(k)), None)
+        if t:
+            ks[key] = {"dram_bytes_per_launch": int(to_bytes(*t["dram read"]) + to_bytes(*t["dram write"])),
+                       "dram_read": t["dram read"], "dram_write": t["dram write"], "duration_under_ncu": t["duration"]}
+    traffic = {k: v["dram_bytes_per_launch"] for k, v in ks.items()}
+    json.dump({"round": R, "workload": "batch1080p", "frames": 512, "kernels": ks,
+               "source": f"gpurun_out/{R}_prof_full.ncu-rep, {R}_prof_tc.ncu-rep (ncu --set full --clock-control none)"},
               open(os.path.join(ROOT, "profiles", f"{R}_transform_ncu_summary.json"), "w"), indent=1)
     print("ok", traffic)

@@ -439,7 +439,7 @@ def test_config3_8k_420_q75_restart(enc, jb):
 
 @pytest.mark.parametrize("q", [50, 75, 90, 100])
 def test_tensor_core_transform_bit_exact(enc, jb, fruit, q):
-    """JB_FLAG_TENSOR_DCT: tcgen05 contraction (bf16x3 split) + binary64 replay == the oracle, bit for bit."""
+    """The default 4:2:0 transform: tcgen05 contraction (fp16 2-split) + binary64 replay == the oracle, bit for bit."""
     ql, qc = ol.quality_tables(q)
     for img in (fruit, ol.synth(21, 1920, 128), noise_image(3, 200, 120)):
         p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, flags=jb.FLAG_TENSOR_DCT)
@@ -459,10 +459,34 @@ def test_tensor_core_raw_error_is_small(enc, jb, fruit):
     assert (got != want).mean() < 2e-3
 
 
+@pytest.mark.parametrize("q", [50, 75, 100])
+def test_fma_transform_bit_exact(enc, jb, fruit, q):
+    """JB_FLAG_FMA_DCT: the CUDA-core 4:2:0 kernel (register AAN FDCT, analytic near-tie band) == the oracle."""
+    ql, qc = ol.quality_tables(q)
+    for img in (fruit, ol.synth(21, 1920, 128), noise_image(3, 200, 120), ol.synth(8, 333, 77)):
+        p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, flags=jb.FLAG_FMA_DCT)
+        got = enc.transform(img, p)
+        want = ol.transform(img, ol.SUB_420, ql, qc)
+        assert np.array_equal(got, want), f"q{q} {img.shape}: " + mismatch_report(got, want)
+
+
+def test_tensor_core_matches_fma_at_bench_size(enc, jb):
+    """16 frames of 1080p (smooth synthetic + full-range noise), q75 and q100: both kernels, same coefficients."""
+    rng = np.random.default_rng(77)
+    frames = np.stack([ol.synth(900 + i, 1920, 1080) for i in range(12)]
+                      + [rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8) for _ in range(4)])
+    for q in (75, 100):
+        a = jb.make_params(ol.SUB_420, quality=q, flags=jb.FLAG_FMA_DCT)
+        b = jb.make_params(ol.SUB_420, quality=q)
+        ca = np.stack([enc.transform(f, a) for f in frames[:: 5 if q == 100 else 1]])
+        cb = np.stack([enc.transform(f, b) for f in frames[:: 5 if q == 100 else 1]])
+        assert np.array_equal(ca, cb), f"q{q}: " + mismatch_report(ca, cb)
+
+
 def test_tensor_core_jfif_equals_fma_path(enc, jb):
     frames = np.stack([ol.synth(300 + i, 640, 360) for i in range(4)])
-    a = jb.make_params(ol.SUB_420, quality=75, restart_interval=40)
-    b = jb.make_params(ol.SUB_420, quality=75, restart_interval=40, flags=jb.FLAG_TENSOR_DCT)
+    a = jb.make_params(ol.SUB_420, quality=75, restart_interval=40, flags=jb.FLAG_FMA_DCT)
+    b = jb.make_params(ol.SUB_420, quality=75, restart_interval=40)
     oa, offa, sza = enc.encode_batch(frames, a)
     ob, offb, szb = enc.encode_batch(frames, b)
     assert np.array_equal(sza, szb) and np.array_equal(oa[: int(sza.sum())], ob[: int(szb.sum())])
