@@ -910,65 +910,78 @@ int launch_transform_edge(const TransformArgs& a_in, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------- fix-up ----
-// One warp per listed coefficient: the 64 samples are produced by the lanes in
-// parallel (two each); lane 0 then adds the 64 terms in the reference's order
-// (utils.cpp:314-347 with the block read from a copy, then utils.cpp:454-467),
-// in binary64 with unfused multiplies and adds.
-__global__ void __launch_bounds__(128) k_fixup(const __grid_constant__ FixupArgs a) {
+// One warp per batch of FIX_BATCH listed coefficients.  For each entry in turn the lanes produce the 64
+// products sample x cos x cos in parallel (two each) into shared memory; then lane L adds the 64
+// terms of entry L in the reference's order (utils.cpp:314-347 with the block read from a copy,
+// then utils.cpp:454-467), in binary64 with unfused multiplies and adds: the serial chains of 32
+// entries run side by side instead of one chain occupying a whole warp.
+#ifndef FIX_BATCH
+#define FIX_BATCH 4
+#endif
+constexpr int FIX_WARPS = 4;  // the kernel is latency-bound: small batches keep 64 warps per SM resident
+__global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant__ FixupArgs a) {
+    __shared__ double s_term[FIX_WARPS][FIX_BATCH][65];  // [entry of the batch][term], padded: conflict-free both ways  // [term][entry of the batch]: conflict-free both ways
     uint32_t n = *a.tie_count;
     if (n > a.tie_cap) n = a.tie_cap;
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
-        uint32_t entry = a.tie_list[e];
-        uint32_t gblock = entry >> 6, k = entry & 63;
-        uint32_t bpf = (uint32_t)a.g.n_mcu * (uint32_t)a.g.bpm;
-        uint32_t f = gblock / bpf, rb = gblock - f * bpf;
-        uint32_t mcu = rb / (uint32_t)a.g.bpm, blk = rb - mcu * (uint32_t)a.g.bpm;
-        int my = (int)(mcu / (uint32_t)a.g.mcux), mx = (int)(mcu - (uint32_t)my * (uint32_t)a.g.mcux);
-        int comp, x0, y0, step;
-        if (a.g.sub == JB_SUB_420) {
-            comp = blk < 4 ? 0 : (int)blk - 3;
-            x0 = mx * 16 + (blk < 4 ? (int)(blk & 1) * 8 : 0);
-            y0 = my * 16 + (blk < 4 ? (int)(blk >> 1) * 8 : 0);
-            step = blk < 4 ? 1 : 2;
-        } else {
-            comp = (int)blk;
-            x0 = mx * 8;
-            y0 = my * 8;
-            step = 1;
-        }
-        Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
-        const int nat = c_zz[k], v = nat >> 3, u = nat & 7;
-        double term[2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t warps = gridDim.x * FIX_WARPS;
+    const uint32_t bpf = (uint32_t)a.g.n_mcu * (uint32_t)a.g.bpm;
+    for (uint32_t e0 = (blockIdx.x * FIX_WARPS + w) * FIX_BATCH; e0 < n; e0 += warps * FIX_BATCH) {
+        const int n_here = (int)min((uint32_t)FIX_BATCH, n - e0);
+        const uint32_t my_entry = lane < n_here ? a.tie_list[e0 + lane] : 0u;
+        for (int j = 0; j < n_here; ++j) {
+            const uint32_t entry = __shfl_sync(0xffffffffu, my_entry, j);
+            const uint32_t gblock = entry >> 6, k = entry & 63;
+            uint32_t f = gblock / bpf, rb = gblock - f * bpf;
+            uint32_t mcu = rb / (uint32_t)a.g.bpm, blk = rb - mcu * (uint32_t)a.g.bpm;
+            int my = (int)(mcu / (uint32_t)a.g.mcux), mx = (int)(mcu - (uint32_t)my * (uint32_t)a.g.mcux);
+            int comp, x0, y0, step;
+            if (a.g.sub == JB_SUB_420) {
+                comp = blk < 4 ? 0 : (int)blk - 3;
+                x0 = mx * 16 + (blk < 4 ? (int)(blk & 1) * 8 : 0);
+                y0 = my * 16 + (blk < 4 ? (int)(blk >> 1) * 8 : 0);
+                step = blk < 4 ? 1 : 2;
+            } else {
+                comp = (int)blk;
+                x0 = mx * 8;
+                y0 = my * 8;
+                step = 1;
+            }
+            Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
+            const int nat = c_zz[k], v = nat >> 3, u = nat & 7;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            int i = lane + 32 * j, x = i & 7, y = i >> 3;
-            uint32_t Y, Cb, Cr;
-            if (a.g.sub == JB_SUB_444)
-                ycc_at<false>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
-            else
-                ycc_at<true>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
-            double smp = (double)(comp == 0 ? Y : comp == 1 ? Cb : Cr);                          // utils.cpp:236
-            smp = __dsub_rn(smp, 128.0);                                                          // utils.cpp:190
-            term[j] = __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), a.costab[v * 8 + y]);        // utils.cpp:330
+            for (int h = 0; h < 2; ++h) {
+                int i = lane + 32 * h, x = i & 7, y = i >> 3;
+                uint32_t Y, Cb, Cr;
+                if (a.g.sub == JB_SUB_444)
+                    ycc_at<false>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
+                else
+                    ycc_at<true>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
+                double smp = (double)(comp == 0 ? Y : comp == 1 ? Cb : Cr);                              // utils.cpp:236
+                smp = __dsub_rn(smp, 128.0);                                                              // utils.cpp:190
+                s_term[w][j][i] = __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), a.costab[v * 8 + y]);    // utils.cpp:330
+            }
         }
-        double sum = 0.0;  // y outer, x inner = index order 0..63
-        for (int i = 0; i < 64; ++i) {
-            double t = __shfl_sync(0xffffffffu, i < 32 ? term[0] : term[1], i & 31);
-            sum = __dadd_rn(sum, t);
-        }
-        if (lane == 0) {
-            sum = __dmul_rn(sum, a.scale[u * 8 + v]);                                             // utils.cpp:336
+        __syncwarp();
+        if (lane < n_here) {
+            const uint32_t gblock = my_entry >> 6, k = my_entry & 63;
+            const uint32_t rb = gblock % bpf, blk = rb % (uint32_t)a.g.bpm;
+            const int comp = a.g.sub == JB_SUB_420 ? (blk < 4 ? 0 : (int)blk - 3) : (int)blk;
+            const int nat = c_zz[k], v = nat >> 3, u = nat & 7;
+            double sum = 0.0;  // y outer, x inner = index order 0..63
+#pragma unroll 8
+            for (int i = 0; i < 64; ++i) sum = __dadd_rn(sum, s_term[w][lane][i]);
+            sum = __dmul_rn(sum, a.scale[u * 8 + v]);                                                     // utils.cpp:336
             double q = (double)a.qt.q[comp ? 1 : 0][nat];
-            double r = round(__ddiv_rn(sum, q));                                                  // utils.cpp:460
-            a.coef[(size_t)gblock * 64 + k] = (int16_t)(int)r;                                    // utils.cpp:490
+            double r = round(__ddiv_rn(sum, q));                                                          // utils.cpp:460
+            a.coef[(size_t)gblock * 64 + k] = (int16_t)(int)r;                                            // utils.cpp:490
         }
+        __syncwarp();
     }
 }
 
 int launch_fixup(const FixupArgs& a, cudaStream_t s) {
-    k_fixup<<<148 * 8, 128, 0, s>>>(a);
+    k_fixup<<<148 * 16, FIX_WARPS * 32, 0, s>>>(a);
     return 1;
 }
 
