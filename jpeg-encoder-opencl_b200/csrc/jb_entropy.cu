@@ -147,19 +147,16 @@ __device__ __forceinline__ uint32_t interleave16(uint32_t x) {
 struct SlotSink {
     uint64_t acc;
     int n;
-    uint32_t bits;
     uint32_t* slot;  // 4 words (shared memory)
-    int wi;
+    int wi;          // words completed so far (only the first four are kept)
     __device__ __forceinline__ void init(uint32_t* s) {
         slot = s;
         acc = 0;
         n = 0;
-        bits = 0;
         wi = 0;
-        s[0] = s[1] = s[2] = s[3] = 0;
+        *reinterpret_cast<uint4*>(s) = make_uint4(0u, 0u, 0u, 0u);
     }
     __device__ __forceinline__ void put(uint32_t code, int len) {
-        bits += (uint32_t)len;
         acc = (acc << len) | code;
         n += len;
         if (n >= 32) {
@@ -171,6 +168,7 @@ struct SlotSink {
     __device__ __forceinline__ void finish() {
         if (n > 0 && wi < 4) slot[wi] = (uint32_t)(acc << (32 - n));
     }
+    __device__ __forceinline__ uint32_t bits() const { return (uint32_t)(wi * 32 + n); }
 };
 
 // The block as HuffmanEncoder codes it (utils.cpp:667-694), visiting only the non-zero AC
@@ -196,7 +194,8 @@ __device__ __forceinline__ void encode_sparse(uint64_t mask, Fetch value, int dc
             cur = pos + 1;
             int v = value(pos);
             if (SMALL && run < 16 && (uint32_t)(v + 15) <= 30u) {
-                e = s_small[(run << 5) | (v & 31)];
+                // byte offset (run * 32 + (v & 31)) * 4: the two fields do not overlap, one IMAD + one LOP3
+                e = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_small) + ((run << 7) | ((v << 2) & 0x7C)));
                 s.put(e >> 5, (int)(e & 31u));
                 continue;
             }
@@ -284,7 +283,10 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
     if (t < n_blk) {
         const uint32_t k = s_perm[t], bk = b0 + k;
         const short* cf = reinterpret_cast<const short*>(s_coef);
-        auto value = [&](int pos) { return (int)cf[(k * 8 + ((pos >> 3) ^ (k & 7))) * 8 + (pos & 7)]; };
+        // coefficient pos of block k: byte k*128 + (((pos >> 3) ^ (k & 7)) << 4) + (pos & 7) * 2 = k*128 | ((2 pos) ^ swz)
+        const char* cblk = reinterpret_cast<const char*>(s_coef) + k * 128;
+        const uint32_t swz = (k & 7) << 4;
+        auto value = [&](int pos) { return (int)*reinterpret_cast<const short*>(cblk + (((uint32_t)pos << 1) ^ swz)); };
         BlockInfo bi = block_info(a, bk);
         const int tab = bi.comp ? 1 : 0;
         int pred = 0;  // DC of the previous block of the component (utils.cpp:669-670)
@@ -300,8 +302,9 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
         s.init(s_slot + k * 4);
         encode_sparse<true>(s_mask[k], value, value(0) - pred, s_ac[tab], s_dc[tab], s_small[tab], a.always_eob != 0, s);
         s.finish();
-        s_len[k] = s.bits;
-        if (s.bits > 128) {  // too long for a slot: k_pack_long re-walks it
+        const uint32_t nbits = s.bits();
+        s_len[k] = nbits;
+        if (nbits > 128) {  // too long for a slot: k_pack_long re-walks it
             uint32_t idx = atomicAdd(a.w.n_long, 1u);
             a.w.long_list[idx] = bk;
         }
