@@ -176,7 +176,8 @@ def run_strips(a, jb, enc, torch, dist, rank, world):
     import importlib
     D = importlib.import_module("jpegb200.dist")
     W, H, subname, q, ri, _ = WORKLOADS[a.workload]
-    params = jb.make_params(jb.SUB_420, quality=q, restart_interval=ri, flags=jb.FLAG_CLAMP_SOF)
+    params = jb.make_params(jb.SUB_420, quality=q, restart_interval=ri,
+                            flags=jb.FLAG_CLAMP_SOF | (0 if a.tensor_dct else jb.FLAG_FMA_DCT))
     row0, row1, first = D.plan_strips(H, 16, 1, world)[rank]
     rows, pitch = row1 - row0, W * 3
     chunk = 8192  # rows per jb_encode_strip call (keeps every call below 2^26 blocks)

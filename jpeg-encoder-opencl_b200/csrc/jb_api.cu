@@ -49,7 +49,9 @@ struct Slot {
     uint64_t* d_frame_size = nullptr;
     uint64_t* d_total = nullptr;
     uint8_t* d_hdr = nullptr;
-    uint8_t* d_tc = nullptr;  // tensor-core variant: the six bf16 matrices
+    uint8_t* d_tc = nullptr;  // tcgen05 transform: the four fp16 W matrices
+    uint8_t* tc_loaded_at = nullptr;  // where, and which generation of, the matrices this slot last uploaded
+    uint64_t tc_loaded_gen = 0;
     uint32_t tie_cap = 0;
     // pinned host mirror: [0..3] status, [4] total, [5] tie_count, then frame_off[n], frame_size[n]
     uint64_t* h_res = nullptr;
@@ -77,6 +79,16 @@ struct jb_ctx {
     jb_timings tm{};
     uint64_t required = 0;
     uint64_t pending_status_slot = 0;
+    // host-side constants derived from the quantisation tables, rebuilt only when the tables change
+    struct TableCache {
+        bool valid = false, tc_valid = false;
+        uint64_t gen = 0;  // bumped whenever the W matrices are rebuilt
+        uint32_t q[128];
+        double tc_scale = 0;
+        QuantConst qc;
+        float tband[2][64];
+        std::vector<uint8_t> tc;  // 32768 bytes: the four fp16 W matrices of the tcgen05 kernel
+    } tables;
 };
 
 namespace {
@@ -168,9 +180,12 @@ size_t plan_bytes(const Plan& p) {
 }
 
 int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
+    const void* base_before = s.arena.base;
     int rc = arena_reserve(ctx, s.arena, plan_bytes(p));
     if (rc) return rc;
     Arena& a = s.arena;
+    if (a.base != base_before) s.tc_loaded_at = nullptr;  // new allocation: nothing of the old arena survives
+    s.d_tc = carve<uint8_t>(a, 32768);                    // first, so that it keeps its place while the plan varies
     s.d_rgb = carve<uint8_t>(a, p.rgb_bytes);
     s.d_coef = carve<int16_t>(a, p.n_blocks * 64);
     s.d_tie_list = carve<uint32_t>(a, p.n_blocks * 64);
@@ -199,7 +214,6 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.d_frame_size = carve<uint64_t>(a, p.n_frames);
     s.d_total = carve<uint64_t>(a, 1);
     s.d_hdr = carve<uint8_t>(a, 1024);
-    s.d_tc = carve<uint8_t>(a, 32768);
     s.w.n_ff_tiles = s.d_scalars + 1;
     s.w.n_long = s.d_scalars + 2;
     s.w.status = reinterpret_cast<uint64_t*>(s.d_scalars + 4);
@@ -319,14 +333,39 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ta.tie_list = s.d_tie_list;
     ta.tie_count = s.d_scalars;
     ta.tie_cap = s.tie_cap;
-    build_quant_const(p->qlum, p->qchrom, &ta.qc);
-    if (!(p->flags & JB_FLAG_FMA_DCT) && pl.g.sub == JB_SUB_420) {  // tcgen05 transform (launch falls back if unaligned)
-        // the six W matrices travel through the pinned result block (asynchronous copy)
-        uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024 - 32768;
-        const char* e = getenv("JB_TC_ERR_SCALE");
-        build_tc_matrices(p->qlum, p->qchrom, e ? atof(e) : JB_TC_ERR_SCALE, h, ta.tband);
-        CK(cudaMemcpyAsync(s.d_tc, h, 32768, cudaMemcpyHostToDevice, s.st));
-        ta.tc_mat = s.d_tc;
+    {
+        jb_ctx::TableCache& tc = ctx->tables;
+        if (!tc.valid || memcmp(tc.q, p->qlum, 256) || memcmp(tc.q + 64, p->qchrom, 256)) {
+            memcpy(tc.q, p->qlum, 256);
+            memcpy(tc.q + 64, p->qchrom, 256);
+            build_quant_const(p->qlum, p->qchrom, &tc.qc);
+            tc.valid = true;
+            tc.tc_valid = false;
+        }
+        ta.qc = tc.qc;
+        if (!(p->flags & JB_FLAG_FMA_DCT) && pl.g.sub == JB_SUB_420) {  // tcgen05 transform (launch falls back if unaligned)
+            const char* e = getenv("JB_TC_ERR_SCALE");
+            const double scale = e ? atof(e) : JB_TC_ERR_SCALE;
+            if (!tc.tc_valid || tc.tc_scale != scale) {
+                for (Slot& o : ctx->slot)  // an earlier asynchronous call may still be copying the old matrices
+                    if (o.st) CK(cudaStreamSynchronize(o.st));
+                tc.tc.resize(32768);
+                build_tc_matrices(p->qlum, p->qchrom, scale, tc.tc.data(), tc.tband);
+                tc.tc_scale = scale;
+                tc.tc_valid = true;
+                ++tc.gen;
+            }
+            memcpy(ta.tband, tc.tband, sizeof(ta.tband));
+            if (s.tc_loaded_at != s.d_tc || s.tc_loaded_gen != tc.gen) {
+                // the W matrices travel through the pinned result block (asynchronous copy on the slot's stream)
+                uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024 - 32768;
+                memcpy(h, tc.tc.data(), 32768);
+                CK(cudaMemcpyAsync(s.d_tc, h, 32768, cudaMemcpyHostToDevice, s.st));
+                s.tc_loaded_at = s.d_tc;
+                s.tc_loaded_gen = tc.gen;
+            }
+            ta.tc_mat = s.d_tc;
+        }
     }
     if (p->flags & JB_FLAG_NO_TIE_FIXUP)
         for (int t = 0; t < 2; ++t)
