@@ -507,7 +507,7 @@ __device__ __forceinline__ uint32_t bf16x2(int lo, int hi) {  // two small integ
 struct Row8T {
     uint32_t y[8], cb[8], cr[8];
 };
-__device__ __forceinline__ void csc_row8_t(const uint32_t (&w)[6], const uint32_t* __restrict__ ydown, Row8T& o) {
+__device__ __forceinline__ void csc_row8_t(const uint32_t (&w)[6], const uint32_t* ydown_sh, Row8T& o) {
     uint32_t tmin = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -520,13 +520,14 @@ __device__ __forceinline__ void csc_row8_t(const uint32_t (&w)[6], const uint32_
         tmin = min(tmin, o.y[i] & Y_TIE_MASK);
     }
     if (tmin == 0) {  // some pixel of the row is a CSC tie (exact integer luma): consult the table
+        // (8 KB, in static shared memory: no global round trip; all eight look-ups are issued unconditionally
+        // so that the path stays branch-free, and only the tied pixels take the correction)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if ((o.y[i] & Y_TIE_MASK) == 0) {
-                const int k = 3 * i;
-                uint32_t idx = (byte_of(w[k >> 2], k & 3) << 8) | byte_of(w[(k + 1) >> 2], (k + 1) & 3);
-                o.y[i] -= ((__ldg(ydown + (idx >> 5)) >> (idx & 31)) & 1u) << 24;  // the fraction is tiny: top byte - 1
-            }
+            const int k = 3 * i;
+            uint32_t idx = (byte_of(w[k >> 2], k & 3) << 8) | byte_of(w[(k + 1) >> 2], (k + 1) & 3);
+            uint32_t bit = (ydown_sh[idx >> 5] >> (idx & 31)) & 1u;
+            o.y[i] -= ((o.y[i] & Y_TIE_MASK) == 0 ? bit : 0u) << 24;  // the fraction is tiny: top byte - 1
         }
     }
 }
@@ -647,6 +648,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar[TC_GROUPS][2];
     __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_ydown[2048];  // the CSC tie table (jb_math.h), 8 KB
     // keep the address arithmetic on the shared-space pointer (1024-byte alignment for the 128B swizzle)
     uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, wg = gt >> 5, lane = tid & 31;
@@ -658,6 +660,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     // ---- one-time setup: W matrices, tensor memory, barriers ---------------------------------------
     for (int i = tid; i < TC_B_BYTES / 16; i += TC_GROUPS * 128)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.tc_mat) + i);
+    for (int i = tid; i < 2048; i += TC_GROUPS * 128) s_ydown[i] = __ldg(a.ydown + i);
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "n"(TC_TMEM_COLS));
@@ -777,8 +780,8 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
             if (it == 4) mbar_wait(mbar0, phase0);  // the MMAs of rows 0-7 have consumed the tile: overwrite it
 
             Row8T o0, o1;
-            csc_row8_t(w0, a.ydown, o0);
-            csc_row8_t(w1, a.ydown, o1);
+            csc_row8_t(w0, s_ydown, o0);
+            csc_row8_t(w1, s_ydown, o1);
             const uint32_t rp = (uint32_t)(it & 3);
             sts128(a_row + (((2 * rp) ^ sw_own) << 4), make_uint4(luma_h2(o0.y[0], o0.y[1]), luma_h2(o0.y[2], o0.y[3]),
                                                                   luma_h2(o0.y[4], o0.y[5]), luma_h2(o0.y[6], o0.y[7])));
