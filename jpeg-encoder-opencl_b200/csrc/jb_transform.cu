@@ -125,6 +125,10 @@ struct Row8 {
     uint32_t cr[8];
 };
 
+// SHARED: `ydown` is the copy of the tie table in shared memory and the eight look-ups of a row with a
+// tie are issued unconditionally (branch-free); otherwise predicated loads from the global table (the
+// 4:2:0 CUDA-core kernel has no registers to spare for the former).
+template <bool SHARED>
 __device__ __forceinline__ void csc_row8(const uint32_t (&w)[6], const uint32_t* __restrict__ ydown, Row8& o) {
     uint32_t ty[8], tmin = 0xFFFFFFFFu;
 #pragma unroll
@@ -141,8 +145,12 @@ __device__ __forceinline__ void csc_row8(const uint32_t (&w)[6], const uint32_t*
     if (tmin == 0) {  // some pixel of the row is a CSC tie (exact integer luma): consult the table
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if ((ty[i] & Y_TIE_MASK) == 0) {
-                const int k = 3 * i;
+            const int k = 3 * i;
+            if (SHARED) {
+                uint32_t idx = (byte_of(w[k >> 2], k & 3) << 8) | byte_of(w[(k + 1) >> 2], (k + 1) & 3);
+                uint32_t bit = (ydown[idx >> 5] >> (idx & 31)) & 1u;
+                o.y[i] -= (int)((ty[i] & Y_TIE_MASK) == 0 ? bit : 0u);
+            } else if ((ty[i] & Y_TIE_MASK) == 0) {
                 uint32_t idx = (byte_of(w[k >> 2], k & 3) << 8) | byte_of(w[(k + 1) >> 2], (k + 1) & 3);
                 o.y[i] -= (int)((__ldg(ydown + (idx >> 5)) >> (idx & 31)) & 1u);
             }
@@ -184,7 +192,7 @@ __device__ __forceinline__ void unit_420(const TransformArgs& a, const Image& im
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 Row8 o;
-                csc_row8(w[r], im.ydown, o);
+                csc_row8<false>(w[r], im.ydown, o);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[r * 8 + i] = (float)o.y[i];
                 uint32_t sb[4], sr[4];
@@ -268,7 +276,7 @@ __device__ __forceinline__ void unit_444(const TransformArgs& a, const Image& im
             uint32_t w[6];
             load24<ALIGN>(col0 + (size_t)mirror(my * 8 + r, im.H) * im.pitch, w);  // mirrored below the image
             Row8 o;
-            csc_row8(w, im.ydown, o);
+            csc_row8<true>(w, im.ydown, o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[r * 8 + i] = (float)o.y[i];
             if (!CDS) {
@@ -348,6 +356,11 @@ template <int SUB, int ALIGN>
 __global__ void __launch_bounds__(TW * 32, 16 / TW) k_transform(const __grid_constant__ TransformArgs a) {
     // dynamic shared memory: 4 staging tiles of 4 KB, then (4:2:0 only) 4 chroma parking areas
     extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_ydown[SUB == JB_SUB_420 ? 1 : 2048];  // 8x8 MCUs: the CSC tie table (jb_math.h) on chip
+    if (SUB != JB_SUB_420) {
+        for (int i = threadIdx.x; i < 2048; i += TW * 32) s_ydown[i] = __ldg(a.ydown + i);
+        __syncthreads();
+    }
     float* chroma = reinterpret_cast<float*>(smem + TW * 256);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* st = smem + warp * 256;
@@ -358,7 +371,7 @@ __global__ void __launch_bounds__(TW * 32, 16 / TW) k_transform(const __grid_con
         const uint32_t unit = active ? base + warp : base;
         uint32_t f = unit / units_per_frame, rem = unit - f * units_per_frame;
         int my = (int)(rem / (uint32_t)a.units_per_row), ux = (int)(rem - (uint32_t)my * (uint32_t)a.units_per_row);
-        Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
+        Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, SUB == JB_SUB_420 ? a.ydown : s_ydown};
         int mcu_x0 = ux * mcus_per_unit;
         int mcus_valid = active ? min(mcus_per_unit, a.fast_mcux - mcu_x0) : 0;
         size_t mcu_g0 = (size_t)f * (size_t)a.g.n_mcu + (size_t)my * (size_t)a.g.mcux + (size_t)mcu_x0;
