@@ -215,15 +215,18 @@ __device__ __forceinline__ void encode_sparse(uint64_t mask, Fetch value, int dc
     }
 }
 
+#ifndef ENC_CTAS
+#define ENC_CTAS 5
+#endif
 // One thread per block.  The tile's coefficients (256 blocks, 32 KB) are staged in shared
 // memory with coalesced 128-bit loads (XOR swizzle: piece p of block t at t*8 + (p ^ (t&7))).
 // Each thread builds the non-zero mask of its block, walks the non-zero coefficients, keeps
 // the first 128 code bits in a slot and the total length; lengths are scanned per tile.
-__global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ EntropyArgs a) {
+__global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant__ EntropyArgs a) {
     __shared__ uint4 s_coef[TILE * 8];
     __shared__ __align__(16) uint32_t s_slot[TILE * 4];
     __shared__ uint64_t s_mask[TILE];
-    __shared__ uint32_t s_ac[2][256], s_dc[2][16], s_warp[8];
+    __shared__ uint32_t s_dc[2][16], s_warp[8];
     __shared__ uint32_t s_small[2][512];
     __shared__ uint32_t s_len[TILE];
     __shared__ uint32_t s_hist[64], s_start[64];
@@ -239,7 +242,8 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
     if (t < 64) s_hist[t] = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) (&s_small[0][0])[i * TILE + t] = (&a.huff->small[0][0])[i * TILE + t];
-    load_tables(a, s_ac, s_dc);  // ends with __syncthreads()
+    if (t < 32) (&s_dc[0][0])[t] = (&a.huff->dc[0][0])[t];
+    __syncthreads();
     // ---- non-zero mask of this thread's block, then a counting sort of the tile's blocks by
     // their number of non-zero AC coefficients: the walk below costs one loop iteration per
     // non-zero, so warps made of similar blocks do not wait for their busiest lane.
@@ -300,7 +304,8 @@ __global__ void __launch_bounds__(TILE) k_encode(const __grid_constant__ Entropy
         }
         SlotSink s;
         s.init(s_slot + k * 4);
-        encode_sparse<true>(s_mask[k], value, value(0) - pred, s_ac[tab], s_dc[tab], s_small[tab], a.always_eob != 0, s);
+        // the full AC table (symbols outside the small-value table, ZRL, EOB) stays in global memory / L1
+        encode_sparse<true>(s_mask[k], value, value(0) - pred, a.huff->ac[tab], s_dc[tab], s_small[tab], a.always_eob != 0, s);
         s.finish();
         const uint32_t nbits = s.bits();
         s_len[k] = nbits;
