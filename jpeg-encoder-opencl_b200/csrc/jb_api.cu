@@ -41,7 +41,7 @@ struct Slot {
     uint8_t* d_rgb = nullptr;
     int16_t* d_coef = nullptr;
     uint32_t* d_tie_list = nullptr;
-    uint32_t* d_scalars = nullptr;  // [0] tie_count, [1] n_ff_tiles, then status[4] (u64, 8-aligned) at +16 bytes
+    uint32_t* d_scalars = nullptr;  // [0] tie_count, [1] n_ff_tiles, [2] n_long, status[4] (u64) at +16 bytes, [12] unit counter
     EntropyWork w{};
     uint8_t* d_out = nullptr;
     size_t d_out_cap = 0;
@@ -332,6 +332,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ta.ydown = ctx->d_ydown;
     ta.tie_list = s.d_tie_list;
     ta.tie_count = s.d_scalars;
+    ta.unit_counter = s.d_scalars + 12;
     ta.tie_cap = s.tie_cap;
     {
         jb_ctx::TableCache& tc = ctx->tables;

@@ -661,6 +661,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar[TC_GROUPS][2];
     __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_next[TC_GROUPS];
     __shared__ uint32_t s_ydown[2048];  // the CSC tie table (jb_math.h), 8 KB
     // keep the address arithmetic on the shared-space pointer (1024-byte alignment for the 128B swizzle)
     uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
@@ -756,6 +757,9 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    // Strips are handed out dynamically (the first one statically): groups that meet cheaper content or
+    // emptier edge strips take more of them, so that all SMs finish together.  One thread of the group
+    // draws the next index at the start of a unit; the group reads it after the first barrier of the unit.
     uint32_t base = (blockIdx.x * TC_GROUPS + g) * 4;
     TcUnit cur = decode(base);
     if (base < a.total_units) {
@@ -763,8 +767,10 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         fetch_pair(0, 0);
         fetch_pair(1, 1);
     }
-    for (; base < a.total_units; base += stride) {
-        const TcUnit nxt = decode(base + stride);  // past the end: an empty unit, nothing is fetched
+    while (base < a.total_units) {
+        if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
+        uint32_t nbase = 0;
+        TcUnit nxt = cur;
         const int mcus_valid = cur.bytes_valid / 48;
         const size_t mcu_g0 = cur.mcu_g0;
         const bool valid = (lane >> 1) < mcus_valid;
@@ -788,7 +794,11 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
                 w1[2 * j + 1] = v1.y;
             }
             if (ALIGN == 16) __syncwarp();  // every lane has read the slot before anyone refills it
-            if (it == 6) aim(nxt);
+            if (it == 6) {
+                nbase = s_next[g];  // written before the barrier of it == 3
+                nxt = decode(nbase);  // past the end: an empty unit, nothing is fetched
+                aim(nxt);
+            }
             fetch_pair((it + 2) & 7, it & 1);
             if (it == 4) mbar_wait(mbar0, phase0);  // the MMAs of rows 0-7 have consumed the tile: overwrite it
 
@@ -843,6 +853,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         phase0 ^= 1;
         finish(tmem_d0, 1, 4, 0, 0);                  // Cb / Cr
         cur = nxt;
+        base = nbase;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
