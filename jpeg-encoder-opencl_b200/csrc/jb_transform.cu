@@ -633,28 +633,15 @@ __device__ __forceinline__ void cp_async(uint32_t dst, const uint8_t* src) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
 }
 
-// One warp's unit of 16 MCUs (a 256-pixel wide, 16-row strip of one frame).
+// One warp's unit: a run of 16 consecutive MCUs of the kernel's MCU sequence (frame-major, then MCU rows,
+// then MCU columns of the region the kernel covers).  A run may wrap to the next MCU row or frame, so every
+// lane pair keeps the coordinates of its own MCU.
 struct TcUnit {
-    const uint8_t* row0;  // first byte of the strip in image row 0
-    int y0;               // first image row
-    int bytes_valid;      // 48 per MCU that exists
-    size_t mcu_g0;        // global index of the first MCU
+    const uint8_t* ptr;  // first byte of the MCU in image row 0 (frame base + 48 bytes per MCU column)
+    int y0;              // first image row of the MCU
+    uint32_t gm;         // index of the MCU in the coefficient array (frame-major over all MCUs of a frame)
+    bool valid;          // the MCU exists
 };
-
-// Asynchronous copy of this lane's share of one 768-byte strip row into the ring (dst and src
-// already include the lane's offset).  16-byte aligned images are copied warp-cooperatively
-// (48 chunks of 16 bytes: lane, and lane + 32 for the first 16 lanes), others by each lane for
-// itself (its own 24 bytes).
-template <int ALIGN>
-__device__ __forceinline__ void tc_async_row(uint32_t dst, const uint8_t* src, bool p0, bool p1) {
-    if (ALIGN == 16) {
-        if (p0) cp_async<16>(dst, src);
-        if (p1) cp_async<16>(dst + 512, src + 512);
-    } else if (p0) {
-#pragma unroll
-        for (int j = 0; j < 24 / ALIGN; ++j) cp_async<ALIGN>(dst + j * ALIGN, src + j * ALIGN);
-    }
-}
 
 template <int ALIGN>
 __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __grid_constant__ TransformArgs a) {
@@ -692,7 +679,6 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     uint32_t phase0 = 0, phase1 = 0;
     uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
     const int half = lane & 1;
-    const uint32_t units_per_frame = (uint32_t)a.units_per_row * (uint32_t)a.fast_mcuy;
     const uint32_t stride = gridDim.x * TC_GROUPS * 4;
     // shared addresses of this thread's A rows: own row (luma), and the rows that take its chroma
     const uint32_t sw_own = (uint32_t)(gt & 7);
@@ -721,38 +707,66 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
     };
     // every warp of the group runs the same control flow; a warp past the end gets an empty unit
+    const uint32_t per_frame = (uint32_t)a.fast_mcux * (uint32_t)a.fast_mcuy;
     auto decode = [&](uint32_t unit_base) {
-        const bool active = unit_base + wg < a.total_units;
-        const uint32_t unit = active ? unit_base + wg : unit_base;
-        uint32_t f = unit / units_per_frame, rem = unit - f * units_per_frame;
-        int my = (int)(rem / (uint32_t)a.units_per_row), ux = (int)(rem - (uint32_t)my * (uint32_t)a.units_per_row);
+        const uint32_t lin = (unit_base + wg) * 16u + (uint32_t)(lane >> 1);  // this lane pair's MCU
         TcUnit u;
-        u.row0 = a.rgb + (size_t)f * a.frame_stride + (size_t)ux * TC_ROW_BYTES;
-        u.y0 = my * 16;
-        u.bytes_valid = active ? min(16, a.fast_mcux - ux * 16) * 48 : 0;
-        u.mcu_g0 = (size_t)f * (size_t)a.g.n_mcu + (size_t)my * (size_t)a.g.mcux + (size_t)ux * 16;
+        u.valid = unit_base + wg < a.total_units && lin < a.tc_mcus;
+        const uint32_t l = u.valid ? lin : 0u;
+        uint32_t f = l / per_frame, rem = l - f * per_frame;
+        uint32_t my = rem / (uint32_t)a.fast_mcux, mx = rem - my * (uint32_t)a.fast_mcux;
+        u.ptr = a.rgb + (size_t)f * a.frame_stride + (size_t)mx * 48;
+        u.y0 = (int)my * 16;
+        u.gm = f * (uint32_t)a.g.n_mcu + my * (uint32_t)a.g.mcux + mx;
         return u;
     };
-    // fetch cursor: the strip whose rows are being copied into the ring, this lane's share folded in
+    // fetch cursor: where this lane's share of the unit's rows comes from.  16-byte aligned images are copied
+    // warp-cooperatively: chunk c (16 bytes) of the 48 chunks of a row belongs to MCU c / 3 — lane takes chunks
+    // lane and, for lane < 16, 32 + lane, and gets the coordinates of their MCUs from the owning lane pairs.
+    // Otherwise every lane copies the 24 bytes of its own half MCU.
     const uint32_t lane_share = (uint32_t)lane * (ALIGN == 16 ? 16u : 24u);
     const uint32_t ring_wr = ring + lane_share, ring_rd = ring + (uint32_t)lane * 24u;
     const uint32_t pitch32 = (uint32_t)a.pitch;
-    const uint8_t* fc_src = nullptr;
-    int fc_y0 = 0;
+    const uint8_t *fc_src0 = nullptr, *fc_src1 = nullptr;
+    int fc_y00 = 0, fc_y01 = 0;
     bool fc_p0 = false, fc_p1 = false;
-    auto aim = [&](const TcUnit& u) {
-        fc_src = u.row0 + lane_share;
-        fc_y0 = u.y0;
-        fc_p0 = (int)lane_share < u.bytes_valid;
-        fc_p1 = ALIGN == 16 && lane < 16 && (int)lane_share + 512 < u.bytes_valid;
+    auto shfl_ptr = [&](const uint8_t* p, int src) {
+        unsigned long long v = (unsigned long long)p;
+        uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+        return (const uint8_t*)(((unsigned long long)hi << 32) | lo);
     };
-    // start the copy of row pair `rp` (image rows 2rp, 2rp+1 of the strip) into ring slot `sl`: one commit group
+    auto aim = [&](const TcUnit& u) {
+        if (ALIGN == 16) {
+            const int c0 = lane, c1 = 32 + (lane & 15);
+            const int m0 = c0 / 3, m1 = c1 / 3;
+            fc_src0 = shfl_ptr(u.ptr, 2 * m0) + (c0 - 3 * m0) * 16;
+            fc_y00 = __shfl_sync(0xffffffffu, u.y0, 2 * m0);
+            fc_p0 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m0) != 0;
+            fc_src1 = shfl_ptr(u.ptr, 2 * m1) + (c1 - 3 * m1) * 16;
+            fc_y01 = __shfl_sync(0xffffffffu, u.y0, 2 * m1);
+            fc_p1 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m1) != 0 && lane < 16;
+        } else {
+            fc_src0 = u.ptr + half * 24;
+            fc_y00 = u.y0;
+            fc_p0 = u.valid;
+        }
+    };
+    // start the copy of row pair `rp` (image rows 2rp, 2rp+1 of every MCU of the unit) into ring slot `sl`: one
+    // commit group
     auto fetch_pair = [&](int rp, int sl) {
         const uint32_t dst = ring_wr + (uint32_t)sl * (2 * 4 * TC_ROW_BYTES);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const uint32_t y = (uint32_t)mirror(fc_y0 + 2 * rp + r, a.g.H);
-            tc_async_row<ALIGN>(dst + r * 4 * TC_ROW_BYTES, fc_src + (uint64_t)y * pitch32, fc_p0, fc_p1);
+            const uint32_t d = dst + r * 4 * TC_ROW_BYTES;
+            const uint8_t* s0 = fc_src0 + (uint64_t)(uint32_t)mirror(fc_y00 + 2 * rp + r, a.g.H) * pitch32;
+            if (ALIGN == 16) {
+                const uint8_t* s1 = fc_src1 + (uint64_t)(uint32_t)mirror(fc_y01 + 2 * rp + r, a.g.H) * pitch32;
+                if (fc_p0) cp_async<16>(d, s0);
+                if (fc_p1) cp_async<16>(d + 512, s1);
+            } else if (fc_p0) {
+#pragma unroll
+                for (int j = 0; j < 24 / ALIGN; ++j) cp_async<ALIGN>(d + j * ALIGN, s0 + j * ALIGN);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -771,10 +785,9 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
         uint32_t nbase = 0;
         TcUnit nxt = cur;
-        const int mcus_valid = cur.bytes_valid / 48;
-        const size_t mcu_g0 = cur.mcu_g0;
-        const bool valid = (lane >> 1) < mcus_valid;
-        const uint32_t gb0 = (uint32_t)(mcu_g0 + (valid ? lane >> 1 : 0)) * 6u;
+        const bool valid = cur.valid;
+        const uint32_t gm = valid ? cur.gm : 0xFFFFFFFFu;  // all ones: no such MCU
+        const uint32_t gb0 = cur.gm * 6u;
 
         // ---- 16 image rows = 8 row pairs: ring -> registers -> colour conversion -> A tiles -----------
         // The ring holds two pairs; the refill of a slot (the pair after next, possibly of the next unit)
@@ -840,7 +853,15 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
                 tc_quant_stage<1>(t, a, st, lane, tl, th, wait_mbar, wait_parity);
             if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + blk + half, tl, th);
             __syncwarp();
-            copy_out<6>(st, coef4, mcu_g0, mcus_valid, blk, lane);
+            // coalesced copy-out: 8 x 32 pieces of 16 bytes; piece g belongs to block g >> 3 of the warp, i.e. to
+            // MCU g >> 4, whose index sits in lane pair g >> 4 (32-bit piece indices: n_blocks * 8 < 2^32)
+            const uint32_t piece0 = (uint32_t)(blk + ((lane >> 3) & 1)) * 8u + (uint32_t)(lane & 7);
+#pragma unroll
+            for (int it8 = 0; it8 < 8; ++it8) {
+                const int sb = it8 * 4 + (lane >> 3), pc = lane & 7;
+                const uint32_t m_gm = __shfl_sync(0xffffffffu, gm, 4 * it8 + 2 * (lane >> 4));
+                if (m_gm != 0xFFFFFFFFu) coef4[m_gm * 48u + piece0] = st[sb * 8 + (pc ^ (sb & 7))];
+            }
             __syncwarp();
         };
         phase0 ^= 1;                                  // (rows 0-7: completion already observed at it == 4)
@@ -899,7 +920,9 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     int align = (bits & 7) == 0 ? 8 : (bits & 3) == 0 ? 4 : 1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    if (a.tc_mat && a.g.sub == JB_SUB_420 && align >= 4) {  // tensor-core variant
+    if (a.tc_mat && a.g.sub == JB_SUB_420 && align >= 4) {  // tensor-core variant: units are runs of 16 MCUs
+        a.tc_mcus = (uint32_t)a.fast_mcux * (uint32_t)a.fast_mcuy * (uint32_t)a.n_frames;
+        a.total_units = (a.tc_mcus + 15) / 16;
         int needg = (int)((a.total_units + 4 * TC_GROUPS - 1) / (4 * TC_GROUPS));
         int gridg = needg < sms ? needg : sms;
         if ((bits & 15) == 0) {
