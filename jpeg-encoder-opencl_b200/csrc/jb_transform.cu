@@ -538,9 +538,20 @@ __device__ __forceinline__ void csc_row8_t(const uint32_t (&w)[6], const uint32_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int k = 3 * i;
-            uint32_t idx = (byte_of(w[k >> 2], k & 3) << 8) | byte_of(w[(k + 1) >> 2], (k + 1) & 3);
-            uint32_t bit = (ydown_sh[idx >> 5] >> (idx & 31)) & 1u;
-            o.y[i] -= ((o.y[i] & Y_TIE_MASK) == 0 ? bit : 0u) << 24;  // the fraction is tiny: top byte - 1
+            const uint32_t R = byte_of(w[k >> 2], k & 3), G = byte_of(w[(k + 1) >> 2], (k + 1) & 3);
+            // word R*8 + G/32 (one IMAD + one shift), bit G % 32 (the funnel shift takes G mod 32 itself)
+            const uint32_t word = ydown_sh[mad(R, 256u, G) >> 5];
+            uint32_t y = o.y[i];
+            // the fraction of a tie is tiny: "top byte - 1" is a subtraction of 2^24
+            asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                "shf.r.wrap.b32 t, %1, %1, %2;\n\t"
+                "and.b32 t, t, 1;\n\t"
+                "setp.ne.u32 p, t, 0;\n\t"
+                "setp.eq.and.u32 p, %3, 0, p;\n\t"
+                "@p sub.u32 %0, %0, 0x1000000;\n\t}"
+                : "+r"(y)
+                : "r"(word), "r"(G), "r"(y & Y_TIE_MASK));
+            o.y[i] = y;
         }
     }
 }
@@ -726,46 +737,64 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     // Otherwise every lane copies the 24 bytes of its own half MCU.
     const uint32_t lane_share = (uint32_t)lane * (ALIGN == 16 ? 16u : 24u);
     const uint32_t ring_wr = ring + lane_share, ring_rd = ring + (uint32_t)lane * 24u;
-    const uint32_t pitch32 = (uint32_t)a.pitch;
-    const uint8_t *fc_src0 = nullptr, *fc_src1 = nullptr;
-    int fc_y00 = 0, fc_y01 = 0;
-    bool fc_p0 = false, fc_p1 = false;
+    // Each cursor walks down the image two rows per fetch: `p` = first row of the next pair, `y` = its
+    // (unmirrored) row index.  Rows at or below the image height are mirrored (utils.cpp:211-233): the hot
+    // kernel only meets them with an even height (plan_fast), so a row pair is either inside (step +pitch)
+    // or mirrored (H-1, H-2, ...: step -pitch), and the walk turns around between two pairs.
+    const int pitch_i = (int)a.pitch, img_h = a.g.H;
+    const uint8_t *fc_p0 = nullptr, *fc_p1 = nullptr;
+    int fc_y0 = 0, fc_y1 = 0;
+    bool fc_v0 = false, fc_v1 = false;
     auto shfl_ptr = [&](const uint8_t* p, int src) {
         unsigned long long v = (unsigned long long)p;
         uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
         return (const uint8_t*)(((unsigned long long)hi << 32) | lo);
     };
     auto aim = [&](const TcUnit& u) {
+        const uint8_t* row0 = u.ptr + (uint64_t)(uint32_t)u.y0 * (uint32_t)pitch_i;  // y0 < H: never mirrored
         if (ALIGN == 16) {
             const int c0 = lane, c1 = 32 + (lane & 15);
             const int m0 = c0 / 3, m1 = c1 / 3;
-            fc_src0 = shfl_ptr(u.ptr, 2 * m0) + (c0 - 3 * m0) * 16;
-            fc_y00 = __shfl_sync(0xffffffffu, u.y0, 2 * m0);
-            fc_p0 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m0) != 0;
-            fc_src1 = shfl_ptr(u.ptr, 2 * m1) + (c1 - 3 * m1) * 16;
-            fc_y01 = __shfl_sync(0xffffffffu, u.y0, 2 * m1);
-            fc_p1 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m1) != 0 && lane < 16;
+            fc_p0 = shfl_ptr(row0, 2 * m0) + (c0 - 3 * m0) * 16;
+            fc_y0 = __shfl_sync(0xffffffffu, u.y0, 2 * m0);
+            fc_v0 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m0) != 0;
+            fc_p1 = shfl_ptr(row0, 2 * m1) + (c1 - 3 * m1) * 16;
+            fc_y1 = __shfl_sync(0xffffffffu, u.y0, 2 * m1);
+            fc_v1 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m1) != 0 && lane < 16;
         } else {
-            fc_src0 = u.ptr + half * 24;
-            fc_y00 = u.y0;
-            fc_p0 = u.valid;
+            fc_p0 = row0 + half * 24;
+            fc_y0 = u.y0;
+            fc_v0 = u.valid;
         }
     };
-    // start the copy of row pair `rp` (image rows 2rp, 2rp+1 of every MCU of the unit) into ring slot `sl`: one
-    // commit group
-    auto fetch_pair = [&](int rp, int sl) {
-        const uint32_t dst = ring_wr + (uint32_t)sl * (2 * 4 * TC_ROW_BYTES);
+    // the two rows of a cursor's next pair, then advance the cursor
+    auto walk = [&](const uint8_t*& p, int& y, const uint8_t*& r0, const uint8_t*& r1) {
+        const int d = y < img_h ? pitch_i : -pitch_i;
+        r0 = p;
+        r1 = p + d;
+        y += 2;
+        p = r1 + (y == img_h ? 0 : d);
+    };
+    // start the copy of the next row pair of every MCU of the unit into ring slot `sl`: one commit group
+    auto fetch_pair = [&](int sl) {
+        const uint32_t d0 = ring_wr + (uint32_t)sl * (2 * 4 * TC_ROW_BYTES), d1 = d0 + 4 * TC_ROW_BYTES;
+        const uint8_t *r0, *r1;
+        walk(fc_p0, fc_y0, r0, r1);
+        if (ALIGN == 16) {
+            if (fc_v0) {
+                cp_async<16>(d0, r0);
+                cp_async<16>(d1, r1);
+            }
+            walk(fc_p1, fc_y1, r0, r1);
+            if (fc_v1) {
+                cp_async<16>(d0 + 512, r0);
+                cp_async<16>(d1 + 512, r1);
+            }
+        } else if (fc_v0) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const uint32_t d = dst + r * 4 * TC_ROW_BYTES;
-            const uint8_t* s0 = fc_src0 + (uint64_t)(uint32_t)mirror(fc_y00 + 2 * rp + r, a.g.H) * pitch32;
-            if (ALIGN == 16) {
-                const uint8_t* s1 = fc_src1 + (uint64_t)(uint32_t)mirror(fc_y01 + 2 * rp + r, a.g.H) * pitch32;
-                if (fc_p0) cp_async<16>(d, s0);
-                if (fc_p1) cp_async<16>(d + 512, s1);
-            } else if (fc_p0) {
-#pragma unroll
-                for (int j = 0; j < 24 / ALIGN; ++j) cp_async<ALIGN>(d + j * ALIGN, s0 + j * ALIGN);
+            for (int j = 0; j < 24 / ALIGN; ++j) {
+                cp_async<ALIGN>(d0 + j * ALIGN, r0 + j * ALIGN);
+                cp_async<ALIGN>(d1 + j * ALIGN, r1 + j * ALIGN);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -778,8 +807,8 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     TcUnit cur = decode(base);
     if (base < a.total_units) {
         aim(cur);
-        fetch_pair(0, 0);
-        fetch_pair(1, 1);
+        fetch_pair(0);
+        fetch_pair(1);
     }
     while (base < a.total_units) {
         if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
@@ -812,7 +841,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
                 nxt = decode(nbase);  // past the end: an empty unit, nothing is fetched
                 aim(nxt);
             }
-            fetch_pair((it + 2) & 7, it & 1);
+            fetch_pair(it & 1);
             if (it == 4) mbar_wait(mbar0, phase0);  // the MMAs of rows 0-7 have consumed the tile: overwrite it
 
             Row8T o0, o1;
