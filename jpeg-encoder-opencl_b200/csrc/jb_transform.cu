@@ -631,6 +631,11 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
+__device__ __forceinline__ uint32_t lds_volatile(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
@@ -660,6 +665,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     __shared__ __align__(8) uint64_t s_mbar[TC_GROUPS][2];
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_next[TC_GROUPS];
+    __shared__ uint32_t s_desc[TC_GROUPS + 1][4];  // descriptor low words: [group]{luma tile, chroma tile}, [TC_GROUPS][table * 2 + split]
     __shared__ uint32_t s_ydown[2048];  // the CSC tie table (jb_math.h), 8 KB
     // keep the address arithmetic on the shared-space pointer (1024-byte alignment for the 128B swizzle)
     uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
@@ -677,6 +683,11 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "n"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (gt == 0) {
+        s_desc[g][0] = (uint32_t)umma_desc(smem_u32(tileA));
+        s_desc[g][1] = (uint32_t)umma_desc(smem_u32(tileC));
+        s_desc[TC_GROUPS][g] = (uint32_t)umma_desc(smem_u32(sB + g * 8192));
     }
     if (tid < TC_GROUPS * 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[0][0]) + 8 * tid));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -698,13 +709,17 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     const uint32_t ac_cb = smem_u32(tileC) + row_cb * 128 + half * 8, ac_cr = smem_u32(tileC) + row_cr * 128 + half * 8;
     const uint32_t sw_cb = (uint32_t)(row_cb & 7), sw_cr = (uint32_t)(row_cr & 7);
 
-    // the 8 MMAs of one tile (issued by one thread); completion arrives on `mbar`
-    auto issue = [&](const uint8_t* tile, int tab, uint32_t tmem_d, uint32_t mbar) {
+    // the 8 MMAs of one tile (issued by one thread); completion arrives on `mbar`.  The low words of the
+    // shared-memory descriptors were put in shared memory at setup and are read back with volatile loads:
+    // computed in place, the compiler hoists their arithmetic (~30 instructions) out of the issuing
+    // branch into every iteration of the row loop of every warp.
+    auto issue = [&](int tile_sel, int tab, uint32_t tmem_d, uint32_t mbar) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint64_t da = umma_desc(smem_u32(tile));
+        const uint64_t hi = (uint64_t)0x40004040u << 32;
+        const uint64_t da = hi | lds_volatile(smem_u32(&s_desc[g][tile_sel]));
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
-            uint64_t db = umma_desc(smem_u32(sB + (tab * 2 + s2) * 8192));
+            const uint64_t db = hi | lds_volatile(smem_u32(&s_desc[TC_GROUPS][tab * 2 + s2]));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
         }
@@ -717,15 +732,24 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
     };
+    // n / d and n % d with the host's m = floor(2^32 / d): the estimate is at most one too small
+    auto divmod = [](uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t& r) {
+        q = __umulhi(n, m);
+        r = n - q * d;
+        if (r >= d) {
+            q += 1;
+            r -= d;
+        }
+    };
     // every warp of the group runs the same control flow; a warp past the end gets an empty unit
-    const uint32_t per_frame = (uint32_t)a.fast_mcux * (uint32_t)a.fast_mcuy;
     auto decode = [&](uint32_t unit_base) {
         const uint32_t lin = (unit_base + wg) * 16u + (uint32_t)(lane >> 1);  // this lane pair's MCU
         TcUnit u;
         u.valid = unit_base + wg < a.total_units && lin < a.tc_mcus;
         const uint32_t l = u.valid ? lin : 0u;
-        uint32_t f = l / per_frame, rem = l - f * per_frame;
-        uint32_t my = rem / (uint32_t)a.fast_mcux, mx = rem - my * (uint32_t)a.fast_mcux;
+        uint32_t f, rem, my, mx;
+        divmod(l, a.tc_per_frame, a.tc_magic_frame, f, rem);
+        divmod(rem, (uint32_t)a.fast_mcux, a.tc_magic_row, my, mx);
         u.ptr = a.rgb + (size_t)f * a.frame_stride + (size_t)mx * 48;
         u.y0 = (int)my * 16;
         u.gm = f * (uint32_t)a.g.n_mcu + my * (uint32_t)a.g.mcux + mx;
@@ -863,11 +887,11 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
             sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(chroma_h2(sr[0], sr[1]), chroma_h2(sr[2], sr[3])));
             if (it == 3) {
                 publish();
-                if (gt == 0) issue(tileA, 0, tmem_d0, mbar0);
+                if (gt == 0) issue(0, 0, tmem_d0, mbar0);
             }
         }
         publish();
-        if (gt == 0) issue(tileA, 0, tmem_d1, mbar1);
+        if (gt == 0) issue(0, 0, tmem_d1, mbar1);
 
         // read this thread's row of the accumulator, round / flag / pack, stage in tileA, store blocks blk, blk+1
         auto finish = [&](uint32_t tmem_d, int tab, int blk, uint32_t wait_mbar, uint32_t wait_parity) {
@@ -897,7 +921,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         finish(tmem_d0, 0, 0, mbar1, phase1);         // Y00 / Y01; staging waits for the MMAs of rows 8-15
         phase1 ^= 1;
         publish();                                    // every thread has read accumulator 0: it takes the chroma tile
-        if (gt == 0) issue(tileC, 1, tmem_d0, mbar0);
+        if (gt == 0) issue(1, 1, tmem_d0, mbar0);
         finish(tmem_d1, 0, 2, 0, 0);                  // Y10 / Y11
         mbar_wait(mbar0, phase0);
         phase0 ^= 1;
@@ -952,6 +976,9 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     if (a.tc_mat && a.g.sub == JB_SUB_420 && align >= 4) {  // tensor-core variant: units are runs of 16 MCUs
         a.tc_mcus = (uint32_t)a.fast_mcux * (uint32_t)a.fast_mcuy * (uint32_t)a.n_frames;
         a.total_units = (a.tc_mcus + 15) / 16;
+        a.tc_per_frame = (uint32_t)a.fast_mcux * (uint32_t)a.fast_mcuy;
+        a.tc_magic_frame = (uint32_t)(0xFFFFFFFFull < (1ull << 32) / a.tc_per_frame ? 0xFFFFFFFFull : (1ull << 32) / a.tc_per_frame);
+        a.tc_magic_row = (uint32_t)(0xFFFFFFFFull < (1ull << 32) / (uint32_t)a.fast_mcux ? 0xFFFFFFFFull : (1ull << 32) / (uint32_t)a.fast_mcux);
         int needg = (int)((a.total_units + 4 * TC_GROUPS - 1) / (4 * TC_GROUPS));
         int gridg = needg < sms ? needg : sms;
         if ((bits & 15) == 0) {
