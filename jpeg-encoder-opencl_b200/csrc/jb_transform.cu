@@ -631,6 +631,11 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ uint32_t lds_volatile(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -709,21 +714,24 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     const uint32_t ac_cb = smem_u32(tileC) + row_cb * 128 + half * 8, ac_cr = smem_u32(tileC) + row_cr * 128 + half * 8;
     const uint32_t sw_cb = (uint32_t)(row_cb & 7), sw_cr = (uint32_t)(row_cr & 7);
 
-    // the 8 MMAs of one tile (issued by one thread); completion arrives on `mbar`.  The low words of the
-    // shared-memory descriptors were put in shared memory at setup and are read back with volatile loads:
-    // computed in place, the compiler hoists their arithmetic (~30 instructions) out of the issuing
-    // branch into every iteration of the row loop of every warp.
+    // the 8 MMAs of one tile, issued by one elected lane of the group's first warp; completion arrives on
+    // `mbar`.  Every operand is computed from warp-uniform values (the group index comes out of a shuffle, so
+    // the compiler keeps it in a uniform register): no per-thread descriptor arithmetic, and no
+    // serialisation loop around each tcgen05.mma.
+    const bool issuer = __shfl_sync(0xffffffffu, (uint32_t)wg, 0) == 0;
     auto issue = [&](int tile_sel, int tab, uint32_t tmem_d, uint32_t mbar) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t hi = (uint64_t)0x40004040u << 32;
-        const uint64_t da = hi | lds_volatile(smem_u32(&s_desc[g][tile_sel]));
+        if (elect_one()) {
+            const uint64_t hi = (uint64_t)0x40004040u << 32;
+            const uint64_t da = hi | lds_volatile(smem_u32(&s_desc[g][tile_sel]));
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-            const uint64_t db = hi | lds_volatile(smem_u32(&s_desc[TC_GROUPS][tab * 2 + s2]));
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const uint64_t db = hi | lds_volatile(smem_u32(&s_desc[TC_GROUPS][tab * 2 + s2]));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
     };
     // writes of this thread to the tiles become visible to the tensor core, all threads of the group arrive
     // (a full group barrier: arrive/wait for the non-issuing warps and CTA-wide barriers both measured slower)
@@ -887,11 +895,11 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
             sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(chroma_h2(sr[0], sr[1]), chroma_h2(sr[2], sr[3])));
             if (it == 3) {
                 publish();
-                if (gt == 0) issue(0, 0, tmem_d0, mbar0);
+                if (issuer) issue(0, 0, tmem_d0, mbar0);
             }
         }
         publish();
-        if (gt == 0) issue(0, 0, tmem_d1, mbar1);
+        if (issuer) issue(0, 0, tmem_d1, mbar1);
 
         // read this thread's row of the accumulator, round / flag / pack, stage in tileA, store blocks blk, blk+1
         auto finish = [&](uint32_t tmem_d, int tab, int blk, uint32_t wait_mbar, uint32_t wait_parity) {
@@ -921,7 +929,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         finish(tmem_d0, 0, 0, mbar1, phase1);         // Y00 / Y01; staging waits for the MMAs of rows 8-15
         phase1 ^= 1;
         publish();                                    // every thread has read accumulator 0: it takes the chroma tile
-        if (gt == 0) issue(1, 1, tmem_d0, mbar0);
+        if (issuer) issue(1, 1, tmem_d0, mbar0);
         finish(tmem_d1, 0, 2, 0, 0);                  // Y10 / Y11
         mbar_wait(mbar0, phase0);
         phase0 ^= 1;
