@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tensor-dct", type=int, default=1,
-                    help="4:2:0 transform kernel: 1 = tcgen05 (library default), 0 = CUDA-core FMA kernel (JB_FLAG_FMA_DCT)")
+                    help="transform kernel: 1 = tcgen05 (library default), 0 = CUDA-core FMA kernel (JB_FLAG_FMA_DCT)")
     return ap.parse_args()
 
 
@@ -327,8 +327,8 @@ def main():
     alg_bytes = F * (3 * W * H + 2 * samples_per_px * padded)  # read RGB8 + write int16 coefficients
     k_us = tm["transform_us"] / max(tm["transform_launches"], 1)
     achieved = alg_bytes / (k_us * 1e-6) / 1e9
-    use_tc = bool(a.tensor_dct) and sub == jb.SUB_420
-    kname = "k_transform_tc" if use_tc else "k_transform"
+    use_tc = bool(a.tensor_dct)
+    kname = ("k_transform_tc" if sub == jb.SUB_420 else "k_transform_tc3") if use_tc else "k_transform"
     traffic = None
     try:  # per-launch DRAM bytes from the committed ncu capture of the same command, if present
         with open(os.path.join(ROOT, "profiles", "r01_transform_ncu_summary.json")) as f:
@@ -401,7 +401,7 @@ def main():
                        "l2": "inputs per step (%.2f GB) far exceed the 126 MB L2" % (F * fstride / 1e9),
                        "bits_per_pixel": round(8.0 * total_bytes / px_per_step, 4),
                        "tie_fixups_per_step": int(tm["tie_fixups"]),
-                       "transform_kernel": "k_transform_tc (tcgen05)" if use_tc else "k_transform (FMA pipe)"},
+                       "transform_kernel": kname + (" (tcgen05)" if use_tc else " (FMA pipe)")},
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": launches_device,
         }

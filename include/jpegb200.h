@@ -53,9 +53,10 @@ typedef enum {
 #define JB_FLAG_NO_TIE_FIXUP 0x10u   /* skip the binary64 replay of near-tie coefficients        */
 #define JB_FLAG_TENSOR_DCT 0x20u     /* accepted, no effect: the tcgen05 transform (FDCT + scale  *
                                       * + zigzag as one tensor-core contraction per block, fp16   *
-                                      * 2-split operands, fp32 in TMEM) is the 4:2:0 default      */
-#define JB_FLAG_FMA_DCT 0x40u        /* 4:2:0: use the CUDA-core kernel (register AAN FDCT, near- *
-                                      * tie band proven analytically) instead of the tcgen05 one  */
+                                      * 2-split operands, fp32 in TMEM) is the default of every   *
+                                      * subsampling mode                                          */
+#define JB_FLAG_FMA_DCT 0x40u        /* use the CUDA-core kernel (register AAN FDCT, near-tie     *
+                                      * band proven analytically) instead of the tcgen05 one      */
 
 typedef struct {
     int32_t subsampling;      /* JB_SUB_*                                                   */

@@ -344,7 +344,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
             tc.tc_valid = false;
         }
         ta.qc = tc.qc;
-        if (!(p->flags & JB_FLAG_FMA_DCT) && pl.g.sub == JB_SUB_420) {  // tcgen05 transform (launch falls back if unaligned)
+        if (!(p->flags & JB_FLAG_FMA_DCT)) {  // tcgen05 transform, every subsampling mode (launch falls back if unaligned)
             const char* e = getenv("JB_TC_ERR_SCALE");
             const double scale = e ? atof(e) : JB_TC_ERR_SCALE;
             if (!tc.tc_valid || tc.tc_scale != scale) {

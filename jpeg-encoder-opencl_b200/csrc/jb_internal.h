@@ -63,9 +63,10 @@ struct TransformArgs {
     uint32_t tie_cap;
     int units_per_row;
     uint32_t total_units;
-    int fast_mcux, fast_mcuy;  // MCUs per row / column that lie completely inside the image
+    int fast_mcux, fast_mcuy;  // MCU columns / rows the hot kernel takes (the rest goes to k_transform_edge)
     uint32_t tc_mcus;          // tcgen05 kernel: MCUs it covers (all frames); its units are runs of 16 of them
-    uint32_t tc_per_frame, tc_magic_frame, tc_magic_row;  // MCUs per frame; floor(2^32 / per-frame), floor(2^32 / per-row)
+    uint32_t tc_per_frame, tc_row_len;         // tcgen05 kernels: MCUs (4:2:0) or MCU pairs (8x8 MCUs) per frame / per MCU row
+    uint32_t tc_magic_frame, tc_magic_row;     // floor(2^32 / tc_per_frame), floor(2^32 / tc_row_len)
     uint32_t* unit_counter;    // zeroed per call: dynamic hand-out of strips in the tcgen05 kernel
     const uint8_t* tc_mat;     // tensor-core variant: 6 pre-swizzled bf16 matrices (null = FMA kernel)
     float tband[2][64];        // tensor-core variant: near-tie bands in zigzag order

@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(TW * 32, 16 / TW) k_transform(const __grid_con
 // the DCT / quantisation arithmetic is the same binary32 code as the hot kernel.
 __global__ void __launch_bounds__(64) k_transform_edge(const __grid_constant__ TransformArgs a) {
     const int bpm = a.g.bpm;
-    const uint32_t col_mcus = a.fast_mcux < a.g.mcux ? (uint32_t)a.g.mcuy : 0u;   // the last MCU column
+    const uint32_t ncol = (uint32_t)(a.g.mcux - a.fast_mcux);                     // trailing MCU columns (0, 1 or 2)
+    const uint32_t col_mcus = ncol * (uint32_t)a.g.mcuy;
     const uint32_t row_mcus = a.fast_mcuy < a.g.mcuy ? (uint32_t)a.fast_mcux : 0u; // the last MCU row (minus the corner)
     const uint32_t per_frame = (col_mcus + row_mcus) * (uint32_t)bpm;
     const uint32_t total = per_frame * (uint32_t)a.n_frames;
@@ -397,8 +398,8 @@ __global__ void __launch_bounds__(64) k_transform_edge(const __grid_constant__ T
         uint32_t e = r / (uint32_t)bpm, blk = r - e * (uint32_t)bpm;
         int mx, my;
         if (e < col_mcus) {
-            mx = a.g.mcux - 1;
-            my = (int)e;
+            my = (int)(e / ncol);
+            mx = a.fast_mcux + (int)(e - (uint32_t)my * ncol);
         } else {
             mx = (int)(e - col_mcus);
             my = a.g.mcuy - 1;
@@ -757,7 +758,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
         const uint32_t l = u.valid ? lin : 0u;
         uint32_t f, rem, my, mx;
         divmod(l, a.tc_per_frame, a.tc_magic_frame, f, rem);
-        divmod(rem, (uint32_t)a.fast_mcux, a.tc_magic_row, my, mx);
+        divmod(rem, a.tc_row_len, a.tc_magic_row, my, mx);
         u.ptr = a.rgb + (size_t)f * a.frame_stride + (size_t)mx * 48;
         u.y0 = (int)my * 16;
         u.gm = f * (uint32_t)a.g.n_mcu + my * (uint32_t)a.g.mcux + mx;
@@ -943,6 +944,290 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_TMEM_COLS));
 }
 
+// ================================================== tensor-core variant, 8x8-pixel MCUs ==
+// 4:4:4 and replicated 4:2:0 (the reference's own mode, utils.cpp:113-141 + 667-695): an MCU is one 8x8
+// block of each component.  Same machinery as k_transform_tc -- exact CSC on CUDA cores, one
+// tcgen05 contraction per block, rounding / near-tie flagging / zigzag-ordered int16 stores in the epilogue --
+// with these differences: a lane owns one MCU and a lane pair one *pair* of MCUs (48 contiguous bytes per image
+// row, like a 16-pixel MCU), a unit is 16 consecutive pairs and 8 image rows; a group has three A tiles (Y,
+// Cb, Cr: all three are produced by the same pass over the pixels), so only three groups fit in shared memory;
+// the two accumulators take Y and Cb, then Cr once Y has been read.  The replicated 4:2:0 mode writes every
+// 2x2 mean to its four samples of the chroma tiles.
+constexpr int T3_GROUPS = 3;
+constexpr int T3_SMEM = TC_B_BYTES + T3_GROUPS * (3 * TC_TILE_BYTES + TC_RING_BYTES) + 1024;
+
+template <int SUB, int ALIGN>
+__global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __grid_constant__ TransformArgs a) {
+    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar[T3_GROUPS][2];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_next[T3_GROUPS];
+    __shared__ uint32_t s_desc[T3_GROUPS + 1][4];  // descriptor low words: [group]{Y, Cb, Cr tile}, [T3_GROUPS][table * 2 + split]
+    __shared__ uint32_t s_ydown[2048];             // the CSC tie table (jb_math.h), 8 KB
+    uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, wg = gt >> 5, lane = tid & 31;
+    uint8_t* sB = smem;
+    uint8_t* tileY = smem + TC_B_BYTES + g * 3 * TC_TILE_BYTES;  // Y, then Cb, then Cr; the Y tile doubles as staging
+    const uint32_t ring = smem_u32(smem + TC_B_BYTES + T3_GROUPS * 3 * TC_TILE_BYTES + g * TC_RING_BYTES) + wg * TC_ROW_BYTES;
+    // ---- one-time setup: W matrices, tensor memory, barriers ---------------------------------------
+    for (int i = tid; i < TC_B_BYTES / 16; i += T3_GROUPS * 128)
+        reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.tc_mat) + i);
+    for (int i = tid; i < 2048; i += T3_GROUPS * 128) s_ydown[i] = __ldg(a.ydown + i);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (gt < 3) s_desc[g][gt] = (uint32_t)umma_desc(smem_u32(tileY + gt * TC_TILE_BYTES));
+    if (tid < 4) s_desc[T3_GROUPS][tid] = (uint32_t)umma_desc(smem_u32(sB + tid * 8192));
+    if (tid < T3_GROUPS * 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[0][0]) + 8 * tid));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d0 = s_tmem + (uint32_t)(g * 128), tmem_d1 = tmem_d0 + 64;  // two accumulators per group
+    const uint32_t lane_off = (uint32_t)(wg * 32) << 16;
+    const uint32_t mbar0 = smem_u32(&s_mbar[g][0]), mbar1 = smem_u32(&s_mbar[g][1]);
+    const uint32_t idesc = (1u << 4) | (8u << 17) | (8u << 24);  // f32 += fp16 x fp16, N=64, M=128
+    uint32_t phase0 = 0, phase1 = 0;
+    uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
+    const int half = lane & 1;
+    const uint32_t stride = gridDim.x * T3_GROUPS * 4;
+    const uint32_t sw_own = (uint32_t)(gt & 7);
+    const uint32_t y_row = smem_u32(tileY) + gt * 128, cb_row = y_row + TC_TILE_BYTES, cr_row = cb_row + TC_TILE_BYTES;
+
+    const bool issuer = __shfl_sync(0xffffffffu, (uint32_t)wg, 0) == 0;
+    auto issue = [&](int tile_sel, int tab, uint32_t tmem_d, uint32_t mbar) {  // see k_transform_tc
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+            const uint64_t hi = (uint64_t)0x40004040u << 32;
+            const uint64_t da = hi | lds_volatile(smem_u32(&s_desc[g][tile_sel]));
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const uint64_t db = hi | lds_volatile(smem_u32(&s_desc[T3_GROUPS][tab * 2 + s2]));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+        }
+    };
+    auto publish = [&]() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    };
+    auto divmod = [](uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t& r) {
+        q = __umulhi(n, m);
+        r = n - q * d;
+        if (r >= d) {
+            q += 1;
+            r -= d;
+        }
+    };
+    // a lane pair's MCU pair: `gm` is the index of its first (even-column) MCU in the coefficient array
+    auto decode = [&](uint32_t unit_base) {
+        const uint32_t lin = (unit_base + wg) * 16u + (uint32_t)(lane >> 1);
+        TcUnit u;
+        u.valid = unit_base + wg < a.total_units && lin < a.tc_mcus;
+        const uint32_t l = u.valid ? lin : 0u;
+        uint32_t f, rem, my, mx;
+        divmod(l, a.tc_per_frame, a.tc_magic_frame, f, rem);
+        divmod(rem, a.tc_row_len, a.tc_magic_row, my, mx);
+        u.ptr = a.rgb + (size_t)f * a.frame_stride + (size_t)mx * 48;
+        u.y0 = (int)my * 8;
+        u.gm = f * (uint32_t)a.g.n_mcu + my * (uint32_t)a.g.mcux + 2u * mx;
+        return u;
+    };
+    // fetch cursors: as in k_transform_tc (a pair of 8-pixel MCUs is 48 bytes = three 16-byte chunks per row)
+    const uint32_t lane_share = (uint32_t)lane * (ALIGN == 16 ? 16u : 24u);
+    const uint32_t ring_wr = ring + lane_share, ring_rd = ring + (uint32_t)lane * 24u;
+    const int pitch_i = (int)a.pitch, img_h = a.g.H;
+    const uint8_t *fc_p0 = nullptr, *fc_p1 = nullptr;
+    int fc_y0 = 0, fc_y1 = 0;
+    bool fc_v0 = false, fc_v1 = false;
+    auto shfl_ptr = [&](const uint8_t* p, int src) {
+        unsigned long long v = (unsigned long long)p;
+        uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+        return (const uint8_t*)(((unsigned long long)hi << 32) | lo);
+    };
+    auto aim = [&](const TcUnit& u) {
+        const uint8_t* row0 = u.ptr + (uint64_t)(uint32_t)u.y0 * (uint32_t)pitch_i;
+        if (ALIGN == 16) {
+            const int c0 = lane, c1 = 32 + (lane & 15);
+            const int m0 = c0 / 3, m1 = c1 / 3;
+            fc_p0 = shfl_ptr(row0, 2 * m0) + (c0 - 3 * m0) * 16;
+            fc_y0 = __shfl_sync(0xffffffffu, u.y0, 2 * m0);
+            fc_v0 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m0) != 0;
+            fc_p1 = shfl_ptr(row0, 2 * m1) + (c1 - 3 * m1) * 16;
+            fc_y1 = __shfl_sync(0xffffffffu, u.y0, 2 * m1);
+            fc_v1 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m1) != 0 && lane < 16;
+        } else {
+            fc_p0 = row0 + half * 24;
+            fc_y0 = u.y0;
+            fc_v0 = u.valid;
+        }
+    };
+    auto walk = [&](const uint8_t*& p, int& y, const uint8_t*& r0, const uint8_t*& r1) {  // even height: see k_transform_tc
+        const int d = y < img_h ? pitch_i : -pitch_i;
+        r0 = p;
+        r1 = p + d;
+        y += 2;
+        p = r1 + (y == img_h ? 0 : d);
+    };
+    auto fetch_pair = [&](int sl) {
+        const uint32_t d0 = ring_wr + (uint32_t)sl * (2 * 4 * TC_ROW_BYTES), d1 = d0 + 4 * TC_ROW_BYTES;
+        const uint8_t *r0, *r1;
+        walk(fc_p0, fc_y0, r0, r1);
+        if (ALIGN == 16) {
+            if (fc_v0) {
+                cp_async<16>(d0, r0);
+                cp_async<16>(d1, r1);
+            }
+            walk(fc_p1, fc_y1, r0, r1);
+            if (fc_v1) {
+                cp_async<16>(d0 + 512, r0);
+                cp_async<16>(d1 + 512, r1);
+            }
+        } else if (fc_v0) {
+#pragma unroll
+            for (int j = 0; j < 24 / ALIGN; ++j) {
+                cp_async<ALIGN>(d0 + j * ALIGN, r0 + j * ALIGN);
+                cp_async<ALIGN>(d1 + j * ALIGN, r1 + j * ALIGN);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // Units are handed out dynamically.  A unit has only four row pairs and the copy of the next unit's
+    // first rows starts at the third, before any barrier of the unit: the index of the next unit is drawn one
+    // unit ahead (after the row loop, read after the barrier that follows).
+    uint32_t base = (blockIdx.x * T3_GROUPS + g) * 4;
+    if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    uint32_t nbase = s_next[g];
+    TcUnit cur = decode(base);
+    if (base < a.total_units) {
+        aim(cur);
+        fetch_pair(0);
+        fetch_pair(1);
+    }
+    while (base < a.total_units) {
+        TcUnit nxt = cur;
+        const bool valid = cur.valid;
+        const uint32_t gp = valid ? cur.gm * 24u : 0xFFFFFFFFu;  // first 16-byte piece of the pair's six blocks
+        const uint32_t gb0 = cur.gm * 3u;
+
+        // ---- 8 image rows = 4 row pairs: ring -> registers -> colour conversion -> the three A tiles ----
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            if (ALIGN == 16) __syncwarp();
+            const uint32_t src = ring_rd + (uint32_t)(it & 1) * (2 * 4 * TC_ROW_BYTES);
+            uint32_t w0[6], w1[6];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                uint2 v0 = lds64(src + 8 * j), v1 = lds64(src + 4 * TC_ROW_BYTES + 8 * j);
+                w0[2 * j] = v0.x;
+                w0[2 * j + 1] = v0.y;
+                w1[2 * j] = v1.x;
+                w1[2 * j + 1] = v1.y;
+            }
+            if (ALIGN == 16) __syncwarp();
+            if (it == 2) {
+                nxt = decode(nbase);
+                aim(nxt);
+            }
+            fetch_pair(it & 1);
+
+            Row8T o0, o1;
+            csc_row8_t(w0, s_ydown, o0);
+            csc_row8_t(w1, s_ydown, o1);
+            const uint32_t c0 = ((uint32_t)(2 * it) ^ sw_own) << 4, c1 = ((uint32_t)(2 * it + 1) ^ sw_own) << 4;
+            sts128(y_row + c0, make_uint4(luma_h2(o0.y[0], o0.y[1]), luma_h2(o0.y[2], o0.y[3]), luma_h2(o0.y[4], o0.y[5]),
+                                          luma_h2(o0.y[6], o0.y[7])));
+            sts128(y_row + c1, make_uint4(luma_h2(o1.y[0], o1.y[1]), luma_h2(o1.y[2], o1.y[3]), luma_h2(o1.y[4], o1.y[5]),
+                                          luma_h2(o1.y[6], o1.y[7])));
+            if (SUB == JB_SUB_444) {  // the top byte of a chroma T value is the sample: same packing as luma
+                sts128(cb_row + c0, make_uint4(luma_h2(o0.cb[0], o0.cb[1]), luma_h2(o0.cb[2], o0.cb[3]),
+                                               luma_h2(o0.cb[4], o0.cb[5]), luma_h2(o0.cb[6], o0.cb[7])));
+                sts128(cb_row + c1, make_uint4(luma_h2(o1.cb[0], o1.cb[1]), luma_h2(o1.cb[2], o1.cb[3]),
+                                               luma_h2(o1.cb[4], o1.cb[5]), luma_h2(o1.cb[6], o1.cb[7])));
+                sts128(cr_row + c0, make_uint4(luma_h2(o0.cr[0], o0.cr[1]), luma_h2(o0.cr[2], o0.cr[3]),
+                                               luma_h2(o0.cr[4], o0.cr[5]), luma_h2(o0.cr[6], o0.cr[7])));
+                sts128(cr_row + c1, make_uint4(luma_h2(o1.cr[0], o1.cr[1]), luma_h2(o1.cr[2], o1.cr[3]),
+                                               luma_h2(o1.cr[4], o1.cr[5]), luma_h2(o1.cr[6], o1.cr[7])));
+            } else {  // performCDS (utils.cpp:113-141): the truncated mean of a 2x2 cell, written to its four samples
+                uint32_t sb[4], sr[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    sb[c] = (o0.cb[2 * c] >> 24) + (o0.cb[2 * c + 1] >> 24) + (o1.cb[2 * c] >> 24) + (o1.cb[2 * c + 1] >> 24);
+                    sr[c] = (o0.cr[2 * c] >> 24) + (o0.cr[2 * c + 1] >> 24) + (o1.cr[2 * c] >> 24) + (o1.cr[2 * c + 1] >> 24);
+                }
+                const uint32_t b01 = chroma_h2(sb[0], sb[1]), b23 = chroma_h2(sb[2], sb[3]);
+                const uint32_t r01 = chroma_h2(sr[0], sr[1]), r23 = chroma_h2(sr[2], sr[3]);
+                const uint4 vb = make_uint4(__byte_perm(b01, 0, 0x1010), __byte_perm(b01, 0, 0x3232), __byte_perm(b23, 0, 0x1010),
+                                            __byte_perm(b23, 0, 0x3232));
+                const uint4 vr = make_uint4(__byte_perm(r01, 0, 0x1010), __byte_perm(r01, 0, 0x3232), __byte_perm(r23, 0, 0x1010),
+                                            __byte_perm(r23, 0, 0x3232));
+                sts128(cb_row + c0, vb);
+                sts128(cb_row + c1, vb);
+                sts128(cr_row + c0, vr);
+                sts128(cr_row + c1, vr);
+            }
+        }
+        publish();
+        if (issuer) {
+            issue(0, 0, tmem_d0, mbar0);  // Y
+            issue(1, 1, tmem_d1, mbar1);  // Cb
+        }
+        if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);  // the unit after next
+
+        // read this thread's row of the accumulator, round / flag / pack, stage in the Y tile, store block `comp`
+        // of both MCUs of every pair
+        auto finish = [&](uint32_t tmem_d, int tab, int comp) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t t[64];
+            tmem_ld64(tmem_d + lane_off, t);
+            uint4* st = reinterpret_cast<uint4*>(tileY) + wg * 256;  // this warp's 32 rows of the tile
+            uint32_t tl = 0, th = 0;
+            if (tab == 0)
+                tc_quant_stage<0>(t, a, st, lane, tl, th, 0, 0);
+            else
+                tc_quant_stage<1>(t, a, st, lane, tl, th, 0, 0);
+            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + 3 * half + comp, tl, th);
+            __syncwarp();
+            // coalesced copy-out: staged block sb belongs to lane sb, i.e. to MCU (sb & 1) of pair sb >> 1
+            const uint32_t piece0 = (uint32_t)(3 * ((lane >> 3) & 1) + comp) * 8u + (uint32_t)(lane & 7);
+#pragma unroll
+            for (int it8 = 0; it8 < 8; ++it8) {
+                const int sb = it8 * 4 + (lane >> 3), pc = lane & 7;
+                const uint32_t m_gp = __shfl_sync(0xffffffffu, gp, 4 * it8 + 2 * (lane >> 4));
+                if (m_gp != 0xFFFFFFFFu) coef4[m_gp + piece0] = st[sb * 8 + (pc ^ (sb & 7))];
+            }
+            __syncwarp();
+        };
+        mbar_wait(mbar0, phase0);  // the Y tile has been consumed: it is the staging area from here on
+        phase0 ^= 1;
+        finish(tmem_d0, 0, 0);
+        publish();                 // every thread has read accumulator 0: it takes Cr
+        if (issuer) issue(2, 1, tmem_d0, mbar0);
+        const uint32_t nnbase = s_next[g];
+        mbar_wait(mbar1, phase1);
+        phase1 ^= 1;
+        finish(tmem_d1, 1, 1);
+        mbar_wait(mbar0, phase0);
+        phase0 ^= 1;
+        finish(tmem_d0, 1, 2);
+        cur = nxt;
+        base = nbase;
+        nbase = nnbase;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_TMEM_COLS));
+}
+
 template <int SUB, int ALIGN>
 static void launch_one(const TransformArgs& a, int grid, cudaStream_t s) {
     const int smem = TW * 256 * 16 + (SUB == JB_SUB_420 ? TW * CH_WARP_WORDS * 4 : 0);
@@ -964,32 +1249,69 @@ static void launch_sub(const TransformArgs& a, int align, int grid, cudaStream_t
 // MCUs the hot kernel can take: all whose 8/16-pixel columns lie inside the image, and rows
 // below the image only when row mirroring reproduces the reference (no chroma cells, or an
 // even height so that a mirrored row pair is again a complete 2x2 cell pair).
+static int input_align(const TransformArgs& a) {
+    uintptr_t bits = (uintptr_t)a.rgb | (uintptr_t)a.pitch | (uintptr_t)a.frame_stride;
+    return (bits & 15) == 0 ? 16 : (bits & 7) == 0 ? 8 : (bits & 3) == 0 ? 4 : 1;
+}
+static bool use_tc(const TransformArgs& a) { return a.tc_mat != nullptr && input_align(a) >= 4; }
+
 static void plan_fast(TransformArgs& a) {
     const int mcus_per_unit = a.g.sub == JB_SUB_420 ? 16 : 32;
-    const bool rows_ok = a.g.sub == JB_SUB_444 || (a.g.H % 2 == 0);
+    const bool tc = use_tc(a);
+    // rows below the image are mirrored inside the hot kernel when that reproduces the reference: no chroma
+    // cells (4:4:4) or an even height; the tcgen05 kernels walk row pairs and need the even height
+    const bool rows_ok = (a.g.sub == JB_SUB_444 && !tc) || (a.g.H % 2 == 0);
     a.fast_mcux = a.g.W % a.g.mcu_px ? a.g.mcux - 1 : a.g.mcux;
+    if (tc && a.g.sub != JB_SUB_420) a.fast_mcux &= ~1;  // the tcgen05 kernel for 8x8 MCUs takes them in pairs
     a.fast_mcuy = (a.g.H % a.g.mcu_px) && !rows_ok ? a.g.mcuy - 1 : a.g.mcuy;
     a.units_per_row = (a.fast_mcux + mcus_per_unit - 1) / mcus_per_unit;
     a.total_units = (uint32_t)a.units_per_row * (uint32_t)a.fast_mcuy * (uint32_t)a.n_frames;
+}
+
+static uint32_t div_magic32(uint32_t d) {  // floor(2^32 / d), saturated (d = 1)
+    const uint64_t m = (1ull << 32) / d;
+    return (uint32_t)(m > 0xFFFFFFFFull ? 0xFFFFFFFFull : m);
+}
+
+template <int SUB>
+static void launch_tc3(const TransformArgs& a, int align, int grid, cudaStream_t s) {
+    if (align == 16) {
+        cudaFuncSetAttribute(k_transform_tc3<SUB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
+        k_transform_tc3<SUB, 16><<<grid, T3_GROUPS * 128, T3_SMEM, s>>>(a);
+    } else if (align == 8) {
+        cudaFuncSetAttribute(k_transform_tc3<SUB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
+        k_transform_tc3<SUB, 8><<<grid, T3_GROUPS * 128, T3_SMEM, s>>>(a);
+    } else {
+        cudaFuncSetAttribute(k_transform_tc3<SUB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
+        k_transform_tc3<SUB, 4><<<grid, T3_GROUPS * 128, T3_SMEM, s>>>(a);
+    }
 }
 
 int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     TransformArgs a = a_in;
     plan_fast(a);
     if (!a.total_units) return 0;
-    uintptr_t bits = (uintptr_t)a.rgb | (uintptr_t)a.pitch | (uintptr_t)a.frame_stride;
-    int align = (bits & 7) == 0 ? 8 : (bits & 3) == 0 ? 4 : 1;
+    const int align16 = input_align(a), align = align16 == 16 ? 8 : align16;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    if (a.tc_mat && a.g.sub == JB_SUB_420 && align >= 4) {  // tensor-core variant: units are runs of 16 MCUs
-        a.tc_mcus = (uint32_t)a.fast_mcux * (uint32_t)a.fast_mcuy * (uint32_t)a.n_frames;
+    if (use_tc(a)) {  // tcgen05 kernels: units are runs of 16 MCUs (4:2:0) or 16 MCU pairs (8x8 MCUs)
+        const bool is420 = a.g.sub == JB_SUB_420;
+        a.tc_row_len = (uint32_t)(is420 ? a.fast_mcux : a.fast_mcux / 2);
+        a.tc_per_frame = a.tc_row_len * (uint32_t)a.fast_mcuy;
+        a.tc_mcus = a.tc_per_frame * (uint32_t)a.n_frames;
         a.total_units = (a.tc_mcus + 15) / 16;
-        a.tc_per_frame = (uint32_t)a.fast_mcux * (uint32_t)a.fast_mcuy;
-        a.tc_magic_frame = (uint32_t)(0xFFFFFFFFull < (1ull << 32) / a.tc_per_frame ? 0xFFFFFFFFull : (1ull << 32) / a.tc_per_frame);
-        a.tc_magic_row = (uint32_t)(0xFFFFFFFFull < (1ull << 32) / (uint32_t)a.fast_mcux ? 0xFFFFFFFFull : (1ull << 32) / (uint32_t)a.fast_mcux);
-        int needg = (int)((a.total_units + 4 * TC_GROUPS - 1) / (4 * TC_GROUPS));
+        if (!a.total_units) return 0;
+        a.tc_magic_frame = div_magic32(a.tc_per_frame);
+        a.tc_magic_row = div_magic32(a.tc_row_len);
+        const int groups = is420 ? TC_GROUPS : T3_GROUPS;
+        int needg = (int)((a.total_units + 4 * groups - 1) / (4 * groups));
         int gridg = needg < sms ? needg : sms;
-        if ((bits & 15) == 0) {
+        if (!is420) {
+            if (a.g.sub == JB_SUB_444)
+                launch_tc3<JB_SUB_444>(a, align16, gridg, s);
+            else
+                launch_tc3<JB_SUB_REPL420>(a, align16, gridg, s);
+        } else if (align16 == 16) {
             cudaFuncSetAttribute(k_transform_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
             k_transform_tc<16><<<gridg, TC_GROUPS * 128, TC_SMEM, s>>>(a);
         } else if (align == 8) {
@@ -1015,7 +1337,7 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
 int launch_transform_edge(const TransformArgs& a_in, cudaStream_t s) {
     TransformArgs a = a_in;
     plan_fast(a);
-    size_t edge = ((a.fast_mcux < a.g.mcux ? (size_t)a.g.mcuy : 0) + (a.fast_mcuy < a.g.mcuy ? (size_t)a.fast_mcux : 0)) *
+    size_t edge = ((size_t)(a.g.mcux - a.fast_mcux) * (size_t)a.g.mcuy + (a.fast_mcuy < a.g.mcuy ? (size_t)a.fast_mcux : 0)) *
                   (size_t)a.g.bpm * (size_t)a.n_frames;
     if (!edge) return 0;
     size_t g = (edge + 63) / 64;

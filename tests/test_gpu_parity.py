@@ -437,15 +437,17 @@ def test_config3_8k_420_q75_restart(enc, jb):
 
 # ------------------------------------------------ tensor-core variant of the fused kernel ------------
 
+@pytest.mark.parametrize("sub", SUBS)
 @pytest.mark.parametrize("q", [50, 75, 90, 100])
-def test_tensor_core_transform_bit_exact(enc, jb, fruit, q):
-    """The default 4:2:0 transform: tcgen05 contraction (fp16 2-split) + binary64 replay == the oracle, bit for bit."""
+def test_tensor_core_transform_bit_exact(enc, jb, fruit, sub, q):
+    """The default transform of every mode: tcgen05 contraction (fp16 2-split) + binary64 replay == the oracle,
+    bit for bit (k_transform_tc for 4:2:0, k_transform_tc3 for 4:4:4 and the reference's replicated 4:2:0)."""
     ql, qc = ol.quality_tables(q)
-    for img in (fruit, ol.synth(21, 1920, 128), noise_image(3, 200, 120)):
-        p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, flags=jb.FLAG_TENSOR_DCT)
+    for img in (fruit, ol.synth(21, 1920, 128), noise_image(3, 200, 120), ol.synth(9, 1928, 70)):
+        p = jb.make_params(sub, qlum=ql, qchrom=qc, flags=jb.FLAG_TENSOR_DCT)
         got = enc.transform(img, p)
-        want = ol.transform(img, ol.SUB_420, ql, qc)
-        assert np.array_equal(got, want), f"q{q} {img.shape}: " + mismatch_report(got, want)
+        want = ol.transform(img, sub, ql, qc)
+        assert np.array_equal(got, want), f"{SUBNAME[sub]} q{q} {img.shape}: " + mismatch_report(got, want)
 
 
 def test_tensor_core_raw_error_is_small(enc, jb, fruit):
@@ -459,28 +461,32 @@ def test_tensor_core_raw_error_is_small(enc, jb, fruit):
     assert (got != want).mean() < 2e-3
 
 
+@pytest.mark.parametrize("sub", SUBS)
 @pytest.mark.parametrize("q", [50, 75, 100])
-def test_fma_transform_bit_exact(enc, jb, fruit, q):
-    """JB_FLAG_FMA_DCT: the CUDA-core 4:2:0 kernel (register AAN FDCT, analytic near-tie band) == the oracle."""
+def test_fma_transform_bit_exact(enc, jb, fruit, sub, q):
+    """JB_FLAG_FMA_DCT: the CUDA-core kernels (register AAN FDCT, analytic near-tie band) == the oracle."""
     ql, qc = ol.quality_tables(q)
     for img in (fruit, ol.synth(21, 1920, 128), noise_image(3, 200, 120), ol.synth(8, 333, 77)):
-        p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, flags=jb.FLAG_FMA_DCT)
+        p = jb.make_params(sub, qlum=ql, qchrom=qc, flags=jb.FLAG_FMA_DCT)
         got = enc.transform(img, p)
-        want = ol.transform(img, ol.SUB_420, ql, qc)
-        assert np.array_equal(got, want), f"q{q} {img.shape}: " + mismatch_report(got, want)
+        want = ol.transform(img, sub, ql, qc)
+        assert np.array_equal(got, want), f"{SUBNAME[sub]} q{q} {img.shape}: " + mismatch_report(got, want)
 
 
-def test_tensor_core_matches_fma_at_bench_size(enc, jb):
-    """16 frames of 1080p (smooth synthetic + full-range noise), q75 and q100: both kernels, same coefficients."""
+@pytest.mark.parametrize("sub", SUBS)
+def test_tensor_core_matches_fma_at_bench_size(enc, jb, sub):
+    """Frames of 1080p (smooth synthetic + full-range noise), q75 and q100: both kernels, same coefficients
+    (16 frames for 4:2:0, 6 for the 8x8-MCU modes)."""
     rng = np.random.default_rng(77)
-    frames = np.stack([ol.synth(900 + i, 1920, 1080) for i in range(12)]
-                      + [rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8) for _ in range(4)])
+    n_s, n_r = (12, 4) if sub == ol.SUB_420 else (4, 2)
+    frames = np.stack([ol.synth(900 + i, 1920, 1080) for i in range(n_s)]
+                      + [rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8) for _ in range(n_r)])
     for q in (75, 100):
-        a = jb.make_params(ol.SUB_420, quality=q, flags=jb.FLAG_FMA_DCT)
-        b = jb.make_params(ol.SUB_420, quality=q)
+        a = jb.make_params(sub, quality=q, flags=jb.FLAG_FMA_DCT)
+        b = jb.make_params(sub, quality=q)
         ca = np.stack([enc.transform(f, a) for f in frames[:: 5 if q == 100 else 1]])
         cb = np.stack([enc.transform(f, b) for f in frames[:: 5 if q == 100 else 1]])
-        assert np.array_equal(ca, cb), f"q{q}: " + mismatch_report(ca, cb)
+        assert np.array_equal(ca, cb), f"{SUBNAME[sub]} q{q}: " + mismatch_report(ca, cb)
 
 
 def test_tensor_core_jfif_equals_fma_path(enc, jb):
