@@ -333,8 +333,9 @@ def main():
     try:  # per-launch DRAM bytes from the committed ncu capture of the same command, if present
         with open(os.path.join(ROOT, "profiles", "r01_transform_ncu_summary.json")) as f:
             prof = json.load(f)
-        if prof.get("workload") == a.workload and prof.get("frames") == F:
-            traffic = prof.get("kernels", {}).get(kname, {}).get("dram_bytes_per_launch")
+        k = prof.get("kernels", {}).get(kname, {})
+        if k.get("workload", prof.get("workload")) == a.workload and k.get("frames", prof.get("frames")) == F:
+            traffic = k.get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"kernel": kname + (" (fused CSC+subsample+shift, tcgen05 FDCT+quant+zigzag)" if use_tc else

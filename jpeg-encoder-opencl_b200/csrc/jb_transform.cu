@@ -1011,10 +1011,15 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
         }
     };
-    auto publish = [&]() {
+    // writes of this thread to the tiles become visible to the tensor core, the group meets.  Where the
+    // barrier only tells the issuing warp that an accumulator has been read, the other warps arrive and go on.
+    auto publish = [&](bool all_wait) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (all_wait || issuer)
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        else
+            asm volatile("bar.arrive %0, 128;" ::"r"(1 + g) : "memory");
     };
     auto divmod = [](uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t& r) {
         q = __umulhi(n, m);
@@ -1100,7 +1105,7 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
 
     // Units are handed out dynamically.  A unit has only four row pairs and the copy of the next unit's
     // first rows starts at the third, before any barrier of the unit: the index of the next unit is drawn one
-    // unit ahead (after the row loop, read after the barrier that follows).
+    // unit ahead (at the start of a unit, read after the barrier that ends its row loop).
     uint32_t base = (blockIdx.x * T3_GROUPS + g) * 4;
     if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
     asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
@@ -1112,6 +1117,7 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
         fetch_pair(1);
     }
     while (base < a.total_units) {
+        if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);  // the unit after next; read after the barrier below
         TcUnit nxt = cur;
         const bool valid = cur.valid;
         const uint32_t gp = valid ? cur.gm * 24u : 0xFFFFFFFFu;  // first 16-byte piece of the pair's six blocks
@@ -1175,12 +1181,12 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
                 sts128(cr_row + c1, vr);
             }
         }
-        publish();
+        publish(true);
         if (issuer) {
             issue(0, 0, tmem_d0, mbar0);  // Y
             issue(1, 1, tmem_d1, mbar1);  // Cb
         }
-        if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);  // the unit after next
+        const uint32_t nnbase = s_next[g];
 
         // read this thread's row of the accumulator, round / flag / pack, stage in the Y tile, store block `comp`
         // of both MCUs of every pair
@@ -1209,9 +1215,8 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
         mbar_wait(mbar0, phase0);  // the Y tile has been consumed: it is the staging area from here on
         phase0 ^= 1;
         finish(tmem_d0, 0, 0);
-        publish();                 // every thread has read accumulator 0: it takes Cr
+        publish(false);            // every thread has read accumulator 0: it takes Cr
         if (issuer) issue(2, 1, tmem_d0, mbar0);
-        const uint32_t nnbase = s_next[g];
         mbar_wait(mbar1, phase1);
         phase1 ^= 1;
         finish(tmem_d1, 1, 1);

@@ -2,8 +2,9 @@
 
   python profiles/summarize.py r01
 reads  gpurun_out/<r>_launches.csv        (ncu --metrics gpu__time_duration.sum launch list)
-       gpurun_out/<r>_prof_full.ncu-rep   (ncu --set full of the step's main kernels)
-       gpurun_out/<r>_prof_tc.ncu-rep     (ncu --set full of the tensor-core transform variant)
+       gpurun_out/<r>_prof_tc.ncu-rep     (ncu --set full of the step's main kernels, default build)
+       gpurun_out/<r>_prof_full.ncu-rep   (ncu --set full of the CUDA-core transform kernel, --tensor-dct 0)
+       gpurun_out/<r>_prof_tc3.ncu-rep    (ncu --set full of the 8x8-MCU tcgen05 transform kernel, --workload 4k444)
 writes profiles/<r>_launches.md, profiles/<r>_kernels.md, profiles/<r>_transform_ncu_summary.json
 """
 import csv, json, os, subprocess, sys
@@ -50,10 +51,12 @@ WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
 
 def kernels():
     md = ["# ncu --set full summaries (round 1)", "",
-          "Workload: `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline` (512 x 1920x1080, 4:2:0, q75).",
+          "Workload: `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline` (512 x 1920x1080, 4:2:0, q75);",
+          "`_prof_full`: the same with `--tensor-dct 0` (CUDA-core transform); `_prof_tc3`: `--workload 4k444` (32 x 3840x2160, 4:4:4, q90).",
+          "Captured by `profiles/capture.sh` (each ncu pass after a plain run of the same command that exited 0).",
           "Numbers taken under the profiler are diagnostics only; bench values come from CUDA events.", ""]
     summary = {}
-    for rep in (f"{R}_prof_full.ncu-rep", f"{R}_prof_tc.ncu-rep"):
+    for rep in (f"{R}_prof_tc.ncu-rep", f"{R}_prof_full.ncu-rep", f"{R}_prof_tc3.ncu-rep"):
         if not os.path.exists(os.path.join(OUT, rep)):
             continue
         hdr, units, rows = raw(rep)
@@ -80,14 +83,18 @@ if __name__ == "__main__":
     step = launches()
     summ = kernels()
     ks = {}
-    for key, pred in (("k_transform_tc", lambda k: "k_transform_tc" in k),
-                      ("k_transform", lambda k: "k_transform<" in k and "k_transform_tc" not in k)):
+    for key, pred in (("k_transform_tc", lambda k: "k_transform_tc<" in k),
+                      ("k_transform_tc3", lambda k: "k_transform_tc3" in k),
+                      ("k_transform", lambda k: "k_transform<" in k)):
         t = next((v for k, v in summ.items() if pred(k)), None)
         if t:
             ks[key] = {"dram_bytes_per_launch": int(to_bytes(*t["dram read"]) + to_bytes(*t["dram write"])),
-                       "dram_read": t["dram read"], "dram_write": t["dram write"], "duration_under_ncu": t["duration"]}
+                       "dram_read": t["dram read"], "dram_write": t["dram write"], "duration_under_ncu": t["duration"],
+                       "workload": "4k444" if key == "k_transform_tc3" else "batch1080p",
+                       "frames": 32 if key == "k_transform_tc3" else 512}
     traffic = {k: v["dram_bytes_per_launch"] for k, v in ks.items()}
     json.dump({"round": R, "workload": "batch1080p", "frames": 512, "kernels": ks,
-               "source": f"gpurun_out/{R}_prof_full.ncu-rep, {R}_prof_tc.ncu-rep (ncu --set full --clock-control none)"},
+               "note": "k_transform_tc3 was captured on the 4k444 workload (32 frames of 3840x2160, 4:4:4, q90)",
+               "source": f"gpurun_out/{R}_prof_tc.ncu-rep, {R}_prof_full.ncu-rep, {R}_prof_tc3.ncu-rep (ncu --set full --clock-control none)"},
               open(os.path.join(ROOT, "profiles", f"{R}_transform_ncu_summary.json"), "w"), indent=1)
     print("ok", traffic)
