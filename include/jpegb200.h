@@ -121,6 +121,20 @@ int jb_blockify(jb_ctx *ctx, const double *img, size_t W, size_t H, int32_t *lin
 /*      replaces void everyMCUisnow2DArray(ppm_d_t*, int[][64])            utils.hpp:122 */
 int jb_zigzag(jb_ctx *ctx, const int32_t *linear, int32_t *zz, size_t rows);
 /*      replaces void performZigZag(int[][64], int[][64], int)             utils.hpp:127 */
+/* The image layout of the reference's OpenCL half: planar uint32, R plane, G plane, B plane of W*H words each
+ * (its kernels read d_input[c*W*H + y*W + x], src/OpenCLProject_JpegEncoder.cl:17-19).
+ * replaces: void copyImageToVector(ppm_t*, std::vector<cl_uint>&)  utils.hpp:116 (utils.cpp:700-707) */
+int jb_planar_u32_from_aos(jb_ctx *ctx, const uint8_t *px, size_t W, size_t H, uint32_t *planar);
+/* replaces: void switchVectorChannelOrdering(std::vector<cl_uint>&, std::vector<cl_uint>&, unsigned, unsigned)
+ *           utils.hpp:119 (utils.cpp:745-754): planes -> interleaved words */
+int jb_planar_u32_interleave(jb_ctx *ctx, const uint32_t *planar, size_t W, size_t H, uint32_t *interleaved);
+/* Device-side hop from that layout to the pitched RGB8 frame the fused entry points read (d_* are device
+ * pointers; asynchronous on jb_stream()): feed the result to jb_encode_batch_device. */
+int jb_planar_u32_to_rgb8_device(jb_ctx *ctx, const uint32_t *d_planar, size_t W, size_t H, uint8_t *d_rgb, size_t pitch);
+/* jb_encode_jfif for a host image in that layout (what the reference's main() holds after copyImageToVector,
+ * src/OpenCLProject_JpegEncoder.cpp:325): upload, convert on the device, fused encode. */
+int jb_encode_jfif_planar_u32(jb_ctx *ctx, const uint32_t *planar, size_t W, size_t H, const jb_params *p, uint8_t *out,
+                              size_t cap, size_t *out_len);
 int jb_rle(jb_ctx *ctx, const int32_t *zz, size_t rows, uint32_t flags, int32_t *pairs, uint32_t *counts);
 /*      replaces void performRLE(int[][64], vector<vector<int>>&, int)     utils.hpp:132
  *      pairs: rows x 128 ints (run,value,...); counts[r] = ints used by row r */

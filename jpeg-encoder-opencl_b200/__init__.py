@@ -29,7 +29,8 @@ SYMBOLS = [
     "jb_u8_to_f64", "jb_levelshift_f64", "jb_dct_f64", "jb_quantize_f64", "jb_blockify", "jb_zigzag", "jb_rle",
     "jb_huffman", "jb_quality_tables", "jb_num_mcus", "jb_blocks_per_mcu", "jb_header_bytes", "jb_required_bytes",
     "jb_transform", "jb_entropy", "jb_encode_jfif", "jb_encode_batch", "jb_encode_batch_device", "jb_encode_strip",
-    "jb_write_header", "jb_synth_rgb_device",
+    "jb_write_header", "jb_synth_rgb_device", "jb_planar_u32_from_aos", "jb_planar_u32_interleave",
+    "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32",
 ]
 
 
@@ -99,6 +100,10 @@ def lib():
     L.jb_blockify.argtypes = [vp, vp, sz, sz, vp]
     L.jb_zigzag.argtypes = [vp, vp, vp, sz]
     L.jb_rle.argtypes = [vp, vp, sz, C.c_uint32, vp, vp]
+    L.jb_planar_u32_from_aos.argtypes = [vp, vp, sz, sz, vp]
+    L.jb_planar_u32_interleave.argtypes = [vp, vp, sz, sz, vp]
+    L.jb_planar_u32_to_rgb8_device.argtypes = [vp, vp, sz, sz, vp, sz]
+    L.jb_encode_jfif_planar_u32.argtypes = [vp, vp, sz, sz, PP, vp, sz, C.POINTER(sz)]
     L.jb_huffman.argtypes = [vp, vp, sz, C.c_uint32, vp, sz, C.POINTER(u64)]
     L.jb_quality_tables.argtypes = [C.c_int, vp, vp]
     L.jb_num_mcus.argtypes = [sz, sz, C.c_int]
@@ -261,6 +266,29 @@ class Encoder:
         out = np.empty(cap, np.uint8)
         n = C.c_size_t()
         self._ck(self.L.jb_encode_jfif(self.h, _ptr(rgb), W, H, W * 3, C.byref(params), _ptr(out), cap, C.byref(n)))
+        return out[: n.value].tobytes()
+
+    # the planar uint32 image layout of the reference's OpenCL half (utils.hpp:116-119)
+    def copyImageToVector(self, rgb):
+        H, W, _ = rgb.shape
+        out = np.empty(3 * W * H, np.uint32)
+        self._ck(self.L.jb_planar_u32_from_aos(self.h, _ptr(np.ascontiguousarray(rgb)), W, H, _ptr(out)))
+        return out
+
+    def switchVectorChannelOrdering(self, planar, W, H):
+        out = np.empty(3 * W * H, np.uint32)
+        self._ck(self.L.jb_planar_u32_interleave(self.h, _ptr(np.ascontiguousarray(planar)), W, H, _ptr(out)))
+        return out
+
+    def planar_u32_to_rgb8_device(self, d_planar, W, H, d_rgb, pitch):
+        self._ck(self.L.jb_planar_u32_to_rgb8_device(self.h, d_planar, W, H, d_rgb, pitch))
+
+    def encode_jfif_planar_u32(self, planar, W, H, params, cap=None):
+        cap = cap if cap is not None else W * H * 3 + 65536
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t()
+        self._ck(self.L.jb_encode_jfif_planar_u32(self.h, _ptr(np.ascontiguousarray(planar, dtype=np.uint32)), W, H,
+                                                  C.byref(params), _ptr(out), cap, C.byref(n)))
         return out[: n.value].tobytes()
 
     def encode_batch(self, frames, params, out=None):

@@ -723,6 +723,66 @@ int jb_zigzag(jb_ctx* ctx, const int32_t* linear, int32_t* zz, size_t rows) {
     STAGE_END()
 }
 
+// ---- the image layout of the reference's OpenCL half: planar uint32 ----------
+int jb_planar_u32_from_aos(jb_ctx* ctx, const uint8_t* px, size_t W, size_t H, uint32_t* planar) {
+    size_t n = W * H;
+    if (!px || !planar || n == 0) return fail(ctx, JB_E_INVALID, "bad arguments");
+    STAGE_BEGIN(n * 15 + 512)
+    uint8_t* d = carve<uint8_t>(A, n * 3);
+    uint32_t* o = carve<uint32_t>(A, n * 3);
+    CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_aos_to_planar_u32(d, n, o, st);
+    CK(cudaMemcpyAsync(planar, o, n * 12, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_planar_u32_interleave(jb_ctx* ctx, const uint32_t* planar, size_t W, size_t H, uint32_t* interleaved) {
+    size_t n = W * H;
+    if (!planar || !interleaved || n == 0) return fail(ctx, JB_E_INVALID, "bad arguments");
+    STAGE_BEGIN(n * 24 + 512)
+    uint32_t* a = carve<uint32_t>(A, n * 3);
+    uint32_t* b = carve<uint32_t>(A, n * 3);
+    CK(cudaMemcpyAsync(a, planar, n * 12, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_planar_u32_interleave(a, n, b, st);
+    CK(cudaMemcpyAsync(interleaved, b, n * 12, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_planar_u32_to_rgb8_device(jb_ctx* ctx, const uint32_t* d_planar, size_t W, size_t H, uint8_t* d_rgb, size_t pitch) {
+    if (!ctx) return JB_E_INVALID;
+    if (!d_planar || !d_rgb || W * H == 0 || pitch < W * 3) return fail(ctx, JB_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.total_launches += launch_planar_u32_to_rgb8(d_planar, W, H, d_rgb, pitch, ctx->slot[0].st);
+    CK(cudaGetLastError());
+    return JB_OK;
+}
+
+int jb_encode_jfif_planar_u32(jb_ctx* ctx, const uint32_t* planar, size_t W, size_t H, const jb_params* p, uint8_t* out,
+                              size_t cap, size_t* out_len) {
+    size_t n = W * H;
+    if (!planar || !p || !out || n == 0) return fail(ctx, JB_E_INVALID, "bad arguments");
+    const size_t pitch = align_up(W * 3, 16);
+    STAGE_BEGIN(n * 12 + pitch * H + cap + 4096)
+    uint32_t* d_pl = carve<uint32_t>(A, n * 3);
+    uint8_t* d_rgb = carve<uint8_t>(A, pitch * H);
+    uint8_t* d_out = carve<uint8_t>(A, cap);
+    uint64_t* d_meta = carve<uint64_t>(A, 4);  // offset, size, total
+    CK(cudaMemcpyAsync(d_pl, planar, n * 12, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_planar_u32_to_rgb8(d_pl, W, H, d_rgb, pitch, st);
+    int rc = jb_encode_batch_device(ctx, d_rgb, 1, W, H, pitch, pitch * H, p, d_out, cap, d_meta, d_meta + 1, d_meta + 2);
+    if (rc == JB_OK) rc = jb_sync(ctx);
+    if (rc != JB_OK) {
+        if (out_len) *out_len = rc == JB_E_NOSPACE ? (size_t)jb_required_bytes(ctx) : 0;
+        return rc;
+    }
+    uint64_t size = 0;
+    CK(cudaMemcpy(&size, d_meta + 1, 8, cudaMemcpyDeviceToHost));
+    if (size > cap) return fail(ctx, JB_E_INTERNAL, "frame larger than its buffer");
+    CK(cudaMemcpy(out, d_out, size, cudaMemcpyDeviceToHost));
+    if (out_len) *out_len = (size_t)size;
+    return JB_OK;
+}
+
 int jb_rle(jb_ctx* ctx, const int32_t* zz, size_t rows, uint32_t flags, int32_t* pairs, uint32_t* counts) {
     if (!zz || !pairs || !counts || rows == 0) return fail(ctx, JB_E_INVALID, "bad arguments");
     STAGE_BEGIN(rows * (256 + 512 + 4) + 1024)

@@ -167,6 +167,9 @@ int launch_dct_f64(double* img, size_t W, size_t H, int inplace, const double* c
                    cudaStream_t s);
 int launch_quant_f64(double* img, size_t W, size_t H, const QuantTables& qt, cudaStream_t s);
 int launch_blockify(const double* img, size_t W, size_t H, int32_t* linear, cudaStream_t s);
+int launch_aos_to_planar_u32(const uint8_t* px, size_t n, uint32_t* out, cudaStream_t s);
+int launch_planar_u32_interleave(const uint32_t* in, size_t n, uint32_t* out, cudaStream_t s);
+int launch_planar_u32_to_rgb8(const uint32_t* in, size_t W, size_t H, uint8_t* out, size_t pitch, cudaStream_t s);
 int launch_zigzag(const int32_t* linear, int32_t* zz, size_t rows, cudaStream_t s);
 int launch_rle(const int32_t* zz, size_t rows, int always_eob, int32_t* pairs, uint32_t* counts, cudaStream_t s);
 int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStream_t s);

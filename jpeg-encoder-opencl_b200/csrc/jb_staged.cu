@@ -188,6 +188,36 @@ __global__ void k_synth(uint64_t seed, size_t W, size_t y0, size_t rows, size_t 
     }
 }
 
+// ---- the planar uint32 image layout of the reference's OpenCL half ----------------------------
+// copyImageToVector, utils.cpp:700-707: AoS bytes -> R plane, G plane, B plane of n = W*H words each
+__global__ void k_aos_to_planar_u32(const uint8_t* px, size_t n, uint32_t* out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        out[i] = px[3 * i];
+        out[i + n] = px[3 * i + 1];
+        out[i + 2 * n] = px[3 * i + 2];
+    }
+}
+// switchVectorChannelOrdering, utils.cpp:745-754: planes -> interleaved words (RGBRGB...)
+__global__ void k_planar_u32_interleave(const uint32_t* in, size_t n, uint32_t* out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        out[3 * i] = in[i];
+        out[3 * i + 1] = in[i + n];
+        out[3 * i + 2] = in[i + 2 * n];
+    }
+}
+// planes (as the reference's kernels index them, .cl:17-19: d_input[c*W*H + y*W + x]) -> the pitched AoS RGB8
+// frame the fused kernels read; the low byte of every word is the sample (the reference stores bytes in words)
+__global__ void k_planar_u32_to_rgb8(const uint32_t* in, size_t W, size_t H, uint8_t* out, size_t pitch) {
+    const size_t n = W * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t y = i / W, x = i - y * W;
+        uint8_t* o = out + y * pitch + 3 * x;
+        o[0] = (uint8_t)in[i];
+        o[1] = (uint8_t)in[i + n];
+        o[2] = (uint8_t)in[i + 2 * n];
+    }
+}
+
 int launch_csc(uint8_t* px, size_t n, const uint32_t* ydown, cudaStream_t s) {
     k_csc<<<grid_for(n, 256), 256, 0, s>>>(px, n, ydown);
     return 1;
@@ -235,6 +265,19 @@ int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStre
 }
 int launch_synth(uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t* d_out, cudaStream_t s) {
     k_synth<<<grid_for(W * rows, 256), 256, 0, s>>>(seed, W, y0, rows, pitch, d_out);
+    return 1;
+}
+
+int launch_aos_to_planar_u32(const uint8_t* px, size_t n, uint32_t* out, cudaStream_t s) {
+    k_aos_to_planar_u32<<<grid_for(n, 256), 256, 0, s>>>(px, n, out);
+    return 1;
+}
+int launch_planar_u32_interleave(const uint32_t* in, size_t n, uint32_t* out, cudaStream_t s) {
+    k_planar_u32_interleave<<<grid_for(n, 256), 256, 0, s>>>(in, n, out);
+    return 1;
+}
+int launch_planar_u32_to_rgb8(const uint32_t* in, size_t W, size_t H, uint8_t* out, size_t pitch, cudaStream_t s) {
+    k_planar_u32_to_rgb8<<<grid_for(W * H, 256), 256, 0, s>>>(in, W, H, out, pitch);
     return 1;
 }
 

@@ -123,6 +123,15 @@ inline void everyMCUisnow2DArray(ppm_d_t* img, int linear_arr[][64]) {         /
 inline void performZigZag(int linear_arr[][64], int zigzag_arr[][64], int numRows) {  // utils.hpp:127
     jb_compat::ck(jb_zigzag(jb_compat::ctx(), (const int32_t*)linear_arr, (int32_t*)zigzag_arr, (size_t)numRows));
 }
+// ---- the planar uint32 image of the reference's OpenCL half (cl_uint = uint32_t) -------------------
+typedef uint32_t cl_uint;
+inline void copyImageToVector(ppm_t* img, std::vector<cl_uint>& v) {           // utils.hpp:116
+    jb_compat::ck(jb_planar_u32_from_aos(jb_compat::ctx(), (const uint8_t*)img->data, img->width, img->height, v.data()));
+}
+inline void switchVectorChannelOrdering(std::vector<cl_uint>& vInput, std::vector<cl_uint>& vOutput,
+                                        const unsigned int width, const unsigned int height) {  // utils.hpp:119
+    jb_compat::ck(jb_planar_u32_interleave(jb_compat::ctx(), vInput.data(), width, height, vOutput.data()));
+}
 inline void performRLE(int zigzag_array[][64], std::vector<std::vector<int>>& rle, int rows) {  // utils.hpp:132
     std::vector<int32_t> pairs((size_t)rows * 128);
     std::vector<uint32_t> counts((size_t)rows);

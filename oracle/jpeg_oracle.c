@@ -237,6 +237,26 @@ void orc_zigzag(const int32_t *linear, int32_t *zz, size_t rows) { /* utils.cpp:
         for (int k = 0; k < 64; ++k) zz[r * 64 + k] = linear[r * 64 + orc_zigzag_order[k]];
 }
 
+/* ---- the planar uint32 image of the reference's OpenCL half ------------------------------- */
+/* copyImageToVector, utils.cpp:700-707: v[idx] = r, v[idx + n] = g, v[idx + 2n] = b */
+void orc_aos_to_planar_u32(const uint8_t *px, size_t W, size_t H, uint32_t *v) {
+    size_t n = W * H;
+    for (size_t idx = 0; idx < n; ++idx) {
+        v[idx] = px[3 * idx];
+        v[idx + n] = px[3 * idx + 1];
+        v[idx + 2 * n] = px[3 * idx + 2];
+    }
+}
+/* switchVectorChannelOrdering, utils.cpp:745-754: out[3y] = in[y], out[3y+1] = in[y + n], out[3y+2] = in[y + 2n] */
+void orc_planar_u32_interleave(const uint32_t *in, size_t W, size_t H, uint32_t *out) {
+    size_t n = W * H;
+    for (size_t y = 0; y < n; ++y) {
+        out[y * 3] = in[y];
+        out[y * 3 + 1] = in[y + n];
+        out[y * 3 + 2] = in[y + 2 * n];
+    }
+}
+
 /* utils.cpp:572-609.  pairs needs room for 2*64 ints; returns ints written. */
 size_t orc_rle_block(const int32_t zz[64], int32_t *pairs, int always_eob) {
     int last = 0;

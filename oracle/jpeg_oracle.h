@@ -47,6 +47,8 @@ void orc_dct_image(double *img, size_t W, size_t H, int inplace);  /* utils.cpp:
 void orc_quantize_image(double *img, size_t W, size_t H, const unsigned ql[64], const unsigned qc[64]); /* :454-467 */
 void orc_blockify(const double *img, size_t W, size_t H, int32_t *linear); /* utils.cpp:482-498 */
 void orc_zigzag(const int32_t *linear, int32_t *zz, size_t rows);          /* utils.cpp:539-558 */
+void orc_aos_to_planar_u32(const uint8_t *px, size_t W, size_t H, uint32_t *v);       /* utils.cpp:700-707 */
+void orc_planar_u32_interleave(const uint32_t *in, size_t W, size_t H, uint32_t *out); /* utils.cpp:745-754 */
 size_t orc_rle_block(const int32_t zz[64], int32_t *pairs, int always_eob); /* utils.cpp:572-609 */
 int orc_category(int v);                                   /* utils.cpp:623-627 */
 int orc_value_bits(int v, uint32_t *bits);                 /* utils.cpp:630-653 */

@@ -285,4 +285,20 @@ int ref_run_pipeline(const uint8_t *rgb, size_t W, size_t H, int dct_mode, const
     return 0;
 }
 
+// The OpenCL half's host helpers (utils.hpp:116,119), called as main() calls them (cpp:325).
+void ref_copyImageToVector(uint8_t *px, size_t W, size_t H, uint32_t *v) {
+    ppm_t img;
+    img.width = W;
+    img.height = H;
+    img.data = reinterpret_cast<rgb_pixel_t *>(px);
+    std::vector<cl_uint> vec(W * H * 3);
+    copyImageToVector(&img, vec);
+    memcpy(v, vec.data(), vec.size() * sizeof(cl_uint));
+}
+void ref_switchVectorChannelOrdering(const uint32_t *in, size_t W, size_t H, uint32_t *out) {
+    std::vector<cl_uint> a(in, in + W * H * 3), b(W * H * 3);
+    switchVectorChannelOrdering(a, b, (unsigned)W, (unsigned)H);
+    memcpy(out, b.data(), b.size() * sizeof(cl_uint));
+}
+
 }  // extern "C"

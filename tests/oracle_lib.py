@@ -73,6 +73,8 @@ def oracle():
     L.orc_encode_jfif.argtypes = [u8p, sz, sz, C.c_int, u32p, u32p, C.c_int, C.c_int, u8p, sz]
     L.orc_encode_jfif.restype = sz
     L.orc_synth_rgb.argtypes = [C.c_uint64, sz, sz, sz, u8p]
+    L.orc_aos_to_planar_u32.argtypes = [u8p, sz, sz, u32p]
+    L.orc_planar_u32_interleave.argtypes = [u32p, sz, sz, u32p]
     L.orc_init()
     _oracle = L
     return L
@@ -111,6 +113,8 @@ def ref(o0=False):
     L.ref_table_code.argtypes = [C.c_int, C.c_int, C.c_int]
     L.ref_table_code.restype = C.c_char_p
     L.ref_quant_tables.argtypes = [u32p, u32p]
+    L.ref_copyImageToVector.argtypes = [u8p, sz, sz, u32p]
+    L.ref_switchVectorChannelOrdering.argtypes = [u32p, sz, sz, u32p]
     L.ref_run_pipeline.argtypes = [u8p, sz, sz, C.c_int, vp, vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp]
     _ref[path] = L
     return L

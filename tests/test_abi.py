@@ -76,5 +76,5 @@ def test_compat_header_covers_the_reference_surface():
     for name in ("performCSC", "performCDS", "getNearest8x8ImageSize", "copyToLargerImage", "addReversedPadding",
                  "copyUIntToDoubleImage", "substractfromAll", "performDCT", "performQuantization",
                  "everyMCUisnow2DArray", "performZigZag", "performRLE", "HuffmanEncoder", "readPPMImage",
-                 "writePPMImage", "quant_mat_lum", "quant_mat_chrom"):
+                 "writePPMImage", "quant_mat_lum", "quant_mat_chrom", "copyImageToVector", "switchVectorChannelOrdering"):
         assert re.search(rf"\b{name}\b", text), name

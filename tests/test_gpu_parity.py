@@ -496,3 +496,38 @@ def test_tensor_core_jfif_equals_fma_path(enc, jb):
     oa, offa, sza = enc.encode_batch(frames, a)
     ob, offb, szb = enc.encode_batch(frames, b)
     assert np.array_equal(sza, szb) and np.array_equal(oa[: int(sza.sum())], ob[: int(szb.sum())])
+
+
+# ------------------------------------------------ planar uint32 input (the reference's OpenCL-half layout) ----
+
+def test_planar_u32_layout_and_fused_input(enc, jb, fruit):
+    """copyImageToVector / switchVectorChannelOrdering (utils.hpp:116,119) == the oracle, and the fused encode fed
+    with the planar uint32 image == the fused encode of the same pixels as RGB8 (host call and device-side hop)."""
+    L = ol.oracle()
+    for img in (fruit, noise_image(12, 37, 21), ol.synth(3, 640, 360)):
+        H, W, _ = img.shape
+        want = np.zeros(3 * W * H, np.uint32)
+        L.orc_aos_to_planar_u32(np.ascontiguousarray(img).reshape(-1), W, H, want)
+        planar = enc.copyImageToVector(img)
+        assert np.array_equal(planar, want)
+        inter = np.zeros_like(want)
+        L.orc_planar_u32_interleave(want, W, H, inter)
+        assert np.array_equal(enc.switchVectorChannelOrdering(planar, W, H), inter)
+        for sub, ri in ((ol.SUB_420, 0), (ol.SUB_REPL420, 7), (ol.SUB_444, 0)):
+            p = jb.make_params(sub, quality=75, restart_interval=ri)
+            assert enc.encode_jfif_planar_u32(planar, W, H, p) == enc.encode_jfif(img, p)
+    # device-side hop: planar words in HBM -> pitched RGB8 in HBM
+    H, W, _ = fruit.shape
+    planar = enc.copyImageToVector(fruit)
+    pitch = (W * 3 + 15) // 16 * 16
+    d_pl, d_rgb = enc.device_alloc(planar.nbytes), enc.device_alloc(pitch * H)
+    try:
+        enc.h2d(d_pl, planar)
+        enc.planar_u32_to_rgb8_device(d_pl, W, H, d_rgb, pitch)
+        back = np.zeros((H, pitch), np.uint8)
+        enc.sync()
+        enc.d2h(back, d_rgb)
+        assert np.array_equal(back[:, : W * 3].reshape(H, W, 3), fruit)
+    finally:
+        enc.device_free(d_pl)
+        enc.device_free(d_rgb)
