@@ -62,6 +62,45 @@ def gather_bytes(payload, dst=0, group=None):
     return None, lengths
 
 
+def gather_stitch(payload, header=None, trailer=None, dst=0, group=None):
+    """The stitch as one exchange step: every rank's byte string lands at its final offset of the output on
+    rank `dst` -- header + payload_0 + ... + payload_{n-1} + trailer -- without padding or a second copy.
+
+    payload/header/trailer: 1-D uint8 torch tensors on the collective's device (header/trailer only matter on
+    `dst`).  One all-gather of the lengths, then point-to-point sends (NCCL over NVLink on GPUs, gloo on CPU)
+    received in place.  Returns (stitched tensor on dst / None elsewhere, lengths).
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = torch.tensor([payload.numel()], dtype=torch.int64, device=payload.device)
+    sizes = torch.zeros(world, dtype=torch.int64, device=payload.device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    lengths = [int(v) for v in sizes.tolist()]
+    if rank != dst:
+        if lengths[rank]:
+            dist.send(payload.contiguous(), dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        return None, lengths
+    nh = header.numel() if header is not None else 0
+    nt = trailer.numel() if trailer is not None else 0
+    out = torch.empty(nh + sum(lengths) + nt, dtype=torch.uint8, device=payload.device)
+    if nh:
+        out[:nh] = header
+    off = nh
+    for r in range(world):
+        if lengths[r]:
+            if r == rank:
+                out[off: off + lengths[r]] = payload
+            else:
+                dist.recv(out[off: off + lengths[r]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        off += lengths[r]
+    if nt:
+        out[off:] = trailer
+    return out, lengths
+
+
 def stitch(header, strips, eoi=b"\xff\xd9"):
     """header + strip_0 + ... + strip_{n-1} + EOI (strips already carry their RSTn separators)."""
     return b"".join([bytes(header)] + [bytes(np.asarray(s, np.uint8)) for s in strips] + [eoi])

@@ -53,6 +53,14 @@ def _worker(rank, world, port, q):
         if rank == 0:
             jf = D.stitch(ol.jfif_header(W, H, ol.SUB_420, ql, qc, mcux), [p.numpy() for p in parts])
             ok = jf == ol.encode_jfif(img, ol.SUB_420, ql, qc, mcux)
+        # the same stitch as one exchange step: strips received at their final offsets on rank 0
+        hdr = torch.from_numpy(np.frombuffer(ol.jfif_header(W, H, ol.SUB_420, ql, qc, mcux), np.uint8).copy())
+        whole, lengths2 = D.gather_stitch(torch.from_numpy(seg.copy()), hdr, torch.tensor([0xFF, 0xD9], dtype=torch.uint8), dst=0)
+        assert lengths2 == lengths
+        if rank == 0:
+            ok = ok and bytes(whole.numpy()) == ol.encode_jfif(img, ol.SUB_420, ql, qc, mcux)
+        else:
+            assert whole is None
         # ---- a batch sharded by image: every rank encodes its range, sizes all-gathered --------
         N = 5
         lo, hi = D.shard_range(N, world, rank)

@@ -36,6 +36,11 @@ def _worker(rank, world, port, q):
         if rank == 0:
             got = D.stitch(enc.write_header(p, W, H), [x.cpu().numpy() for x in parts])
             ok = got == enc.encode_jfif(img, p)
+        hdr = torch.from_numpy(np.frombuffer(enc.write_header(p, W, H), np.uint8).copy()).cuda()
+        eoi = torch.tensor([0xFF, 0xD9], dtype=torch.uint8, device="cuda")
+        whole, lengths2 = D.gather_stitch(torch.from_numpy(seg).cuda(), hdr, eoi, dst=0)  # received in place
+        if rank == 0:
+            ok = ok and lengths2 == lengths and bytes(whole.cpu().numpy()) == enc.encode_jfif(img, p)
         q.put((rank, bool(ok), lengths))
         enc.close()
     finally:
