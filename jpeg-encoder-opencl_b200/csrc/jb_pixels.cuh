@@ -68,6 +68,31 @@ __device__ __noinline__ void ycc_at(const Image& im, int x, int y, uint32_t& Y, 
     }
 }
 
+// One component (0 Y, 1 Cb, 2 Cr) of the same pipeline: what the binary64 replay needs.  `comp` and `cds`
+// are uniform over the warp there, so only the loads and the arithmetic of that component are issued.
+__device__ __forceinline__ uint32_t sample_at(const Image& im, int x, int y, int comp, bool cds) {
+    const int sx = mirror(x, im.W), sy = mirror(y, im.H);
+    uint32_t r, g, b;
+    if (comp == 0) {
+        rgb_at(im, sx, sy, r, g, b);
+        return csc_y(r, g, b, im.ydown);
+    }
+    const int cx = sx & ~1, cy = sy & ~1;
+    if (cds && cx + 1 < im.W && cy + 1 < im.H) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                rgb_at(im, cx + i, cy + j, r, g, b);
+                s += comp == 1 ? csc_cb(r, g, b) : csc_cr(r, g, b);
+            }
+        return s >> 2;
+    }
+    rgb_at(im, sx, sy, r, g, b);
+    return comp == 1 ? csc_cb(r, g, b) : csc_cr(r, g, b);
+}
+
 // 24 bytes (8 RGB pixels) from p into six words, little-endian byte order.
 template <int ALIGN>
 __device__ __forceinline__ void load24(const uint8_t* p, uint32_t (&w)[6]) {

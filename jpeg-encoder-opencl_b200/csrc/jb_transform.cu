@@ -1393,12 +1393,7 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 int i = lane + 32 * h, x = i & 7, y = i >> 3;
-                uint32_t Y, Cb, Cr;
-                if (a.g.sub == JB_SUB_444)
-                    ycc_at<false>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
-                else
-                    ycc_at<true>(im, x0 + x * step, y0 + y * step, Y, Cb, Cr);
-                double smp = (double)(comp == 0 ? Y : comp == 1 ? Cb : Cr);                              // utils.cpp:236
+                double smp = (double)sample_at(im, x0 + x * step, y0 + y * step, comp, a.g.sub != JB_SUB_444);  // utils.cpp:236
                 smp = __dsub_rn(smp, 128.0);                                                              // utils.cpp:190
                 s_term[w][j][i] = __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), a.costab[v * 8 + y]);    // utils.cpp:330
             }
