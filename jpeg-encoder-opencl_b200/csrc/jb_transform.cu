@@ -1370,26 +1370,48 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
     for (uint32_t e0 = (blockIdx.x * FIX_WARPS + w) * FIX_BATCH; e0 < n; e0 += warps * FIX_BATCH) {
         const int n_here = (int)min((uint32_t)FIX_BATCH, n - e0);
         const uint32_t my_entry = lane < n_here ? a.tie_list[e0 + lane] : 0u;
-        for (int j = 0; j < n_here; ++j) {
-            const uint32_t entry = __shfl_sync(0xffffffffu, my_entry, j);
-            const uint32_t gblock = entry >> 6, k = entry & 63;
-            uint32_t f = gblock / bpf, rb = gblock - f * bpf;
-            uint32_t mcu = rb / (uint32_t)a.g.bpm, blk = rb - mcu * (uint32_t)a.g.bpm;
-            int my = (int)(mcu / (uint32_t)a.g.mcux), mx = (int)(mcu - (uint32_t)my * (uint32_t)a.g.mcux);
-            int comp, x0, y0, step;
+        // lane L decodes entry L once (block -> frame, MCU, component, first sample, zigzag position); the
+        // fields travel to the whole warp by shuffles when the entry's turn comes
+        uint32_t d_xy, d_misc, d_flo, d_fhi;
+        int my_comp, my_nat;
+        {
+            const uint32_t gblock = my_entry >> 6, k = my_entry & 63;
+            const uint32_t f = gblock / bpf, rb = gblock - f * bpf;
+            uint32_t mcu, blk;
+            if (a.g.bpm == 6) {
+                mcu = rb / 6u;
+                blk = rb - mcu * 6u;
+            } else {
+                mcu = rb / 3u;
+                blk = rb - mcu * 3u;
+            }
+            const uint32_t my = mcu / (uint32_t)a.g.mcux, mx = mcu - my * (uint32_t)a.g.mcux;
+            uint32_t x0, y0, step;
             if (a.g.sub == JB_SUB_420) {
-                comp = blk < 4 ? 0 : (int)blk - 3;
-                x0 = mx * 16 + (blk < 4 ? (int)(blk & 1) * 8 : 0);
-                y0 = my * 16 + (blk < 4 ? (int)(blk >> 1) * 8 : 0);
+                my_comp = blk < 4 ? 0 : (int)blk - 3;
+                x0 = mx * 16 + (blk < 4 ? (blk & 1) * 8 : 0);
+                y0 = my * 16 + (blk < 4 ? (blk >> 1) * 8 : 0);
                 step = blk < 4 ? 1 : 2;
             } else {
-                comp = (int)blk;
+                my_comp = (int)blk;
                 x0 = mx * 8;
                 y0 = my * 8;
                 step = 1;
             }
-            Image im{a.rgb + (size_t)f * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
-            const int nat = c_zz[k], v = nat >> 3, u = nat & 7;
+            my_nat = c_zz[k];
+            d_xy = x0 | (y0 << 16);  // padded sizes stay below 2^16
+            d_misc = (uint32_t)my_comp | (step << 2) | ((uint32_t)my_nat << 4);
+            const unsigned long long foff = (unsigned long long)f * a.frame_stride;
+            d_flo = (uint32_t)foff;
+            d_fhi = (uint32_t)(foff >> 32);
+        }
+        for (int j = 0; j < n_here; ++j) {
+            const uint32_t xy = __shfl_sync(0xffffffffu, d_xy, j), misc = __shfl_sync(0xffffffffu, d_misc, j);
+            const unsigned long long foff =
+                ((unsigned long long)__shfl_sync(0xffffffffu, d_fhi, j) << 32) | __shfl_sync(0xffffffffu, d_flo, j);
+            const int x0 = (int)(xy & 0xFFFFu), y0 = (int)(xy >> 16), comp = (int)(misc & 3u), step = (int)((misc >> 2) & 3u);
+            const int nat = (int)(misc >> 4), v = nat >> 3, u = nat & 7;
+            Image im{a.rgb + foff, a.pitch, a.g.W, a.g.H, a.ydown};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 int i = lane + 32 * h, x = i & 7, y = i >> 3;
@@ -1400,17 +1422,14 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
         }
         __syncwarp();
         if (lane < n_here) {
-            const uint32_t gblock = my_entry >> 6, k = my_entry & 63;
-            const uint32_t rb = gblock % bpf, blk = rb % (uint32_t)a.g.bpm;
-            const int comp = a.g.sub == JB_SUB_420 ? (blk < 4 ? 0 : (int)blk - 3) : (int)blk;
-            const int nat = c_zz[k], v = nat >> 3, u = nat & 7;
+            const int v = my_nat >> 3, u = my_nat & 7;
             double sum = 0.0;  // y outer, x inner = index order 0..63
 #pragma unroll 8
             for (int i = 0; i < 64; ++i) sum = __dadd_rn(sum, s_term[w][lane][i]);
             sum = __dmul_rn(sum, a.scale[u * 8 + v]);                                                     // utils.cpp:336
-            double q = (double)a.qt.q[comp ? 1 : 0][nat];
+            double q = (double)a.qt.q[my_comp ? 1 : 0][my_nat];
             double r = round(__ddiv_rn(sum, q));                                                          // utils.cpp:460
-            a.coef[(size_t)gblock * 64 + k] = (int16_t)(int)r;                                            // utils.cpp:490
+            a.coef[(size_t)my_entry] = (int16_t)(int)r;  // entry = block * 64 + zigzag position            utils.cpp:490
         }
         __syncwarp();
     }
