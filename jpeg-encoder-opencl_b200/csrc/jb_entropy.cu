@@ -618,29 +618,42 @@ __global__ void k_finalize(const __grid_constant__ EntropyArgs a) {
 // straight to global memory.
 constexpr int STUFF_WIN = 12288;
 
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyArgs a) {
     __shared__ __align__(16) uint8_t win[STUFF_WIN + 32];
     __shared__ uint64_t s_g0, s_g1;
+    __shared__ uint32_t s_i0, s_i1;
     uint64_t total = a.w.int_ubase[a.n_int_total];
     if (total > a.w.ubuf_cap || a.w.int_obase[a.n_int_total] > a.out_cap) return;
     const uint64_t n_chunks = total >> 4;
     const uint32_t n_tiles = (uint32_t)((n_chunks + TILE - 1) / TILE);
     const uint4* p = reinterpret_cast<const uint4*>(a.w.ubuf);
+    // interval i with int_ubase[i] <= pos < int_ubase[i+1], searched in [lo, hi)
+    auto find_interval = [&](uint64_t pos, uint32_t lo, uint32_t hi) {
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (a.w.int_ubase[mid] <= pos) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t c = (uint64_t)tile * TILE + threadIdx.x;
         const bool have = c < n_chunks;
+        // the intervals of the tile's first and last chunk bracket every other chunk's search (mostly to nothing:
+        // an interval is usually much longer than a 4 KB tile)
+        if (threadIdx.x == 0) s_i0 = find_interval(c << 4, 0, a.n_int_total);
+        if (have && (threadIdx.x == TILE - 1 || c + 1 == n_chunks)) s_i1 = find_interval(c << 4, 0, a.n_int_total);
+        __syncthreads();
         uint64_t dst = 0, start = 0, end = 0;
         uint32_t wds[4] = {0, 0, 0, 0}, marker = 0;
         int valid = 0;
         bool hdr = false;
         if (have) {
             uint64_t pos = c << 4;
-            uint32_t lo = 0, hi = a.n_int_total;  // interval i with int_ubase[i] <= pos < int_ubase[i+1]
-            while (hi - lo > 1) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (a.w.int_ubase[mid] <= pos) lo = mid; else hi = mid;
-            }
-            uint32_t i = lo, k = i % (uint32_t)a.g.n_int;
+            uint32_t i = find_interval(pos, s_i0, s_i1 + 1), k = i % (uint32_t)a.g.n_int;
             uint64_t ub = a.w.int_ubase[i];
             uint64_t off = pos - ub, nb = (a.w.int_bits[i] + 7) >> 3;
             hdr = k == 0 && off == 0 && a.fr.hdr_bytes != 0;
@@ -660,17 +673,34 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
         const uintptr_t P0 = reinterpret_cast<uintptr_t>(a.out) + g0;
         const uint32_t base = (uint32_t)(P0 & 15);
         const bool fits = g1 - g0 <= STUFF_WIN;
-        uint8_t* o = fits ? win + base - g0 : a.out;  // o[pos] addresses output byte pos either way
-        if (have) {
+        if (fits) {  // the usual case: 32-bit shared-memory addresses, predicated byte stores
+            if (have) {
+                uint32_t d = (uint32_t)__cvta_generic_to_shared(win) + base + (uint32_t)(start - g0);
+                if (hdr) {
+                    for (uint32_t j = 0; j < a.fr.hdr_bytes; ++j) sts8(d + j, a.hdr[j]);
+                    d += a.fr.hdr_bytes;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t byte = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                    const bool on = j < valid, ff = on && byte == 0xFFu;
+                    if (on) sts8(d, byte);
+                    if (ff) sts8(d + 1, 0u);  // T.81 F.1.2.3 byte stuffing
+                    d += on ? (ff ? 2u : 1u) : 0u;
+                }
+                if (marker) {
+                    sts8(d, 0xFFu);
+                    sts8(d + 1, marker);
+                }
+            }
+        } else if (have) {  // pathological (thousands of tiny frames): bytes go straight to global memory
+            uint8_t* o = a.out;
             if (hdr)
                 for (uint32_t j = 0; j < a.fr.hdr_bytes; ++j) o[start + j] = a.hdr[j];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (j < valid) {
-                    uint32_t byte = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-                    o[dst++] = (uint8_t)byte;
-                    if (byte == 0xFFu) o[dst++] = 0;  // T.81 F.1.2.3 byte stuffing
-                }
+            for (int j = 0; j < valid; ++j) {
+                uint32_t byte = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                o[dst++] = (uint8_t)byte;
+                if (byte == 0xFFu) o[dst++] = 0;
             }
             if (marker) {
                 o[dst] = 0xFF;
