@@ -31,6 +31,8 @@ WORKLOADS = {
     "batch1080p": (1920, 1080, "420", 75, 0, 512),
     "8k": (7680, 4320, "420", 75, 480, 8),
     "4k444": (3840, 2160, "444", 90, 0, 32),
+    # the reference's own mode (replicated 4:2:0 coded as 4:4:4, its q50 tables) on the batch frames
+    "repl1080p": (1920, 1080, "repl420", 50, 0, 256),
     # one image split into strips of whole restart intervals across the GPUs (config #5; strong scaling)
     "gigapixel": (65536, 65536, "420", 75, 4096, 1),
     "strips16k": (16384, 16384, "420", 75, 1024, 1),
@@ -261,7 +263,7 @@ def main():
             dist.destroy_process_group()
         return
     F = a.frames or dflt
-    sub = {"420": jb.SUB_420, "444": jb.SUB_444}[subname]
+    sub = {"420": jb.SUB_420, "444": jb.SUB_444, "repl420": jb.SUB_REPL420}[subname]
     params = jb.make_params(sub, quality=q, restart_interval=ri,
                             flags=0 if a.tensor_dct else jb.FLAG_FMA_DCT)
     pitch, fstride = W * 3, W * H * 3

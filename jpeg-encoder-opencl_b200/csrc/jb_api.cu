@@ -85,6 +85,7 @@ struct jb_ctx {
         uint64_t gen = 0;  // bumped whenever the W matrices are rebuilt
         uint32_t q[128];
         double tc_scale = 0;
+        int tc_repl = -1;  // the chroma slots hold the K = 16 cell matrices of the replicated 4:2:0 mode
         QuantConst qc;
         float tband[2][64];
         std::vector<uint8_t> tc;  // 32768 bytes: the four fp16 W matrices of the tcgen05 kernel
@@ -347,12 +348,14 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         if (!(p->flags & JB_FLAG_FMA_DCT)) {  // tcgen05 transform, every subsampling mode (launch falls back if unaligned)
             const char* e = getenv("JB_TC_ERR_SCALE");
             const double scale = e ? atof(e) : JB_TC_ERR_SCALE;
-            if (!tc.tc_valid || tc.tc_scale != scale) {
+            const int repl = pl.g.sub == JB_SUB_REPL420 ? 1 : 0;
+            if (!tc.tc_valid || tc.tc_scale != scale || tc.tc_repl != repl) {
                 for (Slot& o : ctx->slot)  // an earlier asynchronous call may still be copying the old matrices
                     if (o.st) CK(cudaStreamSynchronize(o.st));
                 tc.tc.resize(32768);
-                build_tc_matrices(p->qlum, p->qchrom, scale, tc.tc.data(), tc.tband);
+                build_tc_matrices(p->qlum, p->qchrom, scale, repl, tc.tc.data(), tc.tband);
                 tc.tc_scale = scale;
+                tc.tc_repl = repl;
                 tc.tc_valid = true;
                 ++tc.gen;
             }

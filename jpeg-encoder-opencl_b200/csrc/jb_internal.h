@@ -177,7 +177,7 @@ int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStre
 // host helpers
 void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out);
 void aan_error_bound(double err[64], double amax[64]);
-void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, uint8_t* out /* 32768 B */,
+void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, int repl_chroma, uint8_t* out /* 32768 B */,
                        float tband[2][64]);  // worst-case |binary32 - exact| per AAN output
 void build_huff(bool typo, HuffDev* out);
 void build_ydown(uint32_t ydown[2048]);

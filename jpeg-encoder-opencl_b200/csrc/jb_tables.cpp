@@ -293,20 +293,32 @@ static uint16_t to_fp16(double x, double* back) {
     return h;
 }
 
-void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, uint8_t* out, float tband[2][64]) {
+void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, int repl_chroma, uint8_t* out,
+                       float tband[2][64]) {
     const double pi = 3.14159265358979323846;
+    memset(out, 0, 32768);
     for (int t = 0; t < 2; ++t) {
         const uint32_t* q = t ? qc : ql;
+        const bool cells = t == 1 && repl_chroma;  // K = 16: one column per 2x2 cell, the sum of its four entries
         for (int n = 0; n < 64; ++n) {
             int nat = kZigzag[n], v = nat >> 3, u = nat & 7;
             double alpha = (u == 0 ? M_SQRT1_2 : 1.0) * (v == 0 ? M_SQRT1_2 : 1.0) / 4.0;
-            double P = 0;
+            double w[64];
             for (int k = 0; k < 64; ++k) {
                 int y = k >> 3, x = k & 7;
-                double w = alpha * cos((2 * x + 1) * u * pi / 16.0) * cos((2 * y + 1) * v * pi / 16.0) / (double)q[nat];
-                P += fabs(w) * 128.0;
+                w[k] = alpha * cos((2 * x + 1) * u * pi / 16.0) * cos((2 * y + 1) * v * pi / 16.0) / (double)q[nat];
+            }
+            double P = 0;
+            const int nk = cells ? 16 : 64;
+            for (int k = 0; k < nk; ++k) {
+                double wk = w[k];
+                if (cells) {
+                    const int i = k >> 2, j = k & 3, k0 = (2 * i) * 8 + 2 * j;
+                    wk = (w[k0] + w[k0 + 1]) + (w[k0 + 8] + w[k0 + 9]);
+                }
+                P += fabs(wk) * 128.0;
                 double b0, b1;
-                uint16_t h0 = to_fp16(w * JB_TC_W_SCALE, &b0), h1 = to_fp16(w * JB_TC_W_SCALE - b0, &b1);
+                uint16_t h0 = to_fp16(wk * JB_TC_W_SCALE, &b0), h1 = to_fp16(wk * JB_TC_W_SCALE - b0, &b1);
                 size_t off = (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
                 memcpy(out + ((size_t)t * 2 + 0) * 8192 + off, &h0, 2);
                 memcpy(out + ((size_t)t * 2 + 1) * 8192 + off, &h1, 2);

@@ -953,11 +953,18 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
 // Cb, Cr: all three are produced by the same pass over the pixels), so only three groups fit in shared memory;
 // the two accumulators take Y and Cb, then Cr once Y has been read.  The replicated 4:2:0 mode writes every
 // 2x2 mean to its four samples of the chroma tiles.
-constexpr int T3_GROUPS = 3;
-constexpr int T3_SMEM = TC_B_BYTES + T3_GROUPS * (3 * TC_TILE_BYTES + TC_RING_BYTES) + 1024;
+// Replicated 4:2:0 has only 4x4 distinct chroma values per block (every 2x2 mean fills its cell), so its
+// chroma contraction is over K = 16: D = C[128 blocks][16 means] x W'^T with W'[n][cell] the sum of the four W
+// entries of the cell (built by the host in the chroma slots of the W buffer).  Cb and Cr means share one tile
+// (32 bytes each per row), a group needs two tiles like the 4:2:0 kernel, and four groups fit again.
+constexpr int t3_groups(int sub) { return sub == JB_SUB_REPL420 ? 4 : 3; }
+constexpr int t3_tiles(int sub) { return sub == JB_SUB_REPL420 ? 2 : 3; }
+constexpr int t3_smem(int sub) { return TC_B_BYTES + t3_groups(sub) * (t3_tiles(sub) * TC_TILE_BYTES + TC_RING_BYTES) + 1024; }
 
 template <int SUB, int ALIGN>
-__global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __grid_constant__ TransformArgs a) {
+__global__ void __launch_bounds__(t3_groups(SUB) * 128, 1) k_transform_tc3(const __grid_constant__ TransformArgs a) {
+    constexpr bool REPL = SUB == JB_SUB_REPL420;
+    constexpr int T3_GROUPS = t3_groups(SUB), T3_TILES = t3_tiles(SUB);
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar[T3_GROUPS][2];
     __shared__ uint32_t s_tmem;
@@ -967,8 +974,8 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
     uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, wg = gt >> 5, lane = tid & 31;
     uint8_t* sB = smem;
-    uint8_t* tileY = smem + TC_B_BYTES + g * 3 * TC_TILE_BYTES;  // Y, then Cb, then Cr; the Y tile doubles as staging
-    const uint32_t ring = smem_u32(smem + TC_B_BYTES + T3_GROUPS * 3 * TC_TILE_BYTES + g * TC_RING_BYTES) + wg * TC_ROW_BYTES;
+    uint8_t* tileY = smem + TC_B_BYTES + g * T3_TILES * TC_TILE_BYTES;  // Y, then Cb, then Cr (or one tile of chroma means); the Y tile doubles as staging
+    const uint32_t ring = smem_u32(smem + TC_B_BYTES + T3_GROUPS * T3_TILES * TC_TILE_BYTES + g * TC_RING_BYTES) + wg * TC_ROW_BYTES;
     // ---- one-time setup: W matrices, tensor memory, barriers ---------------------------------------
     for (int i = tid; i < TC_B_BYTES / 16; i += T3_GROUPS * 128)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.tc_mat) + i);
@@ -978,7 +985,8 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
                      "n"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (gt < 3) s_desc[g][gt] = (uint32_t)umma_desc(smem_u32(tileY + gt * TC_TILE_BYTES));
+    if (gt < 3)  // replicated 4:2:0: Cr means start 32 bytes into the rows of the chroma tile
+        s_desc[g][gt] = (uint32_t)umma_desc(smem_u32(tileY + (REPL && gt == 2 ? 1 : gt) * TC_TILE_BYTES)) + (REPL && gt == 2 ? 2u : 0u);
     if (tid < 4) s_desc[T3_GROUPS][tid] = (uint32_t)umma_desc(smem_u32(sB + tid * 8192));
     if (tid < T3_GROUPS * 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[0][0]) + 8 * tid));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -994,10 +1002,12 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
     const int half = lane & 1;
     const uint32_t stride = gridDim.x * T3_GROUPS * 4;
     const uint32_t sw_own = (uint32_t)(gt & 7);
-    const uint32_t y_row = smem_u32(tileY) + gt * 128, cb_row = y_row + TC_TILE_BYTES, cr_row = cb_row + TC_TILE_BYTES;
+    const uint32_t y_row = smem_u32(tileY) + gt * 128, cb_row = y_row + TC_TILE_BYTES;
+    const uint32_t cr_row = cb_row + TC_TILE_BYTES;  // (4:4:4 only)
 
     const bool issuer = __shfl_sync(0xffffffffu, (uint32_t)wg, 0) == 0;
     auto issue = [&](int tile_sel, int tab, uint32_t tmem_d, uint32_t mbar) {  // see k_transform_tc
+        const int nk = REPL && tab ? 1 : 4;  // K = 16 for the chroma means
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
             const uint64_t hi = (uint64_t)0x40004040u << 32;
@@ -1006,7 +1016,8 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
             for (int s2 = 0; s2 < 2; ++s2) {
                 const uint64_t db = hi | lds_volatile(smem_u32(&s_desc[T3_GROUPS][tab * 2 + s2]));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                    if (k < nk) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
         }
@@ -1171,14 +1182,10 @@ __global__ void __launch_bounds__(T3_GROUPS * 128, 1) k_transform_tc3(const __gr
                 }
                 const uint32_t b01 = chroma_h2(sb[0], sb[1]), b23 = chroma_h2(sb[2], sb[3]);
                 const uint32_t r01 = chroma_h2(sr[0], sr[1]), r23 = chroma_h2(sr[2], sr[3]);
-                const uint4 vb = make_uint4(__byte_perm(b01, 0, 0x1010), __byte_perm(b01, 0, 0x3232), __byte_perm(b23, 0, 0x1010),
-                                            __byte_perm(b23, 0, 0x3232));
-                const uint4 vr = make_uint4(__byte_perm(r01, 0, 0x1010), __byte_perm(r01, 0, 0x3232), __byte_perm(r23, 0, 0x1010),
-                                            __byte_perm(r23, 0, 0x3232));
-                sts128(cb_row + c0, vb);
-                sts128(cb_row + c1, vb);
-                sts128(cr_row + c0, vr);
-                sts128(cr_row + c1, vr);
+                // means (it, 0..3) are K positions 4 it .. 4 it + 3: 8 bytes of the row's first (Cb) / third (Cr) 32 bytes
+                const uint32_t cc = (uint32_t)(it >> 1), co = (uint32_t)(it & 1) * 8u;
+                sts64(cb_row + ((cc ^ sw_own) << 4) + co, make_uint2(b01, b23));
+                sts64(cb_row + (((cc + 2u) ^ sw_own) << 4) + co, make_uint2(r01, r23));
             }
         }
         publish(true);
@@ -1281,14 +1288,14 @@ static uint32_t div_magic32(uint32_t d) {  // floor(2^32 / d), saturated (d = 1)
 template <int SUB>
 static void launch_tc3(const TransformArgs& a, int align, int grid, cudaStream_t s) {
     if (align == 16) {
-        cudaFuncSetAttribute(k_transform_tc3<SUB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
-        k_transform_tc3<SUB, 16><<<grid, T3_GROUPS * 128, T3_SMEM, s>>>(a);
+        cudaFuncSetAttribute(k_transform_tc3<SUB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, t3_smem(SUB));
+        k_transform_tc3<SUB, 16><<<grid, t3_groups(SUB) * 128, t3_smem(SUB), s>>>(a);
     } else if (align == 8) {
-        cudaFuncSetAttribute(k_transform_tc3<SUB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
-        k_transform_tc3<SUB, 8><<<grid, T3_GROUPS * 128, T3_SMEM, s>>>(a);
+        cudaFuncSetAttribute(k_transform_tc3<SUB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, t3_smem(SUB));
+        k_transform_tc3<SUB, 8><<<grid, t3_groups(SUB) * 128, t3_smem(SUB), s>>>(a);
     } else {
-        cudaFuncSetAttribute(k_transform_tc3<SUB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
-        k_transform_tc3<SUB, 4><<<grid, T3_GROUPS * 128, T3_SMEM, s>>>(a);
+        cudaFuncSetAttribute(k_transform_tc3<SUB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, t3_smem(SUB));
+        k_transform_tc3<SUB, 4><<<grid, t3_groups(SUB) * 128, t3_smem(SUB), s>>>(a);
     }
 }
 
@@ -1308,7 +1315,7 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
         if (!a.total_units) return 0;
         a.tc_magic_frame = div_magic32(a.tc_per_frame);
         a.tc_magic_row = div_magic32(a.tc_row_len);
-        const int groups = is420 ? TC_GROUPS : T3_GROUPS;
+        const int groups = is420 ? TC_GROUPS : t3_groups(a.g.sub);
         int needg = (int)((a.total_units + 4 * groups - 1) / (4 * groups));
         int gridg = needg < sms ? needg : sms;
         if (!is420) {
