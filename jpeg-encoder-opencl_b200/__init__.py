@@ -296,7 +296,7 @@ class Encoder:
         N, H, W, _ = frames.shape
         assert frames.flags.c_contiguous
         if out is None:
-            out = np.empty(N * (W * H + 4096), np.uint8)
+            out = np.empty(N * (W * H * 3 + 65536) if N * W * H < (1 << 26) else N * (W * H + 4096), np.uint8)
         offs = np.zeros(N, np.uint64)
         sizes = np.zeros(N, np.uint64)
         self._ck(self.L.jb_encode_batch(self.h, _ptr(frames), N, W, H, W * 3, W * H * 3, C.byref(params), _ptr(out),

@@ -21,7 +21,8 @@ using namespace jb;
 namespace {
 
 constexpr int kSlots = 3;               // in-flight groups of the batched host path
-constexpr size_t kUbufBytesPerBlock = 64;  // unstuffed-buffer budget (typical use: 5-40 B/block)
+constexpr size_t kUbufBytesPerBlock = 64;     // first unstuffed-buffer budget (typical use: 5-40 B/block)
+constexpr size_t kUbufBytesPerBlockMax = 256;  // no block codes longer: 63 x (16 + 10) + 16 + 11 bits = 209 bytes
 
 struct Arena {
     uint8_t* base = nullptr;
@@ -79,6 +80,8 @@ struct jb_ctx {
     jb_timings tm{};
     uint64_t required = 0;
     uint64_t pending_status_slot = 0;
+    size_t ubuf_per_block = kUbufBytesPerBlock;  // grows (sticky) when the entropy workspace overflows
+    bool ubuf_grew = false;                       // set by the overflow: synchronous entry points run again
     // host-side constants derived from the quantisation tables, rebuilt only when the tables change
     struct TableCache {
         bool valid = false, tc_valid = false;
@@ -182,10 +185,13 @@ size_t plan_bytes(const Plan& p) {
 
 int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     const void* base_before = s.arena.base;
+    const size_t cap_before = s.arena.cap;
     int rc = arena_reserve(ctx, s.arena, plan_bytes(p));
     if (rc) return rc;
     Arena& a = s.arena;
-    if (a.base != base_before) s.tc_loaded_at = nullptr;  // new allocation: nothing of the old arena survives
+    // new allocation: nothing of the old arena survives -- also when cudaMalloc hands the old base address back
+    // (a re-allocation always changes the capacity)
+    if (a.base != base_before || a.cap != cap_before) s.tc_loaded_at = nullptr;
     s.d_tc = carve<uint8_t>(a, 32768);                    // first, so that it keeps its place while the plan varies
     s.d_rgb = carve<uint8_t>(a, p.rgb_bytes);
     s.d_coef = carve<int16_t>(a, p.n_blocks * 64);
@@ -256,7 +262,7 @@ int make_plan(jb_ctx* ctx, size_t n_frames, size_t W, size_t H, const jb_params*
     pl.d_pitch = align_up(W * 3, 16);
     pl.d_frame_stride = pl.d_pitch * H;
     pl.rgb_bytes = host_in ? pl.d_frame_stride * n_frames + 64 : 0;
-    pl.ubuf_cap = align_up(pl.n_blocks * kUbufBytesPerBlock + pl.n_int_total * 16, 4096);
+    pl.ubuf_cap = align_up(pl.n_blocks * ctx->ubuf_per_block + pl.n_int_total * 16, 4096);
     pl.chunks_cap = pl.ubuf_cap / 16;
     pl.out_cap = host_out ? pl.ubuf_cap + pl.ubuf_cap / 8 + n_frames * 1024 : 0;
     *out = pl;
@@ -438,8 +444,15 @@ int status_to_rc(jb_ctx* ctx, const uint64_t* st, uint64_t tie_count, uint32_t t
     ctx->tm.tie_fixups = tie_count;
     if (tie_count > tie_cap) return fail(ctx, JB_E_INTERNAL, "near-tie list overflow (%llu > %u)", (unsigned long long)tie_count, tie_cap);
     if (st[0] & JB_STATUS_UBUF_OVERFLOW) {
+        // the library's own workspace, not the caller's buffer: enlarge the per-block budget (sticky) so that the
+        // synchronous entry points can run the call again, and an asynchronous caller's next call succeeds
         ctx->required = st[1];
-        return fail(ctx, JB_E_NOSPACE, "entropy workspace too small: need %llu bytes", (unsigned long long)st[1]);
+        if (ctx->ubuf_per_block < kUbufBytesPerBlockMax) {
+            ctx->ubuf_per_block = std::min(kUbufBytesPerBlockMax, ctx->ubuf_per_block * 2);
+            ctx->ubuf_grew = true;
+        }
+        return fail(ctx, JB_E_NOSPACE, "entropy workspace too small (need %llu bytes): it has been enlarged, run the call again",
+                    (unsigned long long)st[1]);
     }
     if (st[0] & JB_STATUS_OUT_OVERFLOW) {
         ctx->required = st[2];
@@ -449,6 +462,19 @@ int status_to_rc(jb_ctx* ctx, const uint64_t* st, uint64_t tie_count, uint32_t t
 }
 
 int scratch(jb_ctx* ctx, size_t bytes) { return arena_reserve(ctx, ctx->scratch, bytes + 4096); }
+
+// Run a synchronous entry point again while its only failure is the library's own entropy workspace (very
+// high-entropy content at q100 can need more than the first budget per block; status_to_rc enlarges it).
+template <class F>
+int with_workspace_retry(jb_ctx* ctx, F call) {
+    int rc = JB_OK;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (ctx) ctx->ubuf_grew = false;
+        rc = call();
+        if (rc != JB_E_NOSPACE || !ctx || !ctx->ubuf_grew) break;
+    }
+    return rc;
+}
 
 }  // namespace
 
@@ -772,8 +798,10 @@ int jb_encode_jfif_planar_u32(jb_ctx* ctx, const uint32_t* planar, size_t W, siz
     uint64_t* d_meta = carve<uint64_t>(A, 4);  // offset, size, total
     CK(cudaMemcpyAsync(d_pl, planar, n * 12, cudaMemcpyHostToDevice, st));
     ctx->tm.total_launches += launch_planar_u32_to_rgb8(d_pl, W, H, d_rgb, pitch, st);
-    int rc = jb_encode_batch_device(ctx, d_rgb, 1, W, H, pitch, pitch * H, p, d_out, cap, d_meta, d_meta + 1, d_meta + 2);
-    if (rc == JB_OK) rc = jb_sync(ctx);
+    int rc = with_workspace_retry(ctx, [&] {
+        int r = jb_encode_batch_device(ctx, d_rgb, 1, W, H, pitch, pitch * H, p, d_out, cap, d_meta, d_meta + 1, d_meta + 2);
+        return r == JB_OK ? jb_sync(ctx) : r;
+    });
     if (rc != JB_OK) {
         if (out_len) *out_len = rc == JB_E_NOSPACE ? (size_t)jb_required_bytes(ctx) : 0;
         return rc;
@@ -907,8 +935,8 @@ static int entropy_from_slot(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_para
     return JB_OK;
 }
 
-int jb_entropy(jb_ctx* ctx, const int16_t* coef, size_t n_mcu, const jb_params* p, uint8_t* out, size_t cap,
-               size_t* out_len) {
+static int entropy_once(jb_ctx* ctx, const int16_t* coef, size_t n_mcu, const jb_params* p, uint8_t* out, size_t cap,
+                        size_t* out_len) {
     if (!ctx || !coef || !out || !p || n_mcu == 0) return fail(ctx, JB_E_INVALID, "null argument");
     CK(cudaSetDevice(ctx->device));
     // geometry only matters through n_mcu / blocks per MCU / restart interval here
@@ -924,7 +952,7 @@ int jb_entropy(jb_ctx* ctx, const int16_t* coef, size_t n_mcu, const jb_params* 
         pl.n_blocks = n_mcu * (size_t)pl.g.bpm;
         pl.n_tiles = (pl.n_blocks + 255) / 256;
         pl.n_int_total = (size_t)pl.g.n_int;
-        pl.ubuf_cap = align_up(pl.n_blocks * kUbufBytesPerBlock + pl.n_int_total * 16, 4096);
+        pl.ubuf_cap = align_up(pl.n_blocks * ctx->ubuf_per_block + pl.n_int_total * 16, 4096);
         pl.chunks_cap = pl.ubuf_cap / 16;
         pl.out_cap = pl.ubuf_cap + pl.ubuf_cap / 8 + 1024;
     }
@@ -934,6 +962,11 @@ int jb_entropy(jb_ctx* ctx, const int16_t* coef, size_t n_mcu, const jb_params* 
     CK(cudaMemcpyAsync(s.d_coef, coef, pl.n_blocks * 128, cudaMemcpyHostToDevice, s.st));
     Framing fr{};
     return entropy_from_slot(ctx, s, pl, p, fr, out, cap, out_len, nullptr);
+}
+
+int jb_entropy(jb_ctx* ctx, const int16_t* coef, size_t n_mcu, const jb_params* p, uint8_t* out, size_t cap,
+               size_t* out_len) {
+    return with_workspace_retry(ctx, [&] { return entropy_once(ctx, coef, n_mcu, p, out, cap, out_len); });
 }
 
 int jb_huffman(jb_ctx* ctx, const int32_t* zz, size_t rpc, uint32_t flags, uint8_t* bits, size_t cap, uint64_t* nbits) {
@@ -995,9 +1028,9 @@ static int harvest(jb_ctx* ctx, Slot& s, uint8_t* out, size_t cap, uint64_t* off
     return JB_OK;
 }
 
-int jb_encode_batch(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
-                    size_t frame_stride, const jb_params* p, uint8_t* out, size_t cap, uint64_t* offsets,
-                    uint64_t* sizes) {
+static int encode_batch_once(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
+                             size_t frame_stride, const jb_params* p, uint8_t* out, size_t cap, uint64_t* offsets,
+                             uint64_t* sizes) {
     if (!ctx || !rgb || !out) return fail(ctx, JB_E_INVALID, "null argument");
     if (pitch < W * 3 || (n_frames > 1 && frame_stride < pitch * H)) return fail(ctx, JB_E_INVALID, "bad pitch/stride");
     CK(cudaSetDevice(ctx->device));
@@ -1059,6 +1092,12 @@ drain:
     return rc;
 }
 
+int jb_encode_batch(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
+                    size_t frame_stride, const jb_params* p, uint8_t* out, size_t cap, uint64_t* offsets,
+                    uint64_t* sizes) {
+    return with_workspace_retry(ctx, [&] { return encode_batch_once(ctx, rgb, n_frames, W, H, pitch, frame_stride, p, out, cap, offsets, sizes); });
+}
+
 int jb_encode_jfif(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t H, size_t pitch, const jb_params* p, uint8_t* out,
                    size_t cap, size_t* out_len) {
     uint64_t off = 0, size = 0;
@@ -1092,8 +1131,8 @@ int jb_encode_batch_device(jb_ctx* ctx, const uint8_t* d_rgb, size_t n_frames, s
     return JB_OK;
 }
 
-int jb_encode_strip(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params* p,
-                    uint64_t first_interval, int last_strip, int device_io, uint8_t* out, size_t cap, size_t* out_len) {
+static int encode_strip_once(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params* p,
+                             uint64_t first_interval, int last_strip, int device_io, uint8_t* out, size_t cap, size_t* out_len) {
     if (!ctx || !rgb || !out || !out_len) return fail(ctx, JB_E_INVALID, "null argument");
     CK(cudaSetDevice(ctx->device));
     Plan pl;
@@ -1138,6 +1177,11 @@ int jb_encode_strip(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t strip_rows
     }
     resolve_events(ctx);
     return JB_OK;
+}
+
+int jb_encode_strip(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params* p,
+                    uint64_t first_interval, int last_strip, int device_io, uint8_t* out, size_t cap, size_t* out_len) {
+    return with_workspace_retry(ctx, [&] { return encode_strip_once(ctx, rgb, W, strip_rows, pitch, p, first_interval, last_strip, device_io, out, cap, out_len); });
 }
 
 int jb_synth_rgb_device(jb_ctx* ctx, uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t* d_out) {

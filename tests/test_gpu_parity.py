@@ -531,3 +531,22 @@ def test_planar_u32_layout_and_fused_input(enc, jb, fruit):
     finally:
         enc.device_free(d_pl)
         enc.device_free(d_rgb)
+
+
+def test_high_entropy_content_grows_the_workspace(jb):
+    """Full-range noise at q100 needs more than the first entropy-workspace budget per block (64 bytes): the
+    synchronous entry points enlarge it and run again (found by experiments/fuzz_gpu.py); bytes == the oracle."""
+    enc = jb.Encoder(0)  # a fresh context: the budget is sticky per context
+    try:
+        img = noise_image(99, 200, 120)
+        ql, qc = ol.quality_tables(100)
+        for sub in SUBS:
+            p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=3)
+            assert enc.encode_jfif(img, p) == ol.encode_jfif(img, sub, ql, qc, 3), SUBNAME[sub]
+        frames = np.stack([noise_image(5 + i, 96, 64) for i in range(3)])
+        p = jb.make_params(ol.SUB_444, qlum=ql, qchrom=qc)
+        out, offs, sizes = enc.encode_batch(frames, p)
+        for f in range(3):
+            assert bytes(out[int(offs[f]): int(offs[f] + sizes[f])]) == ol.encode_jfif(frames[f], ol.SUB_444, ql, qc)
+    finally:
+        enc.close()
