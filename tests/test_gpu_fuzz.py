@@ -43,3 +43,57 @@ def test_random_shapes_modes_and_contents(jb, seed):
             done += 1
     finally:
         enc.close()
+
+
+def test_many_small_frames_odd_pitches_and_device_api(jb):
+    """Batches of up to 40 small frames (the units of the tcgen05 kernels wrap over MCU rows and frames), rows /
+    frames / first byte at odd offsets (every alignment variant of the kernels), host and device-resident calls."""
+    enc = jb.Encoder(0)
+    rng = np.random.default_rng(3)
+    try:
+        done = 0
+        while done < 40:
+            sub = int(rng.choice([ol.SUB_444, ol.SUB_REPL420, ol.SUB_420]))
+            m = 16 if sub == ol.SUB_420 else 8
+            W, H = int(rng.integers(m, 200)), int(rng.integers(m, 120))
+            if (-W) % m > W or (-H) % m > H:
+                continue
+            N, q = int(rng.integers(1, 40)), int(rng.choice([50, 75, 95]))
+            ri = int(rng.choice([0, 0, 2, -(-W // m)]))
+            pad, gap, lead = int(rng.choice([0, 0, 1, 4, 8, 16, 5])), int(rng.choice([0, 0, 3, 16, 64])), int(rng.choice([0, 0, 1, 4, 8]))
+            pitch = W * 3 + pad
+            stride = pitch * H + gap
+            buf = np.zeros(lead + stride * N + 64, np.uint8)
+            frames = []
+            for f in range(N):
+                img = ol.synth(77 * done + f, W, H) if rng.random() < 0.6 else rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+                frames.append(img)
+                rows = buf[lead + f * stride: lead + f * stride + pitch * H].reshape(H, pitch)
+                rows[:, : W * 3] = img.reshape(H, W * 3)
+            ql, qc = ol.quality_tables(q)
+            p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri)
+            cap = N * (W * H * 6 + 65536)
+            out, offs, sizes = np.empty(cap, np.uint8), np.zeros(N, np.uint64), np.zeros(N, np.uint64)
+            device = rng.random() < 0.5
+            if device:
+                d_in, d_out, d_meta = enc.device_alloc(buf.nbytes), enc.device_alloc(cap), enc.device_alloc(16 * N + 16)
+                try:
+                    enc.h2d(d_in, buf)
+                    enc.encode_batch_device(d_in + lead, N, W, H, pitch, stride, p, d_out, cap, d_meta, d_meta + 8 * N, d_meta + 16 * N)
+                    enc.sync()
+                    meta = np.zeros(2 * N + 1, np.uint64)
+                    enc.d2h(out, d_out)
+                    enc.d2h(meta, d_meta)
+                    offs, sizes = meta[:N], meta[N: 2 * N]
+                finally:
+                    for d in (d_in, d_out, d_meta):
+                        enc.device_free(d)
+            else:
+                enc.encode_batch_ptr(buf.ctypes.data + lead, N, W, H, pitch, stride, p, out.ctypes.data, cap, offs, sizes)
+            for f in range(N):
+                got = bytes(out[int(offs[f]): int(offs[f]) + int(sizes[f])])
+                assert got == ol.encode_jfif(frames[f], sub, ql, qc, ri), \
+                    f"case {done} frame {f}: sub {sub} {W}x{H} N {N} q{q} ri {ri} pad {pad} gap {gap} lead {lead} device {device}"
+            done += 1
+    finally:
+        enc.close()
