@@ -97,3 +97,22 @@ def test_many_small_frames_odd_pitches_and_device_api(jb):
             done += 1
     finally:
         enc.close()
+
+
+@pytest.mark.parametrize("shape", [(65535, 16), (16, 65535), (65535, 9), (9, 4000), (8191, 1001), (65528, 24)])
+def test_extreme_shapes(jb, shape):
+    """Maximal SOF0 width / height, single MCU rows and columns, a large odd size: JFIF bytes == the oracle."""
+    W, H = shape
+    enc = jb.Encoder(0)
+    try:
+        for sub in (ol.SUB_420, ol.SUB_444, ol.SUB_REPL420):
+            m = 16 if sub == ol.SUB_420 else 8
+            if (-W) % m > W or (-H) % m > H:
+                continue
+            img = ol.synth(W * 7 + H, W, H)
+            ql, qc = ol.quality_tables(75)
+            ri = min(-(-W // m), 65535) if W * H > 100000 else 0
+            p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri)
+            assert enc.encode_jfif(img, p, cap=W * H * 3 + (1 << 20)) == ol.encode_jfif(img, sub, ql, qc, ri), f"sub {sub}"
+    finally:
+        enc.close()
