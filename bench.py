@@ -339,7 +339,7 @@ def main():
     roofline = {"kernel": kname + (" (fused CSC+subsample+shift, tcgen05 FDCT+quant+zigzag)" if use_tc else
                                    " (fused CSC+subsample+shift+FDCT+quant+zigzag, CUDA cores)"), "bound": "hbm",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8000": round(achieved / 8000.0, 4), "algorithmic_bytes_per_launch": int(alg_bytes),
                 "kernel_us_per_launch": round(k_us, 2),
                 "step_breakdown_us": {"transform": round(tm["transform_us"] / a.steps, 1),
                                       "edge_mcus": round(tm["edge_us"] / a.steps, 1),

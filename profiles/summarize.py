@@ -37,6 +37,8 @@ def raw(rep):
 
 WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm throughput % of peak"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
         ("launch__registers_per_thread", "regs/thread"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
         ("smsp__inst_executed.sum", "warp instructions"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
         ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe %"),
