@@ -624,8 +624,9 @@ __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
 
 __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyArgs a) {
     __shared__ __align__(16) uint8_t win[STUFF_WIN + 32];
-    __shared__ uint64_t s_g0, s_g1;
-    __shared__ uint32_t s_i0, s_i1;
+    __shared__ uint64_t s_g0, s_g1, s_off0, s_nb;
+    __shared__ uint32_t s_i0, s_i1, s_k, s_n;
+    __shared__ bool s_hdr_first;
     uint64_t total = a.w.int_ubase[a.n_int_total];
     if (total > a.w.ubuf_cap || a.w.int_obase[a.n_int_total] > a.out_cap) return;
     const uint64_t n_chunks = total >> 4;
@@ -644,9 +645,63 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
         const bool have = c < n_chunks;
         // the intervals of the tile's first and last chunk bracket every other chunk's search (mostly to nothing:
         // an interval is usually much longer than a 4 KB tile)
-        if (threadIdx.x == 0) s_i0 = find_interval(c << 4, 0, a.n_int_total);
+        if (threadIdx.x == 0) {
+            const uint32_t i = find_interval(c << 4, 0, a.n_int_total), k = i % (uint32_t)a.g.n_int;
+            const uint64_t ub = a.w.int_ubase[i], off0 = (c << 4) - ub;
+            s_i0 = i;
+            // what a tile that lies inside one interval needs from it (the fast path below)
+            s_k = k;
+            s_off0 = off0;
+            s_nb = (a.w.int_bits[i] + 7) >> 3;
+            s_hdr_first = k == 0 && off0 == 0 && a.fr.hdr_bytes != 0;
+            s_g0 = a.w.int_obase[i] + (k == 0 && off0 != 0 ? a.fr.hdr_bytes : 0u) + off0 +
+                   (a.w.ff_tile_base[tile] - ff_prefix(a, ub >> 4));  // chunk tile * 256 has in-tile prefix 0
+        }
         if (have && (threadIdx.x == TILE - 1 || c + 1 == n_chunks)) s_i1 = find_interval(c << 4, 0, a.n_int_total);
         __syncthreads();
+        if (s_i0 == s_i1 && !s_hdr_first) {
+            // ---- fast path: the whole tile lies in one interval and starts no frame.  Per thread: its chunk and
+            // its in-tile 0xFF prefix; everything else is tile-uniform, offsets are 32 bits relative to the tile.
+            const uint64_t g0 = s_g0, off = s_off0 + 16u * threadIdx.x, nb = s_nb;
+            uint32_t n_here = 0;
+            if (have) {
+                const uint4 q = p[c];
+                const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+                const int valid = off >= nb ? 0 : (nb - off < 16 ? (int)(nb - off) : 16);
+                const uint32_t marker = off + 16 >= nb ? marker_after(a, s_k) : 0u;  // last chunk of the interval
+                const uint32_t rel = 16u * threadIdx.x + (threadIdx.x ? a.w.ff_prefix[c] : 0u);
+                uint32_t d = (uint32_t)__cvta_generic_to_shared(win) + (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + g0) & 15) + rel;
+                const uint32_t d_begin = d;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t byte = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                    const bool on = j < valid, ff = on && byte == 0xFFu;
+                    if (on) sts8(d, byte);
+                    if (ff) sts8(d + 1, 0u);  // T.81 F.1.2.3 byte stuffing
+                    d += on ? (ff ? 2u : 1u) : 0u;
+                }
+                if (marker) {
+                    sts8(d, 0xFFu);
+                    sts8(d + 1, marker);
+                    d += 2;
+                }
+                n_here = rel + (d - d_begin);
+                if (threadIdx.x == TILE - 1 || c + 1 == n_chunks) s_n = n_here;
+            }
+            __syncthreads();
+            {
+                const uint32_t base = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + g0) & 15), n = s_n;
+                const uint32_t head = min(n, (16u - base) & 15u);          // bytes before the first 16-byte boundary
+                const uint32_t n16 = (n - head) >> 4, tail = (n - head) & 15u;
+                if (threadIdx.x < head) a.out[g0 + threadIdx.x] = win[base + threadIdx.x];
+                uint4* gdst = reinterpret_cast<uint4*>(a.out + g0 + head);
+                const uint4* ssrc = reinterpret_cast<const uint4*>(win + base + head);
+                for (uint32_t j = threadIdx.x; j < n16; j += TILE) gdst[j] = ssrc[j];
+                if (threadIdx.x < tail) a.out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = win[base + head + 16 * n16 + threadIdx.x];
+            }
+            __syncthreads();
+            continue;
+        }
         uint64_t dst = 0, start = 0, end = 0;
         uint32_t wds[4] = {0, 0, 0, 0}, marker = 0;
         int valid = 0;
