@@ -58,6 +58,13 @@ typedef enum {
 #define JB_FLAG_FMA_DCT 0x40u        /* use the CUDA-core kernel (register AAN FDCT, near-tie     *
                                       * band proven analytically) instead of the tcgen05 one      */
 
+#define JB_FLAG_OPTIMIZE_HUFFMAN 0x80u /* two passes like libjpeg's optimize_coding: the symbols of the call's   *
+                                      * coefficients are counted on the GPU, optimal tables (T.81 K.2) are built  *
+                                      * per call (shared by the frames of a batch), written into the DHT          *
+                                      * segments and used by the coder; files are 5-12 % smaller, decoded pixels  *
+                                      * identical.  JFIF entry points only (not strips / jb_entropy / jb_huffman); *
+                                      * the header is then shorter than jb_header_bytes() says                    */
+
 typedef struct {
     int32_t subsampling;      /* JB_SUB_*                                                   */
     int32_t restart_interval; /* MCUs per restart interval, 0 = none (<= 65535)            */

@@ -51,6 +51,8 @@ struct Slot {
     uint64_t* d_total = nullptr;
     uint8_t* d_hdr = nullptr;
     uint8_t* d_tc = nullptr;  // tcgen05 transform: the four fp16 W matrices
+    uint32_t* d_hist = nullptr;     // JB_FLAG_OPTIMIZE_HUFFMAN: symbol counts [4][256]
+    HuffDev* d_huff_opt = nullptr;  // ... and the tables derived from them
     uint8_t* tc_loaded_at = nullptr;  // where, and which generation of, the matrices this slot last uploaded
     uint64_t tc_loaded_gen = 0;
     uint32_t tie_cap = 0;
@@ -180,6 +182,8 @@ size_t plan_bytes(const Plan& p) {
     add(8);
     add(1024);
     add(32768);
+    add(4096);
+    add(sizeof(HuffDev));
     return align_up(b, 256) + 4096;
 }
 
@@ -221,11 +225,14 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.d_frame_size = carve<uint64_t>(a, p.n_frames);
     s.d_total = carve<uint64_t>(a, 1);
     s.d_hdr = carve<uint8_t>(a, 1024);
+    s.d_hist = carve<uint32_t>(a, 1024);
+    s.d_huff_opt = carve<HuffDev>(a, 1);
     s.w.n_ff_tiles = s.d_scalars + 1;
     s.w.n_long = s.d_scalars + 2;
     s.w.status = reinterpret_cast<uint64_t*>(s.d_scalars + 4);
     // pinned result block: result words, then (last 1 KB) the staging area of the JFIF header
-    size_t need = (8 + 2 * p.n_frames) * sizeof(uint64_t) + 2048 + 32768;
+    // ... before it the W matrices (32 KB), the symbol counts (4 KB) and the optimised Huffman tables (8 KB)
+    size_t need = (8 + 2 * p.n_frames) * sizeof(uint64_t) + 2048 + 32768 + 4096 + 8192;
     if (need > s.h_res_cap) {
         if (s.h_res) cudaFreeHost(s.h_res);
         s.h_res = nullptr;
@@ -425,11 +432,41 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ea.frame_off = d_off;
     ea.frame_size = d_size;
     ea.total_out = d_total;
+    HuffSpecs specs;
+    const HuffSpecs* custom = nullptr;
+    if (p->flags & JB_FLAG_OPTIMIZE_HUFFMAN) {
+        // Two passes (like libjpeg's optimize_coding): count the symbols of this call's coefficients on the GPU,
+        // derive the optimal tables on the host (T.81 K.2), code with them and write them into the DHT segments.
+        // The counts make this a synchronisation point of the stream.
+        if (!fr.hdr_bytes || (p->flags & JB_FLAG_REF_TYPO_TABLES))
+            return fail(ctx, JB_E_UNSUPPORTED, "optimised Huffman tables need a JFIF header to travel in (no strips, no raw bit strings)");
+        uint8_t* stage = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024 - 32768 - 4096;
+        uint32_t* h_hist = reinterpret_cast<uint32_t*>(stage);
+        HuffDev* h_huff = reinterpret_cast<HuffDev*>(stage - 8192);
+        {
+            Timed t(ctx, s.st, 2);
+            CK(cudaMemsetAsync(s.d_hist, 0, 4096, s.st));
+            ctx->tm.total_launches += launch_symbol_hist(ea, s.d_hist, s.st);
+            CK(cudaMemcpyAsync(h_hist, s.d_hist, 4096, cudaMemcpyDeviceToHost, s.st));
+        }
+        CK(cudaStreamSynchronize(s.st));
+        uint64_t counts[4][256];
+        for (int t = 0; t < 4; ++t)
+            for (int i = 0; i < 256; ++i) counts[t][i] = h_hist[t * 256 + i];
+        optimal_huff_specs(counts, &specs);
+        build_huff_from_specs(specs, h_huff);
+        CK(cudaMemcpyAsync(s.d_huff_opt, h_huff, sizeof(HuffDev), cudaMemcpyHostToDevice, s.st));
+        ea.huff = s.d_huff_opt;
+        custom = &specs;
+    }
     if (fr.hdr_bytes) {
         // the header travels through the pinned result block so that the copy is truly asynchronous
         uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024;
-        size_t n = build_header(p, W, H, h);
-        if (n != fr.hdr_bytes) return fail(ctx, JB_E_INTERNAL, "header size mismatch");
+        size_t n = build_header(p, W, H, h, custom);
+        if (custom)
+            ea.fr.hdr_bytes = (uint32_t)n;  // fewer symbols than Annex K lists: a shorter header
+        else if (n != fr.hdr_bytes)
+            return fail(ctx, JB_E_INTERNAL, "header size mismatch");
         CK(cudaMemcpyAsync(s.d_hdr, h, n, cudaMemcpyHostToDevice, s.st));
     }
     {
@@ -834,13 +871,13 @@ int jb_blocks_per_mcu(int sub) { return sub == JB_SUB_420 ? 6 : 3; }
 
 size_t jb_header_bytes(const jb_params* p) {
     if (!p) return 0;
-    uint8_t tmp[1024];
+    uint8_t tmp[2048];
     return build_header(p, 8, 8, tmp);
 }
 
 int jb_write_header(const jb_params* p, size_t W, size_t H, uint8_t* out, size_t cap, size_t* out_len) {
     if (!p || !out || !out_len) return JB_E_INVALID;
-    uint8_t tmp[1024];
+    uint8_t tmp[2048];
     size_t n = build_header(p, W, H, tmp);
     *out_len = n;
     if (n > cap) return JB_E_NOSPACE;

@@ -779,6 +779,62 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
 
 static uint64_t magic52(uint64_t d) { return ((1ull << 52) + d - 1) / d; }
 
+// ---- symbol histogram for per-call optimal Huffman tables (JB_FLAG_OPTIMIZE_HUFFMAN) ------------------
+// One thread per block, the same symbols k_encode would emit (utils.cpp:572-609, 667-694): DC difference
+// category, (run, size) of every non-zero AC coefficient, ZRL, EOB.  hist = [4][256] in DHT order
+// (DC luma, AC luma, DC chroma, AC chroma); counted in shared memory, flushed with one atomic per used bin.
+__global__ void __launch_bounds__(TILE) k_symbol_hist(const __grid_constant__ EntropyArgs a, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_h[4 * 256];
+    for (int i = threadIdx.x; i < 4 * 256; i += TILE) s_h[i] = 0;
+    __syncthreads();
+    for (uint32_t b = blockIdx.x * TILE + threadIdx.x; b < a.n_blocks; b += gridDim.x * TILE) {
+        const BlockInfo bi = block_info(a, b);
+        const uint4* src = reinterpret_cast<const uint4*>(a.coef) + (size_t)b * 8;
+        uint32_t* dc = s_h + (bi.comp ? 2 : 0) * 256;
+        uint32_t* ac = dc + 256;
+        const int pred = bi.has_prev ? (int)a.coef[(size_t)bi.prev * 64] : 0;
+        int run = 0, last_nz = 0;
+#pragma unroll 1
+        for (int pc = 0; pc < 8; ++pc) {
+            const uint4 q = __ldg(src + pc);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = pc * 8 + i;
+                const int v = (int)(short)(w[i >> 1] >> ((i & 1) * 16));
+                if (k == 0) {
+                    const int d = v - pred;
+                    atomicAdd(&dc[32 - __clz(abs(d))], 1u);
+                } else if (v == 0) {
+                    ++run;
+                } else {
+                    while (run >= 16) {  // ZRL
+                        atomicAdd(&ac[0xF0], 1u);
+                        run -= 16;
+                    }
+                    atomicAdd(&ac[(run << 4) | (32 - __clz(abs(v)))], 1u);
+                    run = 0;
+                    last_nz = k;
+                }
+            }
+        }
+        if (last_nz < 63 || a.always_eob) atomicAdd(&ac[0], 1u);  // EOB
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += TILE)
+        if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
+}
+
+int launch_symbol_hist(const EntropyArgs& a_in, uint32_t* d_hist, cudaStream_t s) {
+    if (a_in.n_blocks == 0) return 0;
+    EntropyArgs a = a_in;
+    a.m_bpf = magic52((uint64_t)a.g.n_mcu * (uint64_t)a.g.bpm);
+    a.m_ri = magic52((uint64_t)a.g.ri);
+    uint32_t n_tiles = (a.n_blocks + TILE - 1) / TILE;
+    k_symbol_hist<<<n_tiles < 148u * 8u ? n_tiles : 148u * 8u, TILE, 0, s>>>(a, d_hist);
+    return 1;
+}
+
 int launch_entropy(const EntropyArgs& a_in, cudaStream_t s) {
     if (a_in.n_blocks == 0) return 0;
     EntropyArgs a = a_in;

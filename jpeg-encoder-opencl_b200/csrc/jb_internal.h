@@ -182,7 +182,17 @@ void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_
 void build_huff(bool typo, HuffDev* out);
 void build_ydown(uint32_t ydown[2048]);
 void build_dct_tables(double costab[64], double scale[64]);
-size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* out);  // out >= 1024 bytes
+// BITS / HUFFVAL lists of the four tables in DHT order: DC luma, AC luma, DC chroma, AC chroma
+struct HuffSpecs {
+    uint8_t bits[4][16];
+    uint8_t vals[4][256];
+    int n[4];
+};
+void annex_k_specs(HuffSpecs* sp);
+void optimal_huff_specs(const uint64_t counts[4][256], HuffSpecs* sp);  // T.81 K.2 as in libjpeg (counts in DHT order)
+void build_huff_from_specs(const HuffSpecs& sp, HuffDev* out);
+size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* out, const HuffSpecs* custom = nullptr);  // out >= 2048 bytes
+int launch_symbol_hist(const EntropyArgs& a, uint32_t* d_hist /* [4][256], DHT order */, cudaStream_t s);
 extern const uint8_t kZigzag[64];  // zigzag position -> natural index
 
 }  // namespace jb

@@ -65,6 +65,100 @@ void assign_codes(const HuffSpec& sp, uint32_t* table /* indexed by symbol */) {
 
 }  // namespace
 
+// run/size code and value bits of small coefficients in one entry (utils.cpp:623-653, 683-691)
+static void build_small(HuffDev* out) {
+    for (int t = 0; t < 2; ++t)
+        for (int run = 0; run < 16; ++run)
+            for (int v = -15; v <= 15; ++v) {
+                if (v == 0) continue;
+                int a = v < 0 ? -v : v, cat = 0;
+                while (a >> cat) ++cat;
+                uint32_t vb = (uint32_t)(v < 0 ? v + (1 << cat) - 1 : v);
+                uint32_t e = out->ac[t][(run << 4) | cat];
+                out->small[t][(run << 5) | (v & 31)] = ((((e >> 5) << cat) | vb) << 5) | ((e & 31u) + (uint32_t)cat);
+            }
+}
+
+void annex_k_specs(HuffSpecs* sp) {
+    memset(sp, 0, sizeof(*sp));
+    for (int t = 0; t < 4; ++t) {
+        memcpy(sp->bits[t], kSpecs[t].bits, 16);
+        memcpy(sp->vals[t], kSpecs[t].vals, (size_t)kSpecs[t].nvals);
+        sp->n[t] = kSpecs[t].nvals;
+    }
+}
+
+void build_huff_from_specs(const HuffSpecs& sp, HuffDev* out) {
+    memset(out, 0, sizeof(*out));
+    uint32_t* tables[4] = {out->dc[0], out->ac[0], out->dc[1], out->ac[1]};
+    for (int t = 0; t < 4; ++t) {
+        HuffSpec one;
+        memcpy(one.bits, sp.bits[t], 16);
+        one.vals = sp.vals[t];
+        one.nvals = sp.n[t];
+        uint32_t full[256] = {0};
+        assign_codes(one, full);
+        memcpy(tables[t], full, (t & 1 ? 256 : 16) * sizeof(uint32_t));
+    }
+    build_small(out);
+}
+
+// Optimal BITS / HUFFVAL for 256 symbol counts: T.81 Annex K.2 (Figures K.1-K.4) in the form libjpeg's
+// jpeg_gen_optimal_table gives it -- a reserved 257th symbol of count 1 keeps the all-ones code free, the two
+// least frequent entries merge (the larger symbol on ties), code lengths above 16 are folded back.
+static void optimal_spec(const uint64_t counts[256], uint8_t bits_out[16], uint8_t vals_out[256], int* n_out) {
+    const int kMax = 32;
+    uint64_t w[257];
+    int len[257], next[257], hist[kMax + 1] = {0};
+    for (int i = 0; i < 256; ++i) w[i] = counts[i];
+    w[256] = 1;
+    for (int i = 0; i < 257; ++i) { len[i] = 0; next[i] = -1; }
+    auto least = [&](int skip) {
+        int best = -1;
+        for (int i = 0; i <= 256; ++i)
+            if (w[i] && i != skip && (best < 0 || w[i] <= w[best])) best = i;
+        return best;
+    };
+    for (;;) {
+        int a = least(-1), b = a < 0 ? -1 : least(a);
+        if (b < 0) break;
+        w[a] += w[b];
+        w[b] = 0;
+        // every symbol of both chains moves one level down; chain b is appended to chain a
+        for (int i = a;; i = next[i]) {
+            ++len[i];
+            if (next[i] < 0) { next[i] = b; break; }
+        }
+        for (int i = b; i >= 0; i = next[i]) ++len[i];
+    }
+    for (int i = 0; i <= 256; ++i)
+        if (len[i]) ++hist[len[i] > kMax ? kMax : len[i]];
+    int l = kMax;
+    for (; l > 16; --l)
+        while (hist[l] > 0) {  // Figure K.3
+            int j = l - 2;
+            while (hist[j] == 0) --j;
+            hist[l] -= 2;
+            ++hist[l - 1];
+            hist[j + 1] += 2;
+            --hist[j];
+        }
+    while (hist[l] == 0) --l;
+    --hist[l];  // the reserved symbol
+    for (int i = 1; i <= 16; ++i) bits_out[i - 1] = (uint8_t)hist[i];
+    int n = 0;
+    memset(vals_out, 0, 256);
+    for (int i = 1; i <= kMax; ++i)
+        for (int sym = 0; sym < 256; ++sym)
+            if (len[sym] == i) vals_out[n++] = (uint8_t)sym;
+    *n_out = n;
+}
+
+void optimal_huff_specs(const uint64_t counts[4][256], HuffSpecs* sp) {
+    memset(sp, 0, sizeof(*sp));
+    for (int t = 0; t < 4; ++t) optimal_spec(counts[t], sp->bits[t], sp->vals[t], &sp->n[t]);
+}
+
 void build_huff(bool typo, HuffDev* out) {
     memset(out, 0, sizeof(*out));
     assign_codes(kSpecs[0], out->dc[0]);
@@ -80,17 +174,7 @@ void build_huff(bool typo, HuffDev* out) {
             out->ac[0][(3 << 4) | cat] = (code << 5) | 17u;
         }
     }
-    // run/size code and value bits of small coefficients in one entry (utils.cpp:623-653, 683-691)
-    for (int t = 0; t < 2; ++t)
-        for (int run = 0; run < 16; ++run)
-            for (int v = -15; v <= 15; ++v) {
-                if (v == 0) continue;
-                int a = v < 0 ? -v : v, cat = 0;
-                while (a >> cat) ++cat;
-                uint32_t vb = (uint32_t)(v < 0 ? v + (1 << cat) - 1 : v);
-                uint32_t e = out->ac[t][(run << 4) | cat];
-                out->small[t][(run << 5) | (v & 31)] = ((((e >> 5) << cat) | vb) << 5) | ((e & 31u) + (uint32_t)cat);
-            }
+    build_small(out);
 }
 
 // ---- worst-case error of the binary32 AAN transform -------------------------------
@@ -228,7 +312,12 @@ static void put16(uint8_t* p, unsigned v) {
     p[1] = (uint8_t)v;
 }
 
-size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* h) {
+size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* h, const HuffSpecs* custom) {
+    HuffSpecs std_specs;
+    if (!custom) {
+        annex_k_specs(&std_specs);
+        custom = &std_specs;
+    }
     size_t n = 0;
     static const uint8_t soi_app0[] = {0xFF, 0xD8, 0xFF, 0xE0, 0x00, 0x10, 'J',  'F',  'I',  'F',
                                        0x00, 0x01, 0x01, 0x00, 0x00, 0x01, 0x00, 0x01, 0x00, 0x00};
@@ -248,10 +337,10 @@ size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* h) {
     h[n++] = 3; h[n++] = 0x11; h[n++] = 1;
     for (int t = 0; t < 4; ++t) {  // DHT x4
         h[n++] = 0xFF; h[n++] = 0xC4;
-        put16(h + n, (unsigned)(2 + 1 + 16 + kSpecs[t].nvals)); n += 2;
+        put16(h + n, (unsigned)(2 + 1 + 16 + custom->n[t])); n += 2;
         h[n++] = kTcTh[t];
-        memcpy(h + n, kSpecs[t].bits, 16); n += 16;
-        memcpy(h + n, kSpecs[t].vals, (size_t)kSpecs[t].nvals); n += (size_t)kSpecs[t].nvals;
+        memcpy(h + n, custom->bits[t], 16); n += 16;
+        memcpy(h + n, custom->vals[t], (size_t)custom->n[t]); n += (size_t)custom->n[t];
     }
     if (p->restart_interval > 0) {  // DRI
         h[n++] = 0xFF; h[n++] = 0xDD; h[n++] = 0x00; h[n++] = 0x04;

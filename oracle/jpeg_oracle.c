@@ -61,6 +61,9 @@ typedef struct {
 } hufftab;
 
 static hufftab g_tab[4]; /* 0 DC lum, 1 DC chr, 2 AC lum, 3 AC chr */
+/* the BITS / HUFFVAL lists in force (Annex K unless orc_set_huffman_specs replaced them), same index */
+static uint8_t g_spec_bits[4][16], g_spec_vals[4][256];
+static int g_spec_n[4];
 uint8_t orc_zigzag_order[64];
 static double g_cos[8][8]; /* g_cos[u][x] = cos((2x+1)*u*pi/16) */
 static int g_init_done = 0;
@@ -82,10 +85,7 @@ static void build_table(hufftab *t, const uint8_t bits[16], const uint8_t *vals)
 
 void orc_init(void) {
     if (g_init_done) return;
-    build_table(&g_tab[0], bits_dc_lum, val_dc);
-    build_table(&g_tab[1], bits_dc_chr, val_dc);
-    build_table(&g_tab[2], bits_ac_lum, val_ac_lum);
-    build_table(&g_tab[3], bits_ac_chr, val_ac_chr);
+    orc_reset_huffman_specs();
     /* zigzag order by the diagonal walk of utils.cpp:539-551 */
     unsigned idx = 0;
     for (int diag = 0; diag < 15; ++diag) {
@@ -522,7 +522,7 @@ static void put_u16(uint8_t *p, unsigned v) {
 size_t orc_jfif_header(size_t W, size_t H, int sub, const unsigned ql[64], const unsigned qc[64],
                        int restart_interval, uint8_t *out, size_t cap) {
     orc_init();
-    uint8_t h[1024];
+    uint8_t h[2048];
     size_t n = 0;
     static const uint8_t app0[] = {0xFF, 0xD8, 0xFF, 0xE0, 0x00, 0x10, 'J', 'F', 'I', 'F', 0x00,
                                    0x01, 0x01, 0x00, 0x00, 0x01, 0x00, 0x01, 0x00, 0x00};
@@ -541,16 +541,15 @@ size_t orc_jfif_header(size_t W, size_t H, int sub, const unsigned ql[64], const
     h[n++] = 1; h[n++] = (uint8_t)(sub == ORC_SUB_420 ? 0x22 : 0x11); h[n++] = 0;
     h[n++] = 2; h[n++] = 0x11; h[n++] = 1;
     h[n++] = 3; h[n++] = 0x11; h[n++] = 1;
-    static const uint8_t *bitsv[4] = {bits_dc_lum, bits_ac_lum, bits_dc_chr, bits_ac_chr};
-    static const uint8_t *valsv[4] = {val_dc, val_ac_lum, val_dc, val_ac_chr};
+    static const int order[4] = {0, 2, 1, 3}; /* DHT segments: DC lum, AC lum, DC chr, AC chr */
     static const uint8_t tcth[4] = {0x00, 0x10, 0x01, 0x11};
     for (int t = 0; t < 4; ++t) {
-        int nv = (t & 1) ? 162 : 12;
+        int i = order[t], nv = g_spec_n[i];
         h[n++] = 0xFF; h[n++] = 0xC4;
         put_u16(h + n, (unsigned)(2 + 1 + 16 + nv)); n += 2;
         h[n++] = tcth[t];
-        memcpy(h + n, bitsv[t], 16); n += 16;
-        memcpy(h + n, valsv[t], (size_t)nv); n += (size_t)nv;
+        memcpy(h + n, g_spec_bits[i], 16); n += 16;
+        memcpy(h + n, g_spec_vals[i], (size_t)nv); n += (size_t)nv;
     }
     if (restart_interval > 0) {
         h[n++] = 0xFF; h[n++] = 0xDD; h[n++] = 0x00; h[n++] = 0x04;
@@ -579,6 +578,142 @@ size_t orc_encode_jfif(const uint8_t *rgb, size_t W, size_t H, int sub, const un
         return (size_t)-1;
     }
     size_t e = orc_entropy(coef, n_mcu, sub, restart_interval, quirks, 0, 0, 0, out + n, cap - n, NULL);
+    free(coef);
+    if (e == (size_t)-1 || n + e + 2 > cap) return (size_t)-1;
+    n += e;
+    out[n++] = 0xFF;
+    out[n++] = 0xD9;
+    return n;
+}
+
+/* ---- optimised Huffman tables [unpinned by the reference: it has fixed tables] ----
+ * Two passes like libjpeg's optimize_coding: count the symbols the coder would emit, derive BITS / HUFFVAL
+ * with the procedure of T.81 Annex K.2 (Figures K.1-K.4) in the form libjpeg's jpeg_gen_optimal_table gives it
+ * (a reserved 257th symbol keeps the all-ones code unused, ties go to the larger symbol, lengths limited to 16),
+ * then code with those tables and write them into the DHT segments. */
+void orc_reset_huffman_specs(void) {
+    static const uint8_t *bitsv[4] = {bits_dc_lum, bits_dc_chr, bits_ac_lum, bits_ac_chr};
+    static const uint8_t *valsv[4] = {val_dc, val_dc, val_ac_lum, val_ac_chr};
+    for (int i = 0; i < 4; ++i) {
+        g_spec_n[i] = i < 2 ? 12 : 162;
+        memcpy(g_spec_bits[i], bitsv[i], 16);
+        memset(g_spec_vals[i], 0, 256);
+        memcpy(g_spec_vals[i], valsv[i], (size_t)g_spec_n[i]);
+        build_table(&g_tab[i], g_spec_bits[i], g_spec_vals[i]);
+    }
+}
+
+/* index: 0 DC lum, 1 DC chr, 2 AC lum, 3 AC chr */
+void orc_set_huffman_specs(const uint8_t bits[4][16], const uint8_t vals[4][256]) {
+    orc_init();
+    for (int i = 0; i < 4; ++i) {
+        int n = 0;
+        for (int l = 0; l < 16; ++l) n += bits[i][l];
+        g_spec_n[i] = n;
+        memcpy(g_spec_bits[i], bits[i], 16);
+        memcpy(g_spec_vals[i], vals[i], 256);
+        build_table(&g_tab[i], g_spec_bits[i], g_spec_vals[i]);
+    }
+}
+
+/* Symbols the entropy coder emits for these coefficients (same walk as orc_entropy). */
+void orc_symbol_histogram(const int16_t *coef, size_t n_mcu, int sub, int restart_interval, int quirks,
+                          uint64_t hist[4][256]) {
+    int bpm = orc_blocks_per_mcu(sub);
+    size_t ri = restart_interval > 0 ? (size_t)restart_interval : n_mcu;
+    memset(hist, 0, 4 * 256 * sizeof(uint64_t));
+    for (size_t m0 = 0; m0 < n_mcu; m0 += ri) {
+        size_t m1 = m0 + ri < n_mcu ? m0 + ri : n_mcu;
+        int pred[3] = {0, 0, 0};
+        for (size_t m = m0; m < m1; ++m)
+            for (int b = 0; b < bpm; ++b) {
+                int comp = sub == ORC_SUB_420 ? (b < 4 ? 0 : b - 3) : b, chroma = comp != 0;
+                int32_t zz[64], pairs[130];
+                const int16_t *cb = coef + (m * (size_t)bpm + (size_t)b) * 64;
+                for (int k = 0; k < 64; ++k) zz[k] = cb[k];
+                hist[chroma][orc_category(zz[0] - pred[comp])]++;
+                pred[comp] = zz[0];
+                size_t n = orc_rle_block(zz, pairs, (quirks & ORC_Q3_ALWAYS_EOB) != 0);
+                for (size_t j = 0; j < n; j += 2) hist[2 + chroma][(pairs[j] << 4) | orc_category(pairs[j + 1])]++;
+            }
+    }
+}
+
+/* T.81 K.2 / libjpeg jpeg_gen_optimal_table.  Returns the number of symbols (HUFFVAL entries). */
+int orc_optimal_spec(const uint64_t freq_in[256], uint8_t bits_out[16], uint8_t vals_out[256]) {
+    enum { MAXLEN = 32 };
+    uint64_t freq[257];
+    int codesize[257], others[257], bits[MAXLEN + 1];
+    for (int i = 0; i < 256; ++i) freq[i] = freq_in[i];
+    freq[256] = 1; /* reserved: guarantees that no real symbol gets the all-ones code */
+    for (int i = 0; i < 257; ++i) { codesize[i] = 0; others[i] = -1; }
+    memset(bits, 0, sizeof(bits));
+    for (;;) {
+        int c1 = -1, c2 = -1;
+        uint64_t v = UINT64_MAX;
+        for (int i = 0; i <= 256; ++i)
+            if (freq[i] && freq[i] <= v) { v = freq[i]; c1 = i; } /* smallest, larger symbol on ties */
+        v = UINT64_MAX;
+        for (int i = 0; i <= 256; ++i)
+            if (freq[i] && freq[i] <= v && i != c1) { v = freq[i]; c2 = i; }
+        if (c2 < 0) break;
+        freq[c1] += freq[c2];
+        freq[c2] = 0;
+        codesize[c1]++;
+        while (others[c1] >= 0) { c1 = others[c1]; codesize[c1]++; }
+        others[c1] = c2;
+        codesize[c2]++;
+        while (others[c2] >= 0) { c2 = others[c2]; codesize[c2]++; }
+    }
+    for (int i = 0; i <= 256; ++i)
+        if (codesize[i]) {
+            if (codesize[i] > MAXLEN) return -1;
+            bits[codesize[i]]++;
+        }
+    int i;
+    for (i = MAXLEN; i > 16; --i) /* Figure K.3: move the deepest pairs up until no code is longer than 16 */
+        while (bits[i] > 0) {
+            int j = i - 2;
+            while (bits[j] == 0) --j;
+            bits[i] -= 2;
+            bits[i - 1]++;
+            bits[j + 1] += 2;
+            bits[j]--;
+        }
+    while (bits[i] == 0) --i;
+    bits[i]--; /* the reserved symbol had the longest code */
+    int n = 0;
+    for (int l = 1; l <= 16; ++l) bits_out[l - 1] = (uint8_t)bits[l];
+    memset(vals_out, 0, 256);
+    for (int l = 1; l <= MAXLEN; ++l) /* Figure K.4: symbols sorted by code size, then by value */
+        for (int j = 0; j < 256; ++j)
+            if (codesize[j] == l) vals_out[n++] = (uint8_t)j;
+    return n;
+}
+
+size_t orc_encode_jfif_optimized(const uint8_t *rgb, size_t W, size_t H, int sub, const unsigned ql[64],
+                                 const unsigned qc[64], int restart_interval, int quirks, uint8_t *out, size_t cap) {
+    if (restart_interval < 0 || restart_interval > 65535) return (size_t)-1;
+    orc_init();
+    size_t n_mcu = orc_num_mcus(W, H, sub);
+    int16_t *coef = (int16_t *)malloc(n_mcu * (size_t)orc_blocks_per_mcu(sub) * 64 * sizeof(int16_t));
+    if (!coef) return (size_t)-1;
+    if (orc_transform(rgb, W, H, sub, ql, qc, quirks, coef)) {
+        free(coef);
+        return (size_t)-1;
+    }
+    uint64_t hist[4][256];
+    uint8_t bits[4][16], vals[4][256];
+    orc_symbol_histogram(coef, n_mcu, sub, restart_interval, quirks, hist);
+    for (int i = 0; i < 4; ++i)
+        if (orc_optimal_spec(hist[i], bits[i], vals[i]) < 0) {
+            free(coef);
+            return (size_t)-1;
+        }
+    orc_set_huffman_specs(bits, vals);
+    size_t n = orc_jfif_header(W, H, sub, ql, qc, restart_interval, out, cap), e = (size_t)-1;
+    if (n <= cap) e = orc_entropy(coef, n_mcu, sub, restart_interval, quirks & ~ORC_Q2_TYPO_TABLES, 0, 0, 0, out + n, cap - n, NULL);
+    orc_reset_huffman_specs();
     free(coef);
     if (e == (size_t)-1 || n + e + 2 > cap) return (size_t)-1;
     n += e;

@@ -88,6 +88,14 @@ size_t orc_encode_jfif(const uint8_t *rgb, size_t W, size_t H, int sub, const un
                        const unsigned qc[64], int restart_interval, int quirks, uint8_t *out, size_t cap);
 /* Deterministic integer-only synthetic image. Fills rows
  * [y0, y0+rows) of a W-wide image into out (rows*W*3 bytes). */
+/* optimised Huffman tables (T.81 K.2 as in libjpeg's jpeg_gen_optimal_table); spec index 0 DC lum, 1 DC chr, 2 AC lum, 3 AC chr */
+void orc_reset_huffman_specs(void);
+void orc_set_huffman_specs(const uint8_t bits[4][16], const uint8_t vals[4][256]);
+void orc_symbol_histogram(const int16_t *coef, size_t n_mcu, int sub, int restart_interval, int quirks,
+                          uint64_t hist[4][256]);
+int orc_optimal_spec(const uint64_t freq[256], uint8_t bits[16], uint8_t vals[256]);
+size_t orc_encode_jfif_optimized(const uint8_t *rgb, size_t W, size_t H, int sub, const unsigned ql[64],
+                                 const unsigned qc[64], int restart_interval, int quirks, uint8_t *out, size_t cap);
 void orc_synth_rgb(uint64_t seed, size_t W, size_t y0, size_t rows, uint8_t *out);
 
 #ifdef __cplusplus

@@ -74,6 +74,10 @@ def oracle():
     L.orc_encode_jfif.restype = sz
     L.orc_synth_rgb.argtypes = [C.c_uint64, sz, sz, sz, u8p]
     L.orc_aos_to_planar_u32.argtypes = [u8p, sz, sz, u32p]
+    L.orc_encode_jfif_optimized.argtypes = [u8p, sz, sz, C.c_int, u32p, u32p, C.c_int, C.c_int, u8p, sz]
+    L.orc_encode_jfif_optimized.restype = sz
+    L.orc_optimal_spec.argtypes = [np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), u8p, u8p]
+    L.orc_symbol_histogram.argtypes = [i16p, sz, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]
     L.orc_planar_u32_interleave.argtypes = [u32p, sz, sz, u32p]
     L.orc_init()
     _oracle = L
@@ -209,6 +213,24 @@ def encode_jfif(rgb, sub, ql, qc, restart_interval=0, quirks=0):
     n = oracle().orc_encode_jfif(np.ascontiguousarray(rgb), W, H, sub, ql, qc, restart_interval, quirks, out, cap)
     assert n != C.c_size_t(-1).value
     return out[:n].tobytes()
+
+
+def encode_jfif_optimized(rgb, sub, ql, qc, restart_interval=0, quirks=0):
+    """Two-pass encode with per-image optimal Huffman tables (T.81 K.2 / libjpeg's jpeg_gen_optimal_table)."""
+    H, W, _ = rgb.shape
+    cap = W * H * 6 + 65536
+    out = np.zeros(cap, np.uint8)
+    n = oracle().orc_encode_jfif_optimized(np.ascontiguousarray(rgb), W, H, sub, ql, qc, restart_interval, quirks, out, cap)
+    assert n != C.c_size_t(-1).value
+    return out[:n].tobytes()
+
+
+def optimal_spec(freq):
+    """(bits[16], vals[n]) of the optimal table for 256 symbol frequencies."""
+    bits, vals = np.zeros(16, np.uint8), np.zeros(256, np.uint8)
+    n = oracle().orc_optimal_spec(np.ascontiguousarray(freq, np.uint64), bits, vals)
+    assert n >= 0
+    return bits, vals[:n]
 
 
 def bits_to_ascii(packed, nbits):

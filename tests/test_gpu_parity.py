@@ -550,3 +550,44 @@ def test_high_entropy_content_grows_the_workspace(jb):
             assert bytes(out[int(offs[f]): int(offs[f] + sizes[f])]) == ol.encode_jfif(frames[f], ol.SUB_444, ql, qc)
     finally:
         enc.close()
+
+
+# ------------------------------------------------ optimised Huffman tables ------------------
+
+@pytest.mark.parametrize("sub", SUBS)
+def test_optimised_huffman_tables_equal_the_oracle(enc, jb, fruit, sub):
+    """JB_FLAG_OPTIMIZE_HUFFMAN: GPU symbol histogram + T.81 K.2 tables + custom DHT == the oracle's two-pass
+    encode byte for byte; the file is smaller and decodes to the same pixels as the Annex-K one."""
+    import cv2
+    for img, q, ri in ((fruit, 75, 0), (ol.synth(5, 640, 360), 50, 40), (noise_image(4, 120, 72), 100, 0), (ol.synth(6, 333, 77), 90, 3)):
+        ql, qc = ol.quality_tables(q)
+        p_std = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri)
+        p_opt = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri, flags=jb.FLAG_OPTIMIZE_HUFFMAN)
+        cap = img.shape[0] * img.shape[1] * 12 + 65536
+        got = enc.encode_jfif(img, p_opt, cap=cap)
+        assert got == ol.encode_jfif_optimized(img, sub, ql, qc, ri), f"{SUBNAME[sub]} {img.shape} q{q} ri{ri}"
+        std = enc.encode_jfif(img, p_std, cap=cap)
+        assert len(got) < len(std)
+        a = cv2.imdecode(np.frombuffer(got, np.uint8), cv2.IMREAD_COLOR)
+        b = cv2.imdecode(np.frombuffer(std, np.uint8), cv2.IMREAD_COLOR)
+        assert a is not None and np.array_equal(a, b)
+
+
+def test_optimised_huffman_batch_and_unsupported_paths(enc, jb):
+    """A batch shares one table set per group of frames: every frame decodes to the pixels of its Annex-K file;
+    strips and header-less entry points refuse the flag."""
+    import cv2
+    frames = np.stack([ol.synth(40 + i, 320, 176) for i in range(5)])
+    p_std = jb.make_params(ol.SUB_420, quality=75)
+    p_opt = jb.make_params(ol.SUB_420, quality=75, flags=jb.FLAG_OPTIMIZE_HUFFMAN)
+    o1, off1, sz1 = enc.encode_batch(frames, p_std)
+    o2, off2, sz2 = enc.encode_batch(frames, p_opt)
+    assert int(sz2.sum()) < int(sz1.sum())
+    for f in range(5):
+        a = cv2.imdecode(o1[int(off1[f]): int(off1[f] + sz1[f])], cv2.IMREAD_COLOR)
+        b = cv2.imdecode(o2[int(off2[f]): int(off2[f] + sz2[f])], cv2.IMREAD_COLOR)
+        assert b is not None and np.array_equal(a, b)
+    ps = jb.make_params(ol.SUB_420, quality=75, restart_interval=20, flags=jb.FLAG_OPTIMIZE_HUFFMAN)
+    with pytest.raises(jb.JbError) as e:
+        enc.encode_strip(frames[0], ps, 0, True)
+    assert e.value.code == jb.E_UNSUPPORTED

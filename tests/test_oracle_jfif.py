@@ -113,3 +113,42 @@ def test_synth_generator_properties():
     assert a.min() >= 28 and a.max() <= 228
     assert np.array_equal(a[10:20], ol.synth(0x4B3840, 128, 10, 10))  # row-addressable
     assert not np.array_equal(a, ol.synth(0x4B3841, 128, 64))
+
+
+def test_optimised_huffman_tables(fruit):
+    """The oracle's two-pass encode (T.81 K.2 tables as libjpeg builds them): legal tables (no code longer than 16
+    bits, the all-ones code unused), optimal cost, smaller files that decode to the same pixels."""
+    import heapq
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(2)
+    for n_sym in (1, 2, 5, 40, 162, 256):
+        freq = np.zeros(256, np.uint64)
+        freq[rng.choice(256, n_sym, replace=False)] = rng.integers(1, 10 ** int(rng.integers(1, 9)), n_sym)
+        bits, vals = ol.optimal_spec(freq)
+        assert len(vals) == n_sym and sorted(vals) == sorted(np.nonzero(freq)[0])
+        kraft = sum(int(bits[l]) * 2.0 ** -(l + 1) for l in range(16))
+        assert kraft < 1.0  # the reserved all-ones code stays free
+        lens, k = {}, 0
+        for l in range(16):
+            for _ in range(int(bits[l])):
+                lens[int(vals[k])] = l + 1
+                k += 1
+        cost = sum(int(freq[s]) * l for s, l in lens.items())
+        heap = [int(f) for f in freq if f] + [1]  # with the reserved symbol, unlimited length: a lower bound
+        heapq.heapify(heap)
+        bound = 0
+        while len(heap) > 1:
+            a, b = heapq.heappop(heap), heapq.heappop(heap)
+            bound += a + b
+            heapq.heappush(heap, a + b)
+        assert cost <= bound  # (equal up to the reserved symbol's own code when no length was folded back)
+    for sub in (ol.SUB_420, ol.SUB_444, ol.SUB_REPL420):
+        for img, ri in ((fruit, 0), (ol.synth(5, 320, 200), 20)):
+            ql, qc = ol.quality_tables(75)
+            std, opt = ol.encode_jfif(img, sub, ql, qc, ri), ol.encode_jfif_optimized(img, sub, ql, qc, ri)
+            assert len(opt) < len(std)
+            assert np.array_equal(np.array(Image.open(io.BytesIO(std))), np.array(Image.open(io.BytesIO(opt))))
+    # the Annex-K tables are back in force afterwards
+    ql, qc = ol.q50()
+    assert ol.encode_jfif(fruit, ol.SUB_REPL420, ql, qc) == ol.encode_jfif(fruit, ol.SUB_REPL420, ql, qc)
