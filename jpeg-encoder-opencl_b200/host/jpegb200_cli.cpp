@@ -3,22 +3,23 @@
 // ../data/fruit.ppm, runs the stages and prints per-stage times and speed-ups but never
 // writes a JPEG.  This one reads any binary P6, encodes on the B200 and writes a JFIF file.
 //
-//   jpegb200_cli in.ppm out.jpg [--quality Q] [--sub 420|444|repl420] [--restart MCUS] [--repeat N]
+//   jpegb200_cli in.ppm out.jpg [--quality Q] [--sub 420|444|repl420] [--restart MCUS] [--repeat N] [--optimize 1]
 #include <chrono>
 
 #include "utils_compat.hpp"
 
 int main(int argc, char** argv) {
     if (argc < 3) {
-        fprintf(stderr, "usage: %s in.ppm out.jpg [--quality Q] [--sub 420|444|repl420] [--restart MCUS] [--repeat N]\n",
+        fprintf(stderr, "usage: %s in.ppm out.jpg [--quality Q] [--sub 420|444|repl420] [--restart MCUS] [--repeat N] [--optimize 1]\n",
                 argv[0]);
         return 2;
     }
-    int quality = 75, restart = 0, repeat = 1, sub = JB_SUB_420;
+    int quality = 75, restart = 0, repeat = 1, sub = JB_SUB_420, optimize = 0;
     for (int i = 3; i + 1 < argc; i += 2) {
         if (!strcmp(argv[i], "--quality")) quality = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--restart")) restart = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--repeat")) repeat = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--optimize")) optimize = atoi(argv[i + 1]);  // per-image optimal Huffman tables
         else if (!strcmp(argv[i], "--sub"))
             sub = !strcmp(argv[i + 1], "444") ? JB_SUB_444 : !strcmp(argv[i + 1], "repl420") ? JB_SUB_REPL420 : JB_SUB_420;
     }
@@ -29,6 +30,7 @@ int main(int argc, char** argv) {
     jb_params p{};
     p.subsampling = sub;
     p.restart_interval = restart;
+    p.flags = optimize ? JB_FLAG_OPTIMIZE_HUFFMAN : 0u;
     jb_quality_tables(quality, p.qlum, p.qchrom);
     size_t cap = img.width * img.height * 3 + 65536, n = 0;
     std::vector<uint8_t> out(cap);
