@@ -46,7 +46,8 @@ typedef enum {
 #define JB_SUB_420 2     /* true 4:2:0: 16x16 MCU = Y00 Y01 Y10 Y11 Cb Cr                         */
 
 /* Flags. The three REF_* flags reproduce the reference's defects for verbatim comparisons. */
-#define JB_FLAG_REF_INPLACE_DCT 0x1u /* Q1 utils.cpp:342-345 (staged jb_dct_f64 only)            */
+#define JB_FLAG_REF_INPLACE_DCT 0x1u /* Q1 utils.cpp:342-345: staged jb_dct_f64, and the fused path  *
+                                      * (tcgen05 transform with the in-place map as its matrix)     */
 #define JB_FLAG_REF_TYPO_TABLES 0x2u /* Q2 huffman.hpp:92-98 17-bit luma AC codes 3/4..3/A       */
 #define JB_FLAG_REF_ALWAYS_EOB 0x4u  /* Q3 utils.cpp:607-608 EOB also after a full block         */
 #define JB_FLAG_CLAMP_SOF 0x8u       /* declare min(dim,65535) in SOF0                */

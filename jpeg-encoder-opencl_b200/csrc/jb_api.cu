@@ -91,6 +91,7 @@ struct jb_ctx {
         uint32_t q[128];
         double tc_scale = 0;
         int tc_repl = -1;  // the chroma slots hold the K = 16 cell matrices of the replicated 4:2:0 mode
+        int tc_inplace = -1;  // the matrices hold the reference's in-place transform (Q1)
         QuantConst qc;
         float tband[2][64];
         std::vector<uint8_t> tc;  // 32768 bytes: the four fp16 W matrices of the tcgen05 kernel
@@ -348,6 +349,14 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ta.tie_count = s.d_scalars;
     ta.unit_counter = s.d_scalars + 12;
     ta.tie_cap = s.tie_cap;
+    ta.inplace_dct = (p->flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0;
+    if (ta.inplace_dct) {
+        // Q1 in the fused path is a different W matrix of the tcgen05 contraction: the CUDA-core kernels (AAN
+        // factorisation) cannot express it, and the near-tie replay must be on
+        const uintptr_t bits = (uintptr_t)d_rgb | (uintptr_t)pitch | (uintptr_t)frame_stride;
+        if ((p->flags & (JB_FLAG_FMA_DCT | JB_FLAG_NO_TIE_FIXUP)) || (bits & 3))
+            return fail(ctx, JB_E_UNSUPPORTED, "JB_FLAG_REF_INPLACE_DCT needs the tcgen05 transform (4-byte aligned input, no JB_FLAG_FMA_DCT) and the tie replay");
+    }
     {
         jb_ctx::TableCache& tc = ctx->tables;
         if (!tc.valid || memcmp(tc.q, p->qlum, 256) || memcmp(tc.q + 64, p->qchrom, 256)) {
@@ -361,14 +370,15 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         if (!(p->flags & JB_FLAG_FMA_DCT)) {  // tcgen05 transform, every subsampling mode (launch falls back if unaligned)
             const char* e = getenv("JB_TC_ERR_SCALE");
             const double scale = e ? atof(e) : JB_TC_ERR_SCALE;
-            const int repl = pl.g.sub == JB_SUB_REPL420 ? 1 : 0;
-            if (!tc.tc_valid || tc.tc_scale != scale || tc.tc_repl != repl) {
+            const int repl = pl.g.sub == JB_SUB_REPL420 ? 1 : 0, inplace = (p->flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0;
+            if (!tc.tc_valid || tc.tc_scale != scale || tc.tc_repl != repl || tc.tc_inplace != inplace) {
                 for (Slot& o : ctx->slot)  // an earlier asynchronous call may still be copying the old matrices
                     if (o.st) CK(cudaStreamSynchronize(o.st));
                 tc.tc.resize(32768);
-                build_tc_matrices(p->qlum, p->qchrom, scale, repl, tc.tc.data(), tc.tband);
+                build_tc_matrices(p->qlum, p->qchrom, scale, repl, inplace, tc.tc.data(), tc.tband);
                 tc.tc_scale = scale;
                 tc.tc_repl = repl;
+                tc.tc_inplace = inplace;
                 tc.tc_valid = true;
                 ++tc.gen;
             }
@@ -408,6 +418,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         fa.tie_list = s.d_tie_list;
         fa.tie_count = s.d_scalars;
         fa.tie_cap = s.tie_cap;
+        fa.inplace_dct = ta.inplace_dct;
         fa.costab = ctx->d_costab;
         fa.scale = ctx->d_scale;
         memcpy(fa.qt.q[0], p->qlum, sizeof(fa.qt.q[0]));

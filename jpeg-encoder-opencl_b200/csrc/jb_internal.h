@@ -70,6 +70,7 @@ struct TransformArgs {
     uint32_t* unit_counter;    // zeroed per call: dynamic hand-out of strips in the tcgen05 kernel
     const uint8_t* tc_mat;     // tensor-core variant: 6 pre-swizzled bf16 matrices (null = FMA kernel)
     float tband[2][64];        // tensor-core variant: near-tie bands in zigzag order
+    int inplace_dct;           // Q1 (utils.cpp:342-345): W holds the in-place map; edge blocks go to the replay whole
     QuantConst qc;
 };
 
@@ -84,6 +85,7 @@ struct FixupArgs {
     uint32_t tie_cap;
     const double* costab;  // [u][x] = cos((2x+1) u pi / 16), from the host's libm
     const double* scale;   // [u][v] = alpha(u) alpha(v) / 4.0
+    int inplace_dct;       // Q1: replay the reference's in-place block transform up to the flagged output
     QuantTables qt;
 };
 
@@ -177,7 +179,8 @@ int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStre
 // host helpers
 void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out);
 void aan_error_bound(double err[64], double amax[64]);
-void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, int repl_chroma, uint8_t* out /* 32768 B */,
+void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, int repl_chroma, int inplace_dct,
+                       uint8_t* out /* 32768 B */,
                        float tband[2][64]);  // worst-case |binary32 - exact| per AAN output
 void build_huff(bool typo, HuffDev* out);
 void build_ydown(uint32_t ydown[2048]);

@@ -382,10 +382,34 @@ static uint16_t to_fp16(double x, double* back) {
     return h;
 }
 
-void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, int repl_chroma, uint8_t* out,
-                       float tband[2][64]) {
+// Q1 (utils.cpp:314-347): performDCTBlock writes every output into the block it is still reading (outputs in
+// the order u outer / v inner, F(u,v) stored at row v, column u).  The result is still a linear function of the 64
+// samples: map[nat][k] = output `nat` for the unit block e_k, obtained by running that very loop in binary64.
+static void inplace_dct_map(double map[64][64]) {
+    const double pi = 3.14159265358979323846;
+    double c[8][8];
+    for (int u = 0; u < 8; ++u)
+        for (int x = 0; x < 8; ++x) c[u][x] = cos((2 * x + 1) * u * pi / 16.0);
+    for (int k = 0; k < 64; ++k) {
+        double blk[64] = {0};
+        blk[k] = 1.0;
+        for (int u = 0; u < 8; ++u)
+            for (int v = 0; v < 8; ++v) {
+                double s = 0.0;
+                for (int y = 0; y < 8; ++y)
+                    for (int x = 0; x < 8; ++x) s += blk[y * 8 + x] * c[u][x] * c[v][y];
+                blk[v * 8 + u] = s * ((u == 0 ? M_SQRT1_2 : 1.0) * (v == 0 ? M_SQRT1_2 : 1.0) / 4.0);
+            }
+        for (int n = 0; n < 64; ++n) map[n][k] = blk[n];
+    }
+}
+
+void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, int repl_chroma, int inplace_dct,
+                       uint8_t* out, float tband[2][64]) {
     const double pi = 3.14159265358979323846;
     memset(out, 0, 32768);
+    static double q1_map[64][64];
+    if (inplace_dct) inplace_dct_map(q1_map);
     for (int t = 0; t < 2; ++t) {
         const uint32_t* q = t ? qc : ql;
         const bool cells = t == 1 && repl_chroma;  // K = 16: one column per 2x2 cell, the sum of its four entries
@@ -396,6 +420,7 @@ void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_
             for (int k = 0; k < 64; ++k) {
                 int y = k >> 3, x = k & 7;
                 w[k] = alpha * cos((2 * x + 1) * u * pi / 16.0) * cos((2 * y + 1) * v * pi / 16.0) / (double)q[nat];
+                if (inplace_dct) w[k] = q1_map[nat][k] / (double)q[nat];
             }
             double P = 0;
             const int nk = cells ? 16 : 64;

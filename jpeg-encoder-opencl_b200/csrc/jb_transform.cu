@@ -438,7 +438,10 @@ __global__ void __launch_bounds__(64) k_transform_edge(const __grid_constant__ T
             int n = c_zz[k];
             bool tie = false;
             uint32_t bits;
-            if (k == 0 && a.qc.dc_exact)
+            if (a.inplace_dct) {  // Q1: this kernel's AAN transform is the true DCT -- the replay computes the block
+                bits = 0;
+                tie = true;
+            } else if (k == 0 && a.qc.dc_exact)
                 bits = tab ? quantize_dc<1>(v[0], a) : quantize_dc<0>(v[0], a);
             else
                 bits = quantize_bits(v[n], a.qc.mul[tab][n], a.qc.band[tab][n], tie);
@@ -1424,16 +1427,32 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
                 int i = lane + 32 * h, x = i & 7, y = i >> 3;
                 double smp = (double)sample_at(im, x0 + x * step, y0 + y * step, comp, a.g.sub != JB_SUB_444);  // utils.cpp:236
                 smp = __dsub_rn(smp, 128.0);                                                              // utils.cpp:190
-                s_term[w][j][i] = __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), a.costab[v * 8 + y]);    // utils.cpp:330
+                s_term[w][j][i] = a.inplace_dct ? smp : __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), a.costab[v * 8 + y]);  // utils.cpp:330
             }
         }
         __syncwarp();
         if (lane < n_here) {
             const int v = my_nat >> 3, u = my_nat & 7;
             double sum = 0.0;  // y outer, x inner = index order 0..63
+            if (!a.inplace_dct) {
 #pragma unroll 8
-            for (int i = 0; i < 64; ++i) sum = __dadd_rn(sum, s_term[w][lane][i]);
-            sum = __dmul_rn(sum, a.scale[u * 8 + v]);                                                     // utils.cpp:336
+                for (int i = 0; i < 64; ++i) sum = __dadd_rn(sum, s_term[w][lane][i]);
+                sum = __dmul_rn(sum, a.scale[u * 8 + v]);                                                 // utils.cpp:336
+            } else {
+                // Q1 (utils.cpp:314-347): the block is overwritten while it is read.  s_term holds the level-shifted
+                // samples here; run the reference's loop (outputs u outer / v inner, each stored at row v, column u
+                // of the block it goes on reading) up to the flagged output.
+                double* blk = s_term[w][lane];
+                for (int uu = 0; uu <= u; ++uu)
+                    for (int vv = 0; vv < (uu == u ? v + 1 : 8); ++vv) {
+                        double acc = 0.0;
+                        for (int i = 0; i < 64; ++i)
+                            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(blk[i], a.costab[uu * 8 + (i & 7)]), a.costab[vv * 8 + (i >> 3)]));
+                        acc = __dmul_rn(acc, a.scale[uu * 8 + vv]);
+                        blk[vv * 8 + uu] = acc;
+                        sum = acc;
+                    }
+            }
             double q = (double)a.qt.q[my_comp ? 1 : 0][my_nat];
             double r = round(__ddiv_rn(sum, q));                                                          // utils.cpp:460
             a.coef[(size_t)my_entry] = (int16_t)(int)r;  // entry = block * 64 + zigzag position            utils.cpp:490

@@ -591,3 +591,36 @@ def test_optimised_huffman_batch_and_unsupported_paths(enc, jb):
     with pytest.raises(jb.JbError) as e:
         enc.encode_strip(frames[0], ps, 0, True)
     assert e.value.code == jb.E_UNSUPPORTED
+
+
+# ------------------------------------------------ Q1 in the fused path ----------------------
+
+def test_fused_path_reproduces_the_reference_as_written(enc, jb, fruit, golden):
+    """JB_FLAG_REF_INPLACE_DCT in the fused path: the tcgen05 contraction runs the reference's in-place transform
+    (utils.cpp:342-345, a different 64x64 matrix) and the binary64 replay re-enacts the overwriting loop, so the
+    fused kernel's coefficients are the unmodified reference's zigzag array (SURVEY 8c digest), and with the two
+    entropy quirks the bit string is the reference's HuffmanEncoder output."""
+    ql, qc = ol.q50()
+    flags = jb.FLAG_REF_INPLACE_DCT
+    p = jb.make_params(ol.SUB_REPL420, qlum=ql, qchrom=qc, flags=flags)
+    coef = enc.transform(fruit, p)
+    assert np.array_equal(coef, ol.transform(fruit, ol.SUB_REPL420, ql, qc, ol.Q1))
+    planar = np.concatenate([coef[:, c, :] for c in range(3)]).astype(np.int32)
+    assert sha(planar.tobytes()) == golden["fruit"]["as_written"]["zigzag_sha256"]
+    # other modes, sizes (edge MCUs go to the replay whole), qualities
+    for sub in SUBS:
+        for img, q in ((ol.synth(4, 320, 200), 75), (noise_image(6, 131, 77), 90), (ol.synth(9, 1928, 70), 50)):
+            tl, tc = ol.quality_tables(q)
+            pp = jb.make_params(sub, qlum=tl, qchrom=tc, flags=flags)
+            got, want = enc.transform(img, pp), ol.transform(img, sub, tl, tc, ol.Q1)
+            assert np.array_equal(got, want), f"{SUBNAME[sub]} {img.shape} q{q}: " + mismatch_report(got, want)
+    # the whole reference pipeline as written, fused: JFIF-less bit string == the reference's digest
+    p3 = jb.make_params(ol.SUB_REPL420, qlum=ql, qchrom=qc, flags=flags | jb.FLAG_REF_TYPO_TABLES | jb.FLAG_REF_ALWAYS_EOB)
+    coef3 = enc.transform(fruit, p3)
+    zz = np.ascontiguousarray(np.concatenate([coef3[:, c, :] for c in range(3)]).astype(np.int32))
+    bits, nbits = enc.HuffmanEncoder(zz, coef3.shape[0], ol.Q2 | ol.Q3)
+    assert nbits == golden["fruit"]["as_written"]["nbits"]
+    assert sha(ol.bits_to_ascii(bits, nbits)) == golden["fruit"]["as_written"]["bits_sha256"]
+    with pytest.raises(jb.JbError) as e:
+        enc.transform(fruit, jb.make_params(ol.SUB_REPL420, qlum=ql, qchrom=qc, flags=flags | jb.FLAG_FMA_DCT))
+    assert e.value.code == jb.E_UNSUPPORTED
