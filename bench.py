@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--optimize-huffman", action="store_true",
                     help="JB_FLAG_OPTIMIZE_HUFFMAN: per-call optimal Huffman tables (two passes; not the headline configuration)")
+    ap.add_argument("--ref-exact", action="store_true",
+                    help="the reference as written: JB_FLAG_REF_INPLACE_DCT | REF_TYPO_TABLES | REF_ALWAYS_EOB (use with --workload repl1080p)")
     ap.add_argument("--tensor-dct", type=int, default=1,
                     help="transform kernel: 1 = tcgen05 (library default), 0 = CUDA-core FMA kernel (JB_FLAG_FMA_DCT)")
     return ap.parse_args()
@@ -267,7 +269,8 @@ def main():
     F = a.frames or dflt
     sub = {"420": jb.SUB_420, "444": jb.SUB_444, "repl420": jb.SUB_REPL420}[subname]
     params = jb.make_params(sub, quality=q, restart_interval=ri,
-                            flags=(0 if a.tensor_dct else jb.FLAG_FMA_DCT) | (jb.FLAG_OPTIMIZE_HUFFMAN if a.optimize_huffman else 0))
+                            flags=(0 if a.tensor_dct else jb.FLAG_FMA_DCT) | (jb.FLAG_OPTIMIZE_HUFFMAN if a.optimize_huffman else 0)
+                            | ((jb.FLAG_REF_INPLACE_DCT | jb.FLAG_REF_TYPO_TABLES | jb.FLAG_REF_ALWAYS_EOB) if a.ref_exact else 0))
     pitch, fstride = W * 3, W * H * 3
     px_per_step = W * H * F  # per GPU
 
@@ -276,7 +279,7 @@ def main():
     for f in range(F):
         enc.synth_device(0xF000 + rank * F + f, W, 0, H, pitch, d_rgb.data_ptr() + f * fstride)
     enc.sync()
-    cap = F * (W * H // 2 + 4096)
+    cap = F * (W * H // (1 if a.ref_exact else 2) + 4096)  # the as-written transform yields ~4 bits/px
     d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
     d_tab = torch.zeros(2 * F + 1, dtype=torch.int64, device="cuda")
     ext = torch.cuda.ExternalStream(enc.stream())
@@ -399,7 +402,7 @@ def main():
             "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a, F), "frames_per_gpu": F, "width": W, "height": H,
-                       "subsampling": subname, "quality": q, "restart_interval": ri, "optimize_huffman": bool(a.optimize_huffman),
+                       "subsampling": subname, "quality": q, "restart_interval": ri, "optimize_huffman": bool(a.optimize_huffman), "ref_exact": bool(a.ref_exact),
                        "l2": "inputs per step (%.2f GB) far exceed the 126 MB L2" % (F * fstride / 1e9),
                        "bits_per_pixel": round(8.0 * total_bytes / px_per_step, 4),
                        "tie_fixups_per_step": int(tm["tie_fixups"]),
