@@ -240,6 +240,22 @@ def run_strips(a, jb, enc, torch, dist, rank, world):
             "gpu_launches": int(enc.timings()["total_launches"])}), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run (and first-touch pinned memory) on the CPUs NVML reports as local to the GPU.
+    A no-op on single-node hosts or when NVML / the cpuset do not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {i for i in allowed if (words[i // 64] >> (i % 64)) & 1}
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -255,6 +271,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: host buffers land next to the GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     jb = entry.load()
