@@ -784,20 +784,35 @@ static uint64_t magic52(uint64_t d) { return ((1ull << 52) + d - 1) / d; }
 // category, (run, size) of every non-zero AC coefficient, ZRL, EOB.  hist = [4][256] in DHT order
 // (DC luma, AC luma, DC chroma, AC chroma); counted in shared memory, flushed with one atomic per used bin.
 __global__ void __launch_bounds__(TILE) k_symbol_hist(const __grid_constant__ EntropyArgs a, uint32_t* __restrict__ hist) {
+    __shared__ uint4 s_coef[TILE * 8];  // the tile's coefficients, staged with coalesced loads as in k_encode
     __shared__ uint32_t s_h[4 * 256];
     for (int i = threadIdx.x; i < 4 * 256; i += TILE) s_h[i] = 0;
-    __syncthreads();
-    for (uint32_t b = blockIdx.x * TILE + threadIdx.x; b < a.n_blocks; b += gridDim.x * TILE) {
+    const uint32_t n_tiles = (a.n_blocks + TILE - 1) / TILE;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t t = threadIdx.x, b0 = tile * TILE, b = b0 + t;
+        const uint4* src = reinterpret_cast<const uint4*>(a.coef) + (size_t)b0 * 8;
+        const uint32_t n_blk = min((uint32_t)TILE, a.n_blocks - b0), n_here = n_blk * 8;
+        __syncthreads();  // the previous tile has been read (and, the first time, the bins are zero)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t g = i * TILE + t, blk = g >> 3, pc = g & 7;
+            if (g < n_here) s_coef[blk * 8 + (pc ^ (blk & 7))] = __ldg(src + g);
+        }
+        __syncthreads();
+        if (t >= n_blk) continue;
         const BlockInfo bi = block_info(a, b);
-        const uint4* src = reinterpret_cast<const uint4*>(a.coef) + (size_t)b * 8;
         uint32_t* dc = s_h + (bi.comp ? 2 : 0) * 256;
         uint32_t* ac = dc + 256;
         const int pred = bi.has_prev ? (int)a.coef[(size_t)bi.prev * 64] : 0;
         int run = 0, last_nz = 0;
 #pragma unroll 1
         for (int pc = 0; pc < 8; ++pc) {
-            const uint4 q = __ldg(src + pc);
+            const uint4 q = s_coef[t * 8 + (pc ^ (t & 7))];
             const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            if (pc && !(q.x | q.y | q.z | q.w)) {  // eight zeros
+                run += 8;
+                continue;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int k = pc * 8 + i;
