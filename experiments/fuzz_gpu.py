@@ -22,23 +22,27 @@ for c in range(cases):
     n_mcu = (-(-W // m)) * (-(-H // m))
     ri = int(rng.choice([0, 0, 1, 3, -(-W // m), 1000]))
     fma = jb.FLAG_FMA_DCT if rng.random() < 0.25 else 0
-    N = int(rng.choice([1, 1, 2, 3]))
+    inplace = (not fma) and rng.random() < 0.2   # Q1: the reference's in-place transform in the fused path
+    optimize = rng.random() < 0.2                # per-call optimal Huffman tables (compared per single frame)
+    quirks = ol.Q1 if inplace else 0
+    if inplace: fma |= jb.FLAG_REF_INPLACE_DCT
+    N = 1 if optimize else int(rng.choice([1, 1, 2, 3]))
     kind = rng.integers(0, 3)
     frames = np.stack([(ol.synth(1000 * c + f, W, H) if kind == 0 else
                         rng.integers(0, 256, (H, W, 3), dtype=np.uint8) if kind == 1 else
                         np.repeat(rng.integers(0, 256, (H, W, 1), dtype=np.uint8), 3, axis=2)) for f in range(N)])
     ql, qc = ol.quality_tables(q)
-    p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri, flags=fma)
+    p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri, flags=fma | (jb.FLAG_OPTIMIZE_HUFFMAN if optimize else 0))
     ok = True
     for f in range(N):
         got = enc.transform(frames[f], p)
-        want = ol.transform(frames[f], sub, ql, qc)
+        want = ol.transform(frames[f], sub, ql, qc, quirks)
         if not np.array_equal(got, want):
             ok = False; print("COEF MISMATCH", c, sub, W, H, q, ri, fma, kind, int((got != want).sum()))
     out, offs, sizes = enc.encode_batch(np.ascontiguousarray(frames), p, out=np.empty(N * (W * H * 12 + 65536), np.uint8))
     for f in range(N):
         jf = bytes(out[int(offs[f]): int(offs[f]) + int(sizes[f])])
-        want = ol.encode_jfif(frames[f], sub, ql, qc, ri)
+        want = (ol.encode_jfif_optimized if optimize else ol.encode_jfif)(frames[f], sub, ql, qc, ri, quirks)
         if jf != want:
             a, b = np.frombuffer(jf, np.uint8), np.frombuffer(want, np.uint8)
             n = min(len(a), len(b)); d = np.nonzero(a[:n] != b[:n])[0]

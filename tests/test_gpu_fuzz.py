@@ -1,5 +1,6 @@
 """Randomised parity sweep through the C ABI on one long-lived context: random sizes, modes, qualities,
-restart intervals, batch sizes and contents (smooth, full-range noise, grey noise), coefficients and JFIF bytes
+restart intervals, batch sizes, contents (smooth, full-range noise, grey noise) and mode flags (CUDA-core kernels,
+the reference's in-place transform, optimised Huffman tables), coefficients and JFIF bytes
 against the oracle.  Calls of very different shapes on the same context exercise the workspace re-use paths
 (arena regrowth, cached tables, the sticky entropy-workspace budget); experiments/fuzz_gpu.py is the long form."""
 import numpy as np
@@ -27,7 +28,11 @@ def test_random_shapes_modes_and_contents(jb, seed):
             q = int(rng.choice([10, 50, 75, 90, 100]))
             ri = int(rng.choice([0, 0, 1, 3, -(-W // m), 1000]))
             flags = jb.FLAG_FMA_DCT if rng.random() < 0.25 else 0
-            N = int(rng.choice([1, 1, 2, 3]))
+            inplace = (not flags) and rng.random() < 0.2  # Q1: the reference's in-place transform, fused path
+            optimize = rng.random() < 0.2                 # per-call optimal Huffman tables (single frames: per-image oracle)
+            quirks = ol.Q1 if inplace else 0
+            flags |= (jb.FLAG_REF_INPLACE_DCT if inplace else 0) | (jb.FLAG_OPTIMIZE_HUFFMAN if optimize else 0)
+            N = 1 if optimize else int(rng.choice([1, 1, 2, 3]))
             kind = int(rng.integers(0, 3))
             frames = np.stack([ol.synth(1000 * done + f, W, H) if kind == 0 else
                                rng.integers(0, 256, (H, W, 3), dtype=np.uint8) if kind == 1 else
@@ -35,11 +40,12 @@ def test_random_shapes_modes_and_contents(jb, seed):
             ql, qc = ol.quality_tables(q)
             p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri, flags=flags)
             tag = f"case {done}: sub {sub} {W}x{H} q{q} ri {ri} flags {flags} kind {kind} N {N}"
-            assert np.array_equal(enc.transform(frames[0], p), ol.transform(frames[0], sub, ql, qc)), tag
+            assert np.array_equal(enc.transform(frames[0], p), ol.transform(frames[0], sub, ql, qc, quirks)), tag
             out, offs, sizes = enc.encode_batch(frames, p, out=np.empty(N * (W * H * 12 + 65536), np.uint8))
             for f in range(N):
                 got = bytes(out[int(offs[f]): int(offs[f] + sizes[f])])
-                assert got == ol.encode_jfif(frames[f], sub, ql, qc, ri), tag + f" frame {f}"
+                want = (ol.encode_jfif_optimized if optimize else ol.encode_jfif)(frames[f], sub, ql, qc, ri, quirks)
+                assert got == want, tag + f" frame {f}"
             done += 1
     finally:
         enc.close()
