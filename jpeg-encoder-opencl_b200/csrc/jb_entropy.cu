@@ -862,19 +862,21 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s) {
     launches += scan_u32(a.w.tile_bits, a.w.tile_base, n_tiles, nullptr, a.w.scan_tmp, s);
     k_intervals<<<gi, 256, 0, s>>>(a);
     launches += scan_u32(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr, a.w.scan_tmp, s);
-    k_zero<<<592, 256, 0, s>>>(a);
+    // grids of the grid-stride kernels are capped by the work the plan allows: a small image launches few CTAs
+    const uint32_t chunk_tiles = (uint32_t)(a.w.ubuf_cap / 16 / TILE + 1);
+    k_zero<<<chunk_tiles < 592u ? chunk_tiles : 592u, 256, 0, s>>>(a);
     k_pack<<<n_tiles, TILE, 0, s>>>(a);
-    k_pack_long<<<296, TILE, 0, s>>>(a);
+    k_pack_long<<<n_tiles < 296u ? n_tiles : 296u, TILE, 0, s>>>(a);
     launches += 5;
     if (a.fr.raw_bits) return launches;
-    k_ff_count<<<1184, TILE, 0, s>>>(a);
+    k_ff_count<<<chunk_tiles < 1184u ? chunk_tiles : 1184u, TILE, 0, s>>>(a);
     launches += scan_u32(a.w.ff_tile, a.w.ff_tile_base, (uint32_t)(a.w.ubuf_cap / 16 / TILE + 1), a.w.n_ff_tiles,
                          a.w.scan_tmp, s);
     k_int_out<<<gi, 256, 0, s>>>(a);
     launches += scan_u32(a.w.int_osize, a.w.int_obase, a.n_int_total, nullptr, a.w.scan_tmp, s);
     uint32_t gf = ((uint32_t)a.n_frames + 255) / 256;
     k_finalize<<<gf, 256, 0, s>>>(a);
-    k_stuff<<<1184, TILE, 0, s>>>(a);
+    k_stuff<<<chunk_tiles < 1184u ? chunk_tiles : 1184u, TILE, 0, s>>>(a);
     launches += 4;
     return launches;
 }
