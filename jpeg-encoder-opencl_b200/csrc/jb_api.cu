@@ -56,6 +56,10 @@ struct Slot {
     uint8_t* tc_loaded_at = nullptr;  // where, and which generation of, the matrices this slot last uploaded
     uint64_t tc_loaded_gen = 0;
     uint32_t tie_cap = 0;
+    // small images: the entropy coder's ~17 launches replayed as one CUDA graph while the arguments repeat
+    cudaGraphExec_t ent_graph = nullptr;
+    EntropyArgs ent_key;
+    int ent_launches = 0;
     // pinned host mirror: [0..3] status, [4] total, [5] tie_count, then frame_off[n], frame_size[n]
     uint64_t* h_res = nullptr;
     size_t h_res_cap = 0;
@@ -332,6 +336,45 @@ void resolve_events(jb_ctx* ctx) {
     ctx->tm.TotalCopyTime = ctx->tm.h2d_us + ctx->tm.d2h_us;
 }
 
+// The entropy coder is ~17 small launches; for a small image (the reference's own use case) their launch
+// overhead is the whole cost.  While a slot sees the same arguments again (same shape, same buffers: a stream of
+// equal frames) the chain is replayed as one CUDA graph captured from the very same launcher.
+constexpr uint32_t kGraphMaxBlocks = 1u << 16;  // ~2.8 Mpx of 4:2:0: beyond that the kernels dominate the launches
+
+int launch_entropy_graphed(jb_ctx* ctx, Slot& s, const EntropyArgs& ea) {
+    if (ea.n_blocks > kGraphMaxBlocks || getenv("JB_NO_GRAPH")) return launch_entropy(ea, s.st);
+    if (s.ent_graph && memcmp(&s.ent_key, &ea, sizeof(ea)) == 0) {
+        if (cudaGraphLaunch(s.ent_graph, s.st) == cudaSuccess) return s.ent_launches;
+        cudaGetLastError();
+    }
+    if (s.ent_graph) {
+        cudaGraphExecDestroy(s.ent_graph);
+        s.ent_graph = nullptr;
+    }
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return launch_entropy(ea, s.st);
+    }
+    const int n = launch_entropy(ea, s.st);
+    if (cudaStreamEndCapture(s.st, &g) != cudaSuccess || !g || cudaGraphInstantiate(&s.ent_graph, g, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        s.ent_graph = nullptr;
+        return launch_entropy(ea, s.st);  // nothing ran during the failed capture
+    }
+    cudaGraphDestroy(g);
+    memcpy(&s.ent_key, &ea, sizeof(ea));
+    s.ent_launches = n;
+    if (cudaGraphLaunch(s.ent_graph, s.st) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphExecDestroy(s.ent_graph);
+        s.ent_graph = nullptr;
+        return launch_entropy(ea, s.st);
+    }
+    return n;
+}
+
 // Enqueue transform (+fix-up) + entropy coder for frames already in device memory.
 int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, const uint8_t* d_rgb, size_t pitch,
                    size_t frame_stride, const Framing& fr, size_t W, size_t H, uint8_t* d_out, size_t out_cap,
@@ -427,7 +470,8 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         ctx->tm.total_launches += launch_fixup(fa, s.st);
     }
     if (!d_out) return JB_OK;  // transform only
-    EntropyArgs ea{};
+    EntropyArgs ea;
+    memset(&ea, 0, sizeof(ea));  // padding too: the graph cache compares the bytes
     ea.coef = s.d_coef;
     ea.g = pl.g;
     ea.n_frames = (int)pl.n_frames;
@@ -482,7 +526,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     }
     {
         Timed t(ctx, s.st, 2);
-        ctx->tm.total_launches += launch_entropy(ea, s.st);
+        ctx->tm.total_launches += launch_entropy_graphed(ctx, s, ea);
     }
     CK(cudaGetLastError());
     return JB_OK;
@@ -580,6 +624,7 @@ void jb_destroy(jb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& s : ctx->slot) {
+        if (s.ent_graph) cudaGraphExecDestroy(s.ent_graph);
         if (s.arena.base) cudaFree(s.arena.base);
         if (s.h_res) cudaFreeHost(s.h_res);
         if (s.ev_scalars) cudaEventDestroy(s.ev_scalars);
