@@ -122,3 +122,58 @@ def test_extreme_shapes(jb, shape):
             assert enc.encode_jfif(img, p, cap=W * H * 3 + (1 << 20)) == ol.encode_jfif(img, sub, ql, qc, ri), f"sub {sub}"
     finally:
         enc.close()
+
+
+def test_staged_functions_random_sizes(jb):
+    """The per-stage entry points (one per reference function) on random image sizes, both DCT variants and both
+    entropy table variants: every stage equals the oracle's (= the reference's) stage bit for bit."""
+    L = ol.oracle()
+    enc = jb.Encoder(0)
+    rng = np.random.default_rng(11)
+    try:
+        for case in range(14):
+            W, H = int(rng.integers(8, 150)), int(rng.integers(8, 100))
+            img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8) if case % 2 else ol.synth(case, W, H)
+            inplace = bool(case % 3 == 0)
+            quirks = (ol.Q1 if inplace else 0) | (ol.Q2 | ol.Q3 if case % 4 == 0 else 0)
+            a, b = img.copy(), img.copy()
+            enc.performCSC(a)
+            L.orc_csc(b.reshape(-1), W * H)
+            assert np.array_equal(a, b), f"CSC {W}x{H}"
+            enc.performCDS(a)
+            L.orc_cds(b.reshape(-1), W, H)
+            assert np.array_equal(a, b), f"CDS {W}x{H}"
+            nW, nH = -(-W // 8) * 8, -(-H // 8) * 8
+            pa, pb = enc.padMirror(a), np.zeros((nH, nW, 3), np.uint8)
+            assert L.orc_pad_mirror(b.reshape(-1), W, H, pb.reshape(-1), nW, nH) == 0
+            assert np.array_equal(pa, pb), f"pad {W}x{H}"
+            da, db = enc.copyUIntToDoubleImage(pa), np.zeros(pb.size, np.float64)
+            L.orc_u8_to_double(pb.reshape(-1), db, pb.size)
+            enc.substractfromAll(da, 128.0)
+            L.orc_subtract(db, db.size, 128.0)
+            enc.performDCT(da, jb.FLAG_REF_INPLACE_DCT if inplace else 0)
+            L.orc_dct_image(db, nW, nH, 1 if inplace else 0)
+            assert np.array_equal(da.reshape(-1), db), f"DCT {W}x{H} inplace={inplace}"  # binary64, bit for bit
+            ql, qc = ol.quality_tables(int(rng.choice([50, 75, 95])))
+            enc.performQuantization(da, ql, qc)
+            L.orc_quantize_image(db, nW, nH, ql, qc)
+            assert np.array_equal(da.reshape(-1), db), f"quant {W}x{H}"
+            rpc = nW * nH // 64
+            la, lb = enc.everyMCUisnow2DArray(da), np.zeros((3 * rpc, 64), np.int32)
+            L.orc_blockify(db, nW, nH, lb)
+            assert np.array_equal(la, lb)
+            za, zb = enc.performZigZag(la), np.zeros_like(lb)
+            L.orc_zigzag(lb, zb, 3 * rpc)
+            assert np.array_equal(za, zb)
+            rle = enc.performRLE(za, jb.FLAG_REF_ALWAYS_EOB if quirks & ol.Q3 else 0)
+            pairs = np.zeros(130, np.int32)
+            for r in range(0, 3 * rpc, max(1, rpc // 5)):
+                n = L.orc_rle_block(np.ascontiguousarray(zb[r]), pairs, 1 if quirks & ol.Q3 else 0)
+                assert np.array_equal(rle[r], pairs[:n]), f"RLE row {r}"
+            flags = (jb.FLAG_REF_TYPO_TABLES if quirks & ol.Q2 else 0) | (jb.FLAG_REF_ALWAYS_EOB if quirks & ol.Q3 else 0)
+            bits, nbits = enc.HuffmanEncoder(za, rpc, flags)
+            packed = np.zeros(zb.size * 4, np.uint8)
+            nb = L.orc_huffman_ref(zb, rpc, quirks & (ol.Q2 | ol.Q3), packed, packed.size)
+            assert nbits == nb and np.array_equal(bits, packed[: (nb + 7) // 8]), f"Huffman {W}x{H} quirks {quirks}"
+    finally:
+        enc.close()
