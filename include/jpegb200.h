@@ -154,6 +154,9 @@ int jb_huffman(jb_ctx *ctx, const int32_t *zz, size_t rows_per_channel, uint32_t
 
 /* ---- fused path ------------------------------------------------------------ */
 int jb_quality_tables(int quality, uint32_t qlum[64], uint32_t qchrom[64]); /* IJG scaling of utils.hpp:42-62 */
+/* The table generator of JB_FLAG_OPTIMIZE_HUFFMAN (host only): BITS / HUFFVAL for 256 symbol counts, T.81 K.2 as
+ * libjpeg's jpeg_gen_optimal_table applies it (reserved all-ones code, code lengths <= 16). */
+int jb_optimal_huffman_spec(const uint64_t counts[256], uint8_t bits[16], uint8_t vals[256], int *n_vals);
 size_t jb_num_mcus(size_t W, size_t H, int subsampling);
 int jb_blocks_per_mcu(int subsampling);
 size_t jb_header_bytes(const jb_params *p);

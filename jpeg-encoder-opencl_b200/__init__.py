@@ -31,7 +31,7 @@ SYMBOLS = [
     "jb_huffman", "jb_quality_tables", "jb_num_mcus", "jb_blocks_per_mcu", "jb_header_bytes", "jb_required_bytes",
     "jb_transform", "jb_entropy", "jb_encode_jfif", "jb_encode_batch", "jb_encode_batch_device", "jb_encode_strip",
     "jb_write_header", "jb_synth_rgb_device", "jb_planar_u32_from_aos", "jb_planar_u32_interleave",
-    "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32",
+    "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32", "jb_optimal_huffman_spec",
 ]
 
 
@@ -107,6 +107,7 @@ def lib():
     L.jb_encode_jfif_planar_u32.argtypes = [vp, vp, sz, sz, PP, vp, sz, C.POINTER(sz)]
     L.jb_huffman.argtypes = [vp, vp, sz, C.c_uint32, vp, sz, C.POINTER(u64)]
     L.jb_quality_tables.argtypes = [C.c_int, vp, vp]
+    L.jb_optimal_huffman_spec.argtypes = [vp, vp, vp, C.POINTER(C.c_int)]
     L.jb_num_mcus.argtypes = [sz, sz, C.c_int]
     L.jb_num_mcus.restype = sz
     L.jb_blocks_per_mcu.argtypes = [C.c_int]
@@ -143,6 +144,16 @@ def make_params(subsampling=SUB_420, quality=None, qlum=None, qchrom=None, resta
         p.qlum[i] = int(qlum[i])
         p.qchrom[i] = int(qchrom[i])
     return p
+
+
+def optimal_huffman_spec(counts):
+    """(bits[16], vals[n]) of the optimal Huffman table for 256 symbol counts (host only)."""
+    c = np.ascontiguousarray(counts, np.uint64)
+    bits, vals, n = np.zeros(16, np.uint8), np.zeros(256, np.uint8), C.c_int()
+    rc = lib().jb_optimal_huffman_spec(c.ctypes.data, bits.ctypes.data, vals.ctypes.data, C.byref(n))
+    if rc:
+        raise JbError(rc, "jb_optimal_huffman_spec")
+    return bits, vals[: n.value]
 
 
 def header_bytes(params):

@@ -192,6 +192,7 @@ struct HuffSpecs {
     int n[4];
 };
 void annex_k_specs(HuffSpecs* sp);
+void optimal_spec(const uint64_t counts[256], uint8_t bits[16], uint8_t vals[256], int* n);
 void optimal_huff_specs(const uint64_t counts[4][256], HuffSpecs* sp);  // T.81 K.2 as in libjpeg (counts in DHT order)
 void build_huff_from_specs(const HuffSpecs& sp, HuffDev* out);
 size_t build_header(const jb_params* p, size_t W, size_t H, uint8_t* out, const HuffSpecs* custom = nullptr);  // out >= 2048 bytes

@@ -106,33 +106,45 @@ void build_huff_from_specs(const HuffSpecs& sp, HuffDev* out) {
 // Optimal BITS / HUFFVAL for 256 symbol counts: T.81 Annex K.2 (Figures K.1-K.4) in the form libjpeg's
 // jpeg_gen_optimal_table gives it -- a reserved 257th symbol of count 1 keeps the all-ones code free, the two
 // least frequent entries merge (the larger symbol on ties), code lengths above 16 are folded back.
-static void optimal_spec(const uint64_t counts[256], uint8_t bits_out[16], uint8_t vals_out[256], int* n_out) {
+void optimal_spec(const uint64_t counts[256], uint8_t bits_out[16], uint8_t vals_out[256], int* n_out) {
     const int kMax = 32;
-    uint64_t w[257];
-    int len[257], next[257], hist[kMax + 1] = {0};
-    for (int i = 0; i < 256; ++i) w[i] = counts[i];
-    w[256] = 1;
-    for (int i = 0; i < 257; ++i) { len[i] = 0; next[i] = -1; }
-    auto least = [&](int skip) {
-        int best = -1;
-        for (int i = 0; i <= 256; ++i)
-            if (w[i] && i != skip && (best < 0 || w[i] <= w[best])) best = i;
-        return best;
-    };
-    for (;;) {
-        int a = least(-1), b = a < 0 ? -1 : least(a);
-        if (b < 0) break;
-        w[a] += w[b];
-        w[b] = 0;
-        // every symbol of both chains moves one level down; chain b is appended to chain a
-        for (int i = a;; i = next[i]) {
-            ++len[i];
-            if (next[i] < 0) { next[i] = b; break; }
+    uint64_t base[256], w[257];
+    int len[257], next[257], hist[kMax + 1];
+    for (int i = 0; i < 256; ++i) base[i] = counts[i];
+    for (bool again = true; again;) {
+        for (int i = 0; i < 256; ++i) w[i] = base[i];
+        w[256] = 1;
+        for (int i = 0; i < 257; ++i) { len[i] = 0; next[i] = -1; }
+        auto least = [&](int skip) {
+            int best = -1;
+            for (int i = 0; i <= 256; ++i)
+                if (w[i] && i != skip && (best < 0 || w[i] <= w[best])) best = i;
+            return best;
+        };
+        for (;;) {
+            int a = least(-1), b = a < 0 ? -1 : least(a);
+            if (b < 0) break;
+            w[a] += w[b];
+            w[b] = 0;
+            // every symbol of both chains moves one level down; chain b is appended to chain a
+            for (int i = a;; i = next[i]) {
+                ++len[i];
+                if (next[i] < 0) { next[i] = b; break; }
+            }
+            for (int i = b; i >= 0; i = next[i]) ++len[i];
         }
-        for (int i = b; i >= 0; i = next[i]) ++len[i];
+        again = false;
+        for (int i = 0; i <= 256; ++i)
+            if (len[i] > kMax) again = true;
+        // a tree deeper than 32 (libjpeg stops with an error there; it takes millions of symbols in a
+        // Fibonacci-like distribution): halve every count, rounding up, and build it again
+        if (again)
+            for (int i = 0; i < 256; ++i)
+                if (base[i]) base[i] = (base[i] + 1) / 2;
     }
+    for (int i = 0; i <= kMax; ++i) hist[i] = 0;
     for (int i = 0; i <= 256; ++i)
-        if (len[i]) ++hist[len[i] > kMax ? kMax : len[i]];
+        if (len[i]) ++hist[len[i]];
     int l = kMax;
     for (; l > 16; --l)
         while (hist[l] > 0) {  // Figure K.3
@@ -446,6 +458,14 @@ void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_
 }  // namespace jb
 
 // ---- host-only entry points of the C ABI (no device needed) ---------------------------
+extern "C" int jb_optimal_huffman_spec(const uint64_t counts[256], uint8_t bits[16], uint8_t vals[256], int* n_vals) {
+    if (!counts || !bits || !vals) return JB_E_INVALID;
+    int n = 0;
+    jb::optimal_spec(counts, bits, vals, &n);
+    if (n_vals) *n_vals = n;
+    return JB_OK;
+}
+
 extern "C" int jb_quality_tables(int quality, uint32_t ql[64], uint32_t qc[64]) {
     // IJG scaling of the reference's q50 tables (utils.hpp:42-62 = T.81 K.1/K.2)
     static const uint32_t l50[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,

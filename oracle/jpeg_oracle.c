@@ -642,34 +642,42 @@ void orc_symbol_histogram(const int16_t *coef, size_t n_mcu, int sub, int restar
 /* T.81 K.2 / libjpeg jpeg_gen_optimal_table.  Returns the number of symbols (HUFFVAL entries). */
 int orc_optimal_spec(const uint64_t freq_in[256], uint8_t bits_out[16], uint8_t vals_out[256]) {
     enum { MAXLEN = 32 };
-    uint64_t freq[257];
+    uint64_t base[256], freq[257];
     int codesize[257], others[257], bits[MAXLEN + 1];
-    for (int i = 0; i < 256; ++i) freq[i] = freq_in[i];
-    freq[256] = 1; /* reserved: guarantees that no real symbol gets the all-ones code */
-    for (int i = 0; i < 257; ++i) { codesize[i] = 0; others[i] = -1; }
-    memset(bits, 0, sizeof(bits));
+    for (int i = 0; i < 256; ++i) base[i] = freq_in[i];
     for (;;) {
-        int c1 = -1, c2 = -1;
-        uint64_t v = UINT64_MAX;
+        for (int i = 0; i < 256; ++i) freq[i] = base[i];
+        freq[256] = 1; /* reserved: guarantees that no real symbol gets the all-ones code */
+        for (int i = 0; i < 257; ++i) { codesize[i] = 0; others[i] = -1; }
+        memset(bits, 0, sizeof(bits));
+        for (;;) {
+            int c1 = -1, c2 = -1;
+            uint64_t v = UINT64_MAX;
+            for (int i = 0; i <= 256; ++i)
+                if (freq[i] && freq[i] <= v) { v = freq[i]; c1 = i; } /* smallest, larger symbol on ties */
+            v = UINT64_MAX;
+            for (int i = 0; i <= 256; ++i)
+                if (freq[i] && freq[i] <= v && i != c1) { v = freq[i]; c2 = i; }
+            if (c2 < 0) break;
+            freq[c1] += freq[c2];
+            freq[c2] = 0;
+            codesize[c1]++;
+            while (others[c1] >= 0) { c1 = others[c1]; codesize[c1]++; }
+            others[c1] = c2;
+            codesize[c2]++;
+            while (others[c2] >= 0) { c2 = others[c2]; codesize[c2]++; }
+        }
+        int too_deep = 0;
         for (int i = 0; i <= 256; ++i)
-            if (freq[i] && freq[i] <= v) { v = freq[i]; c1 = i; } /* smallest, larger symbol on ties */
-        v = UINT64_MAX;
-        for (int i = 0; i <= 256; ++i)
-            if (freq[i] && freq[i] <= v && i != c1) { v = freq[i]; c2 = i; }
-        if (c2 < 0) break;
-        freq[c1] += freq[c2];
-        freq[c2] = 0;
-        codesize[c1]++;
-        while (others[c1] >= 0) { c1 = others[c1]; codesize[c1]++; }
-        others[c1] = c2;
-        codesize[c2]++;
-        while (others[c2] >= 0) { c2 = others[c2]; codesize[c2]++; }
+            if (codesize[i] > MAXLEN) too_deep = 1;
+        if (!too_deep) break;
+        /* libjpeg gives up here (JERR_HUFF_CLEN_OVERFLOW; needs > 9 million symbols in a Fibonacci-like
+         * distribution).  Flatten the distribution instead: halve every count, rounding up, and start over. */
+        for (int i = 0; i < 256; ++i)
+            if (base[i]) base[i] = (base[i] + 1) / 2;
     }
     for (int i = 0; i <= 256; ++i)
-        if (codesize[i]) {
-            if (codesize[i] > MAXLEN) return -1;
-            bits[codesize[i]]++;
-        }
+        if (codesize[i]) bits[codesize[i]]++;
     int i;
     for (i = MAXLEN; i > 16; --i) /* Figure K.3: move the deepest pairs up until no code is longer than 16 */
         while (bits[i] > 0) {

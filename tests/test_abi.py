@@ -61,6 +61,30 @@ def test_host_only_entry_points_match_oracle(jb):
             assert n.value == len(want) == jb.header_bytes(p) and np.array_equal(out[: n.value], want)
 
 
+def test_optimal_huffman_spec_matches_oracle(jb):
+    """The product's table generator (JB_FLAG_OPTIMIZE_HUFFMAN, host code) == the oracle's restatement of T.81 K.2 /
+    jpeg_gen_optimal_table on random histograms: skewed, flat, single-symbol, huge counts, more than 2^16 spread
+    (code lengths above 16 folded back)."""
+    rng = np.random.default_rng(4)
+    for case in range(60):
+        n_sym = int(rng.choice([1, 2, 3, 12, 40, 162, 256]))
+        freq = np.zeros(256, np.uint64)
+        idx = rng.choice(256, n_sym, replace=False)
+        kind = case % 4
+        if kind == 0:
+            freq[idx] = rng.integers(1, 1000, n_sym)
+        elif kind == 1:
+            freq[idx] = (2.0 ** rng.uniform(0, 40, n_sym)).astype(np.uint64) + 1  # forces lengths > 16 before folding
+        elif kind == 2:
+            freq[idx] = 7
+        else:
+            freq[idx] = rng.integers(1, 2 ** 33, n_sym, dtype=np.uint64)
+        gb, gv = jb.optimal_huffman_spec(freq)
+        ob, ov = ol.optimal_spec(freq)
+        assert np.array_equal(gb, ob) and np.array_equal(gv, ov), f"case {case}"
+        assert int(gb.sum()) == n_sym and sum(int(gb[l]) * 2.0 ** -(l + 1) for l in range(16)) < 1.0
+
+
 def test_fails_loudly_without_gpu(jb):
     import torch
     if torch.cuda.is_available():
