@@ -61,6 +61,20 @@ def _worker(rank, world, port, q):
             ok = ok and bytes(whole.numpy()) == ol.encode_jfif(img, ol.SUB_420, ql, qc, mcux)
         else:
             assert whole is None
+        # ---- fewer restart intervals than ranks: the last rank's strip is empty and sends nothing ----
+        small = ol.synth(78, 64, 16)
+        plan1 = D.plan_strips(16, 16, 1, world)
+        r0, r1, f1 = plan1[rank]
+        if r1 > r0:
+            c1 = ol.transform(small[r0:r1], ol.SUB_420, ql, qc)
+            seg1, _ = ol.entropy(c1, ol.SUB_420, 4, rst_phase=f1, final_rst=False)
+        else:
+            seg1 = np.zeros(0, np.uint8)
+        hdr1 = torch.from_numpy(np.frombuffer(ol.jfif_header(64, 16, ol.SUB_420, ql, qc, 4), np.uint8).copy())
+        whole1, len1 = D.gather_stitch(torch.from_numpy(seg1.copy()), hdr1, torch.tensor([0xFF, 0xD9], dtype=torch.uint8), dst=0)
+        assert len1[1:] == [0] * (world - 1)
+        if rank == 0:
+            ok = ok and bytes(whole1.numpy()) == ol.encode_jfif(small, ol.SUB_420, ql, qc, 4)
         # ---- a batch sharded by image: every rank encodes its range, sizes all-gathered --------
         N = 5
         lo, hi = D.shard_range(N, world, rank)
