@@ -177,3 +177,53 @@ def test_staged_functions_random_sizes(jb):
             assert nbits == nb and np.array_equal(bits, packed[: (nb + 7) // 8]), f"Huffman {W}x{H} quirks {quirks}"
     finally:
         enc.close()
+
+
+def test_device_api_respects_buffer_bounds(jb):
+    """Guard bands around the caller's device buffers (input, output, frame tables) stay untouched, and an output
+    buffer that is too small is reported, not overrun (compute-sanitizer is not available on the GPU pool)."""
+    enc = jb.Encoder(0)
+    rng = np.random.default_rng(17)
+    G = 4096
+    try:
+        for case in range(8):
+            sub = int(rng.choice([ol.SUB_444, ol.SUB_REPL420, ol.SUB_420]))
+            m = 16 if sub == ol.SUB_420 else 8
+            W, H, N = int(rng.integers(m, 300)), int(rng.integers(m, 150)), int(rng.integers(1, 6))
+            if (-W) % m > W or (-H) % m > H:
+                continue
+            frames = np.stack([rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(N)])
+            p = jb.make_params(sub, quality=int(rng.choice([50, 95])), restart_interval=int(rng.choice([0, 2])))
+            want = [enc.encode_jfif(f, p, cap=W * H * 12 + 65536) for f in frames]
+            need = sum(len(w) for w in want)
+            for cap in (need, need - 1):  # exact fit, then one byte short
+                n_in = frames.nbytes
+                d_in, d_out, d_meta = enc.device_alloc(n_in + 2 * G), enc.device_alloc(need + 2 * G), enc.device_alloc(16 * N + 8 + 2 * G)
+                try:
+                    guard = np.full(G, 0xA5, np.uint8)
+                    for d, n in ((d_in, n_in), (d_out, need), (d_meta, 16 * N + 8)):
+                        enc.h2d(d, guard)
+                        enc.h2d(d + G + n, guard)
+                    enc.h2d(d_in + G, frames)
+                    ok = True
+                    try:
+                        enc.encode_batch_device(d_in + G, N, W, H, W * 3, W * H * 3, p, d_out + G, cap, d_meta + G, d_meta + G + 8 * N, d_meta + G + 16 * N)
+                        enc.sync()
+                    except jb.JbError as e:
+                        ok = False
+                        assert e.code == jb.E_NOSPACE and cap < need
+                    assert ok == (cap >= need)
+                    back = np.zeros(G, np.uint8)
+                    for d, n in ((d_in, n_in), (d_out, need), (d_meta, 16 * N + 8)):
+                        for off in (0, G + n):
+                            enc.d2h(back, d + off)
+                            assert np.array_equal(back, guard), f"guard band overwritten (case {case}, cap {cap})"
+                    if ok:
+                        out = np.zeros(need, np.uint8)
+                        enc.d2h(out, d_out + G)
+                        assert bytes(out) == b"".join(want)
+                finally:
+                    for d in (d_in, d_out, d_meta):
+                        enc.device_free(d)
+    finally:
+        enc.close()
