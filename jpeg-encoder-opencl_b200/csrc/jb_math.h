@@ -155,7 +155,7 @@ JB_HD uint32_t quantize_bits(float a, float mul, float band, bool& near_tie) {
 
 // Tensor-core variant: bound on |t_mma - t_exact| relative to the largest possible partial sum
 // P = 128 * sum|W|.  The products (8-bit sample x bf16) are exact and each of the 12 MMAs adds
-// 16 of them to the fp32 accumulator; measured on the B200 (experiments/tc_band_scan.py, 6.6 M
+// 16 of them to the fp32 accumulator; measured on the B200 (tests/tools/tc_band_scan.py, 6.6 M
 // coefficients incl. +-255 noise at q100) no coefficient outside a band of 1e-7 * P ever
 // differs from the binary64 reference, so 2e-6 * P (~ 12 accumulation steps x 3 ulp of P)
 // leaves a 20x margin.  Unlike the FMA kernel's band this one is empirical, not analytic.

@@ -2,7 +2,7 @@
 restart intervals, batch sizes, contents (smooth, full-range noise, grey noise) and mode flags (CUDA-core kernels,
 the reference's in-place transform, optimised Huffman tables), coefficients and JFIF bytes
 against the oracle.  Calls of very different shapes on the same context exercise the workspace re-use paths
-(arena regrowth, cached tables, the sticky entropy-workspace budget); experiments/fuzz_gpu.py is the long form."""
+(arena regrowth, cached tables, the sticky entropy-workspace budget); tests/tools/fuzz_gpu.py is the long form."""
 import numpy as np
 import pytest
 

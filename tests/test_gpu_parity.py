@@ -535,7 +535,7 @@ def test_planar_u32_layout_and_fused_input(enc, jb, fruit):
 
 def test_high_entropy_content_grows_the_workspace(jb):
     """Full-range noise at q100 needs more than the first entropy-workspace budget per block (64 bytes): the
-    synchronous entry points enlarge it and run again (found by experiments/fuzz_gpu.py); bytes == the oracle."""
+    synchronous entry points enlarge it and run again (found by tests/tools/fuzz_gpu.py); bytes == the oracle."""
     enc = jb.Encoder(0)  # a fresh context: the budget is sticky per context
     try:
         img = noise_image(99, 200, 120)

@@ -1,7 +1,7 @@
 """Second randomised sweep: many small frames per batch (units of the tcgen05 kernels wrap over MCU rows and
 frames), odd pitches / frame strides / base offsets (alignment variants of the kernels), device-resident API."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import __graft_entry__ as g

@@ -1,7 +1,7 @@
 """Randomised parity sweep on the GPU box: random sizes / modes / qualities / restart intervals / batch sizes,
-coefficients and JFIF bytes against the oracle.  python experiments/fuzz_gpu.py [cases] [seed]"""
+coefficients and JFIF bytes against the oracle.  python tests/tools/fuzz_gpu.py [cases] [seed]"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import __graft_entry__ as g

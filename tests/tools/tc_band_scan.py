@@ -1,7 +1,7 @@
 """Scan the tensor-core near-tie band: for each JB_TC_ERR_SCALE count coefficients that differ from the
 oracle after the binary64 replay (0 = band wide enough) and the number of replayed coefficients."""
 import os, sys, subprocess, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1:
     os.environ["JB_TC_ERR_SCALE"] = sys.argv[1]
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
