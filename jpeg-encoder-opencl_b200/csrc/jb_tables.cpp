@@ -420,8 +420,12 @@ void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_
                        uint8_t* out, float tband[2][64]) {
     const double pi = 3.14159265358979323846;
     memset(out, 0, 32768);
-    static double q1_map[64][64];
-    if (inplace_dct) inplace_dct_map(q1_map);
+    struct Q1Map {
+        double m[64][64];
+        Q1Map() { inplace_dct_map(m); }
+    };
+    static const Q1Map q1;  // built once (thread-safe static initialisation)
+    const double (*q1_map)[64] = q1.m;
     for (int t = 0; t < 2; ++t) {
         const uint32_t* q = t ? qc : ql;
         const bool cells = t == 1 && repl_chroma;  // K = 16: one column per 2x2 cell, the sum of its four entries
