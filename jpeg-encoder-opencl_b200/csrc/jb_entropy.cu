@@ -673,12 +673,25 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
                 uint32_t d = (uint32_t)__cvta_generic_to_shared(win) + (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + g0) & 15) + rel;
                 const uint32_t d_begin = d;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint32_t byte = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-                    const bool on = j < valid, ff = on && byte == 0xFFu;
-                    if (on) sts8(d, byte);
-                    if (ff) sts8(d + 1, 0u);  // T.81 F.1.2.3 byte stuffing
-                    d += on ? (ff ? 2u : 1u) : 0u;
+                for (int wq = 0; wq < 4; ++wq) {
+                    const uint32_t w = wds[wq];
+                    if (valid >= 4 * wq + 4 && __vcmpeq4(w, 0xFFFFFFFFu) == 0u) {  // four plain bytes: no tests
+                        sts8(d, w);
+                        sts8(d + 1, w >> 8);
+                        sts8(d + 2, w >> 16);
+                        sts8(d + 3, w >> 24);
+                        d += 4;
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = 4 * wq + jj;
+                            const uint32_t byte = (w >> (jj * 8)) & 0xFFu;
+                            const bool on = j < valid, ff = on && byte == 0xFFu;
+                            if (on) sts8(d, byte);
+                            if (ff) sts8(d + 1, 0u);  // T.81 F.1.2.3 byte stuffing
+                            d += on ? (ff ? 2u : 1u) : 0u;
+                        }
+                    }
                 }
                 if (marker) {
                     sts8(d, 0xFFu);
