@@ -354,11 +354,12 @@ def main():
     achieved = alg_bytes / (k_us * 1e-6) / 1e9
     use_tc = bool(a.tensor_dct)
     kname = ("k_transform_tc" if sub == jb.SUB_420 else "k_transform_tc3") if use_tc else "k_transform"
+    pname = "k_transform_tc3_repl" if (use_tc and sub == jb.SUB_REPL420) else kname  # key in the ncu summary
     traffic = None
     try:  # per-launch DRAM bytes from the committed ncu capture of the same command, if present
         with open(os.path.join(ROOT, "profiles", "r01_transform_ncu_summary.json")) as f:
             prof = json.load(f)
-        k = prof.get("kernels", {}).get(kname, {})
+        k = prof.get("kernels", {}).get(pname, {})
         if k.get("workload", prof.get("workload")) == a.workload and k.get("frames", prof.get("frames")) == F:
             traffic = k.get("dram_bytes_per_launch")
     except Exception:

@@ -22,4 +22,8 @@ ncu --set full --import-source on --clock-control none -k 'regex:^k_transform$' 
 $B --workload 4k444 > gpurun_out/${R}_plain444.json 2>> gpurun_out/${R}_plain.err || exit 1
 ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tc3' --launch-skip 3 --launch-count 1 -f \
     -o gpurun_out/${R}_prof_tc3 $B --workload 4k444 > /dev/null 2>&1
+# the K = 16 chroma contraction of the replicated 4:2:0 mode (the reference's own mode)
+$B --workload repl1080p > gpurun_out/${R}_plainrepl.json 2>> gpurun_out/${R}_plain.err || exit 1
+ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tc3' --launch-skip 3 --launch-count 1 -f \
+    -o gpurun_out/${R}_prof_tc3r $B --workload repl1080p > /dev/null 2>&1
 ls -la gpurun_out/${R}_*

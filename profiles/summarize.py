@@ -54,11 +54,12 @@ WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
 def kernels():
     md = ["# ncu --set full summaries (round 1)", "",
           "Workload: `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline` (512 x 1920x1080, 4:2:0, q75);",
-          "`_prof_full`: the same with `--tensor-dct 0` (CUDA-core transform); `_prof_tc3`: `--workload 4k444` (32 x 3840x2160, 4:4:4, q90).",
+          "`_prof_full`: the same with `--tensor-dct 0` (CUDA-core transform); `_prof_tc3`: `--workload 4k444` (32 x 3840x2160, 4:4:4, q90);",
+          "`_prof_tc3r`: `--workload repl1080p` (256 x 1920x1080, replicated 4:2:0, q50: K = 16 chroma contraction).",
           "Captured by `profiles/capture.sh` (each ncu pass after a plain run of the same command that exited 0).",
           "Numbers taken under the profiler are diagnostics only; bench values come from CUDA events.", ""]
     summary = {}
-    for rep in (f"{R}_prof_tc.ncu-rep", f"{R}_prof_full.ncu-rep", f"{R}_prof_tc3.ncu-rep"):
+    for rep in (f"{R}_prof_tc.ncu-rep", f"{R}_prof_full.ncu-rep", f"{R}_prof_tc3.ncu-rep", f"{R}_prof_tc3r.ncu-rep"):
         if not os.path.exists(os.path.join(OUT, rep)):
             continue
         hdr, units, rows = raw(rep)
@@ -86,14 +87,15 @@ if __name__ == "__main__":
     summ = kernels()
     ks = {}
     for key, pred in (("k_transform_tc", lambda k: "k_transform_tc<" in k),
-                      ("k_transform_tc3", lambda k: "k_transform_tc3" in k),
+                      ("k_transform_tc3", lambda k: "k_transform_tc3<0" in k),
+                      ("k_transform_tc3_repl", lambda k: "k_transform_tc3<1" in k),
                       ("k_transform", lambda k: "k_transform<" in k)):
         t = next((v for k, v in summ.items() if pred(k)), None)
         if t:
             ks[key] = {"dram_bytes_per_launch": int(to_bytes(*t["dram read"]) + to_bytes(*t["dram write"])),
                        "dram_read": t["dram read"], "dram_write": t["dram write"], "duration_under_ncu": t["duration"],
-                       "workload": "4k444" if key == "k_transform_tc3" else "batch1080p",
-                       "frames": 32 if key == "k_transform_tc3" else 512}
+                       "workload": {"k_transform_tc3": "4k444", "k_transform_tc3_repl": "repl1080p"}.get(key, "batch1080p"),
+                       "frames": {"k_transform_tc3": 32, "k_transform_tc3_repl": 256}.get(key, 512)}
     traffic = {k: v["dram_bytes_per_launch"] for k, v in ks.items()}
     json.dump({"round": R, "workload": "batch1080p", "frames": 512, "kernels": ks,
                "note": "k_transform_tc3 was captured on the 4k444 workload (32 frames of 3840x2160, 4:4:4, q90)",
