@@ -143,6 +143,20 @@ int jb_planar_u32_to_rgb8_device(jb_ctx *ctx, const uint32_t *d_planar, size_t W
  * src/OpenCLProject_JpegEncoder.cpp:325): upload, convert on the device, fused encode. */
 int jb_encode_jfif_planar_u32(jb_ctx *ctx, const uint32_t *planar, size_t W, size_t H, const jb_params *p, uint8_t *out,
                               size_t cap, size_t *out_len);
+int jb_pad_mirror_planar_u32(jb_ctx *ctx, const uint32_t *planar, size_t W, size_t H, uint32_t *out, size_t nW, size_t nH);
+/*      replaces void copyOntoLargerVectorWithPadding(std::vector<cl_uint>&, std::vector<cl_uint>&, ...)  utils.hpp:118
+ *      (mirror padding of the planar uint32 image; the bottom-right corner mirrors both ways like
+ *      addReversedPadding, where the reference's loop reads past the row, utils.cpp:733-740) */
+int jb_blockify_planar_i32(jb_ctx *ctx, const int32_t *planar, size_t W, size_t H, int32_t *linear);
+/*      replaces void everyMCUisnow1DArray(std::vector<int>&, int[], unsigned, unsigned)   utils.hpp:123 */
+int jb_f64_to_u8(jb_ctx *ctx, const double *src, uint8_t *dst, size_t n);
+/*      replaces void copyDoubleToUIntImage(ppm_d_t*, ppm_t*)              utils.hpp:95  */
+int jb_remove_red_aos(jb_ctx *ctx, uint8_t *px, size_t W, size_t H);
+/*      replaces void removeRedChannel(ppm_t*)  ("TEST FUNCTION")          utils.hpp:79  */
+int jb_value_categories(jb_ctx *ctx, const int16_t *v, size_t n, uint8_t *cat, uint16_t *bits);
+/*      replaces const int16_t getValueCategory(const int16_t) and const std::string valueToBitString(const int16_t)
+ *      utils.hpp:134-135, for n values at once: cat[i] = category (bit length of |v|), bits[i] = the cat[i] value
+ *      bits (MSB first when written out), computed by the device function the entropy coder itself uses */
 int jb_rle(jb_ctx *ctx, const int32_t *zz, size_t rows, uint32_t flags, int32_t *pairs, uint32_t *counts);
 /*      replaces void performRLE(int[][64], vector<vector<int>>&, int)     utils.hpp:132
  *      pairs: rows x 128 ints (run,value,...); counts[r] = ints used by row r */
@@ -188,6 +202,26 @@ int jb_encode_batch_device(jb_ctx *ctx, const uint8_t *d_rgb, size_t n_frames, s
  * last_strip.  rgb is a device pointer when d_out is (device_io != 0). */
 int jb_encode_strip(jb_ctx *ctx, const uint8_t *rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params *p,
                     uint64_t first_interval, int last_strip, int device_io, uint8_t *out, size_t cap, size_t *out_len);
+/* The same strip in two asynchronous halves, for a stitch that never visits the host (all pointers are device
+ * pointers; both calls only enqueue work on jb_stream(); status at jb_sync()):
+ *   begin   transform + entropy coder up to the sizes; *d_len = byte count of the strip
+ *   finish  the final placement kernel writes the strip to d_out + *d_off (cap = bytes available from d_out).
+ * Between the two the caller all-gathers the lengths and prefix-sums them on the device (NCCL, 8 bytes per rank).
+ * d_out may be memory of ANOTHER GPU mapped with jb_ipc_open: the placement kernel's coalesced 128-bit stores then
+ * travel over NVLink and land at the strip's final position in the stitching rank's file -- compute and exchange in
+ * one kernel, no gather, no second copy. */
+int jb_encode_strip_begin(jb_ctx *ctx, const uint8_t *d_rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params *p,
+                          uint64_t first_interval, int last_strip, uint64_t *d_len);
+int jb_encode_strip_finish(jb_ctx *ctx, uint8_t *d_out, size_t cap, const uint64_t *d_off);
+/* d_dst[*d_dst_off ...] = d_src[0 .. *d_len) with device-side length and offset (d_dst may be peer memory): pushes the
+ * strips a rank coded in several calls, stitched locally, to their place in the stitching rank's file. */
+int jb_copy_bytes_device(jb_ctx *ctx, uint8_t *d_dst, size_t cap, const uint64_t *d_dst_off, const uint8_t *d_src,
+                         const uint64_t *d_len);
+/* CUDA IPC for one process per GPU: export a jb_device_alloc'd buffer, map it in another process (peer access over
+ * NVLink is enabled on open), unmap. */
+int jb_ipc_export(jb_ctx *ctx, void *d_ptr, uint8_t handle[64]);
+int jb_ipc_open(jb_ctx *ctx, const uint8_t handle[64], void **d_ptr);
+int jb_ipc_close(jb_ctx *ctx, void *d_ptr);
 /* JFIF header (SOI..SOS) for a W x H image with these parameters (host) */
 int jb_write_header(const jb_params *p, size_t W, size_t H, uint8_t *out, size_t cap, size_t *out_len);
 

@@ -10,6 +10,7 @@ library or a missing GPU raises.
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -32,6 +33,8 @@ SYMBOLS = [
     "jb_transform", "jb_entropy", "jb_encode_jfif", "jb_encode_batch", "jb_encode_batch_device", "jb_encode_strip",
     "jb_write_header", "jb_synth_rgb_device", "jb_planar_u32_from_aos", "jb_planar_u32_interleave",
     "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32", "jb_optimal_huffman_spec",
+    "jb_encode_strip_begin", "jb_encode_strip_finish", "jb_copy_bytes_device", "jb_ipc_export", "jb_ipc_open", "jb_ipc_close",
+    "jb_pad_mirror_planar_u32", "jb_blockify_planar_i32", "jb_f64_to_u8", "jb_remove_red_aos", "jb_value_categories",
 ]
 
 
@@ -105,6 +108,11 @@ def lib():
     L.jb_planar_u32_interleave.argtypes = [vp, vp, sz, sz, vp]
     L.jb_planar_u32_to_rgb8_device.argtypes = [vp, vp, sz, sz, vp, sz]
     L.jb_encode_jfif_planar_u32.argtypes = [vp, vp, sz, sz, PP, vp, sz, C.POINTER(sz)]
+    L.jb_pad_mirror_planar_u32.argtypes = [vp, vp, sz, sz, vp, sz, sz]
+    L.jb_blockify_planar_i32.argtypes = [vp, vp, sz, sz, vp]
+    L.jb_f64_to_u8.argtypes = [vp, vp, vp, sz]
+    L.jb_remove_red_aos.argtypes = [vp, vp, sz, sz]
+    L.jb_value_categories.argtypes = [vp, vp, sz, vp, vp]
     L.jb_huffman.argtypes = [vp, vp, sz, C.c_uint32, vp, sz, C.POINTER(u64)]
     L.jb_quality_tables.argtypes = [C.c_int, vp, vp]
     L.jb_optimal_huffman_spec.argtypes = [vp, vp, vp, C.POINTER(C.c_int)]
@@ -121,6 +129,12 @@ def lib():
     L.jb_encode_batch.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp]
     L.jb_encode_batch_device.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, vp]
     L.jb_encode_strip.argtypes = [vp, vp, sz, sz, sz, PP, u64, C.c_int, C.c_int, vp, sz, C.POINTER(sz)]
+    L.jb_encode_strip_begin.argtypes = [vp, vp, sz, sz, sz, PP, u64, C.c_int, vp]
+    L.jb_encode_strip_finish.argtypes = [vp, vp, sz, vp]
+    L.jb_copy_bytes_device.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.jb_ipc_export.argtypes = [vp, vp, vp]
+    L.jb_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.jb_ipc_close.argtypes = [vp, vp]
     L.jb_write_header.argtypes = [PP, sz, sz, vp, sz, C.POINTER(sz)]
     L.jb_synth_rgb_device.argtypes = [vp, u64, sz, sz, sz, sz, vp]
     _lib = L
@@ -244,6 +258,34 @@ class Encoder:
         self._ck(self.L.jb_rle(self.h, _ptr(np.ascontiguousarray(zz)), rows, flags, _ptr(pairs), _ptr(counts)))
         return [pairs[i, :counts[i]].copy() for i in range(rows)]
 
+    def removeRedChannel(self, img):
+        """In place; utils.hpp:79."""
+        assert img.dtype == np.uint8 and img.flags.c_contiguous
+        self._ck(self.L.jb_remove_red_aos(self.h, _ptr(img), img.shape[1], img.shape[0]))
+        return img
+
+    def copyDoubleToUIntImage(self, imgd):
+        out = np.empty(imgd.shape, np.uint8)
+        self._ck(self.L.jb_f64_to_u8(self.h, _ptr(np.ascontiguousarray(imgd, np.float64)), _ptr(out), imgd.size))
+        return out
+
+    def valueCategories(self, values):
+        """(categories uint8, value bits uint16) of int16 values: getValueCategory / valueToBitString, utils.hpp:134-135."""
+        v = np.ascontiguousarray(values, np.int16).ravel()
+        cat, bits = np.empty(v.size, np.uint8), np.empty(v.size, np.uint16)
+        self._ck(self.L.jb_value_categories(self.h, _ptr(v), v.size, _ptr(cat), _ptr(bits)))
+        return cat, bits
+
+    def copyOntoLargerVectorWithPadding(self, planar, W, H, nW, nH):
+        out = np.empty(3 * nW * nH, np.uint32)
+        self._ck(self.L.jb_pad_mirror_planar_u32(self.h, _ptr(np.ascontiguousarray(planar, np.uint32)), W, H, _ptr(out), nW, nH))
+        return out
+
+    def everyMCUisnow1DArray(self, planar_i32, W, H):
+        out = np.empty((3 * W * H // 64, 64), np.int32)
+        self._ck(self.L.jb_blockify_planar_i32(self.h, _ptr(np.ascontiguousarray(planar_i32, np.int32)), W, H, _ptr(out)))
+        return out
+
     def HuffmanEncoder(self, zz, rows_per_channel, flags=0):
         """Returns (packed MSB-first bytes, nbits): the bit sequence of utils.hpp:137."""
         cap = zz.shape[0] * 64 * 4 + 64
@@ -337,6 +379,30 @@ class Encoder:
                                         int(last_strip), int(device_io), _ptr(out), cap, C.byref(n)))
         return out[: n.value].copy() if not device_io else n.value
 
+    def encode_strip_begin(self, d_rgb, params, first_interval, last_strip, W, rows, pitch, d_len):
+        """Asynchronous first half of a strip (device pointers as ints): *d_len = its byte count."""
+        self._ck(self.L.jb_encode_strip_begin(self.h, d_rgb, W, rows, pitch, C.byref(params), first_interval, int(last_strip), d_len))
+
+    def encode_strip_finish(self, d_out, cap, d_off):
+        """Asynchronous second half: the strip is written to d_out + *d_off (d_out may be peer memory)."""
+        self._ck(self.L.jb_encode_strip_finish(self.h, d_out, cap, d_off))
+
+    def copy_bytes_device(self, d_dst, cap, d_dst_off, d_src, d_len):
+        self._ck(self.L.jb_copy_bytes_device(self.h, d_dst, cap, d_dst_off, d_src, d_len))
+
+    def ipc_export(self, d_ptr):
+        h = np.zeros(64, np.uint8)
+        self._ck(self.L.jb_ipc_export(self.h, d_ptr, _ptr(h)))
+        return h
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._ck(self.L.jb_ipc_open(self.h, _ptr(np.ascontiguousarray(handle, np.uint8)), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, d_ptr):
+        self._ck(self.L.jb_ipc_close(self.h, d_ptr))
+
     def write_header(self, params, W, H):
         out = np.empty(1024, np.uint8)
         n = C.c_size_t()
@@ -392,11 +458,14 @@ class Encoder:
 
 
 def pinned_empty(shape, dtype=np.uint8):
-    """numpy array over cudaMallocHost memory (kept alive by the returned array's base)."""
+    """numpy array over cudaMallocHost memory; the block is freed (jb_host_free) once the array and all its
+    views have been collected."""
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = C.c_void_p()
     if lib().jb_host_alloc(C.byref(p), max(n, 1)) != OK:
         raise MemoryError("jb_host_alloc failed")
     buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    # views keep `buf` alive through their .base chain; when the last one is collected the pinned block is released
+    weakref.finalize(buf, lib().jb_host_free, p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr

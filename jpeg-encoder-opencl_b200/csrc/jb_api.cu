@@ -21,6 +21,8 @@ using namespace jb;
 namespace {
 
 constexpr int kSlots = 3;               // in-flight groups of the batched host path
+constexpr int kDevStages = 4;           // header / status staging blocks of back-to-back asynchronous device calls
+constexpr size_t kDevStageBytes = 2048; // 1 KB JFIF header + result words
 constexpr size_t kUbufBytesPerBlock = 64;     // first unstuffed-buffer budget (typical use: 5-40 B/block)
 constexpr size_t kUbufBytesPerBlockMax = 256;  // no block codes longer: 63 x (16 + 10) + 16 + 11 bits = 209 bytes
 
@@ -65,6 +67,15 @@ struct Slot {
     size_t h_res_cap = 0;
     cudaEvent_t ev_scalars = nullptr, ev_done = nullptr;
     bool busy = false;
+    // Asynchronous device-resident calls (jb_encode_batch_device): the pinned header and status words of a call must
+    // stay untouched until its copies have run, so every call takes the next of kDevStages staging blocks
+    // (1 KB header + result words) and waits only for the call that used that block kDevStages calls ago.
+    EntropyArgs strip_ea;        // jb_encode_strip_begin -> jb_encode_strip_finish
+    bool strip_pending = false;
+    uint8_t* h_dev = nullptr;
+    cudaEvent_t dev_ev[kDevStages] = {};
+    bool dev_used[kDevStages] = {};
+    unsigned dev_seq = 0;
     // bookkeeping of the group in flight
     size_t first_frame = 0, n_frames = 0;
 };
@@ -88,6 +99,8 @@ struct jb_ctx {
     uint64_t pending_status_slot = 0;
     size_t ubuf_per_block = kUbufBytesPerBlock;  // grows (sticky) when the entropy workspace overflows
     bool ubuf_grew = false;                       // set by the overflow: synchronous entry points run again
+    bool out_internal = false;  // the output buffer of the call in flight is the library's own staging (host-output paths)
+    bool out_full = false;      // sticky: size that staging for the worst case (every byte stuffed) after it overflowed once
     // host-side constants derived from the quantisation tables, rebuilt only when the tables change
     struct TableCache {
         bool valid = false, tc_valid = false;
@@ -276,7 +289,7 @@ int make_plan(jb_ctx* ctx, size_t n_frames, size_t W, size_t H, const jb_params*
     pl.rgb_bytes = host_in ? pl.d_frame_stride * n_frames + 64 : 0;
     pl.ubuf_cap = align_up(pl.n_blocks * ctx->ubuf_per_block + pl.n_int_total * 16, 4096);
     pl.chunks_cap = pl.ubuf_cap / 16;
-    pl.out_cap = host_out ? pl.ubuf_cap + pl.ubuf_cap / 8 + n_frames * 1024 : 0;
+    pl.out_cap = host_out ? pl.ubuf_cap + (ctx->out_full ? pl.ubuf_cap : pl.ubuf_cap / 8) + n_frames * 1024 : 0;
     *out = pl;
     return JB_OK;
 }
@@ -342,12 +355,13 @@ void resolve_events(jb_ctx* ctx) {
 constexpr uint32_t kGraphMaxBlocks = 1u << 16;  // ~2.8 Mpx of 4:2:0: beyond that the kernels dominate the launches
 
 int launch_entropy_graphed(jb_ctx* ctx, Slot& s, const EntropyArgs& ea) {
-    if (ea.n_blocks > kGraphMaxBlocks || getenv("JB_NO_GRAPH")) return launch_entropy(ea, s.st);
+    if (ea.n_blocks > kGraphMaxBlocks) return launch_entropy(ea, s.st);
     if (s.ent_graph && memcmp(&s.ent_key, &ea, sizeof(ea)) == 0) {
         if (cudaGraphLaunch(s.ent_graph, s.st) == cudaSuccess) return s.ent_launches;
         cudaGetLastError();
     }
     if (s.ent_graph) {
+        cudaStreamSynchronize(s.st);  // an asynchronous caller may still be running the old graph
         cudaGraphExecDestroy(s.ent_graph);
         s.ent_graph = nullptr;
     }
@@ -378,7 +392,8 @@ int launch_entropy_graphed(jb_ctx* ctx, Slot& s, const EntropyArgs& ea) {
 // Enqueue transform (+fix-up) + entropy coder for frames already in device memory.
 int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, const uint8_t* d_rgb, size_t pitch,
                    size_t frame_stride, const Framing& fr, size_t W, size_t H, uint8_t* d_out, size_t out_cap,
-                   uint64_t* d_off, uint64_t* d_size, uint64_t* d_total) {
+                   uint64_t* d_off, uint64_t* d_size, uint64_t* d_total, uint8_t* h_hdr_stage = nullptr,
+                   EntropyArgs* two_phase = nullptr) {
     CK(cudaMemsetAsync(s.d_scalars, 0, 64, s.st));
     TransformArgs ta{};
     ta.rgb = d_rgb;
@@ -411,8 +426,12 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         }
         ta.qc = tc.qc;
         if (!(p->flags & JB_FLAG_FMA_DCT)) {  // tcgen05 transform, every subsampling mode (launch falls back if unaligned)
+#ifdef JB_DEBUG_KNOBS  // tests/tools/tc_band_scan.py only (a separate build): the shipped library reads no environment
             const char* e = getenv("JB_TC_ERR_SCALE");
             const double scale = e ? atof(e) : JB_TC_ERR_SCALE;
+#else
+            const double scale = JB_TC_ERR_SCALE;
+#endif
             const int repl = pl.g.sub == JB_SUB_REPL420 ? 1 : 0, inplace = (p->flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0;
             if (!tc.tc_valid || tc.tc_scale != scale || tc.tc_repl != repl || tc.tc_inplace != inplace) {
                 for (Slot& o : ctx->slot)  // an earlier asynchronous call may still be copying the old matrices
@@ -516,7 +535,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     }
     if (fr.hdr_bytes) {
         // the header travels through the pinned result block so that the copy is truly asynchronous
-        uint8_t* h = reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024;
+        uint8_t* h = h_hdr_stage ? h_hdr_stage : reinterpret_cast<uint8_t*>(s.h_res) + s.h_res_cap - 1024;
         size_t n = build_header(p, W, H, h, custom);
         if (custom)
             ea.fr.hdr_bytes = (uint32_t)n;  // fewer symbols than Annex K lists: a shorter header
@@ -524,7 +543,12 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
             return fail(ctx, JB_E_INTERNAL, "header size mismatch");
         CK(cudaMemcpyAsync(s.d_hdr, h, n, cudaMemcpyHostToDevice, s.st));
     }
-    {
+    if (two_phase) {  // strips placed later (jb_encode_strip_finish): stop once the segment's length is known
+        ea.out_off = reinterpret_cast<const uint64_t*>(ea.total_out);  // any non-null pointer: k_finalize leaves the capacity check to k_stuff
+        Timed t(ctx, s.st, 2);
+        ctx->tm.total_launches += launch_entropy(ea, s.st, 1);
+        *two_phase = ea;
+    } else {
         Timed t(ctx, s.st, 2);
         ctx->tm.total_launches += launch_entropy_graphed(ctx, s, ea);
     }
@@ -548,6 +572,14 @@ int status_to_rc(jb_ctx* ctx, const uint64_t* st, uint64_t tie_count, uint32_t t
     }
     if (st[0] & JB_STATUS_OUT_OVERFLOW) {
         ctx->required = st[2];
+        if (ctx->out_internal && !ctx->out_full) {
+            // the library's own staging buffer (sized for 1/8 of stuffing), not the caller's: size it for the worst case
+            // from now on and let the synchronous entry points run the call again
+            ctx->out_full = true;
+            ctx->ubuf_grew = true;
+            return fail(ctx, JB_E_NOSPACE, "output staging too small (need %llu bytes): it has been enlarged, run the call again",
+                        (unsigned long long)st[2]);
+        }
         return fail(ctx, JB_E_NOSPACE, "output buffer too small: need %llu bytes", (unsigned long long)st[2]);
     }
     return JB_OK;
@@ -596,6 +628,15 @@ int jb_create(int device, jb_ctx** out) {
             return JB_E_CUDA;
         }
     }
+    {
+        Slot& s0 = ctx->slot[0];
+        bool ok = cudaMallocHost(&s0.h_dev, kDevStages * kDevStageBytes) == cudaSuccess;
+        for (int k = 0; ok && k < kDevStages; ++k) ok = cudaEventCreateWithFlags(&s0.dev_ev[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            jb_destroy(ctx);
+            return JB_E_CUDA;
+        }
+    }
     std::vector<uint32_t> ydown(2048);
     double costab[64], scale[64];
     build_ydown(ydown.data());
@@ -627,6 +668,9 @@ void jb_destroy(jb_ctx* ctx) {
         if (s.ent_graph) cudaGraphExecDestroy(s.ent_graph);
         if (s.arena.base) cudaFree(s.arena.base);
         if (s.h_res) cudaFreeHost(s.h_res);
+        if (s.h_dev) cudaFreeHost(s.h_dev);
+        for (auto e : s.dev_ev)
+            if (e) cudaEventDestroy(e);
         if (s.ev_scalars) cudaEventDestroy(s.ev_scalars);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         if (s.st) cudaStreamDestroy(s.st);
@@ -655,11 +699,19 @@ int jb_sync(jb_ctx* ctx) {
     resolve_events(ctx);
     // device-resident calls report their status here
     Slot& s = ctx->slot[0];
+    int rc = JB_OK;
     if (s.busy) {
         s.busy = false;
-        return status_to_rc(ctx, s.h_res, s.h_res[5], s.tie_cap);
+        ctx->out_internal = false;  // device-resident calls write the caller's buffer
+        for (int k = 0; k < kDevStages; ++k) {  // every call since the last jb_sync; the first failure is reported
+            if (!s.dev_used[k]) continue;
+            s.dev_used[k] = false;
+            const uint64_t* res = reinterpret_cast<const uint64_t*>(s.h_dev + k * kDevStageBytes + 1024);
+            const int r = status_to_rc(ctx, res, res[5], s.tie_cap);
+            if (rc == JB_OK) rc = r;
+        }
     }
-    return JB_OK;
+    return rc;
 }
 
 int jb_set_profiling(jb_ctx* ctx, int on) {
@@ -842,6 +894,65 @@ int jb_zigzag(jb_ctx* ctx, const int32_t* linear, int32_t* zz, size_t rows) {
     CK(cudaMemcpyAsync(a, linear, n * 4, cudaMemcpyHostToDevice, st));
     ctx->tm.total_launches += launch_zigzag(a, b, rows, st);
     CK(cudaMemcpyAsync(zz, b, n * 4, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_f64_to_u8(jb_ctx* ctx, const double* src, uint8_t* dst, size_t n) {
+    if (!src || !dst || n == 0) return fail(ctx, JB_E_INVALID, "empty input");
+    STAGE_BEGIN(n * 9 + 512)
+    double* ds = carve<double>(A, n);
+    uint8_t* dd = carve<uint8_t>(A, n);
+    CK(cudaMemcpyAsync(ds, src, n * 8, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_f64_to_u8(ds, dd, n, st);
+    CK(cudaMemcpyAsync(dst, dd, n, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_remove_red_aos(jb_ctx* ctx, uint8_t* px, size_t W, size_t H) {
+    size_t n = W * H;
+    if (!px || n == 0) return fail(ctx, JB_E_INVALID, "empty image");
+    STAGE_BEGIN(n * 3)
+    uint8_t* d = carve<uint8_t>(A, n * 3);
+    CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_remove_red(d, n, st);
+    CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_value_categories(jb_ctx* ctx, const int16_t* v, size_t n, uint8_t* cat, uint16_t* bits) {
+    if (!v || !cat || !bits || n == 0) return fail(ctx, JB_E_INVALID, "bad arguments");
+    STAGE_BEGIN(n * 5 + 1024)
+    int16_t* dv = carve<int16_t>(A, n);
+    uint16_t* db = carve<uint16_t>(A, n);
+    uint8_t* dc = carve<uint8_t>(A, n);
+    CK(cudaMemcpyAsync(dv, v, n * 2, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_value_categories(dv, n, dc, db, st);
+    CK(cudaMemcpyAsync(cat, dc, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(bits, db, n * 2, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_pad_mirror_planar_u32(jb_ctx* ctx, const uint32_t* in, size_t W, size_t H, uint32_t* out, size_t nW, size_t nH) {
+    if (!in || !out || W == 0 || H == 0 || nW < W || nH < H) return fail(ctx, JB_E_INVALID, "bad sizes");
+    if (nW - W > W || nH - H > H) return fail(ctx, JB_E_UNSUPPORTED, "padding larger than the image");
+    STAGE_BEGIN((W * H + nW * nH) * 12 + 512)
+    uint32_t* a = carve<uint32_t>(A, W * H * 3);
+    uint32_t* b = carve<uint32_t>(A, nW * nH * 3);
+    CK(cudaMemcpyAsync(a, in, W * H * 12, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_pad_planar_u32(a, W, H, b, nW, nH, st);
+    CK(cudaMemcpyAsync(out, b, nW * nH * 12, cudaMemcpyDeviceToHost, st));
+    STAGE_END()
+}
+
+int jb_blockify_planar_i32(jb_ctx* ctx, const int32_t* planar, size_t W, size_t H, int32_t* linear) {
+    if (!planar || !linear || W == 0 || H == 0 || (W & 7) || (H & 7)) return fail(ctx, JB_E_INVALID, "bad arguments");
+    size_t n = W * H * 3;
+    STAGE_BEGIN(n * 8 + 512)
+    int32_t* a = carve<int32_t>(A, n);
+    int32_t* b = carve<int32_t>(A, n);
+    CK(cudaMemcpyAsync(a, planar, n * 4, cudaMemcpyHostToDevice, st));
+    ctx->tm.total_launches += launch_blockify_planar_i32(a, W, H, b, st);
+    CK(cudaMemcpyAsync(linear, b, n * 4, cudaMemcpyDeviceToHost, st));
     STAGE_END()
 }
 
@@ -1047,8 +1158,9 @@ static int entropy_once(jb_ctx* ctx, const int16_t* coef, size_t n_mcu, const jb
         pl.n_int_total = (size_t)pl.g.n_int;
         pl.ubuf_cap = align_up(pl.n_blocks * ctx->ubuf_per_block + pl.n_int_total * 16, 4096);
         pl.chunks_cap = pl.ubuf_cap / 16;
-        pl.out_cap = pl.ubuf_cap + pl.ubuf_cap / 8 + 1024;
+        pl.out_cap = pl.ubuf_cap + (ctx->out_full ? pl.ubuf_cap : pl.ubuf_cap / 8) + 1024;
     }
+    ctx->out_internal = true;
     Slot& s = ctx->slot[0];
     if ((rc = slot_prepare(ctx, s, pl))) return rc;
     CK(cudaMemsetAsync(s.d_scalars, 0, 64, s.st));
@@ -1083,6 +1195,7 @@ int jb_huffman(jb_ctx* ctx, const int32_t* zz, size_t rpc, uint32_t flags, uint8
     pl.chunks_cap = pl.ubuf_cap / 16;
     pl.out_cap = 4096;
     pl.rgb_bytes = rpc * 3 * 64 * 4;  // staging for the int32 planar input
+    ctx->out_internal = true;
     Slot& s = ctx->slot[0];
     if ((rc = slot_prepare(ctx, s, pl))) return rc;
     CK(cudaMemsetAsync(s.d_scalars, 0, 64, s.st));
@@ -1097,15 +1210,19 @@ int jb_huffman(jb_ctx* ctx, const int32_t* zz, size_t rpc, uint32_t flags, uint8
 
 // Harvest a finished group of the batched host path: read its totals, copy its bytes out.
 static int harvest(jb_ctx* ctx, Slot& s, uint8_t* out, size_t cap, uint64_t* offsets, uint64_t* sizes,
-                   uint64_t* running) {
+                   uint64_t* running, bool* overflow) {
     CK(cudaEventSynchronize(s.ev_scalars));
     int rc = status_to_rc(ctx, s.h_res, (uint32_t)s.h_res[5], s.tie_cap);
     if (rc) return rc;
     uint64_t total = s.h_res[4];
-    if (*running + total > cap) {
-        ctx->required = *running + total;
-        return fail(ctx, JB_E_NOSPACE, "output buffer too small: need more than %llu bytes",
-                    (unsigned long long)(*running + total));
+    if (*overflow || *running + total > cap) {
+        // the caller's buffer is too small: keep going without copying, so that jb_required_bytes() is the size
+        // of the whole batch and not of the groups up to here
+        *overflow = true;
+        *running += total;
+        CK(cudaEventRecord(s.ev_done, s.st));
+        s.busy = false;
+        return JB_OK;
     }
     {
         Timed t(ctx, s.st, 4);
@@ -1140,11 +1257,13 @@ static int encode_batch_once(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, s
     size_t n_groups = (n_frames + fpg - 1) / fpg;
     uint64_t running = 0;
     size_t harvested = 0;
+    bool overflow = false;
+    ctx->out_internal = true;
     for (auto& s : ctx->slot) s.busy = false;
     for (size_t gi = 0; gi < n_groups; ++gi) {
         Slot& s = ctx->slot[gi % kSlots];
         if (s.busy) {  // the slot still holds group gi - kSlots: drain it first (in order)
-            if ((rc = harvest(ctx, s, out, cap, offsets, sizes, &running))) goto drain;
+            if ((rc = harvest(ctx, s, out, cap, offsets, sizes, &running, &overflow))) goto drain;
             ++harvested;
         }
         CK(cudaEventSynchronize(s.ev_done));  // its previous D2H must have left the device buffer
@@ -1173,9 +1292,13 @@ static int encode_batch_once(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, s
     // drain the remaining groups in submission order
     for (size_t gi = harvested; gi < n_groups; ++gi) {
         Slot& s = ctx->slot[gi % kSlots];
-        if (s.busy && (rc = harvest(ctx, s, out, cap, offsets, sizes, &running))) goto drain;
+        if (s.busy && (rc = harvest(ctx, s, out, cap, offsets, sizes, &running, &overflow))) goto drain;
     }
     rc = JB_OK;
+    if (overflow) {
+        ctx->required = running;
+        rc = fail(ctx, JB_E_NOSPACE, "output buffer too small: the batch needs %llu bytes", (unsigned long long)running);
+    }
 drain:
     for (auto& s : ctx->slot) {
         cudaStreamSynchronize(s.st);
@@ -1214,13 +1337,20 @@ int jb_encode_batch_device(jb_ctx* ctx, const uint8_t* d_rgb, size_t n_frames, s
     Framing fr{};
     fr.hdr_bytes = (uint32_t)jb_header_bytes(p);
     fr.emit_eoi = 1;
+    // this call's pinned staging block; the call that used it kDevStages calls ago must have finished its copies
+    const unsigned k = s.dev_seq++ % kDevStages;
+    if (s.dev_used[k]) CK(cudaEventSynchronize(s.dev_ev[k]));
+    uint8_t* stage = s.h_dev + k * kDevStageBytes;
+    uint64_t* res = reinterpret_cast<uint64_t*>(stage + 1024);
     if ((rc = enqueue_encode(ctx, s, pl, p, d_rgb, pitch, frame_stride, fr, W, H, d_out, cap, d_offsets, d_sizes,
-                             d_total ? d_total : s.d_total)))
+                             d_total ? d_total : s.d_total, stage)))
         return rc;
-    CK(cudaMemcpyAsync(s.h_res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
-    s.h_res[5] = 0;
-    CK(cudaMemcpyAsync(s.h_res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
-    s.busy = true;  // status is examined by jb_sync
+    memset(res, 0, 64);
+    CK(cudaMemcpyAsync(res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpyAsync(res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaEventRecord(s.dev_ev[k], s.st));
+    s.dev_used[k] = true;
+    s.busy = true;  // the status words are examined by jb_sync
     return JB_OK;
 }
 
@@ -1237,6 +1367,7 @@ static int encode_strip_once(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t s
         return fail(ctx, JB_E_INVALID, "only the last strip may have a partial MCU row");
     Slot& s = ctx->slot[0];
     CK(cudaStreamSynchronize(s.st));
+    ctx->out_internal = !device_io;
     if ((rc = slot_prepare(ctx, s, pl))) return rc;
     Framing fr{};
     fr.final_rst = last_strip ? 0u : 1u;
@@ -1275,6 +1406,100 @@ static int encode_strip_once(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t s
 int jb_encode_strip(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params* p,
                     uint64_t first_interval, int last_strip, int device_io, uint8_t* out, size_t cap, size_t* out_len) {
     return with_workspace_retry(ctx, [&] { return encode_strip_once(ctx, rgb, W, strip_rows, pitch, p, first_interval, last_strip, device_io, out, cap, out_len); });
+}
+
+// ---- multi-GPU strip stitch without a host round trip ------------------------------------------------------------
+// begin: transform + entropy coder up to the sizes, asynchronous; *d_len (device) receives the strip's byte count.
+// finish: the final placement (0xFF00 stuffing, RSTn) writes the strip to d_out + *d_off -- d_off is a device scalar
+// the caller computes from the all-gathered lengths, and d_out may be another GPU's buffer mapped with jb_ipc_open:
+// the kernel's coalesced 128-bit stores are then the NVLink transfer, there is no separate gather.
+int jb_encode_strip_begin(jb_ctx* ctx, const uint8_t* d_rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params* p,
+                          uint64_t first_interval, int last_strip, uint64_t* d_len) {
+    if (!ctx || !d_rgb || !d_len) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    Plan pl;
+    int rc = make_plan(ctx, 1, W, strip_rows, p, false, false, &pl);
+    if (rc) return rc;
+    if (p->restart_interval <= 0 || pl.g.ri % pl.g.mcux != 0)
+        return fail(ctx, JB_E_INVALID, "strips need a restart interval that is a whole number of MCU rows");
+    if (!last_strip && strip_rows % (size_t)pl.g.mcu_px)
+        return fail(ctx, JB_E_INVALID, "only the last strip may have a partial MCU row");
+    if (p->flags & JB_FLAG_OPTIMIZE_HUFFMAN) return fail(ctx, JB_E_UNSUPPORTED, "strips carry no tables");
+    Slot& s = ctx->slot[0];
+    if (s.strip_pending) return fail(ctx, JB_E_INVALID, "jb_encode_strip_begin twice without jb_encode_strip_finish");
+    if (s.arena.cap < plan_bytes(pl)) CK(cudaStreamSynchronize(s.st));  // regrowing frees the arena
+    ctx->out_internal = false;
+    if ((rc = slot_prepare(ctx, s, pl))) return rc;
+    Framing fr{};
+    fr.final_rst = last_strip ? 0u : 1u;
+    fr.rst_phase = (uint32_t)(first_interval & 7);
+    // d_out only has to be non-null here: nothing is written before jb_encode_strip_finish
+    if ((rc = enqueue_encode(ctx, s, pl, p, d_rgb, pitch, pitch * strip_rows, fr, W, strip_rows, reinterpret_cast<uint8_t*>(d_len), 0,
+                             nullptr, nullptr, d_len, nullptr, &s.strip_ea)))
+        return rc;
+    s.strip_pending = true;
+    return JB_OK;
+}
+
+int jb_encode_strip_finish(jb_ctx* ctx, uint8_t* d_out, size_t cap, const uint64_t* d_off) {
+    if (!ctx || !d_out) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    if (!s.strip_pending) return fail(ctx, JB_E_INVALID, "jb_encode_strip_finish without jb_encode_strip_begin");
+    s.strip_pending = false;
+    EntropyArgs ea = s.strip_ea;
+    ea.out = d_out;
+    ea.out_cap = cap;
+    ea.out_off = d_off;
+    {
+        Timed t(ctx, s.st, 2);
+        ctx->tm.total_launches += launch_entropy(ea, s.st, 2);
+    }
+    CK(cudaGetLastError());
+    const unsigned k = s.dev_seq++ % kDevStages;  // status words: as for jb_encode_batch_device, examined by jb_sync
+    if (s.dev_used[k]) CK(cudaEventSynchronize(s.dev_ev[k]));
+    uint64_t* res = reinterpret_cast<uint64_t*>(s.h_dev + k * kDevStageBytes + 1024);
+    memset(res, 0, 64);
+    CK(cudaMemcpyAsync(res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpyAsync(res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaEventRecord(s.dev_ev[k], s.st));
+    s.dev_used[k] = true;
+    s.busy = true;
+    return JB_OK;
+}
+
+int jb_copy_bytes_device(jb_ctx* ctx, uint8_t* d_dst, size_t cap, const uint64_t* d_dst_off, const uint8_t* d_src,
+                         const uint64_t* d_len) {
+    if (!ctx || !d_dst || !d_src || !d_len) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.total_launches += launch_copy_bytes(d_dst, d_dst_off, d_src, d_len, cap, nullptr, ctx->slot[0].st);
+    CK(cudaGetLastError());
+    return JB_OK;
+}
+
+// CUDA IPC: one process per GPU (torch.distributed), so the stitching rank's buffer is shared by handle
+int jb_ipc_export(jb_ctx* ctx, void* d_ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!ctx || !d_ptr || !handle) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return JB_OK;
+}
+int jb_ipc_open(jb_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
+    if (!ctx || !handle || !d_ptr) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return JB_OK;
+}
+int jb_ipc_close(jb_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return fail(ctx, JB_E_INVALID, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return JB_OK;
 }
 
 int jb_synth_rgb_device(jb_ctx* ctx, uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t* d_out) {

@@ -21,7 +21,7 @@
 // Bit order is MSB first; the unstuffed buffer is addressed as big-endian words.
 #include <cuda_fp16.h>
 
-#include "jb_internal.h"
+#include "jb_pixels.cuh"  // cat_bits (utils.cpp:623-653)
 
 namespace jb {
 
@@ -50,12 +50,6 @@ struct BitSink {
         if (n > 0) atomicOr(wp, __byte_perm((uint32_t)(acc << (32 - n)), 0, 0x0123));
     }
 };
-
-// value bits of v in `cat` bits: v >= 0 -> v, v < 0 -> v + 2^cat - 1 (utils.cpp:630-653)
-__device__ __forceinline__ void cat_bits(int v, int& cat, uint32_t& vb) {
-    cat = 32 - __clz(abs(v));  // utils.cpp:623-627
-    vb = (uint32_t)(v + (v >> 31)) & ((1u << cat) - 1u);
-}
 
 struct BlockInfo {
     int comp;          // 0 Y, 1 Cb, 2 Cr
@@ -598,7 +592,7 @@ __global__ void k_finalize(const __grid_constant__ EntropyArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         a.w.status[2] = total;
-        if (total > a.out_cap) atomicOr((unsigned long long*)&a.w.status[0], JB_STATUS_OUT_OVERFLOW);
+        if (!a.out_off && total > a.out_cap) atomicOr((unsigned long long*)&a.w.status[0], JB_STATUS_OUT_OVERFLOW);
         if (a.total_out) *a.total_out = total;
     }
     if (i < (uint32_t)a.n_frames) {
@@ -628,7 +622,19 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
     __shared__ uint32_t s_i0, s_i1, s_k, s_n;
     __shared__ bool s_hdr_first;
     uint64_t total = a.w.int_ubase[a.n_int_total];
-    if (total > a.w.ubuf_cap || a.w.int_obase[a.n_int_total] > a.out_cap) return;
+    // The segment may be placed at a byte offset that is only known on the device (a.out_off): a strip's place in
+    // the stitched file follows from the lengths of the strips before it, and a.out may then be another GPU's
+    // memory mapped over NVLink -- the stores below are the stitch.
+    const uint64_t out_off = a.out_off ? *a.out_off : 0ull;
+    if (total > a.w.ubuf_cap) return;
+    if (out_off + a.w.int_obase[a.n_int_total] > a.out_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.w.status[2] = out_off + a.w.int_obase[a.n_int_total];
+            atomicOr((unsigned long long*)&a.w.status[0], JB_STATUS_OUT_OVERFLOW);
+        }
+        return;
+    }
+    uint8_t* const out = a.out + out_off;
     const uint64_t n_chunks = total >> 4;
     const uint32_t n_tiles = (uint32_t)((n_chunks + TILE - 1) / TILE);
     const uint4* p = reinterpret_cast<const uint4*>(a.w.ubuf);
@@ -670,7 +676,7 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
                 const int valid = off >= nb ? 0 : (nb - off < 16 ? (int)(nb - off) : 16);
                 const uint32_t marker = off + 16 >= nb ? marker_after(a, s_k) : 0u;  // last chunk of the interval
                 const uint32_t rel = 16u * threadIdx.x + (threadIdx.x ? a.w.ff_prefix[c] : 0u);
-                uint32_t d = (uint32_t)__cvta_generic_to_shared(win) + (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + g0) & 15) + rel;
+                uint32_t d = (uint32_t)__cvta_generic_to_shared(win) + (uint32_t)((reinterpret_cast<uintptr_t>(out) + g0) & 15) + rel;
                 const uint32_t d_begin = d;
 #pragma unroll
                 for (int wq = 0; wq < 4; ++wq) {
@@ -703,14 +709,14 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
             }
             __syncthreads();
             {
-                const uint32_t base = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + g0) & 15), n = s_n;
+                const uint32_t base = (uint32_t)((reinterpret_cast<uintptr_t>(out) + g0) & 15), n = s_n;
                 const uint32_t head = min(n, (16u - base) & 15u);          // bytes before the first 16-byte boundary
                 const uint32_t n16 = (n - head) >> 4, tail = (n - head) & 15u;
-                if (threadIdx.x < head) a.out[g0 + threadIdx.x] = win[base + threadIdx.x];
-                uint4* gdst = reinterpret_cast<uint4*>(a.out + g0 + head);
+                if (threadIdx.x < head) out[g0 + threadIdx.x] = win[base + threadIdx.x];
+                uint4* gdst = reinterpret_cast<uint4*>(out + g0 + head);
                 const uint4* ssrc = reinterpret_cast<const uint4*>(win + base + head);
                 for (uint32_t j = threadIdx.x; j < n16; j += TILE) gdst[j] = ssrc[j];
-                if (threadIdx.x < tail) a.out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = win[base + head + 16 * n16 + threadIdx.x];
+                if (threadIdx.x < tail) out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = win[base + head + 16 * n16 + threadIdx.x];
             }
             __syncthreads();
             continue;
@@ -738,7 +744,7 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
         if (have && (threadIdx.x == TILE - 1 || c + 1 == n_chunks)) s_g1 = end;
         __syncthreads();
         const uint64_t g0 = s_g0, g1 = s_g1;
-        const uintptr_t P0 = reinterpret_cast<uintptr_t>(a.out) + g0;
+        const uintptr_t P0 = reinterpret_cast<uintptr_t>(out) + g0;
         const uint32_t base = (uint32_t)(P0 & 15);
         const bool fits = g1 - g0 <= STUFF_WIN;
         if (fits) {  // the usual case: 32-bit shared-memory addresses, predicated byte stores
@@ -762,7 +768,7 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
                 }
             }
         } else if (have) {  // pathological (thousands of tiny frames): bytes go straight to global memory
-            uint8_t* o = a.out;
+            uint8_t* o = out;
             if (hdr)
                 for (uint32_t j = 0; j < a.fr.hdr_bytes; ++j) o[start + j] = a.hdr[j];
             for (int j = 0; j < valid; ++j) {
@@ -780,14 +786,53 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
             const uint32_t n = (uint32_t)(g1 - g0);
             const uint32_t head = min(n, (16u - base) & 15u);          // bytes before the first 16-byte boundary
             const uint32_t n16 = (n - head) >> 4, tail = (n - head) & 15u;
-            if (threadIdx.x < head) a.out[g0 + threadIdx.x] = win[base + threadIdx.x];
-            uint4* gdst = reinterpret_cast<uint4*>(a.out + g0 + head);
+            if (threadIdx.x < head) out[g0 + threadIdx.x] = win[base + threadIdx.x];
+            uint4* gdst = reinterpret_cast<uint4*>(out + g0 + head);
             const uint4* ssrc = reinterpret_cast<const uint4*>(win + base + head);
             for (uint32_t j = threadIdx.x; j < n16; j += TILE) gdst[j] = ssrc[j];
-            if (threadIdx.x < tail) a.out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = win[base + head + 16 * n16 + threadIdx.x];
+            if (threadIdx.x < tail) out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = win[base + head + 16 * n16 + threadIdx.x];
         }
         __syncthreads();
     }
+}
+
+// Byte copy whose length and destination offset are only known on the device: pushes a rank's locally stitched strips
+// to their place in another GPU's buffer (peer memory over NVLink) when the rank coded them in several calls.
+// Destination-aligned 128-bit stores; the source is read as aligned words and realigned with funnel shifts.
+__global__ void __launch_bounds__(256) k_copy_bytes(uint8_t* __restrict__ dst_base, const uint64_t* __restrict__ d_dst_off,
+                                                    const uint8_t* __restrict__ src, const uint64_t* __restrict__ d_len, uint64_t cap,
+                                                    uint64_t* status) {
+    const uint64_t off = d_dst_off ? *d_dst_off : 0ull, n = *d_len;
+    if (off + n > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && status) {
+            status[2] = off + n;
+            atomicOr((unsigned long long*)&status[0], JB_STATUS_OUT_OVERFLOW);
+        }
+        return;
+    }
+    uint8_t* dst = dst_base + off;
+    const uint64_t head = min(n, (uint64_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
+    const uint64_t n16 = (n - head) >> 4, tail = (n - head) & 15u;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+    if (tid < head) dst[tid] = src[tid];
+    if (tid < tail) dst[head + 16 * n16 + tid] = src[head + 16 * n16 + tid];
+    const uint8_t* s0 = src + head;                                  // source of the first aligned destination vector
+    const uint32_t r = (uint32_t)(reinterpret_cast<uintptr_t>(s0) & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - (r >> 3));
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    for (uint64_t j = tid; j < n16; j += nthreads) {
+        const uint32_t* w = sw + 4 * j;
+        // (the fifth word may lie past the last source byte when r == 0: it is then not needed, and not read)
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = r ? w[4] : 0u;
+        d4[j] = make_uint4(__funnelshift_r(w0, w1, r), __funnelshift_r(w1, w2, r), __funnelshift_r(w2, w3, r),
+                           __funnelshift_r(w3, w4, r));
+    }
+}
+
+int launch_copy_bytes(uint8_t* dst_base, const uint64_t* d_dst_off, const uint8_t* src, const uint64_t* d_len, uint64_t cap,
+                      uint64_t* status, cudaStream_t s) {
+    k_copy_bytes<<<148 * 8, 256, 0, s>>>(dst_base, d_dst_off, src, d_len, cap, status);
+    return 1;
 }
 
 static uint64_t magic52(uint64_t d) { return ((1ull << 52) + d - 1) / d; }
@@ -863,7 +908,10 @@ int launch_symbol_hist(const EntropyArgs& a_in, uint32_t* d_hist, cudaStream_t s
     return 1;
 }
 
-int launch_entropy(const EntropyArgs& a_in, cudaStream_t s) {
+// phase 0: the whole coder; 1: everything up to the sizes (k_finalize: the segment's length is known on the device,
+// nothing has been written to a.out); 2: the final placement alone (k_stuff) -- a.out / a.out_cap / a.out_off may
+// differ from phase 1: between the two the caller learns where the segment goes (multi-GPU strip stitch).
+int launch_entropy(const EntropyArgs& a_in, cudaStream_t s, int phase) {
     if (a_in.n_blocks == 0) return 0;
     EntropyArgs a = a_in;
     a.m_bpf = magic52((uint64_t)a.g.n_mcu * (uint64_t)a.g.bpm);
@@ -871,12 +919,16 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s) {
     int launches = 0;
     uint32_t n_tiles = (a.n_blocks + TILE - 1) / TILE;
     uint32_t gi = (a.n_int_total + 255) / 256;
+    const uint32_t chunk_tiles = (uint32_t)(a.w.ubuf_cap / 16 / TILE + 1);
+    if (phase == 2) {
+        k_stuff<<<chunk_tiles < 1184u ? chunk_tiles : 1184u, TILE, 0, s>>>(a);
+        return 1;
+    }
     k_encode<<<n_tiles, TILE, 0, s>>>(a);
     launches += scan_u32(a.w.tile_bits, a.w.tile_base, n_tiles, nullptr, a.w.scan_tmp, s);
     k_intervals<<<gi, 256, 0, s>>>(a);
     launches += scan_u32(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr, a.w.scan_tmp, s);
     // grids of the grid-stride kernels are capped by the work the plan allows: a small image launches few CTAs
-    const uint32_t chunk_tiles = (uint32_t)(a.w.ubuf_cap / 16 / TILE + 1);
     k_zero<<<chunk_tiles < 592u ? chunk_tiles : 592u, 256, 0, s>>>(a);
     k_pack<<<n_tiles, TILE, 0, s>>>(a);
     k_pack_long<<<n_tiles < 296u ? n_tiles : 296u, TILE, 0, s>>>(a);
@@ -889,9 +941,10 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s) {
     launches += scan_u32(a.w.int_osize, a.w.int_obase, a.n_int_total, nullptr, a.w.scan_tmp, s);
     uint32_t gf = ((uint32_t)a.n_frames + 255) / 256;
     k_finalize<<<gf, 256, 0, s>>>(a);
+    launches += 3;
+    if (phase == 1) return launches;
     k_stuff<<<chunk_tiles < 1184u ? chunk_tiles : 1184u, TILE, 0, s>>>(a);
-    launches += 4;
-    return launches;
+    return launches + 1;
 }
 
 }  // namespace jb

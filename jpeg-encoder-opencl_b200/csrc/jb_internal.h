@@ -146,6 +146,7 @@ struct EntropyArgs {
     uint64_t* frame_off;   // [n_frames] (may be null)
     uint64_t* frame_size;  // [n_frames] (may be null)
     uint64_t* total_out;   // device scalar (may be null)
+    const uint64_t* out_off;  // device scalar (may be null): the segment goes to out + *out_off (strip stitch)
 };
 
 #define JB_STATUS_UBUF_OVERFLOW 1ull
@@ -156,7 +157,9 @@ struct EntropyArgs {
 int launch_transform(const TransformArgs& a, cudaStream_t s);       // MCUs inside the image (hot kernel)
 int launch_transform_edge(const TransformArgs& a, cudaStream_t s);  // MCUs that need mirror padding
 int launch_fixup(const FixupArgs& a, cudaStream_t s);
-int launch_entropy(const EntropyArgs& a, cudaStream_t s);
+int launch_entropy(const EntropyArgs& a, cudaStream_t s, int phase = 0);  // 1: up to the sizes, 2: final placement only
+int launch_copy_bytes(uint8_t* dst_base, const uint64_t* d_dst_off, const uint8_t* src, const uint64_t* d_len, uint64_t cap,
+                      uint64_t* status, cudaStream_t s);
 int launch_synth(uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t* d_out, cudaStream_t s);
 
 // staged kernels (device pointers)
@@ -172,6 +175,11 @@ int launch_blockify(const double* img, size_t W, size_t H, int32_t* linear, cuda
 int launch_aos_to_planar_u32(const uint8_t* px, size_t n, uint32_t* out, cudaStream_t s);
 int launch_planar_u32_interleave(const uint32_t* in, size_t n, uint32_t* out, cudaStream_t s);
 int launch_planar_u32_to_rgb8(const uint32_t* in, size_t W, size_t H, uint8_t* out, size_t pitch, cudaStream_t s);
+int launch_pad_planar_u32(const uint32_t* in, size_t W, size_t H, uint32_t* out, size_t nW, size_t nH, cudaStream_t s);
+int launch_blockify_planar_i32(const int32_t* in, size_t W, size_t H, int32_t* linear, cudaStream_t s);
+int launch_f64_to_u8(const double* src, uint8_t* dst, size_t n, cudaStream_t s);
+int launch_value_categories(const int16_t* v, size_t n, uint8_t* cat, uint16_t* bits, cudaStream_t s);
+int launch_remove_red(uint8_t* px, size_t n, cudaStream_t s);
 int launch_zigzag(const int32_t* linear, int32_t* zz, size_t rows, cudaStream_t s);
 int launch_rle(const int32_t* zz, size_t rows, int always_eob, int32_t* pairs, uint32_t* counts, cudaStream_t s);
 int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStream_t s);

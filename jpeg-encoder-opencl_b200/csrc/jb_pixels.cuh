@@ -112,6 +112,13 @@ __device__ __forceinline__ void load24(const uint8_t* p, uint32_t (&w)[6]) {
     }
 }
 
+// getValueCategory / valueToBitString (utils.cpp:623-653): category = bit length of |v| (0 for v == 0); the value
+// bits are v for v > 0 and v + 2^cat - 1 for v < 0, in `cat` bits.
+__device__ __forceinline__ void cat_bits(int v, int& cat, uint32_t& vb) {
+    cat = 32 - __clz(abs(v));
+    vb = (uint32_t)(v + (v >> 31)) & ((1u << cat) - 1u);
+}
+
 // byte k (0..23, compile time) of the six words
 __device__ __forceinline__ uint32_t byte24(const uint32_t (&w)[6], int k) { return (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu; }
 

@@ -218,6 +218,76 @@ __global__ void k_planar_u32_to_rgb8(const uint32_t* in, size_t W, size_t H, uin
     }
 }
 
+// copyOntoLargerVectorWithPadding, utils.cpp:710-741: the mirror padding of addReversedPadding on the planar
+// uint32 image of the OpenCL half.  (The reference's bottom loop indexes the *unpadded* input with x up to the new
+// width, i.e. it reads the next row -- and past the vector for the last plane -- in the bottom-right corner; here
+// the corner mirrors in both directions like the CPU path, utils.cpp:223-232.)
+__global__ void k_pad_planar_u32(const uint32_t* in, size_t W, size_t H, uint32_t* out, size_t nW, size_t nH) {
+    const size_t n = nW * nH;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % nW), y = (int)(i / nW);
+        const size_t s = (size_t)mirror(y, (int)H) * W + (size_t)mirror(x, (int)W);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[i + c * n] = in[s + c * W * H];
+    }
+}
+
+// everyMCUisnow1DArray, utils.cpp:501-515: planar int image (plane c at c*W*H) -> int[3*rpc][64], blocks in raster
+// order, planar by channel -- the block array of everyMCUisnow2DArray built from the OpenCL half's layout
+__global__ void k_blockify_planar_i32(const int32_t* in, size_t W, size_t H, int32_t* linear) {
+    const size_t n = W * H, rpc = n / 64, bx = W / 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t x = i % W, y = i / W;
+        const size_t blk = (y / 8) * bx + x / 8, k = (y & 7) * 8 + (x & 7);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) linear[(blk + rpc * c) * 64 + k] = in[i + c * n];
+    }
+}
+
+// copyDoubleToUIntImage, utils.cpp:249-259: (uint8_t) of a double (truncation; out-of-range values wrap like the
+// reference's x86-64 build: cvttsd2si, low byte)
+__global__ void k_f64_to_u8(const double* src, uint8_t* dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (uint8_t)(uint32_t)__double2int_rz(src[i]);
+}
+
+// getValueCategory / valueToBitString, utils.cpp:623-653, for n values: the very cat_bits() the entropy coder uses
+__global__ void k_value_categories(const int16_t* v, size_t n, uint8_t* cat, uint16_t* bits) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int c;
+        uint32_t vb;
+        cat_bits((int)v[i], c, vb);
+        cat[i] = (uint8_t)c;
+        bits[i] = (uint16_t)vb;
+    }
+}
+
+// removeRedChannel, utils.cpp:84-89 (the reference's "TEST FUNCTION"): r = 0 for every pixel
+__global__ void k_remove_red(uint8_t* px, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) px[3 * i] = 0;
+}
+
+int launch_pad_planar_u32(const uint32_t* in, size_t W, size_t H, uint32_t* out, size_t nW, size_t nH, cudaStream_t s) {
+    k_pad_planar_u32<<<grid_for(nW * nH, 256), 256, 0, s>>>(in, W, H, out, nW, nH);
+    return 1;
+}
+int launch_blockify_planar_i32(const int32_t* in, size_t W, size_t H, int32_t* linear, cudaStream_t s) {
+    k_blockify_planar_i32<<<grid_for(W * H, 256), 256, 0, s>>>(in, W, H, linear);
+    return 1;
+}
+int launch_f64_to_u8(const double* src, uint8_t* dst, size_t n, cudaStream_t s) {
+    k_f64_to_u8<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
+    return 1;
+}
+int launch_value_categories(const int16_t* v, size_t n, uint8_t* cat, uint16_t* bits, cudaStream_t s) {
+    k_value_categories<<<grid_for(n, 256), 256, 0, s>>>(v, n, cat, bits);
+    return 1;
+}
+int launch_remove_red(uint8_t* px, size_t n, cudaStream_t s) {
+    k_remove_red<<<grid_for(n, 256), 256, 0, s>>>(px, n);
+    return 1;
+}
+
 int launch_csc(uint8_t* px, size_t n, const uint32_t* ydown, cudaStream_t s) {
     k_csc<<<grid_for(n, 256), 256, 0, s>>>(px, n, ydown);
     return 1;

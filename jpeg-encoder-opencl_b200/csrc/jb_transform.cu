@@ -1307,8 +1307,9 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     plan_fast(a);
     if (!a.total_units) return 0;
     const int align16 = input_align(a), align = align16 == 16 ? 8 : align16;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);  // the context's device (jb_api sets it before every launch), not device 0
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (use_tc(a)) {  // tcgen05 kernels: units are runs of 16 MCUs (4:2:0) or 16 MCU pairs (8x8 MCUs)
         const bool is420 = a.g.sub == JB_SUB_420;
         a.tc_row_len = (uint32_t)(is420 ? a.fast_mcux : a.fast_mcux / 2);
@@ -1382,7 +1383,7 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
         const uint32_t my_entry = lane < n_here ? a.tie_list[e0 + lane] : 0u;
         // lane L decodes entry L once (block -> frame, MCU, component, first sample, zigzag position); the
         // fields travel to the whole warp by shuffles when the entry's turn comes
-        uint32_t d_xy, d_misc, d_flo, d_fhi;
+        uint32_t d_x0, d_y0, d_misc, d_flo, d_fhi;  // (two words for the origin: dimensions go up to 2^24 under JB_FLAG_CLAMP_SOF)
         int my_comp, my_nat;
         {
             const uint32_t gblock = my_entry >> 6, k = my_entry & 63;
@@ -1409,17 +1410,19 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
                 step = 1;
             }
             my_nat = c_zz[k];
-            d_xy = x0 | (y0 << 16);  // padded sizes stay below 2^16
+            d_x0 = x0;
+            d_y0 = y0;
             d_misc = (uint32_t)my_comp | (step << 2) | ((uint32_t)my_nat << 4);
             const unsigned long long foff = (unsigned long long)f * a.frame_stride;
             d_flo = (uint32_t)foff;
             d_fhi = (uint32_t)(foff >> 32);
         }
         for (int j = 0; j < n_here; ++j) {
-            const uint32_t xy = __shfl_sync(0xffffffffu, d_xy, j), misc = __shfl_sync(0xffffffffu, d_misc, j);
+            const uint32_t misc = __shfl_sync(0xffffffffu, d_misc, j);
             const unsigned long long foff =
                 ((unsigned long long)__shfl_sync(0xffffffffu, d_fhi, j) << 32) | __shfl_sync(0xffffffffu, d_flo, j);
-            const int x0 = (int)(xy & 0xFFFFu), y0 = (int)(xy >> 16), comp = (int)(misc & 3u), step = (int)((misc >> 2) & 3u);
+            const int x0 = (int)__shfl_sync(0xffffffffu, d_x0, j), y0 = (int)__shfl_sync(0xffffffffu, d_y0, j);
+            const int comp = (int)(misc & 3u), step = (int)((misc >> 2) & 3u);
             const int nat = (int)(misc >> 4), v = nat >> 3, u = nat & 7;
             Image im{a.rgb + foff, a.pitch, a.g.W, a.g.H, a.ydown};
 #pragma unroll

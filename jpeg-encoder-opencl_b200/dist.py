@@ -23,7 +23,9 @@ def plan_strips(height, mcu_px, restart_mcu_rows, world):
     """Split `height` pixel rows into `world` strips of whole restart intervals.
 
     restart_mcu_rows = MCU rows per restart interval.  Returns a list of
-    (row0, row1, first_interval) per rank; ranks beyond the available intervals get empty strips.
+    (row0, row1, first_interval, is_last) per rank; ranks beyond the available intervals get empty strips
+    (row0 == row1: nothing to encode, nothing to send).  is_last marks the strip that ends the image -- the one
+    that is coded without a trailing RSTn -- which is not rank world-1 when there are fewer intervals than ranks.
     """
     mcu_rows = -(-height // mcu_px)
     n_int = -(-mcu_rows // restart_mcu_rows)
@@ -32,7 +34,7 @@ def plan_strips(height, mcu_px, restart_mcu_rows, world):
         i0, i1 = shard_range(n_int, world, r)
         row0 = min(i0 * restart_mcu_rows * mcu_px, height)
         row1 = min(i1 * restart_mcu_rows * mcu_px, height)
-        out.append((row0, row1, i0))
+        out.append((row0, row1, i0, row1 == height and row1 > row0))
     return out
 
 
@@ -67,8 +69,11 @@ def gather_stitch(payload, header=None, trailer=None, dst=0, group=None):
     rank `dst` -- header + payload_0 + ... + payload_{n-1} + trailer -- without padding or a second copy.
 
     payload/header/trailer: 1-D uint8 torch tensors on the collective's device (header/trailer only matter on
-    `dst`).  One all-gather of the lengths, then point-to-point sends (NCCL over NVLink on GPUs, gloo on CPU)
-    received in place.  Returns (stitched tensor on dst / None elsewhere, lengths).
+    `dst`).  One all-gather of the lengths, then ONE grouped exchange: all receives are posted together
+    (batch_isend_irecv = ncclGroupStart ... ncclGroupEnd on GPUs, so the strips of all peers stream into `dst`
+    concurrently over NVLink; plain isend/irecv on gloo) and every strip is received in place.  This is the
+    library-collective form of the stitch; PeerStitch below is the one that needs no host round trip.
+    Returns (stitched tensor on dst / None elsewhere, lengths).
     """
     import torch
     import torch.distributed as dist
@@ -78,27 +83,108 @@ def gather_stitch(payload, header=None, trailer=None, dst=0, group=None):
     n = torch.tensor([payload.numel()], dtype=torch.int64, device=payload.device)
     sizes = torch.zeros(world, dtype=torch.int64, device=payload.device)
     dist.all_gather_into_tensor(sizes, n, group=group)
-    lengths = [int(v) for v in sizes.tolist()]
+    lengths = [int(v) for v in sizes.tolist()]  # the receive sizes must be known on the host: one sync per stitch
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     if rank != dst:
         if lengths[rank]:
-            dist.send(payload.contiguous(), dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, payload.contiguous(), peer(dst), group)]):
+                w.wait()
         return None, lengths
     nh = header.numel() if header is not None else 0
     nt = trailer.numel() if trailer is not None else 0
     out = torch.empty(nh + sum(lengths) + nt, dtype=torch.uint8, device=payload.device)
     if nh:
         out[:nh] = header
-    off = nh
+    ops, off = [], nh
     for r in range(world):
         if lengths[r]:
             if r == rank:
                 out[off: off + lengths[r]] = payload
             else:
-                dist.recv(out[off: off + lengths[r]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+                ops.append(dist.P2POp(dist.irecv, out[off: off + lengths[r]], peer(r), group))
         off += lengths[r]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
     if nt:
         out[off:] = trailer
     return out, lengths
+
+
+class PeerStitch:
+    """The strip stitch over NVLink peer memory, with no host round trip and no separate gather.
+
+    Rank `dst` owns the output file's buffer (a plain cudaMalloc through the library); every other rank maps it with
+    CUDA IPC.  One step, entirely stream-ordered on the encoder's stream:
+        jb_encode_strip_begin   transform + entropy coder up to the sizes; the strip's length stays on the device
+        all_gather_into_tensor  the N lengths (8 bytes per rank, NCCL)
+        cumsum                  every rank's offset = header + lengths of the ranks before it (device)
+        jb_encode_strip_finish  the final placement kernel stores the strip at dst's buffer + offset: on ranks other
+                                than dst these coalesced 128-bit stores ARE the NVLink transfer
+        all_reduce (1 word)     orders dst's later reads after every peer's stores
+    A rank that codes its strip in several calls (more than 2^26 blocks) stitches them locally with device-side running
+    offsets and pushes the result with jb_copy_bytes_device.  `cap` bytes are allocated on dst.
+    """
+
+    def __init__(self, enc, cap, dst=0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.enc, self.cap, self.dst, self.group = enc, int(cap), dst, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+        self.local = None
+        if self.rank == dst:
+            self.local = enc.device_alloc(self.cap)
+            handle.copy_(torch.from_numpy(enc.ipc_export(self.local)))
+        dist.broadcast(handle, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        self.base = self.local if self.rank == dst else enc.ipc_open(handle.cpu().numpy())
+        self.lens = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        self.mine = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.offs = torch.zeros(self.world + 1, dtype=torch.int64, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()  # the tensors above are used on the encoder's (non-blocking) stream from here on
+
+    def exchange_offsets(self, header_bytes):
+        """lens[r] <- every rank's self.mine; offs[r] = header_bytes + sum(lens[:r]); offs[world] = end of the data."""
+        import torch
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.lens, self.mine, group=self.group)
+        self.offs[0] = header_bytes
+        torch.cumsum(self.lens, 0, out=self.offs[1:])
+        self.offs[1:] += header_bytes
+        return self.offs
+
+    def fence(self):
+        """After this (stream-ordered) collective every peer's stores into dst's buffer have been issued and completed."""
+        import torch.distributed as dist
+        dist.all_reduce(self.flag, group=self.group)
+
+    def view(self, nbytes=None):
+        """dst's buffer as a torch uint8 tensor (dst only)."""
+        import torch
+
+        class _Buf:
+            pass
+        b = _Buf()
+        n = self.cap if nbytes is None else int(nbytes)
+        b.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (self.local, False), "version": 2}
+        t = torch.as_tensor(b, device=torch.device("cuda", torch.cuda.current_device()))
+        t._jb_keepalive = self
+        return t
+
+    def close(self):
+        """Collective: importers unmap first, then the owner frees."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        if self.rank != self.dst and self.base:
+            self.enc.ipc_close(self.base)
+        dist.barrier(group=self.group)
+        if self.local:
+            self.enc.device_free(self.local)
+        self.base = self.local = None
 
 
 def stitch(header, strips, eoi=b"\xff\xd9"):

@@ -301,4 +301,28 @@ void ref_switchVectorChannelOrdering(const uint32_t *in, size_t W, size_t H, uin
     memcpy(out, b.data(), b.size() * sizeof(cl_uint));
 }
 
+// The remaining helpers of utils.hpp that the product mirrors (utils.hpp:79, 95, 118, 123), called verbatim.
+void ref_removeRedChannel(uint8_t *px, size_t W, size_t H) {
+    ppm_t img{W, H, reinterpret_cast<rgb_pixel_t *>(px)};
+    removeRedChannel(&img);
+}
+void ref_copyDoubleToUIntImage(double *src, size_t W, size_t H, uint8_t *dst) {
+    ppm_d_t a{W, H, reinterpret_cast<rgb_pixel_d_t *>(src)};
+    ppm_t b{W, H, reinterpret_cast<rgb_pixel_t *>(dst)};
+    copyDoubleToUIntImage(&a, &b);
+}
+// The reference's bottom loop reads vInput[(oldH - diff) * oldW + x] with x up to newW (utils.cpp:733-740): past
+// the row, and for the last plane past the vector.  The input is therefore handed over with newW spare words at
+// its end so that the call is defined; the corner region it fills is not compared by the tests.
+void ref_copyOntoLargerVectorWithPadding(const uint32_t *in, size_t W, size_t H, uint32_t *out, size_t nW, size_t nH) {
+    std::vector<cl_uint> a(in, in + W * H * 3), b(nW * nH * 3);
+    a.resize(W * H * 3 + nW + 8, 0);
+    copyOntoLargerVectorWithPadding(a, b, (unsigned)W, (unsigned)H, (unsigned)nW, (unsigned)nH);
+    memcpy(out, b.data(), b.size() * sizeof(cl_uint));
+}
+void ref_everyMCUisnow1DArray(const int32_t *in, size_t W, size_t H, int32_t *out) {
+    std::vector<int> a(in, in + W * H * 3);
+    everyMCUisnow1DArray(a, out, (unsigned)W, (unsigned)H);
+}
+
 }  // extern "C"

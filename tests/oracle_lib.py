@@ -119,6 +119,11 @@ def ref(o0=False):
     L.ref_quant_tables.argtypes = [u32p, u32p]
     L.ref_copyImageToVector.argtypes = [u8p, sz, sz, u32p]
     L.ref_switchVectorChannelOrdering.argtypes = [u32p, sz, sz, u32p]
+    for name, at in (("ref_removeRedChannel", [u8p, sz, sz]), ("ref_copyDoubleToUIntImage", [f64p, sz, sz, u8p]),
+                     ("ref_copyOntoLargerVectorWithPadding", [u32p, sz, sz, u32p, sz, sz]),
+                     ("ref_everyMCUisnow1DArray", [i32p, sz, sz, i32p])):
+        if hasattr(L, name):  # a prebuilt harness from an earlier round lacks them
+            getattr(L, name).argtypes = at
     L.ref_run_pipeline.argtypes = [u8p, sz, sz, C.c_int, vp, vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp]
     _ref[path] = L
     return L

@@ -94,11 +94,43 @@ def test_fails_loudly_without_gpu(jb):
     assert e.value.code == jb.E_CUDA
 
 
+REF_DRIVER = "/root/reference/src/OpenCLProject_JpegEncoder.cpp"
+REF_HEADER = "/root/reference/src/utils.hpp"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="the reference sources are not on this machine")
+def test_reference_driver_compiles_against_the_compat_header(tmp_path):
+    """The reference's own JpegEncoderHost (cpp:28-250), unmodified, compiles against host/utils_compat.hpp +
+    host/core_compat.hpp (oracle/Makefile also links it with libjpegb200.so into oracle/_ref/ref_host_b200, which the
+    GPU tests run)."""
+    import subprocess
+    lines = open(REF_DRIVER).read().split("\n")[27:250]
+    src = tmp_path / "ref_host.cpp"
+    src.write_text("#include <cmath>\n#include <fstream>\n#include <sstream>\n#include \"utils_compat.hpp\"\n"
+                   "#include \"core_compat.hpp\"\n" + "\n".join(lines) + "\n")
+    r = subprocess.run(["g++", "-std=c++17", "-w", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"),
+                        "-I" + os.path.join(ROOT, "jpeg-encoder-opencl_b200", "host"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HEADER), reason="the reference sources are not on this machine")
+def test_compat_header_declares_every_name_of_utils_hpp():
+    """Every function and type name the reference's utils.hpp declares (utils.hpp:7-137) exists in utils_compat.hpp."""
+    ref = re.sub(r"//.*", "", open(REF_HEADER).read())
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", ref)) - {"FIX", "defined"}
+    names |= set(re.findall(r"\b(?:struct|typedef struct \w+)\s+(\w+)", ref))
+    text = open(os.path.join(ROOT, "jpeg-encoder-opencl_b200", "host", "utils_compat.hpp")).read()
+    missing = sorted(n for n in names if not re.search(rf"\b{n}\b", text))
+    assert not missing, missing
+
+
 def test_compat_header_covers_the_reference_surface():
     """utils_compat.hpp re-declares the reference's stage functions (utils.hpp:81-137) by name."""
     text = open(os.path.join(ROOT, "jpeg-encoder-opencl_b200", "host", "utils_compat.hpp")).read()
     for name in ("performCSC", "performCDS", "getNearest8x8ImageSize", "copyToLargerImage", "addReversedPadding",
                  "copyUIntToDoubleImage", "substractfromAll", "performDCT", "performQuantization",
                  "everyMCUisnow2DArray", "performZigZag", "performRLE", "HuffmanEncoder", "readPPMImage",
-                 "writePPMImage", "quant_mat_lum", "quant_mat_chrom", "copyImageToVector", "switchVectorChannelOrdering"):
+                 "writePPMImage", "quant_mat_lum", "quant_mat_chrom", "copyImageToVector", "switchVectorChannelOrdering",
+                 "CPUTelemetry", "removeRedChannel", "getValueCategory", "valueToBitString", "everyMCUisnow1DArray",
+                 "copyOntoLargerVectorWithPadding", "writeVectorToFile", "copyDoubleToUIntImage", "previewImage"):
         assert re.search(rf"\b{name}\b", text), name

@@ -44,9 +44,9 @@ def _worker(rank, world, port, q):
         ql, qc = ol.quality_tables(75)
         mcux = W // 16
         plan = D.plan_strips(H, 16, 1, world)
-        row0, row1, first = plan[rank]
+        row0, row1, first, is_last = plan[rank]
         coef = ol.transform(img[row0:row1], ol.SUB_420, ql, qc)
-        seg, _ = ol.entropy(coef, ol.SUB_420, mcux, rst_phase=first, final_rst=rank != world - 1)
+        seg, _ = ol.entropy(coef, ol.SUB_420, mcux, rst_phase=first, final_rst=not is_last)
         parts, lengths = D.gather_bytes(torch.from_numpy(seg.copy()), dst=0)
         assert lengths[rank] == len(seg)
         ok = True
@@ -64,10 +64,11 @@ def _worker(rank, world, port, q):
         # ---- fewer restart intervals than ranks: the last rank's strip is empty and sends nothing ----
         small = ol.synth(78, 64, 16)
         plan1 = D.plan_strips(16, 16, 1, world)
-        r0, r1, f1 = plan1[rank]
+        r0, r1, f1, last1 = plan1[rank]
+        assert last1 == (rank == 0)  # the strip that ends the image is rank 0's, not rank world-1's
         if r1 > r0:
             c1 = ol.transform(small[r0:r1], ol.SUB_420, ql, qc)
-            seg1, _ = ol.entropy(c1, ol.SUB_420, 4, rst_phase=f1, final_rst=False)
+            seg1, _ = ol.entropy(c1, ol.SUB_420, 4, rst_phase=f1, final_rst=not last1)
         else:
             seg1 = np.zeros(0, np.uint8)
         hdr1 = torch.from_numpy(np.frombuffer(ol.jfif_header(64, 16, ol.SUB_420, ql, qc, 4), np.uint8).copy())
@@ -118,3 +119,8 @@ def test_shard_and_strip_plans():
     plan = D.plan_strips(1080, 16, 1, 4)
     assert plan[-1][1] == 1080 and sum(p[1] - p[0] for p in plan) == 1080
     assert all(p[0] % 16 == 0 for p in plan)
+    assert [p[3] for p in plan] == [False, False, False, True]
+    # fewer restart intervals than ranks: empty strips at the end, and the LAST NON-EMPTY strip ends the image
+    plan = D.plan_strips(40, 16, 1, 8)  # 3 MCU rows on 8 ranks
+    assert [p[1] - p[0] for p in plan] == [16, 16, 8, 0, 0, 0, 0, 0]
+    assert [p[3] for p in plan] == [False, False, True, False, False, False, False, False]

@@ -80,3 +80,85 @@ def test_cli_writes_the_same_jfif(tmp_path, enc, jb, fruit):
     assert data == ol.encode_jfif(fruit, ol.SUB_420, ql, qc, 16)
     assert np.array(Image.open(io.BytesIO(data))).shape == fruit.shape
     assert "MP/s" in r.stdout
+
+
+# ---- the rest of utils.hpp's surface (round 2): helpers of the reference's driver and of its OpenCL half ----------
+def test_value_categories_equal_the_reference_for_every_int16(enc):
+    """getValueCategory / valueToBitString (utils.cpp:623-653) on the device function the entropy coder uses, for every
+    int16 the reference's functions are defined on, against the oracle and -- when it is built -- the reference itself."""
+    v = np.arange(-32767, 32768, dtype=np.int16)
+    cat, bits = enc.valueCategories(v)
+    L = ol.oracle()
+    import ctypes as C
+    R = ol.ref() if ol.have_ref() else None
+    buf = C.create_string_buffer(32)
+    for i in list(range(0, v.size, 97)) + list(range(32767 - 2100, 32767 + 2100)):
+        x = int(v[i])
+        w = C.c_uint32()
+        c = L.orc_value_bits(x, C.byref(w))
+        assert c == int(cat[i]) == L.orc_category(x) and int(bits[i]) == w.value, x
+        if R is not None:
+            assert R.ref_getValueCategory(x) == c
+            n = R.ref_valueToBitString(x, buf)
+            assert n == c and buf.value[:n].decode() == (format(int(bits[i]), "0%db" % c) if c else "")
+
+
+def test_helpers_of_the_opencl_half(enc):
+    """copyOntoLargerVectorWithPadding (utils.cpp:710-741), everyMCUisnow1DArray (:501-515), removeRedChannel (:84-89),
+    copyDoubleToUIntImage (:249-259) against the reference's own functions."""
+    rng = np.random.default_rng(11)
+    W, H, nW, nH = 45, 37, 48, 40
+    rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    planar = enc.copyImageToVector(rgb)
+    padded = enc.copyOntoLargerVectorWithPadding(planar, W, H, nW, nH).reshape(3, nH, nW)
+    want = np.stack([np.pad(rgb[:, :, c].astype(np.uint32), ((0, nH - H), (0, nW - W)), mode="symmetric") for c in range(3)])
+    assert np.array_equal(padded, want)  # mirror including the edge, corner mirrored both ways (utils.cpp:211-233)
+    ints = rng.integers(-2000, 2000, 3 * nW * nH).astype(np.int32)
+    lin = enc.everyMCUisnow1DArray(ints, nW, nH)
+    img = ints.reshape(3, nH // 8, 8, nW // 8, 8).transpose(0, 1, 3, 2, 4).reshape(-1, 64)
+    assert np.array_equal(lin, img)
+    d = rng.uniform(0, 255.9, (H, W, 3))
+    assert np.array_equal(enc.copyDoubleToUIntImage(d), d.astype(np.uint8))
+    nored = enc.removeRedChannel(rgb.copy())
+    assert not nored[:, :, 0].any() and np.array_equal(nored[:, :, 1:], rgb[:, :, 1:])
+    if ol.have_ref() and hasattr(ol.ref(), "ref_everyMCUisnow1DArray"):
+        R = ol.ref()
+        out = np.zeros(3 * nW * nH, np.uint32)
+        R.ref_copyOntoLargerVectorWithPadding(planar, W, H, out, nW, nH)
+        out = out.reshape(3, nH, nW)
+        assert np.array_equal(out[:, :H, :], padded[:, :H, :]) and np.array_equal(out[:, H:, :W], padded[:, H:, :W])
+        lin2 = np.zeros_like(lin)
+        R.ref_everyMCUisnow1DArray(ints, nW, nH, lin2)
+        assert np.array_equal(lin, lin2)
+        a = rgb.copy()
+        R.ref_removeRedChannel(a, W, H)
+        assert np.array_equal(a, nored)
+        b = np.zeros((H, W, 3), np.uint8)
+        R.ref_copyDoubleToUIntImage(np.ascontiguousarray(d), W, H, b)
+        assert np.array_equal(b, enc.copyDoubleToUIntImage(d))
+
+
+REF_HOST = os.path.join(ROOT, "oracle", "_ref", "ref_host_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HOST), reason="oracle/_ref/ref_host_b200 was not built (needs /root/reference at build time)")
+def test_the_references_own_driver_function_runs_on_the_gpu(tmp_path, golden):
+    """JpegEncoderHost (src/OpenCLProject_JpegEncoder.cpp:28-250) compiled UNMODIFIED against utils_compat.hpp and linked
+    with libjpegb200.so: it runs, fills CPUTelemetry, and the PPM dumps it writes between the stages carry the
+    reference's own bytes (padded YCbCr after CSC + CDS + mirror padding: SURVEY 8c digest a19bc1f1...)."""
+    import hashlib
+    (tmp_path / "data").mkdir()
+    (tmp_path / "run").mkdir()
+    r = subprocess.run([REF_HOST, os.path.join(GOLDEN, "fruit.ppm")], capture_output=True, text=True, timeout=300,
+                       cwd=str(tmp_path / "run"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for label in ("CSC", "CDS", "Total Copy", "Level Shifting", "DCT", "Quantization", "ZigZag", "RLE", "Huffman", "Total"):
+        assert f"{label} Time CPU:" in r.stdout, label  # the reference's own output lines (it calls every stage "CPU")
+    m = re.search(r"telemetry_us CSC (\d+) CDS (\d+) levelShift (\d+) DCT (\d+) Quant (\d+) TotalCopy (\d+) zigZag (\d+) RLE (\d+) Huffman (\d+)", r.stdout)
+    assert m and int(m.group(4)) > 0 and int(m.group(9)) > 0
+    padded = ol.read_ppm(str(tmp_path / "data" / "fruitCPU_copy_larger_padded.ppm"))
+    assert padded.shape == (256, 256, 3)
+    assert hashlib.sha256(padded.tobytes()).hexdigest() == "a19bc1f13b7d3327ddd8ca495dd704331c4852ec228d23b36a78e69590d289b3"
+    nored = ol.read_ppm(str(tmp_path / "data" / "fruitCPU_no_blue.ppm"))
+    fruit = ol.read_ppm(os.path.join(GOLDEN, "fruit.ppm"))
+    assert not nored[:, :, 0].any() and np.array_equal(nored[:, :, 1:], fruit[:, :, 1:])

@@ -11,7 +11,7 @@ import oracle_lib as ol
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("seed", [7, 8, 21, 22, 23, 24])
 def test_random_shapes_modes_and_contents(jb, seed):
     enc = jb.Encoder(0)
     rng = np.random.default_rng(seed)

@@ -29,8 +29,8 @@ def _worker(rank, world, port, q):
         W, H = 2048, 1000  # the last strip ends in a partial MCU row (mirror padding)
         img = enc.synth(0xABCD, W, H)
         p = jb.make_params(jb.SUB_420, quality=75, restart_interval=W // 16)
-        row0, row1, first = D.plan_strips(H, 16, 1, world)[rank]
-        seg = enc.encode_strip(np.ascontiguousarray(img[row0:row1]), p, first, rank == world - 1)
+        row0, row1, first, is_last = D.plan_strips(H, 16, 1, world)[rank]
+        seg = enc.encode_strip(np.ascontiguousarray(img[row0:row1]), p, first, is_last)
         parts, lengths = D.gather_bytes(torch.from_numpy(seg).cuda(), dst=0)
         ok = True
         if rank == 0:
@@ -41,6 +41,61 @@ def _worker(rank, world, port, q):
         whole, lengths2 = D.gather_stitch(torch.from_numpy(seg).cuda(), hdr, eoi, dst=0)  # received in place
         if rank == 0:
             ok = ok and lengths2 == lengths and bytes(whole.cpu().numpy()) == enc.encode_jfif(img, p)
+        # ---- the same stitch over NVLink peer memory: no host round trip, the placement kernel of every rank stores
+        # its strip straight into rank 0's buffer at the offset computed on the device (dist.PeerStitch)
+        want = enc.encode_jfif(img, p) if rank == 0 else None
+        ext = torch.cuda.ExternalStream(enc.stream())
+        d_img = torch.from_numpy(np.ascontiguousarray(img[row0:row1])).cuda()
+        ps = D.PeerStitch(enc, cap=W * H + 65536, dst=0)
+        hdr_n = hdr.numel()
+        for rep in range(3):  # repeated: the pinned staging ring and the workspace are reused
+            with torch.cuda.stream(ext):
+                enc.encode_strip_begin(d_img.data_ptr(), p, first, is_last, W, row1 - row0, W * 3, ps.mine.data_ptr())
+                offs = ps.exchange_offsets(hdr_n)
+                enc.encode_strip_finish(ps.base, ps.cap, offs[rank:].data_ptr())
+                ps.fence()
+            enc.sync()
+            if rank == 0:
+                total = int(offs[world].item())
+                out = ps.view()
+                out[:hdr_n] = hdr
+                out[total: total + 2] = eoi
+                torch.cuda.synchronize()
+                ok = ok and bytes(out[: total + 2].cpu().numpy()) == want
+        # ---- a rank that codes its strip in two calls: local stitch with device-side running offsets, then one push
+        half = ((row1 - row0) // 32) * 16
+        if half and row1 - row0 - half:
+            local = torch.empty(W * H, dtype=torch.uint8, device="cuda")
+            run = torch.zeros(3, dtype=torch.int64, device="cuda")
+            with torch.cuda.stream(ext):
+                enc.encode_strip_begin(d_img.data_ptr(), p, first, False, W, half, W * 3, ps.mine.data_ptr())
+                enc.encode_strip_finish(local.data_ptr(), local.numel(), run[0:].data_ptr())
+                torch.add(run[0], ps.mine[0], out=run[1])
+                enc.encode_strip_begin(d_img.data_ptr() + half * W * 3, p, first + half // 16, is_last, W, row1 - row0 - half, W * 3,
+                                       ps.mine.data_ptr())
+                enc.encode_strip_finish(local.data_ptr(), local.numel(), run[1:].data_ptr())
+                torch.add(run[1], ps.mine[0], out=run[2])
+                ps.mine.copy_(run[2:3])
+                offs = ps.exchange_offsets(hdr_n)
+                enc.copy_bytes_device(ps.base, ps.cap, offs[rank:].data_ptr(), local.data_ptr(), run[2:].data_ptr())
+                ps.fence()
+            enc.sync()
+            if rank == 0:
+                total = int(offs[world].item())
+                out = ps.view()
+                out[total: total + 2] = eoi
+                torch.cuda.synchronize()
+                ok = ok and bytes(out[: total + 2].cpu().numpy()) == want
+        # ---- fewer restart intervals than ranks: the strip that ends the image is rank 0's; rank 1 has nothing to code
+        small = enc.synth(0x51, 256, 16)
+        p1 = jb.make_params(jb.SUB_420, quality=75, restart_interval=16)
+        r0, r1, f1, last1 = D.plan_strips(16, 16, 1, world)[rank]
+        seg1 = enc.encode_strip(np.ascontiguousarray(small[r0:r1]), p1, f1, last1) if r1 > r0 else np.zeros(0, np.uint8)
+        hdr1 = torch.from_numpy(np.frombuffer(enc.write_header(p1, 256, 16), np.uint8).copy()).cuda()
+        whole1, len1 = D.gather_stitch(torch.from_numpy(seg1).cuda(), hdr1, eoi, dst=0)
+        if rank == 0:
+            ok = ok and len1[1] == 0 and bytes(whole1.cpu().numpy()) == enc.encode_jfif(small, p1)
+        ps.close()
         q.put((rank, bool(ok), lengths))
         enc.close()
     finally:

@@ -624,3 +624,160 @@ def test_fused_path_reproduces_the_reference_as_written(enc, jb, fruit, golden):
     with pytest.raises(jb.JbError) as e:
         enc.transform(fruit, jb.make_params(ol.SUB_REPL420, qlum=ql, qchrom=qc, flags=flags | jb.FLAG_FMA_DCT))
     assert e.value.code == jb.E_UNSUPPORTED
+
+
+# ------------------------------------------------ whole frames at the benchmark's sizes against the oracle (round 2) ----
+
+@pytest.mark.parametrize("sub", SUBS)
+def test_whole_1080p_frame_equals_the_oracle(enc, jb, sub):
+    """One full 1920x1080 frame of the batch configuration per subsampling mode: coefficients and the JFIF file equal the
+    oracle's, byte for byte (1080 = 67.5 MCU rows of 16: the last MCU row is mirrored inside the hot kernel)."""
+    img = enc.synth(0xF000 + 17, 1920, 1080)
+    assert np.array_equal(img, ol.synth(0xF000 + 17, 1920, 1080))
+    for q, ri in ((75, 0), (50, 120)):
+        ql, qc = ol.quality_tables(q)
+        p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri)
+        got, want = enc.transform(img, p), ol.transform(img, sub, ql, qc)
+        assert np.array_equal(got, want), f"{SUBNAME[sub]} q{q}: " + mismatch_report(got, want)
+        assert enc.encode_jfif(img, p) == ol.encode_jfif(img, sub, ql, qc, ri), f"{SUBNAME[sub]} q{q} ri {ri}"
+
+
+def test_config2_whole_4k_frame_equals_the_oracle(enc, jb):
+    """Config #2 in full: the 3840x2160 4:4:4 q90 file (no restart markers, as the benchmark codes it) == the oracle's."""
+    img = enc.synth(0x4B3840, 3840, 2160)
+    ql, qc = ol.quality_tables(90)
+    p = jb.make_params(ol.SUB_444, qlum=ql, qchrom=qc)
+    assert enc.encode_jfif(img, p) == ol.encode_jfif(img, ol.SUB_444, ql, qc, 0)
+
+
+def test_config3_whole_8k_frame_equals_the_oracle(enc, jb):
+    """Config #3 in full: the 7680x4320 4:2:0 q75 file with DRI = one MCU row == the oracle's."""
+    img = enc.synth(0x4B7680, 7680, 4320)
+    ql, qc = ol.quality_tables(75)
+    p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, restart_interval=480)
+    got, want = enc.transform(img, p), ol.transform(img, ol.SUB_420, ql, qc)
+    assert np.array_equal(got, want), mismatch_report(got, want)
+    assert enc.encode_jfif(img, p, cap=7680 * 4320) == ol.encode_jfif(img, ol.SUB_420, ql, qc, 480)
+
+
+@pytest.mark.parametrize("sub", [ol.SUB_420, ol.SUB_444])
+def test_wider_and_taller_than_65536_with_clamped_sof(enc, jb, sub):
+    """Dimensions above 2^16 (JB_FLAG_CLAMP_SOF): every coordinate of the pipeline -- including the block origins that
+    the binary64 near-tie replay unpacks -- is 32 bits wide.  Noise at q100 flags thousands of coefficients beyond
+    x = 65536 (resp. y = 65536); coefficients == oracle."""
+    rng = np.random.default_rng(65536)
+    ql, qc = ol.quality_tables(100)
+    p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=0, flags=jb.FLAG_CLAMP_SOF)
+    for W, H in ((65536 + 2048, 16), (64, 65536 + 1024)):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        got, want = enc.transform(img, p), ol.transform(img, sub, ql, qc)
+        assert enc.timings()["tie_fixups"] > 100
+        assert np.array_equal(got, want), f"{W}x{H}: " + mismatch_report(got, want)
+    with pytest.raises(jb.JbError) as e:
+        enc.transform(np.zeros((16, 65536 + 48, 3), np.uint8), jb.make_params(sub, qlum=ql, qchrom=qc))  # no JB_FLAG_CLAMP_SOF
+    assert e.value.code == jb.E_UNSUPPORTED
+
+
+def test_back_to_back_device_calls_keep_their_own_headers(enc, jb):
+    """jb_encode_batch_device is asynchronous: several calls with DIFFERENT headers (size, restart interval) queued
+    without jb_sync must each get their own header and status (pinned staging ring, jb_api.cu)."""
+    import torch
+    shapes = [(64, 48, 0), (80, 32, 2), (48, 64, 3), (96, 16, 0), (32, 32, 1), (128, 48, 4)]
+    ql, qc = ol.quality_tables(75)
+    imgs = [ol.synth(900 + i, w, h) for i, (w, h, _) in enumerate(shapes)]
+    d_in = [torch.from_numpy(im.copy()).cuda() for im in imgs]
+    d_out = [torch.zeros(w * h * 3 + 4096, dtype=torch.uint8, device="cuda") for w, h, _ in shapes]
+    d_tab = [torch.zeros(3, dtype=torch.int64, device="cuda") for _ in shapes]
+    torch.cuda.synchronize()
+    for rep in range(2):
+        for i, (w, h, ri) in enumerate(shapes):
+            p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, restart_interval=ri)
+            enc.encode_batch_device(d_in[i].data_ptr(), 1, w, h, w * 3, w * h * 3, p, d_out[i].data_ptr(), d_out[i].numel(),
+                                    d_tab[i].data_ptr(), d_tab[i].data_ptr() + 8, d_tab[i].data_ptr() + 16)
+        enc.sync()
+        for i, (w, h, ri) in enumerate(shapes):
+            n = int(d_tab[i][2].item())
+            assert bytes(d_out[i][:n].cpu().numpy()) == ol.encode_jfif(imgs[i], ol.SUB_420, ql, qc, ri), f"call {i}"
+    # a too-small caller buffer in the middle of the queue is reported by jb_sync, the other calls are intact
+    p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc)
+    enc.encode_batch_device(d_in[0].data_ptr(), 1, 64, 48, 192, 64 * 48 * 3, p, d_out[0].data_ptr(), 700, d_tab[0].data_ptr(),
+                            d_tab[0].data_ptr() + 8, d_tab[0].data_ptr() + 16)
+    enc.encode_batch_device(d_in[1].data_ptr(), 1, 80, 32, 240, 80 * 32 * 3, p, d_out[1].data_ptr(), d_out[1].numel(), d_tab[1].data_ptr(),
+                            d_tab[1].data_ptr() + 8, d_tab[1].data_ptr() + 16)
+    with pytest.raises(jb.JbError) as e:
+        enc.sync()
+    assert e.value.code == jb.E_NOSPACE
+    n = int(d_tab[1][2].item())
+    assert bytes(d_out[1][:n].cpu().numpy()) == ol.encode_jfif(imgs[1], ol.SUB_420, ql, qc, 0)
+
+
+def test_batch_reports_the_size_of_the_whole_batch_on_overflow(enc, jb):
+    """JB_E_NOSPACE from jb_encode_batch: jb_required_bytes() is what the WHOLE batch needs (several in-flight groups),
+    and a second call with that capacity succeeds."""
+    frames = np.stack([ol.synth(70 + f, 2048, 1536) for f in range(24)])  # 24 x 9.4 MB: three groups of 96 MB
+    p = jb.make_params(ol.SUB_420, quality=75)
+    small = np.empty(1 << 20, np.uint8)
+    with pytest.raises(jb.JbError) as e:
+        enc.encode_batch(frames, p, out=small)
+    assert e.value.code == jb.E_NOSPACE
+    need = enc.L.jb_required_bytes(enc.h)
+    out, offs, sizes = enc.encode_batch(frames, p, out=np.empty(need, np.uint8))
+    assert int(sizes.sum()) == need and int(offs[-1] + sizes[-1]) == need
+    ql, qc = ol.quality_tables(75)
+    for f in (0, 23):
+        assert bytes(out[int(offs[f]): int(offs[f] + sizes[f])]) == ol.encode_jfif(frames[f], ol.SUB_420, ql, qc, 0)
+
+
+def test_strip_in_two_asynchronous_halves(enc, jb):
+    """jb_encode_strip_begin / _finish on one GPU: the strip written at a device-side offset equals jb_encode_strip, for
+    aligned and odd offsets, chained calls (running offsets kept on the device) and jb_copy_bytes_device."""
+    import torch
+    W, H = 1024, 208
+    img = ol.synth(0x77, W, H)
+    ql, qc = ol.quality_tables(75)
+    p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, restart_interval=W // 16)
+    want = enc.encode_strip(img, p, 0, True)
+    d_img = torch.from_numpy(img.copy()).cuda()
+    ext = torch.cuda.ExternalStream(enc.stream())
+    out = torch.zeros(W * H, dtype=torch.uint8, device="cuda")
+    for off0 in (0, 1, 13, 16, 4099):
+        ln = torch.zeros(1, dtype=torch.int64, device="cuda")
+        off = torch.tensor([off0], dtype=torch.int64, device="cuda")
+        out.zero_()
+        torch.cuda.synchronize()
+        enc.encode_strip_begin(d_img.data_ptr(), p, 0, True, W, H, W * 3, ln.data_ptr())
+        enc.encode_strip_finish(out.data_ptr(), out.numel(), off.data_ptr())
+        enc.sync()
+        n = int(ln.item())
+        assert n == len(want) and np.array_equal(out[off0: off0 + n].cpu().numpy(), want)
+        assert not out[:off0].any() and not out[off0 + n: off0 + n + 64].any()
+    # two chained halves with running offsets on the device == the whole strip; then pushed elsewhere with copy_bytes
+    run = torch.zeros(3, dtype=torch.int64, device="cuda")
+    run[0] = 5
+    out.zero_()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(ext):
+        enc.encode_strip_begin(d_img.data_ptr(), p, 0, False, W, 96, W * 3, run.data_ptr() + 8)
+        enc.encode_strip_finish(out.data_ptr(), out.numel(), run.data_ptr())
+        run[1] += run[0]
+        enc.encode_strip_begin(d_img.data_ptr() + 96 * W * 3, p, 6, True, W, H - 96, W * 3, run.data_ptr() + 16)
+        enc.encode_strip_finish(out.data_ptr(), out.numel(), run.data_ptr() + 8)
+        run[2] += run[1]
+    enc.sync()
+    end = int(run[2].item())
+    assert end - 5 == len(want) and np.array_equal(out[5:end].cpu().numpy(), want)
+    for dst_off, src_off in ((0, 5), (3, 5), (16, 6), (7, 8)):
+        dst = torch.zeros(W * H, dtype=torch.uint8, device="cuda")
+        o = torch.tensor([dst_off], dtype=torch.int64, device="cuda")
+        ln = torch.tensor([end - src_off], dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        enc.copy_bytes_device(dst.data_ptr(), dst.numel(), o.data_ptr(), out.data_ptr() + src_off, ln.data_ptr())
+        enc.sync()
+        assert torch.equal(dst[dst_off: dst_off + end - src_off], out[src_off:end]) and not dst[dst_off + end - src_off:][:64].any()
+        assert not dst[:dst_off].any()
+    # a destination that is too small is reported at jb_sync and nothing is written
+    enc.encode_strip_begin(d_img.data_ptr(), p, 0, True, W, H, W * 3, run.data_ptr())
+    enc.encode_strip_finish(out.data_ptr(), 100, run.data_ptr() + 8)
+    with pytest.raises(jb.JbError) as e:
+        enc.sync()
+    assert e.value.code == jb.E_NOSPACE
