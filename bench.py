@@ -58,8 +58,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of sampled frames after the timed region")
     ap.add_argument("--no-others", action="store_true", help="skip the brief runs of the other single-GPU workloads")
-    ap.add_argument("--stitch", default="peer", choices=["peer", "nccl"],
-                    help="strip workloads: peer = placement kernel stores through NVLink peer memory (default), nccl = grouped send/recv")
+    ap.add_argument("--stitch", default="peer", choices=["peer", "peer-nccl", "nccl"],
+                    help="strip workloads: peer = placement kernel stores through NVLink peer memory, lengths / completion as "
+                         "flags on peer memory (default); peer-nccl = same placement, lengths by NCCL all-gather; nccl = grouped send/recv")
     ap.add_argument("--optimize-huffman", action="store_true",
                     help="JB_FLAG_OPTIMIZE_HUFFMAN: per-call optimal Huffman tables (two passes; not the headline configuration)")
     ap.add_argument("--ref-exact", action="store_true",
@@ -428,7 +429,7 @@ def run_strips(a, jb, enc, torch, dd):
     plan = D.plan_strips(H, 16, 1, world)
     row0, row1, first, is_last = plan[rank]
     rows, pitch = row1 - row0, W * 3
-    chunk = 8192  # rows per call (keeps every call below 2^26 blocks)
+    chunk = 16384  # rows per call (keeps every call below 2^26 blocks at W = 65536)
     chunks = [(y, min(chunk, rows - y)) for y in range(0, rows, chunk)]
     d_rgb = torch.empty(max(rows, 1) * pitch, dtype=torch.uint8, device="cuda")
     for y in range(0, rows, 1024):
@@ -445,7 +446,7 @@ def run_strips(a, jb, enc, torch, dd):
     ext = torch.cuda.ExternalStream(enc.stream())
     mode = a.stitch if world > 1 else "single"
     ps = None
-    if world > 1 and mode == "peer":
+    if world > 1 and mode.startswith("peer"):
         try:
             ps = D.PeerStitch(enc, cap_file, dst=0)
         except Exception as e:  # no CUDA IPC between the ranks (containers without a shared IPC namespace)
@@ -485,11 +486,17 @@ def run_strips(a, jb, enc, torch, dd):
                 end = run[len(chunks):]
                 own.index_copy_(0, end + two, eoi)
                 return end
+            def offsets():  # -> (pointer to this rank's offset, device tensor [end of the data])
+                if mode == "peer":
+                    off2 = ps.exchange(hdr_n)
+                    return off2.data_ptr(), off2[1:]
+                offs = ps.exchange_offsets(hdr_n)
+                return offs.data_ptr() + 8 * rank, offs[world:]
             if len(chunks) == 1:      # the fused form: placement kernel -> peer memory
                 y, n = chunks[0]
                 enc.encode_strip_begin(d_rgb.data_ptr(), params, first, is_last, W, n, pitch, ps.mine.data_ptr())
-                offs = ps.exchange_offsets(hdr_n)
-                enc.encode_strip_finish(ps.base, cap_file, offs.data_ptr() + 8 * rank)
+                p_off, end = offsets()
+                enc.encode_strip_finish(ps.base, cap_file, p_off)
             else:                     # several calls per rank: local stitch with device-side running offsets, one push
                 run[0] = 0
                 for c, (y, n) in enumerate(chunks):
@@ -498,10 +505,12 @@ def run_strips(a, jb, enc, torch, dd):
                     enc.encode_strip_finish(local.data_ptr(), cap_local, run.data_ptr() + 8 * c)
                     run[c + 1] += run[c]
                 ps.mine.copy_(run[len(chunks):])
-                offs = ps.exchange_offsets(hdr_n)
-                enc.copy_bytes_device(ps.base, cap_file, offs.data_ptr() + 8 * rank, local.data_ptr(), run.data_ptr() + 8 * len(chunks))
-            ps.fence()
-            end = offs[world:]
+                p_off, end = offsets()
+                enc.copy_bytes_device(ps.base, cap_file, p_off, local.data_ptr(), run.data_ptr() + 8 * len(chunks))
+            if mode == "peer":
+                ps.complete()
+            else:
+                ps.fence()
             if rank == 0:
                 ps.view().index_copy_(0, end + two, eoi)
             return end
@@ -548,8 +557,8 @@ def run_strips(a, jb, enc, torch, dd):
             final = res[0]
             total = int(final.numel())
     lens = None
-    if world > 1 and ps is not None:
-        lens = [int(v) for v in ps.lens.cpu().tolist()]
+    if world > 1 and ps is not None and rank == 0:
+        lens = ps.lengths() if mode == "peer" else [int(v) for v in ps.lens.cpu().tolist()]
 
     # ---- stage times of one step on this rank (event-timed, outside the timed region) -----------------------
     stage_ms = None
@@ -560,17 +569,23 @@ def run_strips(a, jb, enc, torch, dd):
             evs[0].record()
             enc.encode_strip_begin(d_rgb.data_ptr(), params, first, is_last, W, rows, pitch, ps.mine.data_ptr())
             evs[1].record()
-            offs = ps.exchange_offsets(hdr_n)
+            if mode == "peer":
+                p_off = ps.exchange(hdr_n).data_ptr()
+            else:
+                p_off = ps.exchange_offsets(hdr_n).data_ptr() + 8 * rank
             evs[2].record()
-            enc.encode_strip_finish(ps.base, cap_file, offs.data_ptr() + 8 * rank)
-            ps.fence()
+            enc.encode_strip_finish(ps.base, cap_file, p_off)
+            if mode == "peer":
+                ps.complete()
+            else:
+                ps.fence()
             evs[3].record()
         enc.sync()
         torch.cuda.synchronize()
         mine_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(3)]
         t = torch.tensor(mine_ms, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        stage_ms = dict(zip(["encode_to_sizes", "lengths_allgather_cumsum", "placement_over_nvlink_and_fence"], [round(float(v), 4) for v in t.tolist()]))
+        stage_ms = dict(zip(["encode_to_sizes", "lengths_exchange", "placement_over_nvlink_and_completion"], [round(float(v), 4) for v in t.tolist()]))
 
     # ---- parity of the stitched file (outside the timing) ----------------------------------------------------
     parity = None
@@ -654,8 +669,8 @@ def run_strips(a, jb, enc, torch, dd):
         payload = (total - (lens[0] if lens else total)) if world > 1 else 0
         stitch = {"mode": mode, "bytes_crossing_nvlink_per_step": int(payload), "stage_ms_max_over_ranks": stage_ms}
         if stage_ms and payload:
-            stitch["placement_GBps_into_rank0"] = round(payload / 1e9 / (stage_ms["placement_over_nvlink_and_fence"] / 1e3), 1)
-            stitch["exchange_share_of_step"] = round((stage_ms["lengths_allgather_cumsum"] + stage_ms["placement_over_nvlink_and_fence"])
+            stitch["placement_GBps_into_rank0"] = round(payload / 1e9 / (stage_ms["placement_over_nvlink_and_completion"] / 1e3), 1)
+            stitch["exchange_share_of_step"] = round((stage_ms["lengths_exchange"] + stage_ms["placement_over_nvlink_and_completion"])
                                                      / sum(stage_ms.values()), 4)
         print(json.dumps({
             "metric": METRIC, "value": round(W * H / 1e6 / (ms_step / 1e3), 1), "unit": "MP/s", "n_gpus": world,

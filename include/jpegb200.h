@@ -217,6 +217,18 @@ int jb_encode_strip_finish(jb_ctx *ctx, uint8_t *d_out, size_t cap, const uint64
  * strips a rank coded in several calls, stitched locally, to their place in the stitching rank's file. */
 int jb_copy_bytes_device(jb_ctx *ctx, uint8_t *d_dst, size_t cap, const uint64_t *d_dst_off, const uint8_t *d_src,
                          const uint64_t *d_len);
+/* The exchange step itself, without a collective library.  d_ctl = a zero-initialised 512-byte control block on the
+ * stitching rank (jb_device_alloc + memset; every rank maps it with jb_ipc_open).  epoch = 1, 2, 3, ... per step.
+ *   exchange  publishes *d_len as this rank's strip length (stores over NVLink), waits until all `world` ranks have
+ *             published theirs, and writes d_off[0] = base + lengths of the ranks before this one (where this
+ *             rank's strip goes), d_off[1] = base + all lengths (where the data ends: EOI goes there)
+ *   complete  ranks other than dst: signal that their bytes have landed (call after jb_encode_strip_finish /
+ *             jb_copy_bytes_device); dst: wait for every other rank's signal.
+ * Both only enqueue a one-warp kernel on jb_stream().  A peer that never reports is given up on after ~2 s
+ * (JB_E_INTERNAL / JB_E_NOSPACE at jb_sync; nothing is written). */
+int jb_stitch_exchange(jb_ctx *ctx, uint64_t *d_ctl, int rank, int world, uint64_t epoch, uint64_t base,
+                       const uint64_t *d_len, uint64_t *d_off);
+int jb_stitch_complete(jb_ctx *ctx, uint64_t *d_ctl, int rank, int world, int dst, uint64_t epoch);
 /* CUDA IPC for one process per GPU: export a jb_device_alloc'd buffer, map it in another process (peer access over
  * NVLink is enabled on open), unmap. */
 int jb_ipc_export(jb_ctx *ctx, void *d_ptr, uint8_t handle[64]);

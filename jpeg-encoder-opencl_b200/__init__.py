@@ -34,6 +34,7 @@ SYMBOLS = [
     "jb_write_header", "jb_synth_rgb_device", "jb_planar_u32_from_aos", "jb_planar_u32_interleave",
     "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32", "jb_optimal_huffman_spec",
     "jb_encode_strip_begin", "jb_encode_strip_finish", "jb_copy_bytes_device", "jb_ipc_export", "jb_ipc_open", "jb_ipc_close",
+    "jb_stitch_exchange", "jb_stitch_complete",
     "jb_pad_mirror_planar_u32", "jb_blockify_planar_i32", "jb_f64_to_u8", "jb_remove_red_aos", "jb_value_categories",
 ]
 
@@ -132,6 +133,8 @@ def lib():
     L.jb_encode_strip_begin.argtypes = [vp, vp, sz, sz, sz, PP, u64, C.c_int, vp]
     L.jb_encode_strip_finish.argtypes = [vp, vp, sz, vp]
     L.jb_copy_bytes_device.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.jb_stitch_exchange.argtypes = [vp, vp, C.c_int, C.c_int, u64, u64, vp, vp]
+    L.jb_stitch_complete.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, u64]
     L.jb_ipc_export.argtypes = [vp, vp, vp]
     L.jb_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.jb_ipc_close.argtypes = [vp, vp]
@@ -389,6 +392,12 @@ class Encoder:
 
     def copy_bytes_device(self, d_dst, cap, d_dst_off, d_src, d_len):
         self._ck(self.L.jb_copy_bytes_device(self.h, d_dst, cap, d_dst_off, d_src, d_len))
+
+    def stitch_exchange(self, d_ctl, rank, world, epoch, base, d_len, d_off):
+        self._ck(self.L.jb_stitch_exchange(self.h, d_ctl, rank, world, epoch, base, d_len, d_off))
+
+    def stitch_complete(self, d_ctl, rank, world, dst, epoch):
+        self._ck(self.L.jb_stitch_complete(self.h, d_ctl, rank, world, dst, epoch))
 
     def ipc_export(self, d_ptr):
         h = np.zeros(64, np.uint8)

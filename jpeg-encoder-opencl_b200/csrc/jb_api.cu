@@ -427,10 +427,10 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         ta.qc = tc.qc;
         if (!(p->flags & JB_FLAG_FMA_DCT)) {  // tcgen05 transform, every subsampling mode (launch falls back if unaligned)
 #ifdef JB_DEBUG_KNOBS  // tests/tools/tc_band_scan.py only (a separate build): the shipped library reads no environment
-            const char* e = getenv("JB_TC_ERR_SCALE");
-            const double scale = e ? atof(e) : JB_TC_ERR_SCALE;
+            const char* e = getenv("JB_TC_STEP_ULPS");
+            const double scale = e ? atof(e) : JB_TC_STEP_ULPS;
 #else
-            const double scale = JB_TC_ERR_SCALE;
+            const double scale = JB_TC_STEP_ULPS;
 #endif
             const int repl = pl.g.sub == JB_SUB_REPL420 ? 1 : 0, inplace = (p->flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0;
             if (!tc.tc_valid || tc.tc_scale != scale || tc.tc_repl != repl || tc.tc_inplace != inplace) {
@@ -559,6 +559,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
 int status_to_rc(jb_ctx* ctx, const uint64_t* st, uint64_t tie_count, uint32_t tie_cap) {
     ctx->tm.tie_fixups = tie_count;
     if (tie_count > tie_cap) return fail(ctx, JB_E_INTERNAL, "near-tie list overflow (%llu > %u)", (unsigned long long)tie_count, tie_cap);
+    if (st[0] & JB_STATUS_PEER_TIMEOUT) return fail(ctx, JB_E_INTERNAL, "strip stitch: a peer rank never reported its strip (timeout)");
     if (st[0] & JB_STATUS_UBUF_OVERFLOW) {
         // the library's own workspace, not the caller's buffer: enlarge the per-block budget (sticky) so that the
         // synchronous entry points can run the call again, and an asynchronous caller's next call succeeds
@@ -1474,6 +1475,37 @@ int jb_copy_bytes_device(jb_ctx* ctx, uint8_t* d_dst, size_t cap, const uint64_t
     CK(cudaSetDevice(ctx->device));
     ctx->tm.total_launches += launch_copy_bytes(d_dst, d_dst_off, d_src, d_len, cap, nullptr, ctx->slot[0].st);
     CK(cudaGetLastError());
+    return JB_OK;
+}
+
+// The exchange step of the stitch without a collective library: lengths and completion flags are plain stores and
+// polls on a 512-byte control block of the stitching rank, mapped by every rank over NVLink (jb_entropy.cu).
+int jb_stitch_exchange(jb_ctx* ctx, uint64_t* d_ctl, int rank, int world, uint64_t epoch, uint64_t base, const uint64_t* d_len,
+                       uint64_t* d_off) {
+    if (!ctx || !d_ctl || !d_len || !d_off || world < 1 || world > 16 || rank < 0 || rank >= world || epoch == 0)
+        return fail(ctx, JB_E_INVALID, "bad arguments (1 <= world <= 16, epoch >= 1)");
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.total_launches += launch_stitch_exchange(d_ctl, rank, world, epoch, base, d_len, d_off, ctx->slot[0].st);
+    CK(cudaGetLastError());
+    return JB_OK;
+}
+int jb_stitch_complete(jb_ctx* ctx, uint64_t* d_ctl, int rank, int world, int dst, uint64_t epoch) {
+    if (!ctx || !d_ctl || world < 1 || world > 16 || rank < 0 || rank >= world || dst < 0 || dst >= world || epoch == 0)
+        return fail(ctx, JB_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    ctx->tm.total_launches += launch_stitch_complete(d_ctl, rank, world, dst, epoch, s.w.status, s.st);
+    CK(cudaGetLastError());
+    if (rank == dst && s.w.status) {  // a peer that never reported shows up at jb_sync
+        const unsigned k = s.dev_seq++ % kDevStages;
+        if (s.dev_used[k]) CK(cudaEventSynchronize(s.dev_ev[k]));
+        uint64_t* res = reinterpret_cast<uint64_t*>(s.h_dev + k * kDevStageBytes + 1024);
+        memset(res, 0, 64);
+        CK(cudaMemcpyAsync(res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaEventRecord(s.dev_ev[k], s.st));
+        s.dev_used[k] = true;
+        s.busy = true;
+    }
     return JB_OK;
 }
 

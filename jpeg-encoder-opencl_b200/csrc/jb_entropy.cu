@@ -829,6 +829,90 @@ __global__ void __launch_bounds__(256) k_copy_bytes(uint8_t* __restrict__ dst_ba
     }
 }
 
+// ---- the strip lengths' all-gather and the completion signal as plain stores / polls on peer memory --------------
+// One control block (64 x uint64, zero-initialised) lives on the stitching rank; every rank maps it over NVLink.
+//   words  0..31  len[parity][rank]   byte count of the rank's strip in step `epoch` (parity = epoch & 1)
+//   words 32..47  len_epoch[rank]     epoch of the newest published length
+//   words 48..63  done_epoch[rank]    epoch up to which the rank's bytes have landed in the stitched file
+// k_stitch_exchange (one warp): publish this rank's length, wait until every rank has published the step's length,
+// prefix-sum them: off[0] = base + lengths of the ranks before this one, off[1] = base + all lengths.  A rank can be
+// at most one step ahead of the slowest one (it needs everybody's length to pass), hence the two parities.
+// Polling gives up after ~2 s (a peer died): the offsets become 2^62, which the placement kernel's capacity check
+// rejects -- nothing is written and jb_sync reports the overflow.
+constexpr int STITCH_MAX_RANKS = 16;
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool poll_at_least(const uint64_t* p, uint64_t epoch) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < epoch) {
+        if (clock64() - t0 > 4000000000ll) return false;  // ~2 s at 1.9 GHz
+        __nanosleep(200);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(32) k_stitch_exchange(uint64_t* ctl, int rank, int world, uint64_t epoch, uint64_t base,
+                                                        const uint64_t* __restrict__ d_len, uint64_t* __restrict__ d_off) {
+    const int lane = threadIdx.x;
+    uint64_t* len = ctl + (epoch & 1) * STITCH_MAX_RANKS;
+    if (lane == 0) {
+        len[rank] = *d_len;
+        st_release_sys(ctl + 32 + rank, epoch);  // the length is visible before the epoch
+    }
+    bool ok = true;
+    uint64_t mine = 0;
+    if (lane < world) {
+        ok = poll_at_least(ctl + 32 + lane, epoch);
+        mine = ok ? len[lane] : 0ull;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    uint64_t inc = mine;  // inclusive scan over the ranks
+#pragma unroll
+    for (int o = 1; o < STITCH_MAX_RANKS; o <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    const uint64_t before = __shfl_sync(0xffffffffu, inc - mine, rank), all = __shfl_sync(0xffffffffu, inc, world - 1);
+    if (lane == 0) {
+        d_off[0] = ok ? base + before : (1ull << 62);
+        d_off[1] = ok ? base + all : (1ull << 62);
+    }
+}
+
+// after the placement kernel (stream order: its stores have been performed): tell the stitching rank
+__global__ void k_stitch_done(uint64_t* ctl, int rank, uint64_t epoch) {
+    __threadfence_system();
+    st_release_sys(ctl + 48 + rank, epoch);
+}
+
+// stitching rank: every other rank's bytes of this step have landed; *d_ok = 0 if a peer never reported
+__global__ void __launch_bounds__(32) k_stitch_wait(const uint64_t* ctl, int rank, int world, uint64_t epoch, uint64_t* status) {
+    const int lane = threadIdx.x;
+    bool ok = true;
+    if (lane < world && lane != rank) ok = poll_at_least(ctl + 48 + lane, epoch);
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok && lane == 0 && status) atomicOr((unsigned long long*)&status[0], JB_STATUS_PEER_TIMEOUT);
+}
+
+int launch_stitch_exchange(uint64_t* ctl, int rank, int world, uint64_t epoch, uint64_t base, const uint64_t* d_len, uint64_t* d_off,
+                           cudaStream_t s) {
+    k_stitch_exchange<<<1, 32, 0, s>>>(ctl, rank, world, epoch, base, d_len, d_off);
+    return 1;
+}
+int launch_stitch_complete(uint64_t* ctl, int rank, int world, int dst, uint64_t epoch, uint64_t* status, cudaStream_t s) {
+    if (rank == dst)
+        k_stitch_wait<<<1, 32, 0, s>>>(ctl, rank, world, epoch, status);
+    else
+        k_stitch_done<<<1, 1, 0, s>>>(ctl, rank, epoch);
+    return 1;
+}
+
 int launch_copy_bytes(uint8_t* dst_base, const uint64_t* d_dst_off, const uint8_t* src, const uint64_t* d_len, uint64_t cap,
                       uint64_t* status, cudaStream_t s) {
     k_copy_bytes<<<148 * 8, 256, 0, s>>>(dst_base, d_dst_off, src, d_len, cap, status);

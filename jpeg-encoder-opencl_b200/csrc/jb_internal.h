@@ -152,12 +152,16 @@ struct EntropyArgs {
 #define JB_STATUS_UBUF_OVERFLOW 1ull
 #define JB_STATUS_OUT_OVERFLOW 2ull
 #define JB_STATUS_TIE_OVERFLOW 4ull
+#define JB_STATUS_PEER_TIMEOUT 8ull
 
 // ---- launchers (each returns the number of kernels it launched) -------------
 int launch_transform(const TransformArgs& a, cudaStream_t s);       // MCUs inside the image (hot kernel)
 int launch_transform_edge(const TransformArgs& a, cudaStream_t s);  // MCUs that need mirror padding
 int launch_fixup(const FixupArgs& a, cudaStream_t s);
 int launch_entropy(const EntropyArgs& a, cudaStream_t s, int phase = 0);  // 1: up to the sizes, 2: final placement only
+int launch_stitch_exchange(uint64_t* ctl, int rank, int world, uint64_t epoch, uint64_t base, const uint64_t* d_len, uint64_t* d_off,
+                           cudaStream_t s);
+int launch_stitch_complete(uint64_t* ctl, int rank, int world, int dst, uint64_t epoch, uint64_t* status, cudaStream_t s);
 int launch_copy_bytes(uint8_t* dst_base, const uint64_t* d_dst_off, const uint8_t* src, const uint64_t* d_len, uint64_t cap,
                       uint64_t* status, cudaStream_t s);
 int launch_synth(uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t* d_out, cudaStream_t s);
@@ -187,7 +191,7 @@ int launch_planar_to_scan(const int32_t* zz, size_t rpc, int16_t* coef, cudaStre
 // host helpers
 void build_quant_const(const uint32_t ql[64], const uint32_t qc[64], QuantConst* out);
 void aan_error_bound(double err[64], double amax[64]);
-void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double err_scale, int repl_chroma, int inplace_dct,
+void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double step_ulps, int repl_chroma, int inplace_dct,
                        uint8_t* out /* 32768 B */,
                        float tband[2][64]);  // worst-case |binary32 - exact| per AAN output
 void build_huff(bool typo, HuffDev* out);

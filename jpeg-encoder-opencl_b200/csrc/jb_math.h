@@ -153,13 +153,12 @@ JB_HD uint32_t quantize_bits(float a, float mul, float band, bool& near_tie) {
 // 1.2e-3; the analytic worst case (tests/test_math_host.py) is below 1.2e-2.
 #define JB_DCT_ERR_BOUND 0.015625  // 2^-6
 
-// Tensor-core variant: bound on |t_mma - t_exact| relative to the largest possible partial sum
-// P = 128 * sum|W|.  The products (8-bit sample x bf16) are exact and each of the 12 MMAs adds
-// 16 of them to the fp32 accumulator; measured on the B200 (tests/tools/tc_band_scan.py, 6.6 M
-// coefficients incl. +-255 noise at q100) no coefficient outside a band of 1e-7 * P ever
-// differs from the binary64 reference, so 2e-6 * P (~ 12 accumulation steps x 3 ulp of P)
-// leaves a 20x margin.  Unlike the FMA kernel's band this one is empirical, not analytic.
-#define JB_TC_ERR_SCALE 2.0e-6
+// Tensor-core variant (jb_tables.cpp: build_tc_matrices derives the near-tie band from it): one tcgen05 MMA step --
+// the fp32 accumulator plus 16 exact fp16 x fp16 products -- deviates from the exact sum by fewer than this many ulps of
+// the largest magnitude involved.  The datapath aligns the addends to the largest exponent with three guard bits and
+// truncates them (16 x 2^-3 ulp), then truncates the sum to binary32 (1 ulp): 3 ulps; measured maximum on the B200
+// 2.95 (tests/tools/tc_model_scan.py, profiles/r02_tc_numerics.md), asserted below 3.5 by tests/test_gpu_tc_model.py.
+#define JB_TC_STEP_ULPS 4.0
 #define JB_TC_W_SCALE 1024.0  // power of two folded into the fp16 matrices, undone by the rounding FMA
 
 }  // namespace jb

@@ -112,39 +112,71 @@ def gather_stitch(payload, header=None, trailer=None, dst=0, group=None):
 
 
 class PeerStitch:
-    """The strip stitch over NVLink peer memory, with no host round trip and no separate gather.
+    """The strip stitch over NVLink peer memory: no host round trip, no gather, no collective library in the data path.
 
-    Rank `dst` owns the output file's buffer (a plain cudaMalloc through the library); every other rank maps it with
-    CUDA IPC.  One step, entirely stream-ordered on the encoder's stream:
+    Rank `dst` owns the output file's buffer and a 512-byte control block (plain cudaMalloc through the library); every
+    other rank maps both with CUDA IPC.  One step, entirely stream-ordered on the encoder's stream:
         jb_encode_strip_begin   transform + entropy coder up to the sizes; the strip's length stays on the device
-        all_gather_into_tensor  the N lengths (8 bytes per rank, NCCL)
-        cumsum                  every rank's offset = header + lengths of the ranks before it (device)
+        jb_stitch_exchange      one warp: store the length into dst's control block, poll until all N lengths of this
+                                step are there, prefix-sum them -> this rank's offset and the end of the data
         jb_encode_strip_finish  the final placement kernel stores the strip at dst's buffer + offset: on ranks other
                                 than dst these coalesced 128-bit stores ARE the NVLink transfer
-        all_reduce (1 word)     orders dst's later reads after every peer's stores
+        jb_stitch_complete      others: release-store a completion flag; dst: poll the N-1 flags
     A rank that codes its strip in several calls (more than 2^26 blocks) stitches them locally with device-side running
     offsets and pushes the result with jb_copy_bytes_device.  `cap` bytes are allocated on dst.
+    exchange_offsets() / fence() are the same two steps through NCCL (all-gather + cumsum, all-reduce), kept for
+    comparison (bench.py --stitch peer-nccl).
     """
 
     def __init__(self, enc, cap, dst=0, group=None):
+        import numpy as np
         import torch
         import torch.distributed as dist
         self.enc, self.cap, self.dst, self.group = enc, int(cap), dst, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise ValueError("PeerStitch: at most 16 ranks (one NVLink domain)")
         dev = torch.device("cuda", torch.cuda.current_device())
-        handle = torch.zeros(64, dtype=torch.uint8, device=dev)
-        self.local = None
+        handles = torch.zeros(128, dtype=torch.uint8, device=dev)
+        self.local = self.local_ctl = None
         if self.rank == dst:
             self.local = enc.device_alloc(self.cap)
-            handle.copy_(torch.from_numpy(enc.ipc_export(self.local)))
-        dist.broadcast(handle, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
-        self.base = self.local if self.rank == dst else enc.ipc_open(handle.cpu().numpy())
+            self.local_ctl = enc.device_alloc(512)
+            enc.h2d(self.local_ctl, np.zeros(512, np.uint8))
+            handles.copy_(torch.from_numpy(np.concatenate([enc.ipc_export(self.local), enc.ipc_export(self.local_ctl)])))
+        dist.broadcast(handles, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        h = handles.cpu().numpy()
+        self.base = self.local if self.rank == dst else enc.ipc_open(h[:64])
+        self.ctl = self.local_ctl if self.rank == dst else enc.ipc_open(h[64:])
+        self.epoch = 0
         self.lens = torch.zeros(self.world, dtype=torch.int64, device=dev)
         self.mine = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.offs = torch.zeros(self.world + 1, dtype=torch.int64, device=dev)
+        self.offs = torch.zeros(self.world + 1, dtype=torch.int64, device=dev)  # NCCL variant
+        self.off2 = torch.zeros(2, dtype=torch.int64, device=dev)               # [this rank's offset, end of the data]
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()  # the tensors above are used on the encoder's (non-blocking) stream from here on
 
+    # ---- the exchange as stores / polls on peer memory (default) -----------------------------------------------------
+    def exchange(self, header_bytes):
+        """Enqueue: publish self.mine, wait for every rank's length of this step; returns the device tensor
+        [offset of this rank's strip, end of the data] (both include header_bytes)."""
+        self.epoch += 1
+        self.enc.stitch_exchange(self.ctl, self.rank, self.world, self.epoch, int(header_bytes), self.mine.data_ptr(), self.off2.data_ptr())
+        return self.off2
+
+    def complete(self):
+        """Enqueue after the placement: ranks other than dst signal, dst waits for all of them."""
+        self.enc.stitch_complete(self.ctl, self.rank, self.world, self.dst, self.epoch)
+
+    def lengths(self):
+        """The strip lengths of the last step (dst only; synchronises)."""
+        import numpy as np
+        w = np.zeros(64, np.uint64)
+        self.enc.sync()
+        self.enc.d2h(w, self.local_ctl)
+        return [int(v) for v in w[(self.epoch & 1) * 16: (self.epoch & 1) * 16 + self.world]]
+
+    # ---- the same through NCCL ------------------------------------------------------------------------------------------
     def exchange_offsets(self, header_bytes):
         """lens[r] <- every rank's self.mine; offs[r] = header_bytes + sum(lens[:r]); offs[world] = end of the data."""
         import torch
@@ -181,10 +213,12 @@ class PeerStitch:
         dist.barrier(group=self.group)
         if self.rank != self.dst and self.base:
             self.enc.ipc_close(self.base)
+            self.enc.ipc_close(self.ctl)
         dist.barrier(group=self.group)
         if self.local:
             self.enc.device_free(self.local)
-        self.base = self.local = None
+            self.enc.device_free(self.local_ctl)
+        self.base = self.local = self.ctl = self.local_ctl = None
 
 
 def stitch(header, strips, eoi=b"\xff\xd9"):

@@ -32,6 +32,91 @@ static void ref_dct_quant(const int* smp, const uint32_t* q, int* out /* natural
         }
 }
 
+// ---- 5. the tcgen05 transform under the measured datapath model (jb_tables.cpp: build_tc_matrices) --------------
+// fp16 bit pattern -> double (normal and subnormal)
+static double h2d(uint16_t h) {
+    int s = h >> 15, e = (h >> 10) & 31, f = h & 1023;
+    double v = e ? std::ldexp(1.0 + f / 1024.0, e - 15) : std::ldexp((double)f, -24);
+    return s ? -v : v;
+}
+// one MMA step: accumulator + 16 exact products, aligned to the largest exponent with `guard` guard bits, every
+// addend truncated toward zero, exact sum, result truncated toward zero to 24 significant bits
+static double mma_step(double acc, const double* prod, int guard) {
+    double m = std::fabs(acc);
+    for (int i = 0; i < 16; ++i) m = std::fmax(m, std::fabs(prod[i]));
+    if (m == 0) return 0;
+    const double g = std::ldexp(1.0, std::ilogb(m) - 23 - guard);
+    double s = std::trunc(acc / g);
+    for (int i = 0; i < 16; ++i) s += std::trunc(prod[i] / g);
+    s *= g;
+    if (s == 0) return 0;
+    const double u = std::ldexp(1.0, std::ilogb(s) - 23);
+    return std::trunc(s / u) * u;
+}
+struct TcReport {
+    long coefs = 0, flagged = 0, unflagged_wrong = 0;
+    double worst_err_over_bound = 0, min_band = 1;
+};
+static void tc_model_check(TcReport& rep) {
+    const int qualities[5] = {10, 50, 75, 90, 100};
+    std::vector<uint8_t> mat(32768);
+    srand(777);
+    for (int qi = 0; qi < 5; ++qi) {
+        uint32_t ql[64], qc[64];
+        jb_quality_tables(qualities[qi], ql, qc);
+        float tband[2][64];
+        build_tc_matrices(ql, qc, JB_TC_STEP_ULPS, 0, 0, mat.data(), tband);
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t* q = t ? qc : ql;
+            double hi[64][64], lo[64][64];
+            for (int n = 0; n < 64; ++n)
+                for (int k = 0; k < 64; ++k) {
+                    size_t off = (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+                    uint16_t a, b;
+                    memcpy(&a, mat.data() + ((size_t)t * 2 + 0) * 8192 + off, 2);
+                    memcpy(&b, mat.data() + ((size_t)t * 2 + 1) * 8192 + off, 2);
+                    hi[n][k] = h2d(a);
+                    lo[n][k] = h2d(b);
+                }
+            for (int n = 0; n < 64; ++n) rep.min_band = std::fmin(rep.min_band, (double)tband[t][n]);
+            for (int trial = 0; trial < 1500; ++trial) {
+                int smp[64];
+                const int mode = trial % 5;
+                for (int i = 0; i < 64; ++i)
+                    smp[i] = mode == 0 ? rand() % 256 - 128 : mode == 1 ? ((rand() & 1) ? 127 : -128)
+                             : mode == 2 ? (rand() % 9 - 4) + (i % 8) * 16 - 60 : mode == 3 ? (trial / 5) % 256 - 128
+                                                                                            : ((rand() & 3) ? -128 : 127);
+                int want[64];
+                ref_dct_quant(smp, q, want);
+                for (int n = 1; n < 64; ++n) {  // (the DC coefficient takes the integer path)
+                    double acc = 0, prod[16];
+                    for (int phase = 0; phase < 2; ++phase)
+                        for (int c = 0; c < 4; ++c) {
+                            for (int i = 0; i < 16; ++i) prod[i] = smp[c * 16 + i] * (phase ? lo[n][c * 16 + i] : hi[n][c * 16 + i]);
+                            acc = mma_step(acc, prod, 3);
+                        }
+                    // exact scaled quotient, for the error ratio
+                    const int nat = kZigzag[n], v = nat >> 3, u = nat & 7;
+                    double s = 0;
+                    for (int y = 0; y < 8; ++y)
+                        for (int x = 0; x < 8; ++x) s += smp[y * 8 + x] * cs[u][x] * cs[v][y];
+                    s *= ((u == 0 ? 1.0 / std::sqrt(2) : 1.0) * (v == 0 ? 1.0 / std::sqrt(2) : 1.0) / 4.0) / q[nat] * JB_TC_W_SCALE;
+                    const double bound = (0.5 - 1e-6 - tband[t][n]) * JB_TC_W_SCALE;
+                    rep.worst_err_over_bound = std::fmax(rep.worst_err_over_bound, std::fabs(acc - s) / bound);
+                    // the epilogue of the kernel (tc_quant_stage): round, distance from the integer, band test
+                    const float x = (float)acc, inv = (float)(1.0 / JB_TC_W_SCALE);
+                    const float r = fmaf(x, inv, JB_ROUND_MAGIC), d = fmaf(x, inv, JB_ROUND_MAGIC - r);
+                    const bool tie = std::fabs(d) > tband[t][n];
+                    const int got = (int)(r - JB_ROUND_MAGIC);
+                    ++rep.coefs;
+                    if (tie) ++rep.flagged;
+                    else if (got != want[nat]) ++rep.unflagged_wrong;
+                }
+            }
+        }
+    }
+}
+
 int main() {
     for (size_t u = 0; u < 8; ++u)
         for (size_t x = 0; x < 8; ++x) cs[u][x] = std::cos((2 * x + 1) * u * M_PI / 16.0);
@@ -132,10 +217,14 @@ int main() {
         if (!k.dc_exact) ++dc_rule_failures;
     }
 
+    TcReport tc;
+    tc_model_check(tc);
+
     printf("{\"csc_mismatches\": %ld, \"y_ties\": %ld, \"y_ties_down\": %ld, \"max_err\": %.6e, \"max_bound\": %.6e, "
            "\"worst_err_over_bound\": %.4f, \"coefs\": %ld, \"flagged\": %ld, \"unflagged_wrong\": %ld, "
-           "\"flagged_differ\": %ld, \"max_lsb\": %ld, \"dc_rule_failures\": %d}\n",
+           "\"flagged_differ\": %ld, \"max_lsb\": %ld, \"dc_rule_failures\": %d, "
+           "\"tc_coefs\": %ld, \"tc_flagged\": %ld, \"tc_unflagged_wrong\": %ld, \"tc_worst_err_over_bound\": %.4f, \"tc_min_band\": %.6f}\n",
            csc_bad, y_ties, y_down, max_err, max_bound, worst_ratio, coefs, flagged, unflagged_wrong, flagged_differ,
-           max_lsb, dc_rule_failures);
+           max_lsb, dc_rule_failures, tc.coefs, tc.flagged, tc.unflagged_wrong, tc.worst_err_over_bound, tc.min_band);
     return 0;
 }

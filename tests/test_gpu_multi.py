@@ -48,15 +48,23 @@ def _worker(rank, world, port, q):
         d_img = torch.from_numpy(np.ascontiguousarray(img[row0:row1])).cuda()
         ps = D.PeerStitch(enc, cap=W * H + 65536, dst=0)
         hdr_n = hdr.numel()
-        for rep in range(3):  # repeated: the pinned staging ring and the workspace are reused
+        for rep in range(4):  # repeated: the pinned staging ring, the workspace and both flag parities are reused
             with torch.cuda.stream(ext):
                 enc.encode_strip_begin(d_img.data_ptr(), p, first, is_last, W, row1 - row0, W * 3, ps.mine.data_ptr())
-                offs = ps.exchange_offsets(hdr_n)
-                enc.encode_strip_finish(ps.base, ps.cap, offs[rank:].data_ptr())
-                ps.fence()
+                if rep == 3:  # the exchange through NCCL instead (all-gather + cumsum, all-reduce as the fence)
+                    offs = ps.exchange_offsets(hdr_n)
+                    enc.encode_strip_finish(ps.base, ps.cap, offs[rank:].data_ptr())
+                    ps.fence()
+                    end = offs[world:]
+                else:         # lengths and completion flags as stores / polls on rank 0's memory over NVLink
+                    off2 = ps.exchange(hdr_n)
+                    enc.encode_strip_finish(ps.base, ps.cap, off2.data_ptr())
+                    ps.complete()
+                    end = off2[1:]
             enc.sync()
             if rank == 0:
-                total = int(offs[world].item())
+                assert rep == 3 or ps.lengths() == lengths
+                total = int(end[0].item())
                 out = ps.view()
                 out[:hdr_n] = hdr
                 out[total: total + 2] = eoi
@@ -76,12 +84,12 @@ def _worker(rank, world, port, q):
                 enc.encode_strip_finish(local.data_ptr(), local.numel(), run[1:].data_ptr())
                 torch.add(run[1], ps.mine[0], out=run[2])
                 ps.mine.copy_(run[2:3])
-                offs = ps.exchange_offsets(hdr_n)
-                enc.copy_bytes_device(ps.base, ps.cap, offs[rank:].data_ptr(), local.data_ptr(), run[2:].data_ptr())
-                ps.fence()
+                off2 = ps.exchange(hdr_n)
+                enc.copy_bytes_device(ps.base, ps.cap, off2.data_ptr(), local.data_ptr(), run[2:].data_ptr())
+                ps.complete()
             enc.sync()
             if rank == 0:
-                total = int(offs[world].item())
+                total = int(off2[1].item())
                 out = ps.view()
                 out[total: total + 2] = eoi
                 torch.cuda.synchronize()
