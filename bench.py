@@ -647,6 +647,7 @@ def run_strips(a, jb, enc, torch, dd):
                         h_out[:n].copy_((own if world == 1 else ps.view())[:n], non_blocking=True)
                 enc.sync()
 
+            dd.barrier()  # pinning gigabytes takes the ranks different times: line them up before the first exchange
             step_e2e()
             dd.barrier()
             w0 = time.perf_counter()

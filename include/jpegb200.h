@@ -74,10 +74,12 @@ typedef struct {
     uint32_t qchrom[64];      /* row-major [v][u], as quant_mat_chrom (utils.hpp:53-62)     */
 } jb_params;
 
-/* Per-stage device times of the last fused call, in microseconds; the first
- * nine fields mirror CPUTelemetry (utils.hpp:65-75).  In the fused path CSC,
- * CDS, level shift, DCT, quantisation and zigzag are one kernel: its time is
- * reported in DCTTime and the others are 0. */
+/* Per-stage device times since jb_reset_counters (recorded with CUDA events when jb_set_profiling is on), in
+ * microseconds; the first nine fields mirror CPUTelemetry (utils.hpp:65-75) -- a jb_timings* can be read as a
+ * CPUTelemetry*.  Every staged entry point adds its kernel's time to the field of the reference stage it replaces
+ * (jb_csc_rgb8_aos -> CSCTime, ... jb_huffman -> HuffmanTime; TotalCopyTime = padding / conversion kernels +
+ * host<->device transfers).  In the fused path CSC, CDS, level shift, DCT, quantisation and zigzag are ONE kernel:
+ * its time goes to DCTTime, the entropy coder's (RLE + Huffman + packing) to HuffmanTime. */
 typedef struct {
     double CSCTime, CDSTime, levelShiftTime, DCTTime, QuantTime, TotalCopyTime, zigZagTime, RLETime, HuffmanTime;
     double transform_us; /* fused transform kernel (== DCTTime)                     */
@@ -87,6 +89,10 @@ typedef struct {
     double edge_us;      /* generic kernel for MCUs that need mirror padding            */
     uint64_t transform_launches, total_launches; /* kernels launched by the library since jb_reset_counters */
     uint64_t tie_fixups;                         /* coefficients replayed in binary64 in the last call      */
+    /* staged entry points (kernel time only, with jb_set_profiling): what the sums above are made of */
+    double staged_dct_us;     /* jb_dct_f64                                          (in DCTTime)       */
+    double staged_copy_us;    /* jb_pad_mirror_aos, jb_u8_to_f64, layout conversions (in TotalCopyTime) */
+    double staged_huffman_us; /* jb_huffman                                          (in HuffmanTime)   */
 } jb_timings;
 
 /* ---- context ------------------------------------------------------------- */
@@ -224,7 +230,7 @@ int jb_copy_bytes_device(jb_ctx *ctx, uint8_t *d_dst, size_t cap, const uint64_t
  *             rank's strip goes), d_off[1] = base + all lengths (where the data ends: EOI goes there)
  *   complete  ranks other than dst: signal that their bytes have landed (call after jb_encode_strip_finish /
  *             jb_copy_bytes_device); dst: wait for every other rank's signal.
- * Both only enqueue a one-warp kernel on jb_stream().  A peer that never reports is given up on after ~2 s
+ * Both only enqueue a one-warp kernel on jb_stream().  A peer that never reports is given up on after ~20 s
  * (JB_E_INTERNAL / JB_E_NOSPACE at jb_sync; nothing is written). */
 int jb_stitch_exchange(jb_ctx *ctx, uint64_t *d_ctl, int rank, int world, uint64_t epoch, uint64_t base,
                        const uint64_t *d_len, uint64_t *d_off);

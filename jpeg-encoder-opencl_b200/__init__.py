@@ -54,7 +54,8 @@ class Timings(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("CSCTime", "CDSTime", "levelShiftTime", "DCTTime", "QuantTime",
                                           "TotalCopyTime", "zigZagTime", "RLETime", "HuffmanTime", "transform_us",
                                           "fixup_us", "entropy_us", "h2d_us", "d2h_us", "edge_us")] + \
-               [(n, C.c_uint64) for n in ("transform_launches", "total_launches", "tie_fixups")]
+               [(n, C.c_uint64) for n in ("transform_launches", "total_launches", "tie_fixups")] + \
+               [(n, C.c_double) for n in ("staged_dct_us", "staged_copy_us", "staged_huffman_us")]
 
 
 def build(verbose=False):

@@ -337,6 +337,17 @@ void resolve_events(jb_ctx* ctx) {
                 case 2: ctx->tm.entropy_us += us; break;
                 case 3: ctx->tm.h2d_us += us; break;
                 case 5: ctx->tm.edge_us += us; break;
+                // staged entry points: one reference stage each (CPUTelemetry, utils.hpp:65-75)
+                case 6: ctx->tm.CSCTime += us; break;
+                case 7: ctx->tm.CDSTime += us; break;
+                case 8: ctx->tm.levelShiftTime += us; break;
+                case 9: ctx->tm.staged_dct_us += us; break;
+                case 10: ctx->tm.QuantTime += us; break;
+                case 11: ctx->tm.zigZagTime += us; break;
+                case 12: ctx->tm.RLETime += us; break;
+                case 13: ctx->tm.staged_copy_us += us; break;
+                case 14: break;  // helpers outside the telemetry set
+                case 15: ctx->tm.staged_huffman_us += us; break;
                 default: ctx->tm.d2h_us += us; break;
             }
         }
@@ -344,9 +355,11 @@ void resolve_events(jb_ctx* ctx) {
         ctx->event_pool.push_back(ep.b);
     }
     ctx->events.clear();
-    ctx->tm.DCTTime = ctx->tm.transform_us;
-    ctx->tm.HuffmanTime = ctx->tm.entropy_us;
-    ctx->tm.TotalCopyTime = ctx->tm.h2d_us + ctx->tm.d2h_us;
+    // CPUTelemetry view: the fused transform kernel is reported as DCT time, the whole entropy coder as Huffman time;
+    // TotalCopyTime = the staged copy / padding / conversion kernels (the reference's meaning, cpp:93-139) + transfers
+    ctx->tm.DCTTime = ctx->tm.transform_us + ctx->tm.staged_dct_us;
+    ctx->tm.HuffmanTime = ctx->tm.entropy_us + ctx->tm.staged_huffman_us;
+    ctx->tm.TotalCopyTime = ctx->tm.staged_copy_us + ctx->tm.h2d_us + ctx->tm.d2h_us;
 }
 
 // The entropy coder is ~17 small launches; for a small image (the reference's own use case) their launch
@@ -784,6 +797,7 @@ int jb_memcpy_d2h(jb_ctx* ctx, void* dst, const void* src, size_t bytes) {
 #define STAGE_END()                   \
     CK(cudaGetLastError());           \
     CK(cudaStreamSynchronize(st));    \
+    resolve_events(ctx);              \
     return JB_OK;
 
 int jb_csc_rgb8_aos(jb_ctx* ctx, uint8_t* px, size_t W, size_t H) {
@@ -791,9 +805,9 @@ int jb_csc_rgb8_aos(jb_ctx* ctx, uint8_t* px, size_t W, size_t H) {
     if (!px || n == 0) return fail(ctx, JB_E_INVALID, "empty image");
     STAGE_BEGIN(n * 3)
     uint8_t* d = carve<uint8_t>(A, n * 3);
-    CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_csc(d, n, ctx->d_ydown, st);
-    CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 6); ctx->tm.total_launches += launch_csc(d, n, ctx->d_ydown, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -802,9 +816,9 @@ int jb_cds_aos(jb_ctx* ctx, uint8_t* px, size_t W, size_t H) {
     if (!px || n == 0) return fail(ctx, JB_E_INVALID, "empty image");
     STAGE_BEGIN(n * 3)
     uint8_t* d = carve<uint8_t>(A, n * 3);
-    CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st));
-    if (W >= 2 && H >= 2) ctx->tm.total_launches += launch_cds(d, W, H, st);
-    CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 7); if (W >= 2 && H >= 2) ctx->tm.total_launches += launch_cds(d, W, H, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -821,9 +835,9 @@ int jb_pad_mirror_aos(jb_ctx* ctx, const uint8_t* src, size_t W, size_t H, uint8
     STAGE_BEGIN(W * H * 3 + nW * nH * 3 + 512)
     uint8_t* ds = carve<uint8_t>(A, W * H * 3);
     uint8_t* dd = carve<uint8_t>(A, nW * nH * 3);
-    CK(cudaMemcpyAsync(ds, src, W * H * 3, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_pad(ds, W, H, dd, nW, nH, st);
-    CK(cudaMemcpyAsync(dst, dd, nW * nH * 3, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(ds, src, W * H * 3, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 13); ctx->tm.total_launches += launch_pad(ds, W, H, dd, nW, nH, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(dst, dd, nW * nH * 3, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -832,9 +846,9 @@ int jb_u8_to_f64(jb_ctx* ctx, const uint8_t* src, double* dst, size_t n) {
     STAGE_BEGIN(n * 9 + 512)
     double* dd = carve<double>(A, n);
     uint8_t* ds = carve<uint8_t>(A, n);
-    CK(cudaMemcpyAsync(ds, src, n, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_u8_to_f64(ds, dd, n, st);
-    CK(cudaMemcpyAsync(dst, dd, n * 8, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(ds, src, n, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 13); ctx->tm.total_launches += launch_u8_to_f64(ds, dd, n, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(dst, dd, n * 8, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -842,9 +856,9 @@ int jb_levelshift_f64(jb_ctx* ctx, double* img, size_t n, double val) {
     if (!img || n == 0) return fail(ctx, JB_E_INVALID, "empty input");
     STAGE_BEGIN(n * 8)
     double* d = carve<double>(A, n);
-    CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_sub_f64(d, n, val, st);
-    CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 8); ctx->tm.total_launches += launch_sub_f64(d, n, val, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -853,10 +867,12 @@ int jb_dct_f64(jb_ctx* ctx, double* img, size_t W, size_t H, uint32_t flags) {
     size_t n = W * H * 3;
     STAGE_BEGIN(n * 8)
     double* d = carve<double>(A, n);
-    CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches +=
-        launch_dct_f64(d, W, H, (flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0, ctx->d_costab, ctx->d_scale, st);
-    CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st)); }
+    {
+        Timed t_(ctx, st, 9);
+        ctx->tm.total_launches += launch_dct_f64(d, W, H, (flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0, ctx->d_costab, ctx->d_scale, st);
+    }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -868,9 +884,9 @@ int jb_quantize_f64(jb_ctx* ctx, double* img, size_t W, size_t H, const uint32_t
     QuantTables qt;
     memcpy(qt.q[0], ql, sizeof(qt.q[0]));
     memcpy(qt.q[1], qc, sizeof(qt.q[1]));
-    CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_quant_f64(d, W, H, qt, st);
-    CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 10); ctx->tm.total_launches += launch_quant_f64(d, W, H, qt, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(img, d, n * 8, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -880,9 +896,9 @@ int jb_blockify(jb_ctx* ctx, const double* img, size_t W, size_t H, int32_t* lin
     STAGE_BEGIN(n * 12 + 512)
     double* d = carve<double>(A, n);
     int32_t* o = carve<int32_t>(A, n);
-    CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_blockify(d, W, H, o, st);
-    CK(cudaMemcpyAsync(linear, o, n * 4, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d, img, n * 8, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 11); ctx->tm.total_launches += launch_blockify(d, W, H, o, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(linear, o, n * 4, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -892,9 +908,9 @@ int jb_zigzag(jb_ctx* ctx, const int32_t* linear, int32_t* zz, size_t rows) {
     STAGE_BEGIN(n * 8 + 512)
     int32_t* a = carve<int32_t>(A, n);
     int32_t* b = carve<int32_t>(A, n);
-    CK(cudaMemcpyAsync(a, linear, n * 4, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_zigzag(a, b, rows, st);
-    CK(cudaMemcpyAsync(zz, b, n * 4, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(a, linear, n * 4, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 11); ctx->tm.total_launches += launch_zigzag(a, b, rows, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(zz, b, n * 4, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -903,9 +919,9 @@ int jb_f64_to_u8(jb_ctx* ctx, const double* src, uint8_t* dst, size_t n) {
     STAGE_BEGIN(n * 9 + 512)
     double* ds = carve<double>(A, n);
     uint8_t* dd = carve<uint8_t>(A, n);
-    CK(cudaMemcpyAsync(ds, src, n * 8, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_f64_to_u8(ds, dd, n, st);
-    CK(cudaMemcpyAsync(dst, dd, n, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(ds, src, n * 8, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 13); ctx->tm.total_launches += launch_f64_to_u8(ds, dd, n, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(dst, dd, n, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -914,9 +930,9 @@ int jb_remove_red_aos(jb_ctx* ctx, uint8_t* px, size_t W, size_t H) {
     if (!px || n == 0) return fail(ctx, JB_E_INVALID, "empty image");
     STAGE_BEGIN(n * 3)
     uint8_t* d = carve<uint8_t>(A, n * 3);
-    CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_remove_red(d, n, st);
-    CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 13); ctx->tm.total_launches += launch_remove_red(d, n, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(px, d, n * 3, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -926,10 +942,10 @@ int jb_value_categories(jb_ctx* ctx, const int16_t* v, size_t n, uint8_t* cat, u
     int16_t* dv = carve<int16_t>(A, n);
     uint16_t* db = carve<uint16_t>(A, n);
     uint8_t* dc = carve<uint8_t>(A, n);
-    CK(cudaMemcpyAsync(dv, v, n * 2, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_value_categories(dv, n, dc, db, st);
-    CK(cudaMemcpyAsync(cat, dc, n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(bits, db, n * 2, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(dv, v, n * 2, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 14); ctx->tm.total_launches += launch_value_categories(dv, n, dc, db, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(cat, dc, n, cudaMemcpyDeviceToHost, st)); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(bits, db, n * 2, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -939,9 +955,9 @@ int jb_pad_mirror_planar_u32(jb_ctx* ctx, const uint32_t* in, size_t W, size_t H
     STAGE_BEGIN((W * H + nW * nH) * 12 + 512)
     uint32_t* a = carve<uint32_t>(A, W * H * 3);
     uint32_t* b = carve<uint32_t>(A, nW * nH * 3);
-    CK(cudaMemcpyAsync(a, in, W * H * 12, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_pad_planar_u32(a, W, H, b, nW, nH, st);
-    CK(cudaMemcpyAsync(out, b, nW * nH * 12, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(a, in, W * H * 12, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 13); ctx->tm.total_launches += launch_pad_planar_u32(a, W, H, b, nW, nH, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(out, b, nW * nH * 12, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -951,9 +967,9 @@ int jb_blockify_planar_i32(jb_ctx* ctx, const int32_t* planar, size_t W, size_t 
     STAGE_BEGIN(n * 8 + 512)
     int32_t* a = carve<int32_t>(A, n);
     int32_t* b = carve<int32_t>(A, n);
-    CK(cudaMemcpyAsync(a, planar, n * 4, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_blockify_planar_i32(a, W, H, b, st);
-    CK(cudaMemcpyAsync(linear, b, n * 4, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(a, planar, n * 4, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 11); ctx->tm.total_launches += launch_blockify_planar_i32(a, W, H, b, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(linear, b, n * 4, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -964,9 +980,9 @@ int jb_planar_u32_from_aos(jb_ctx* ctx, const uint8_t* px, size_t W, size_t H, u
     STAGE_BEGIN(n * 15 + 512)
     uint8_t* d = carve<uint8_t>(A, n * 3);
     uint32_t* o = carve<uint32_t>(A, n * 3);
-    CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_aos_to_planar_u32(d, n, o, st);
-    CK(cudaMemcpyAsync(planar, o, n * 12, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d, px, n * 3, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 13); ctx->tm.total_launches += launch_aos_to_planar_u32(d, n, o, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(planar, o, n * 12, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -976,9 +992,9 @@ int jb_planar_u32_interleave(jb_ctx* ctx, const uint32_t* planar, size_t W, size
     STAGE_BEGIN(n * 24 + 512)
     uint32_t* a = carve<uint32_t>(A, n * 3);
     uint32_t* b = carve<uint32_t>(A, n * 3);
-    CK(cudaMemcpyAsync(a, planar, n * 12, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_planar_u32_interleave(a, n, b, st);
-    CK(cudaMemcpyAsync(interleaved, b, n * 12, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(a, planar, n * 12, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 13); ctx->tm.total_launches += launch_planar_u32_interleave(a, n, b, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(interleaved, b, n * 12, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 
@@ -1001,7 +1017,7 @@ int jb_encode_jfif_planar_u32(jb_ctx* ctx, const uint32_t* planar, size_t W, siz
     uint8_t* d_rgb = carve<uint8_t>(A, pitch * H);
     uint8_t* d_out = carve<uint8_t>(A, cap);
     uint64_t* d_meta = carve<uint64_t>(A, 4);  // offset, size, total
-    CK(cudaMemcpyAsync(d_pl, planar, n * 12, cudaMemcpyHostToDevice, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(d_pl, planar, n * 12, cudaMemcpyHostToDevice, st)); }
     ctx->tm.total_launches += launch_planar_u32_to_rgb8(d_pl, W, H, d_rgb, pitch, st);
     int rc = with_workspace_retry(ctx, [&] {
         int r = jb_encode_batch_device(ctx, d_rgb, 1, W, H, pitch, pitch * H, p, d_out, cap, d_meta, d_meta + 1, d_meta + 2);
@@ -1025,10 +1041,10 @@ int jb_rle(jb_ctx* ctx, const int32_t* zz, size_t rows, uint32_t flags, int32_t*
     int32_t* a = carve<int32_t>(A, rows * 64);
     int32_t* b = carve<int32_t>(A, rows * 128);
     uint32_t* c = carve<uint32_t>(A, rows);
-    CK(cudaMemcpyAsync(a, zz, rows * 256, cudaMemcpyHostToDevice, st));
-    ctx->tm.total_launches += launch_rle(a, rows, (flags & JB_FLAG_REF_ALWAYS_EOB) ? 1 : 0, b, c, st);
-    CK(cudaMemcpyAsync(pairs, b, rows * 512, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(counts, c, rows * 4, cudaMemcpyDeviceToHost, st));
+    { Timed t_(ctx, st, 3); CK(cudaMemcpyAsync(a, zz, rows * 256, cudaMemcpyHostToDevice, st)); }
+    { Timed t_(ctx, st, 12); ctx->tm.total_launches += launch_rle(a, rows, (flags & JB_FLAG_REF_ALWAYS_EOB) ? 1 : 0, b, c, st); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(pairs, b, rows * 512, cudaMemcpyDeviceToHost, st)); }
+    { Timed t_(ctx, st, 4); CK(cudaMemcpyAsync(counts, c, rows * 4, cudaMemcpyDeviceToHost, st)); }
     STAGE_END()
 }
 

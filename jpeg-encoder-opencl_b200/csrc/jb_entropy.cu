@@ -837,7 +837,7 @@ __global__ void __launch_bounds__(256) k_copy_bytes(uint8_t* __restrict__ dst_ba
 // k_stitch_exchange (one warp): publish this rank's length, wait until every rank has published the step's length,
 // prefix-sum them: off[0] = base + lengths of the ranks before this one, off[1] = base + all lengths.  A rank can be
 // at most one step ahead of the slowest one (it needs everybody's length to pass), hence the two parities.
-// Polling gives up after ~2 s (a peer died): the offsets become 2^62, which the placement kernel's capacity check
+// Polling gives up after ~20 s (a peer died): the offsets become 2^62, which the placement kernel's capacity check
 // rejects -- nothing is written and jb_sync reports the overflow.
 constexpr int STITCH_MAX_RANKS = 16;
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
@@ -851,7 +851,7 @@ __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
 __device__ __forceinline__ bool poll_at_least(const uint64_t* p, uint64_t epoch) {
     const long long t0 = clock64();
     while (ld_acquire_sys(p) < epoch) {
-        if (clock64() - t0 > 4000000000ll) return false;  // ~2 s at 1.9 GHz
+        if (clock64() - t0 > 40000000000ll) return false;  // ~20 s at 1.9 GHz
         __nanosleep(200);
     }
     return true;

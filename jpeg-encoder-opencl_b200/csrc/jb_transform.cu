@@ -78,8 +78,11 @@ __device__ __forceinline__ void quant_stage(const float (&v)[64], const Transfor
         st[lane * 8 + (p ^ (lane & 7))] = make_uint4(wd[4 * p], wd[4 * p + 1], wd[4 * p + 2], wd[4 * p + 3]);
 }
 
+// The flagged coefficients of one block take consecutive places of the list (one atomic per block, not per
+// coefficient): k_fixup then fetches the block's samples once for all of them.
 __device__ __noinline__ void append_ties(uint32_t* list, uint32_t* count, uint32_t cap, uint32_t gblock, uint32_t lo,
                                          uint32_t hi) {
+    uint32_t idx = atomicAdd(count, (uint32_t)(__popc(lo) + __popc(hi)));
     while (lo | hi) {
         int k;
         if (lo) {
@@ -89,8 +92,8 @@ __device__ __noinline__ void append_ties(uint32_t* list, uint32_t* count, uint32
             k = 31 + __ffs(hi);
             hi &= hi - 1;
         }
-        uint32_t idx = atomicAdd(count, 1u);
         if (idx < cap) list[idx] = gblock * 64u + (uint32_t)k;
+        ++idx;
     }
 }
 
@@ -1372,7 +1375,8 @@ int launch_transform_edge(const TransformArgs& a_in, cudaStream_t s) {
 #endif
 constexpr int FIX_WARPS = 4;  // the kernel is latency-bound: small batches keep 64 warps per SM resident
 __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant__ FixupArgs a) {
-    __shared__ double s_term[FIX_WARPS][FIX_BATCH][65];  // [entry of the batch][term], padded: conflict-free both ways  // [term][entry of the batch]: conflict-free both ways
+    __shared__ double s_term[FIX_WARPS][FIX_BATCH][65];  // [entry of the batch][term], padded: conflict-free both ways
+    __shared__ double s_smp[FIX_WARPS][64];              // level-shifted samples of the block being replayed
     uint32_t n = *a.tie_count;
     if (n > a.tie_cap) n = a.tie_cap;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1417,19 +1421,30 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
             d_flo = (uint32_t)foff;
             d_fhi = (uint32_t)(foff >> 32);
         }
+        uint32_t have_block = 0xFFFFFFFFu;  // consecutive entries of one block (append_ties) share its samples
         for (int j = 0; j < n_here; ++j) {
-            const uint32_t misc = __shfl_sync(0xffffffffu, d_misc, j);
+            const uint32_t misc = __shfl_sync(0xffffffffu, d_misc, j), gblock = __shfl_sync(0xffffffffu, my_entry, j) >> 6;
             const unsigned long long foff =
                 ((unsigned long long)__shfl_sync(0xffffffffu, d_fhi, j) << 32) | __shfl_sync(0xffffffffu, d_flo, j);
             const int x0 = (int)__shfl_sync(0xffffffffu, d_x0, j), y0 = (int)__shfl_sync(0xffffffffu, d_y0, j);
             const int comp = (int)(misc & 3u), step = (int)((misc >> 2) & 3u);
             const int nat = (int)(misc >> 4), v = nat >> 3, u = nat & 7;
-            Image im{a.rgb + foff, a.pitch, a.g.W, a.g.H, a.ydown};
+            if (gblock != have_block) {  // (warp-uniform)
+                Image im{a.rgb + foff, a.pitch, a.g.W, a.g.H, a.ydown};
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = lane + 32 * h, x = i & 7, y = i >> 3;
+                    const double smp = (double)sample_at(im, x0 + x * step, y0 + y * step, comp, a.g.sub != JB_SUB_444);  // utils.cpp:236
+                    s_smp[w][i] = __dsub_rn(smp, 128.0);                                                                  // utils.cpp:190
+                }
+                __syncwarp();
+                have_block = gblock;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                int i = lane + 32 * h, x = i & 7, y = i >> 3;
-                double smp = (double)sample_at(im, x0 + x * step, y0 + y * step, comp, a.g.sub != JB_SUB_444);  // utils.cpp:236
-                smp = __dsub_rn(smp, 128.0);                                                              // utils.cpp:190
+                const int i = lane + 32 * h, x = i & 7, y = i >> 3;
+                const double smp = s_smp[w][i];
                 s_term[w][j][i] = a.inplace_dct ? smp : __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), a.costab[v * 8 + y]);  // utils.cpp:330
             }
         }

@@ -162,3 +162,30 @@ def test_the_references_own_driver_function_runs_on_the_gpu(tmp_path, golden):
     nored = ol.read_ppm(str(tmp_path / "data" / "fruitCPU_no_blue.ppm"))
     fruit = ol.read_ppm(os.path.join(GOLDEN, "fruit.ppm"))
     assert not nored[:, :, 0].any() and np.array_equal(nored[:, :, 1:], fruit[:, :, 1:])
+
+
+def test_cli_staged_mode_and_speedup_table(tmp_path, fruit):
+    """jpegb200_cli --staged 1 --cpu-telemetry FILE: the reference's stage sequence through the staged entry points with a
+    kernel time per stage (the reference's "<stage> time (GPU)" lines, cpp:362 ff.), Huffman and transfers included, the
+    "## Speedups: ##" table of cpp:621-629 against the reference's own CPU times (measured here with oracle/_ref when it
+    is built), and the check that the staged zigzag array equals the fused path's coefficients."""
+    tools()
+    tel = tmp_path / "cpu.txt"
+    if ol.have_ref():
+        us = ol.ref_pipeline(fruit, 0)["stage_us"]
+    else:  # no reference build on this machine: any positive numbers exercise the table
+        us = dict(CSC=300.0, CDS=100.0, levelShift=160.0, DCT=68000.0, Quant=2200.0, TotalCopy=1700.0, zigZag=1200.0, RLE=1900.0, Huffman=5500.0)
+    tel.write_text("".join(f"{k}Time {v}\n" for k, v in us.items()))
+    out = tmp_path / "fruit.jpg"
+    r = subprocess.run([os.path.join(HOST, "jpegb200_cli"), os.path.join(GOLDEN, "fruit.ppm"), str(out), "--quality", "50", "--sub", "repl420",
+                        "--staged", "1", "--cpu-telemetry", str(tel)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for label in ("Color conversion", "Chroma subsampling", "Level shifting", "DCT", "Quantization", "ZigZag", "RLE", "Huffman"):
+        m = re.search(rf"^{label} time \(GPU\): ([0-9.]+) us", r.stdout, re.M)
+        assert m and float(m.group(1)) > 0, label
+        assert re.search(rf"^{label}: [0-9.]+$", r.stdout, re.M), "speed-up line of " + label
+    assert "## Speedups: ##" in r.stdout and "## Speedups (fused path): ##" in r.stdout
+    assert "staged zigzag array == fused coefficients: yes" in r.stdout
+    assert re.search(r"Huffman time \(GPU\): [0-9.]+ us   \(129097 bits", r.stdout)  # SURVEY 8c: conformant bit count of fruit.ppm
+    ql, qc = ol.q50()
+    assert out.read_bytes() == ol.encode_jfif(fruit, ol.SUB_REPL420, ql, qc, 0)
