@@ -65,6 +65,7 @@ def parse():
                     help="JB_FLAG_OPTIMIZE_HUFFMAN: per-call optimal Huffman tables (two passes; not the headline configuration)")
     ap.add_argument("--ref-exact", action="store_true",
                     help="the reference as written: JB_FLAG_REF_INPLACE_DCT | REF_TYPO_TABLES | REF_ALWAYS_EOB (use with --workload repl1080p)")
+    ap.add_argument("--tma", action="store_true", help="JB_FLAG_TMA: stage the image tiles with TMA boxes instead of per-lane cp.async (A/B)")
     ap.add_argument("--tensor-dct", type=int, default=1,
                     help="transform kernel: 1 = tcgen05 (library default), 0 = CUDA-core FMA kernel (JB_FLAG_FMA_DCT)")
     return ap.parse_args()
@@ -290,7 +291,7 @@ def run_batch(a, jb, enc, torch, dd, workload, F, steps, warmup, want_e2e, want_
     W, H, subname, q, ri, _, seed0 = WORKLOADS[workload]
     rank, world, local_rank = dd.rank, dd.world, dd.local_rank
     sub = {"420": jb.SUB_420, "444": jb.SUB_444, "repl420": jb.SUB_REPL420}[subname]
-    flags = (0 if a.tensor_dct else jb.FLAG_FMA_DCT) | (jb.FLAG_OPTIMIZE_HUFFMAN if a.optimize_huffman else 0) \
+    flags = (0 if a.tensor_dct else jb.FLAG_FMA_DCT) | (jb.FLAG_OPTIMIZE_HUFFMAN if a.optimize_huffman else 0) | (jb.FLAG_TMA if a.tma else 0) \
         | ((jb.FLAG_REF_INPLACE_DCT | jb.FLAG_REF_TYPO_TABLES | jb.FLAG_REF_ALWAYS_EOB) if ref_exact else 0)
     params = jb.make_params(sub, quality=q, restart_interval=ri, flags=flags)
     pitch, fstride = W * 3, W * H * 3

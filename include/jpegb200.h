@@ -59,6 +59,11 @@ typedef enum {
 #define JB_FLAG_FMA_DCT 0x40u        /* use the CUDA-core kernel (register AAN FDCT, near-tie     *
                                       * band proven analytically) instead of the tcgen05 one      */
 
+#define JB_FLAG_TMA 0x100u            /* 4:2:0 tcgen05 transform: stage the image tiles with TMA (cp.async.bulk.tensor  *
+                                      * boxes of a 3-D tensor map, k_transform_tma) instead of per-lane cp.async.     *
+                                      * Bit-identical output; needs 16-byte aligned base / pitch / frame stride (else *
+                                      * ignored).  Measured 6 % slower than the cp.async kernel on the B200 (DESIGN    *
+                                      * 3.1d), hence opt-in                                                           */
 #define JB_FLAG_OPTIMIZE_HUFFMAN 0x80u /* two passes like libjpeg's optimize_coding: the symbols of the call's   *
                                       * coefficients are counted on the GPU, optimal tables (T.81 K.2) are built  *
                                       * per call (shared by the frames of a batch), written into the DHT          *

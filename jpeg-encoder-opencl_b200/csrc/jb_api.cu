@@ -421,6 +421,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ta.unit_counter = s.d_scalars + 12;
     ta.tie_cap = s.tie_cap;
     ta.inplace_dct = (p->flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0;
+    ta.use_tma = (p->flags & JB_FLAG_TMA) ? 1 : 0;
     if (ta.inplace_dct) {
         // Q1 in the fused path is a different W matrix of the tcgen05 contraction: the CUDA-core kernels (AAN
         // factorisation) cannot express it, and the near-tie replay must be on

@@ -71,6 +71,7 @@ struct TransformArgs {
     const uint8_t* tc_mat;     // tensor-core variant: 6 pre-swizzled bf16 matrices (null = FMA kernel)
     float tband[2][64];        // tensor-core variant: near-tie bands in zigzag order
     int inplace_dct;           // Q1 (utils.cpp:342-345): W holds the in-place map; edge blocks go to the replay whole
+    int use_tma;               // JB_FLAG_TMA: stage pixels with TMA boxes (k_transform_tma) instead of per-lane cp.async
     QuantConst qc;
 };
 

@@ -19,6 +19,7 @@
 // keeps the hot kernel free of the padding code (instruction-cache footprint).
 // Algorithmic HBM traffic: 3 B/px read + 2 B/sample written = 6 B/px (4:2:0) or
 // 9 B/px (4:4:4, replicated 4:2:0).
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
 #include "jb_pixels.cuh"
@@ -950,6 +951,256 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_TMEM_COLS));
 }
 
+// ================================================== tensor-core variant with TMA-staged image tiles (4:2:0) ==
+// Same pipeline as k_transform_tc; what changes is how pixels reach shared memory.  A warp's unit is a RECTANGLE of
+// 8 x 2 MCUs (128 x 32 px), so every row pair of the unit is two boxes of a 3-D tensor map over the RGB batch
+// (uint32 elements: x = pitch / 4, y = image row, z = frame; box 96 x 2 x 1 = 2 image rows x 384 bytes): one elected
+// lane issues two cp.async.bulk.tensor (SASS UTMALDG) per row pair, completion arrives on an mbarrier.  The per-lane
+// cp.async of k_transform_tc and its pointer-walking cursors (two 64-bit pointers, row counters, validity flags per
+// lane; ~30 instructions per row pair in every lane) are gone; coordinates are warp-uniform integers.  Rows below an
+// (even) image height are fetched from their mirror image (utils.cpp:223-232): the box of the pair (y, y+1) with
+// y >= H is the box at 2H-2-y, and the lanes read its two rows in swapped order.  Needs a 16-byte aligned base,
+// pitch and frame stride (the tensor map's rules); other inputs take k_transform_tc<8 / 4>.
+constexpr int TM_BOX_BYTES = 2 * 8 * 48;                    // one box: 2 image rows x 8 MCUs x 48 bytes
+constexpr int TM_SLOT_BYTES = 2 * TM_BOX_BYTES;             // one row pair of a warp's unit: MCU row 0, MCU row 1
+constexpr int TM_RING_BYTES = 2 * 4 * TM_SLOT_BYTES;        // per group: [slot][warp]; = TC_RING_BYTES
+static_assert(TM_RING_BYTES == TC_RING_BYTES, "the TMA ring takes the place of the cp.async ring");
+
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const void* tmap, int x, int y, int z, uint32_t mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(mbar)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tma(const __grid_constant__ TransformArgs a,
+                                                                      const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar[TC_GROUPS][2];
+    __shared__ __align__(8) uint64_t s_ring_bar[TC_GROUPS][4][2];  // [group][warp][slot]: a row pair of the unit has landed
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_next[TC_GROUPS];
+    __shared__ uint32_t s_desc[TC_GROUPS + 1][4];
+    __shared__ uint32_t s_ydown[2048];
+    uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, wg = gt >> 5, lane = tid & 31;
+    uint8_t* sB = smem;
+    uint8_t* tileA = smem + TC_B_BYTES + g * 2 * TC_TILE_BYTES;
+    uint8_t* tileC = tileA + TC_TILE_BYTES;
+    // ring of raw pixels: this warp's two slots (one row pair each: box of MCU row 0, box of MCU row 1)
+    const uint32_t ring = smem_u32(smem + TC_B_BYTES + TC_GROUPS * 2 * TC_TILE_BYTES + g * TM_RING_BYTES) + wg * TM_SLOT_BYTES;
+    constexpr uint32_t kSlotStride = 4 * TM_SLOT_BYTES;
+    for (int i = tid; i < TC_B_BYTES / 16; i += TC_GROUPS * 128)
+        reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.tc_mat) + i);
+    for (int i = tid; i < 2048; i += TC_GROUPS * 128) s_ydown[i] = __ldg(a.ydown + i);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (gt == 0) {
+        s_desc[g][0] = (uint32_t)umma_desc(smem_u32(tileA));
+        s_desc[g][1] = (uint32_t)umma_desc(smem_u32(tileC));
+        s_desc[TC_GROUPS][g] = (uint32_t)umma_desc(smem_u32(sB + g * 8192));
+    }
+    if (tid < TC_GROUPS * 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[0][0]) + 8 * tid));
+    if (tid < TC_GROUPS * 8) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_ring_bar[0][0][0]) + 8 * tid));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d0 = s_tmem + (uint32_t)(g * 128), tmem_d1 = tmem_d0 + 64;
+    const uint32_t lane_off = (uint32_t)(wg * 32) << 16;
+    const uint32_t mbar0 = smem_u32(&s_mbar[g][0]), mbar1 = smem_u32(&s_mbar[g][1]);
+    const uint32_t rbar = smem_u32(&s_ring_bar[g][wg][0]);  // + 8 * slot
+    const uint32_t idesc = (1u << 4) | (8u << 17) | (8u << 24);
+    uint32_t phase0 = 0, phase1 = 0, rphase = 0;  // rphase: bit s = parity the next wait on ring slot s expects
+    uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
+    const int half = lane & 1;
+    const uint32_t stride = gridDim.x * TC_GROUPS * 4;
+    const uint32_t sw_own = (uint32_t)(gt & 7);
+    const uint32_t a_row = smem_u32(tileA) + gt * 128;
+    const int row_cb = gt & ~1, row_cr = gt | 1;
+    const uint32_t ac_cb = smem_u32(tileC) + row_cb * 128 + half * 8, ac_cr = smem_u32(tileC) + row_cr * 128 + half * 8;
+    const uint32_t sw_cb = (uint32_t)(row_cb & 7), sw_cr = (uint32_t)(row_cr & 7);
+    // this lane's MCU inside the unit: column c (0..7), MCU row r (0..1); its 24 bytes of a box row
+    const int mc = (lane >> 1) & 7, mr = lane >> 4;
+    const uint32_t lane_rd = ring + (uint32_t)mr * TM_BOX_BYTES + (uint32_t)mc * 48u + (uint32_t)half * 24u;
+    const int img_h = a.g.H;
+
+    const bool issuer = __shfl_sync(0xffffffffu, (uint32_t)wg, 0) == 0;
+    auto issue = [&](int tile_sel, int tab, uint32_t tmem_d, uint32_t mbar) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+            const uint64_t hi = (uint64_t)0x40004040u << 32;
+            const uint64_t da = hi | lds_volatile(smem_u32(&s_desc[g][tile_sel]));
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const uint64_t db = hi | lds_volatile(smem_u32(&s_desc[TC_GROUPS][tab * 2 + s2]));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+        }
+    };
+    auto publish = [&]() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    };
+    auto divmod = [](uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t& r) {
+        q = __umulhi(n, m);
+        r = n - q * d;
+        if (r >= d) {
+            q += 1;
+            r -= d;
+        }
+    };
+    // A warp's unit: warp-uniform coordinates (frame, first image row, first element column of its boxes)
+    struct Unit {
+        int f, y0, x_el;   // frame, first image row (MCU row 2 uy), first uint32 column (96 per 8 MCUs)
+        bool valid, row1;  // the unit exists; its second MCU row exists
+        uint32_t gm;       // this LANE's MCU in the coefficient array (0xFFFFFFFF: none)
+    };
+    auto decode = [&](uint32_t unit_base) {
+        const uint32_t U = unit_base + (uint32_t)wg;
+        Unit u;
+        u.valid = U < a.total_units;
+        uint32_t f, rem, uy, ux;
+        divmod(u.valid ? U : 0u, a.tc_per_frame, a.tc_magic_frame, f, rem);
+        divmod(rem, a.tc_row_len, a.tc_magic_row, uy, ux);
+        u.f = (int)f;
+        u.y0 = (int)uy * 32;
+        u.x_el = (int)ux * 96;
+        u.row1 = (int)(2 * uy + 1) < a.fast_mcuy;
+        const int mx = (int)ux * 8 + mc, my = (int)uy * 2 + mr;
+        u.gm = u.valid && mx < a.fast_mcux && my < a.fast_mcuy ? f * (uint32_t)a.g.n_mcu + (uint32_t)my * (uint32_t)a.g.mcux + (uint32_t)mx
+                                                                : 0xFFFFFFFFu;
+        return u;
+    };
+    // start the copy of row pair `pi` (0..7) of unit `u` into ring slot `sl`: lane 0 posts the byte count and the boxes
+    auto fetch_pair = [&](const Unit& u, int pi, int sl) {
+        if (lane == 0) {
+            const uint32_t bar = rbar + 8u * (uint32_t)sl, dst = ring + (uint32_t)sl * kSlotStride;
+            const uint32_t bytes = u.valid ? (u.row1 ? 2u * TM_BOX_BYTES : (uint32_t)TM_BOX_BYTES) : 0u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            if (u.valid) {
+                int ya = u.y0 + 2 * pi, yb = ya + 16;
+                ya = ya < img_h ? ya : 2 * img_h - 2 - ya;  // mirrored pair: fetched from its mirror image, rows swapped by the readers
+                yb = yb < img_h ? yb : 2 * img_h - 2 - yb;
+                tma_load_box(dst, &tmap, u.x_el, ya, u.f, bar);
+                if (u.row1) tma_load_box(dst + TM_BOX_BYTES, &tmap, u.x_el, yb, u.f, bar);
+            }
+        }
+    };
+
+    uint32_t base = (blockIdx.x * TC_GROUPS + g) * 4;
+    Unit cur = decode(base);
+    if (base < a.total_units) {
+        fetch_pair(cur, 0, 0);
+        fetch_pair(cur, 1, 1);
+    }
+    while (base < a.total_units) {
+        if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
+        uint32_t nbase = 0;
+        Unit nxt = cur;
+        const uint32_t gm = cur.gm;
+        const bool valid = gm != 0xFFFFFFFFu;
+        const uint32_t gb0 = gm * 6u;
+        const int y_lane = cur.y0 + 16 * mr;
+
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            const int sl = it & 1;
+            mbar_wait(rbar + 8u * (uint32_t)sl, (rphase >> sl) & 1u);
+            rphase ^= 1u << sl;
+            // the two image rows of this pair; below the image the box holds the mirror image: swapped order
+            const bool swapped = y_lane + 2 * it >= img_h;
+            const uint32_t src = lane_rd + (uint32_t)sl * kSlotStride;
+            const uint32_t src0 = src + (swapped ? 384u : 0u), src1 = src + (swapped ? 0u : 384u);
+            uint32_t w0[6], w1[6];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                uint2 v0 = lds64(src0 + 8 * j), v1 = lds64(src1 + 8 * j);
+                w0[2 * j] = v0.x;
+                w0[2 * j + 1] = v0.y;
+                w1[2 * j] = v1.x;
+                w1[2 * j + 1] = v1.y;
+            }
+            __syncwarp();  // every lane has read the slot before lane 0 lets the TMA refill it
+            if (it == 6) {
+                nbase = s_next[g];  // written before the barrier of it == 3
+                nxt = decode(nbase);
+            }
+            if (it < 6)
+                fetch_pair(cur, it + 2, sl);
+            else
+                fetch_pair(nxt, it - 6, sl);
+            if (it == 4) mbar_wait(mbar0, phase0);
+
+            Row8T o0, o1;
+            csc_row8_t(w0, s_ydown, o0);
+            csc_row8_t(w1, s_ydown, o1);
+            const uint32_t rp = (uint32_t)(it & 3);
+            sts128(a_row + (((2 * rp) ^ sw_own) << 4), make_uint4(luma_h2(o0.y[0], o0.y[1]), luma_h2(o0.y[2], o0.y[3]),
+                                                                  luma_h2(o0.y[4], o0.y[5]), luma_h2(o0.y[6], o0.y[7])));
+            sts128(a_row + (((2 * rp + 1) ^ sw_own) << 4), make_uint4(luma_h2(o1.y[0], o1.y[1]), luma_h2(o1.y[2], o1.y[3]),
+                                                                      luma_h2(o1.y[4], o1.y[5]), luma_h2(o1.y[6], o1.y[7])));
+            uint32_t sb[4], sr[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                sb[c] = (o0.cb[2 * c] >> 24) + (o0.cb[2 * c + 1] >> 24) + (o1.cb[2 * c] >> 24) + (o1.cb[2 * c + 1] >> 24);
+                sr[c] = (o0.cr[2 * c] >> 24) + (o0.cr[2 * c + 1] >> 24) + (o1.cr[2 * c] >> 24) + (o1.cr[2 * c + 1] >> 24);
+            }
+            const uint32_t crow = (uint32_t)it;
+            sts64(ac_cb + ((crow ^ sw_cb) << 4), make_uint2(chroma_h2(sb[0], sb[1]), chroma_h2(sb[2], sb[3])));
+            sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(chroma_h2(sr[0], sr[1]), chroma_h2(sr[2], sr[3])));
+            if (it == 3) {
+                publish();
+                if (issuer) issue(0, 0, tmem_d0, mbar0);
+            }
+        }
+        publish();
+        if (issuer) issue(0, 0, tmem_d1, mbar1);
+
+        auto finish = [&](uint32_t tmem_d, int tab, int blk, uint32_t wait_mbar, uint32_t wait_parity) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t t[64];
+            tmem_ld64(tmem_d + lane_off, t);
+            uint4* st = reinterpret_cast<uint4*>(tileA) + wg * 256;
+            uint32_t tl = 0, th = 0;
+            if (tab == 0)
+                tc_quant_stage<0>(t, a, st, lane, tl, th, wait_mbar, wait_parity);
+            else
+                tc_quant_stage<1>(t, a, st, lane, tl, th, wait_mbar, wait_parity);
+            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + blk + half, tl, th);
+            __syncwarp();
+            const uint32_t piece0 = (uint32_t)(blk + ((lane >> 3) & 1)) * 8u + (uint32_t)(lane & 7);
+#pragma unroll
+            for (int it8 = 0; it8 < 8; ++it8) {
+                const int sb = it8 * 4 + (lane >> 3), pc = lane & 7;
+                const uint32_t m_gm = __shfl_sync(0xffffffffu, gm, 4 * it8 + 2 * (lane >> 4));
+                if (m_gm != 0xFFFFFFFFu) coef4[m_gm * 48u + piece0] = st[sb * 8 + (pc ^ (sb & 7))];
+            }
+            __syncwarp();
+        };
+        phase0 ^= 1;
+        finish(tmem_d0, 0, 0, mbar1, phase1);
+        phase1 ^= 1;
+        publish();
+        if (issuer) issue(1, 1, tmem_d0, mbar0);
+        finish(tmem_d1, 0, 2, 0, 0);
+        mbar_wait(mbar0, phase0);
+        phase0 ^= 1;
+        finish(tmem_d0, 1, 4, 0, 0);
+        cur = nxt;
+        base = nbase;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_TMEM_COLS));
+}
+
 // ================================================== tensor-core variant, 8x8-pixel MCUs ==
 // 4:4:4 and replicated 4:2:0 (the reference's own mode, utils.cpp:113-141 + 667-695): an MCU is one 8x8
 // block of each component.  Same machinery as k_transform_tc -- exact CSC on CUDA cores, one
@@ -1305,6 +1556,50 @@ static void launch_tc3(const TransformArgs& a, int align, int grid, cudaStream_t
     }
 }
 
+// The 4:2:0 kernel with TMA-staged tiles: units are rectangles of 8 x 2 MCUs; the RGB batch is described by one 3-D
+// tensor map (uint32 elements: pitch / 4 columns, H rows, n_frames frames; box = 96 x 2 x 1).  Returns false when the
+// driver has no tensor-map encoder or rejects the shape (the caller then takes the cp.async kernel).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static bool launch_tma(const TransformArgs& a_in, int sms, cudaStream_t s) {
+    EncodeTiledFn encode = tensor_map_encoder();
+    if (!encode) return false;
+    TransformArgs a = a_in;
+    const size_t fstride = a.n_frames > 1 ? a.frame_stride : a.pitch * (size_t)a.g.H;
+    if ((a.pitch >> 2) >= (1ull << 32) || a.pitch >= (1ull << 40) || fstride >= (1ull << 40)) return false;
+    CUtensorMap tm;
+    const cuuint64_t dims[3] = {(cuuint64_t)(a.pitch / 4), (cuuint64_t)a.g.H, (cuuint64_t)a.n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.pitch, (cuuint64_t)fstride};
+    const cuuint32_t box[3] = {96, 2, 1}, estr[3] = {1, 1, 1};
+    if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(a.rgb), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    const uint32_t units_x = (uint32_t)((a.fast_mcux + 7) / 8), units_y = (uint32_t)((a.fast_mcuy + 1) / 2);
+    a.tc_row_len = units_x;
+    a.tc_per_frame = units_x * units_y;
+    a.total_units = a.tc_per_frame * (uint32_t)a.n_frames;
+    if (!a.total_units) return false;
+    a.tc_magic_frame = div_magic32(a.tc_per_frame);
+    a.tc_magic_row = div_magic32(a.tc_row_len);
+    const int needg = (int)((a.total_units + 4 * TC_GROUPS - 1) / (4 * TC_GROUPS));
+    cudaFuncSetAttribute(k_transform_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    k_transform_tma<<<needg < sms ? needg : sms, TC_GROUPS * 128, TC_SMEM, s>>>(a, tm);
+    return true;
+}
+
 int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
     TransformArgs a = a_in;
     plan_fast(a);
@@ -1330,6 +1625,8 @@ int launch_transform(const TransformArgs& a_in, cudaStream_t s) {
                 launch_tc3<JB_SUB_444>(a, align16, gridg, s);
             else
                 launch_tc3<JB_SUB_REPL420>(a, align16, gridg, s);
+        } else if (align16 == 16 && a.use_tma && launch_tma(a, sms, s)) {
+            // TMA-staged tiles (k_transform_tma): 16-byte aligned base / pitch / frame stride
         } else if (align16 == 16) {
             cudaFuncSetAttribute(k_transform_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
             k_transform_tc<16><<<gridg, TC_GROUPS * 128, TC_SMEM, s>>>(a);

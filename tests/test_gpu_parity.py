@@ -781,3 +781,26 @@ def test_strip_in_two_asynchronous_halves(enc, jb):
     with pytest.raises(jb.JbError) as e:
         enc.sync()
     assert e.value.code == jb.E_NOSPACE
+
+
+def test_tma_staged_transform_is_bit_identical(enc, jb, fruit):
+    """JB_FLAG_TMA: the 4:2:0 tcgen05 transform with TMA-staged image tiles (k_transform_tma: cp.async.bulk.tensor boxes of a
+    3-D tensor map, units of 8 x 2 MCUs, rows below the image fetched from their mirror image) == the oracle, for widths
+    that are / are not multiples of the 128-pixel unit, heights with a mirrored last MCU row, odd numbers of MCU rows,
+    batches (frame coordinate of the tensor map) and whole 1080p frames."""
+    ql, qc = ol.quality_tables(75)
+    p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, flags=jb.FLAG_TMA)
+    p0 = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc)
+    for W, H in ((1920, 1080), (128, 32), (256, 40), (1024, 16), (2048, 1000), (144, 72), (16, 16), (4096, 56), (336, 264)):
+        img = ol.synth(W * 7 + H, W, H)
+        got, want = enc.transform(img, p), ol.transform(img, ol.SUB_420, ql, qc)
+        assert np.array_equal(got, want), f"{W}x{H}: " + mismatch_report(got, want)
+        assert enc.encode_jfif(img, p) == enc.encode_jfif(img, p0) == ol.encode_jfif(img, ol.SUB_420, ql, qc, 0)
+    frames = np.stack([ol.synth(300 + f, 640, 360) for f in range(7)])
+    out, offs, sizes = enc.encode_batch(frames, p)
+    for f in range(7):
+        assert bytes(out[int(offs[f]): int(offs[f] + sizes[f])]) == ol.encode_jfif(frames[f], ol.SUB_420, ql, qc, 0), f
+    noise = noise_image(5, 1280, 720)
+    q100 = ol.quality_tables(100)
+    pn = jb.make_params(ol.SUB_420, qlum=q100[0], qchrom=q100[1], flags=jb.FLAG_TMA)
+    assert np.array_equal(enc.transform(noise, pn), ol.transform(noise, ol.SUB_420, *q100))
