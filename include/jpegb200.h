@@ -202,11 +202,30 @@ int jb_encode_jfif(jb_ctx *ctx, const uint8_t *rgb, size_t W, size_t H, size_t p
 int jb_encode_batch(jb_ctx *ctx, const uint8_t *rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
                     size_t frame_stride, const jb_params *p, uint8_t *out, size_t cap, uint64_t *offsets,
                     uint64_t *sizes);
+/* One image of ANY size as a grid of independent JFIF files -- the way past SOF0's 16-bit X / Y (DNL cannot
+ * help: its NL field is 16 bits too, T.81 B.2.5).  Tiles are tile_w x tile_h pixels (multiples of the MCU, <= 65535),
+ * the last column / row of tiles is narrower / shorter and mirror-padded like any image; tile (tx, ty) is file
+ * ty * ceil(W / tile_w) + tx: offsets[] / sizes[] (host arrays of *n_tiles entries) locate it in `out`.  Every tile
+ * column is coded as one batch (the tiles of a column are equally sized frames tile_h * pitch bytes apart). */
+int jb_encode_tiles(jb_ctx *ctx, const uint8_t *rgb, size_t W, size_t H, size_t pitch, size_t tile_w, size_t tile_h,
+                    const jb_params *p, uint8_t *out, size_t cap, uint64_t *offsets, uint64_t *sizes, size_t *n_tiles);
 /* Same with every buffer resident in HBM (d_* are device pointers); asynchronous on jb_stream(),
  * complete after jb_sync().  d_total receives the total bytes (1 x uint64). */
 int jb_encode_batch_device(jb_ctx *ctx, const uint8_t *d_rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
                            size_t frame_stride, const jb_params *p, uint8_t *d_out, size_t cap, uint64_t *d_offsets,
                            uint64_t *d_sizes, uint64_t *d_total);
+/* NV12-style device input: the frames are YCbCr 4:2:0 already -- a full-resolution Y plane (pitch_y)
+ * and a plane of interleaved Cb,Cr pairs at half resolution (ceil(W/2) pairs x ceil(H/2) rows, pitch_uv), as video
+ * decoders and camera pipelines leave them in HBM.  No colour conversion and no chroma averaging happen; the
+ * reference's stages from the mirror padding on apply unchanged (the pairs replicated over their 2x2 cells are the
+ * plane performCDS, utils.cpp:113-141, leaves behind).  JB_SUB_420 only; everything else as jb_encode_batch_device. */
+int jb_encode_nv12_device(jb_ctx *ctx, const uint8_t *d_y, size_t pitch_y, size_t frame_stride_y, const uint8_t *d_uv,
+                          size_t pitch_uv, size_t frame_stride_uv, size_t n_frames, size_t W, size_t H, const jb_params *p,
+                          uint8_t *d_out, size_t cap, uint64_t *d_offsets, uint64_t *d_sizes, uint64_t *d_total);
+/* RGB8 -> NV12 on the device with the reference's own arithmetic: performCSC (utils.cpp:92-110) and performCDS
+ * (truncated mean of every complete 2x2 cell; a cell cut by an odd edge keeps its top-left pixel's chroma). */
+int jb_rgb8_to_nv12_device(jb_ctx *ctx, const uint8_t *d_rgb, size_t W, size_t H, size_t pitch, uint8_t *d_y, size_t pitch_y,
+                           uint8_t *d_uv, size_t pitch_uv);
 /* One horizontal strip of a large image whose restart intervals are whole MCU rows groups
  * (multi-GPU: strip s on GPU s).  Produces only entropy bytes (no header, no EOI); RST
  * numbering starts at first_interval; a RST marker follows the last interval unless

@@ -35,7 +35,7 @@ SYMBOLS = [
     "jb_write_header", "jb_synth_rgb_device", "jb_planar_u32_from_aos", "jb_planar_u32_interleave",
     "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32", "jb_optimal_huffman_spec",
     "jb_encode_strip_begin", "jb_encode_strip_finish", "jb_copy_bytes_device", "jb_ipc_export", "jb_ipc_open", "jb_ipc_close",
-    "jb_stitch_exchange", "jb_stitch_complete",
+    "jb_stitch_exchange", "jb_stitch_complete", "jb_encode_tiles", "jb_encode_nv12_device", "jb_rgb8_to_nv12_device",
     "jb_pad_mirror_planar_u32", "jb_blockify_planar_i32", "jb_f64_to_u8", "jb_remove_red_aos", "jb_value_categories",
 ]
 
@@ -130,6 +130,9 @@ def lib():
     L.jb_entropy.argtypes = [vp, vp, sz, PP, vp, sz, C.POINTER(sz)]
     L.jb_encode_jfif.argtypes = [vp, vp, sz, sz, sz, PP, vp, sz, C.POINTER(sz)]
     L.jb_encode_batch.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp]
+    L.jb_encode_nv12_device.argtypes = [vp, vp, sz, sz, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, vp]
+    L.jb_rgb8_to_nv12_device.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp, sz]
+    L.jb_encode_tiles.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, C.POINTER(sz)]
     L.jb_encode_batch_device.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, vp]
     L.jb_encode_strip.argtypes = [vp, vp, sz, sz, sz, PP, u64, C.c_int, C.c_int, vp, sz, C.POINTER(sz)]
     L.jb_encode_strip_begin.argtypes = [vp, vp, sz, sz, sz, PP, u64, C.c_int, vp]
@@ -362,6 +365,20 @@ class Encoder:
                                         out.size, _ptr(offs), _ptr(sizes)))
         return out, offs, sizes
 
+    def encode_tiles(self, rgb, tile_w, tile_h, params, cap=None):
+        """(H, W, 3) uint8 of any size -> list of rows of JFIF files (bytes), tiles of tile_w x tile_h pixels."""
+        H, W, _ = rgb.shape
+        rgb = np.ascontiguousarray(rgb)
+        ntx, nty = -(-W // tile_w), -(-H // tile_h)
+        cap = cap if cap is not None else W * H * 3 + ntx * nty * 65536
+        out = np.empty(cap, np.uint8)
+        offs, sizes, n = np.zeros(ntx * nty, np.uint64), np.zeros(ntx * nty, np.uint64), C.c_size_t()
+        self._ck(self.L.jb_encode_tiles(self.h, _ptr(rgb), W, H, W * 3, tile_w, tile_h, C.byref(params), _ptr(out), cap, _ptr(offs),
+                                        _ptr(sizes), C.byref(n)))
+        assert n.value == ntx * nty
+        return [[out[int(offs[ty * ntx + tx]): int(offs[ty * ntx + tx] + sizes[ty * ntx + tx])].tobytes() for tx in range(ntx)]
+                for ty in range(nty)]
+
     def encode_batch_ptr(self, rgb_ptr, N, W, H, pitch, frame_stride, params, out_ptr, cap, offs, sizes):
         self._ck(self.L.jb_encode_batch(self.h, rgb_ptr, N, W, H, pitch, frame_stride, C.byref(params), out_ptr, cap,
                                         _ptr(offs), _ptr(sizes)))
@@ -370,6 +387,14 @@ class Encoder:
         """All pointers are device addresses (ints); asynchronous, finish with sync()."""
         self._ck(self.L.jb_encode_batch_device(self.h, d_rgb, N, W, H, pitch, frame_stride, C.byref(params), d_out, cap,
                                                d_offs, d_sizes, d_total))
+
+    def encode_nv12_device(self, d_y, pitch_y, fs_y, d_uv, pitch_uv, fs_uv, N, W, H, params, d_out, cap, d_offs, d_sizes, d_total):
+        """NV12-style frames in HBM (device addresses as ints) -> JFIF files; asynchronous, finish with sync()."""
+        self._ck(self.L.jb_encode_nv12_device(self.h, d_y, pitch_y, fs_y, d_uv, pitch_uv, fs_uv, N, W, H, C.byref(params), d_out, cap,
+                                              d_offs, d_sizes, d_total))
+
+    def rgb8_to_nv12_device(self, d_rgb, W, H, pitch, d_y, pitch_y, d_uv, pitch_uv):
+        self._ck(self.L.jb_rgb8_to_nv12_device(self.h, d_rgb, W, H, pitch, d_y, pitch_y, d_uv, pitch_uv))
 
     def encode_strip(self, rgb, params, first_interval, last_strip, W=None, rows=None, pitch=None, device_io=False,
                      out=None, cap=None):

@@ -162,6 +162,12 @@ T* carve(Arena& a, size_t count) {
     return reinterpret_cast<T*>(a.base + off);
 }
 
+// NV12-style input: d_rgb / pitch / frame_stride of enqueue_encode describe the Y plane, this the Cb,Cr plane
+struct Nv12Src {
+    const uint8_t* uv;
+    size_t pitch_uv, frame_stride_uv;
+};
+
 struct Plan {
     Geometry g;
     size_t n_frames;
@@ -406,7 +412,7 @@ int launch_entropy_graphed(jb_ctx* ctx, Slot& s, const EntropyArgs& ea) {
 int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, const uint8_t* d_rgb, size_t pitch,
                    size_t frame_stride, const Framing& fr, size_t W, size_t H, uint8_t* d_out, size_t out_cap,
                    uint64_t* d_off, uint64_t* d_size, uint64_t* d_total, uint8_t* h_hdr_stage = nullptr,
-                   EntropyArgs* two_phase = nullptr) {
+                   EntropyArgs* two_phase = nullptr, const Nv12Src* nv = nullptr) {
     CK(cudaMemsetAsync(s.d_scalars, 0, 64, s.st));
     TransformArgs ta{};
     ta.rgb = d_rgb;
@@ -422,6 +428,13 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ta.tie_cap = s.tie_cap;
     ta.inplace_dct = (p->flags & JB_FLAG_REF_INPLACE_DCT) ? 1 : 0;
     ta.use_tma = (p->flags & JB_FLAG_TMA) ? 1 : 0;
+    if (nv) {
+        if (pl.g.sub != JB_SUB_420 || (p->flags & JB_FLAG_REF_INPLACE_DCT))
+            return fail(ctx, JB_E_UNSUPPORTED, "NV12-style input is 4:2:0 (JB_SUB_420) and takes the true DCT");
+        ta.uv = nv->uv;
+        ta.pitch_uv = nv->pitch_uv;
+        ta.frame_stride_uv = nv->frame_stride_uv;
+    }
     if (ta.inplace_dct) {
         // Q1 in the fused path is a different W matrix of the tcgen05 contraction: the CUDA-core kernels (AAN
         // factorisation) cannot express it, and the near-tie replay must be on
@@ -439,7 +452,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
             tc.tc_valid = false;
         }
         ta.qc = tc.qc;
-        if (!(p->flags & JB_FLAG_FMA_DCT)) {  // tcgen05 transform, every subsampling mode (launch falls back if unaligned)
+        if (!(p->flags & JB_FLAG_FMA_DCT) && !nv) {  // tcgen05 transform, every subsampling mode (launch falls back if unaligned)
 #ifdef JB_DEBUG_KNOBS  // tests/tools/tc_band_scan.py only (a separate build): the shipped library reads no environment
             const char* e = getenv("JB_TC_STEP_ULPS");
             const double scale = e ? atof(e) : JB_TC_STEP_ULPS;
@@ -473,15 +486,22 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     if (p->flags & JB_FLAG_NO_TIE_FIXUP)
         for (int t = 0; t < 2; ++t)
             for (int i = 0; i < 64; ++i) ta.qc.band[t][i] = ta.tband[t][i] = 1.0f;  // never flag
-    {
+    if (nv) {
         Timed t(ctx, s.st, 0);
-        int n = launch_transform(ta, s.st);
+        int n = launch_transform_nv12(ta, s.st);
         ctx->tm.transform_launches += n;
         ctx->tm.total_launches += n;
-    }
-    {
-        Timed t(ctx, s.st, 5);
-        ctx->tm.total_launches += launch_transform_edge(ta, s.st);
+    } else {
+        {
+            Timed t(ctx, s.st, 0);
+            int n = launch_transform(ta, s.st);
+            ctx->tm.transform_launches += n;
+            ctx->tm.total_launches += n;
+        }
+        {
+            Timed t(ctx, s.st, 5);
+            ctx->tm.total_launches += launch_transform_edge(ta, s.st);
+        }
     }
     if (!(p->flags & JB_FLAG_NO_TIE_FIXUP)) {
         FixupArgs fa{};
@@ -495,6 +515,9 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         fa.tie_count = s.d_scalars;
         fa.tie_cap = s.tie_cap;
         fa.inplace_dct = ta.inplace_dct;
+        fa.uv = ta.uv;
+        fa.pitch_uv = ta.pitch_uv;
+        fa.frame_stride_uv = ta.frame_stride_uv;
         fa.costab = ctx->d_costab;
         fa.scale = ctx->d_scale;
         memcpy(fa.qt.q[0], p->qlum, sizeof(fa.qt.q[0]));
@@ -613,6 +636,25 @@ int with_workspace_retry(jb_ctx* ctx, F call) {
         if (rc != JB_E_NOSPACE || !ctx || !ctx->ubuf_grew) break;
     }
     return rc;
+}
+
+// ---- tiling: images beyond SOF0's 16-bit dimensions as a grid of independent JFIF files -------
+// Tiles of one tile column are equally sized frames `tile_h * pitch` bytes apart, i.e. a batch; the bottom row of
+// tiles (when H is not a multiple of tile_h) is a second, shorter batch of one frame per column.
+template <class Encode>
+static int for_each_tile_batch(jb_ctx* ctx, size_t W, size_t H, size_t tile_w, size_t tile_h, const jb_params* p, Encode encode) {
+    if (!p) return fail(ctx, JB_E_INVALID, "null parameters");
+    const size_t m = p->subsampling == JB_SUB_420 ? 16 : 8;
+    if (W == 0 || H == 0 || tile_w == 0 || tile_h == 0 || tile_w % m || tile_h % m || tile_w > 65535 || tile_h > 65535)
+        return fail(ctx, JB_E_INVALID, "tile sizes must be multiples of the MCU (%zu) and at most 65535", m);
+    const size_t ntx = (W + tile_w - 1) / tile_w, nty = (H + tile_h - 1) / tile_h, full_y = H / tile_h;
+    for (size_t tx = 0; tx < ntx; ++tx) {
+        const size_t w = std::min(tile_w, W - tx * tile_w);
+        int rc;
+        if (full_y && (rc = encode(tx, 0, w, tile_h, full_y, ntx))) return rc;                             // tiles (tx, 0 .. full_y-1)
+        if (nty > full_y && (rc = encode(tx, full_y, w, H - full_y * tile_h, (size_t)1, ntx))) return rc;  // bottom tile
+    }
+    return JB_OK;
 }
 
 }  // namespace
@@ -1372,6 +1414,42 @@ int jb_encode_batch_device(jb_ctx* ctx, const uint8_t* d_rgb, size_t n_frames, s
     return JB_OK;
 }
 
+int jb_encode_tiles(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t H, size_t pitch, size_t tile_w, size_t tile_h,
+                               const jb_params* p, uint8_t* out, size_t cap, uint64_t* offsets, uint64_t* sizes, size_t* n_tiles) {
+    if (!ctx || !rgb || !out || !offsets || !sizes) return fail(ctx, JB_E_INVALID, "null argument");
+    if (pitch < W * 3) return fail(ctx, JB_E_INVALID, "pitch smaller than a row");
+    size_t used = 0, needed = 0;
+    bool overflow = false;
+    std::vector<uint64_t> o, z;
+    int rc = for_each_tile_batch(ctx, W, H, tile_w, tile_h, p, [&](size_t tx, size_t ty0, size_t w, size_t h, size_t count, size_t ntx) {
+        o.assign(count, 0);
+        z.assign(count, 0);
+        const uint8_t* base = rgb + ty0 * tile_h * pitch + tx * tile_w * 3;
+        int r = jb_encode_batch(ctx, base, count, w, h, pitch, tile_h * pitch, p, out + used, overflow ? 0 : cap - used, o.data(), z.data());
+        if (r == JB_E_NOSPACE) {  // keep going so that jb_required_bytes() covers the whole grid
+            overflow = true;
+            needed += jb_required_bytes(ctx);
+            return (int)JB_OK;
+        }
+        if (r) return r;
+        for (size_t k = 0; k < count; ++k) {
+            offsets[(ty0 + k) * ntx + tx] = used + o[k];
+            sizes[(ty0 + k) * ntx + tx] = z[k];
+        }
+        const size_t bytes = count ? (size_t)(o[count - 1] + z[count - 1]) : 0;
+        used += bytes;
+        needed += bytes;
+        return (int)JB_OK;
+    });
+    if (rc) return rc;
+    if (n_tiles) *n_tiles = ((W + tile_w - 1) / tile_w) * ((H + tile_h - 1) / tile_h);
+    if (overflow) {
+        ctx->required = needed;
+        return fail(ctx, JB_E_NOSPACE, "output buffer too small: the tiles need %zu bytes", needed);
+    }
+    return JB_OK;
+}
+
 static int encode_strip_once(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params* p,
                              uint64_t first_interval, int last_strip, int device_io, uint8_t* out, size_t cap, size_t* out_len) {
     if (!ctx || !rgb || !out || !out_len) return fail(ctx, JB_E_INVALID, "null argument");
@@ -1424,6 +1502,51 @@ static int encode_strip_once(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t s
 int jb_encode_strip(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t strip_rows, size_t pitch, const jb_params* p,
                     uint64_t first_interval, int last_strip, int device_io, uint8_t* out, size_t cap, size_t* out_len) {
     return with_workspace_retry(ctx, [&] { return encode_strip_once(ctx, rgb, W, strip_rows, pitch, p, first_interval, last_strip, device_io, out, cap, out_len); });
+}
+
+// ---- NV12-style device input -----------------------------------------------------------------------
+int jb_encode_nv12_device(jb_ctx* ctx, const uint8_t* d_y, size_t pitch_y, size_t frame_stride_y, const uint8_t* d_uv, size_t pitch_uv,
+                          size_t frame_stride_uv, size_t n_frames, size_t W, size_t H, const jb_params* p, uint8_t* d_out, size_t cap,
+                          uint64_t* d_offsets, uint64_t* d_sizes, uint64_t* d_total) {
+    if (!ctx || !d_y || !d_uv || !d_out) return fail(ctx, JB_E_INVALID, "null argument");
+    if (pitch_y < W || pitch_uv < 2 * ((W + 1) / 2) || (n_frames > 1 && (frame_stride_y < pitch_y * H || frame_stride_uv < pitch_uv * ((H + 1) / 2))))
+        return fail(ctx, JB_E_INVALID, "bad pitch/stride");
+    CK(cudaSetDevice(ctx->device));
+    Plan pl;
+    int rc = make_plan(ctx, n_frames, W, H, p, false, false, &pl);
+    if (rc) return rc;
+    Slot& s = ctx->slot[0];
+    if (s.arena.cap < plan_bytes(pl)) CK(cudaStreamSynchronize(s.st));  // regrowing frees the arena
+    ctx->out_internal = false;
+    if ((rc = slot_prepare(ctx, s, pl))) return rc;
+    Framing fr{};
+    fr.hdr_bytes = (uint32_t)jb_header_bytes(p);
+    fr.emit_eoi = 1;
+    const unsigned k = s.dev_seq++ % kDevStages;
+    if (s.dev_used[k]) CK(cudaEventSynchronize(s.dev_ev[k]));
+    uint8_t* stage = s.h_dev + k * kDevStageBytes;
+    uint64_t* res = reinterpret_cast<uint64_t*>(stage + 1024);
+    const Nv12Src nv{d_uv, pitch_uv, frame_stride_uv};
+    if ((rc = enqueue_encode(ctx, s, pl, p, d_y, pitch_y, frame_stride_y, fr, W, H, d_out, cap, d_offsets, d_sizes,
+                             d_total ? d_total : s.d_total, stage, nullptr, &nv)))
+        return rc;
+    memset(res, 0, 64);
+    CK(cudaMemcpyAsync(res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpyAsync(res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaEventRecord(s.dev_ev[k], s.st));
+    s.dev_used[k] = true;
+    s.busy = true;
+    return JB_OK;
+}
+
+int jb_rgb8_to_nv12_device(jb_ctx* ctx, const uint8_t* d_rgb, size_t W, size_t H, size_t pitch, uint8_t* d_y, size_t pitch_y, uint8_t* d_uv,
+                           size_t pitch_uv) {
+    if (!ctx || !d_rgb || !d_y || !d_uv || W == 0 || H == 0 || pitch < W * 3 || pitch_y < W || pitch_uv < 2 * ((W + 1) / 2))
+        return fail(ctx, JB_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    ctx->tm.total_launches += launch_rgb_to_nv12(d_rgb, W, H, pitch, ctx->d_ydown, d_y, pitch_y, d_uv, pitch_uv, ctx->slot[0].st);
+    CK(cudaGetLastError());
+    return JB_OK;
 }
 
 // ---- multi-GPU strip stitch without a host round trip ------------------------------------------------------------

@@ -71,6 +71,8 @@ struct TransformArgs {
     const uint8_t* tc_mat;     // tensor-core variant: 6 pre-swizzled bf16 matrices (null = FMA kernel)
     float tband[2][64];        // tensor-core variant: near-tie bands in zigzag order
     int inplace_dct;           // Q1 (utils.cpp:342-345): W holds the in-place map; edge blocks go to the replay whole
+    const uint8_t* uv;         // NV12-style input (jb_encode_nv12_device): rgb / pitch / frame_stride describe the Y plane,
+    size_t pitch_uv, frame_stride_uv;  // these the plane of interleaved Cb,Cr pairs (null: RGB input)
     int use_tma;               // JB_FLAG_TMA: stage pixels with TMA boxes (k_transform_tma) instead of per-lane cp.async
     QuantConst qc;
 };
@@ -87,6 +89,8 @@ struct FixupArgs {
     const double* costab;  // [u][x] = cos((2x+1) u pi / 16), from the host's libm
     const double* scale;   // [u][v] = alpha(u) alpha(v) / 4.0
     int inplace_dct;       // Q1: replay the reference's in-place block transform up to the flagged output
+    const uint8_t* uv;     // NV12-style input: see TransformArgs
+    size_t pitch_uv, frame_stride_uv;
     QuantTables qt;
 };
 
@@ -158,6 +162,9 @@ struct EntropyArgs {
 // ---- launchers (each returns the number of kernels it launched) -------------
 int launch_transform(const TransformArgs& a, cudaStream_t s);       // MCUs inside the image (hot kernel)
 int launch_transform_edge(const TransformArgs& a, cudaStream_t s);  // MCUs that need mirror padding
+int launch_transform_nv12(const TransformArgs& a, cudaStream_t s);  // all MCUs of an NV12-style input
+int launch_rgb_to_nv12(const uint8_t* rgb, size_t W, size_t H, size_t pitch, const uint32_t* ydown, uint8_t* y, size_t pitch_y, uint8_t* uv,
+                       size_t pitch_uv, cudaStream_t s);
 int launch_fixup(const FixupArgs& a, cudaStream_t s);
 int launch_entropy(const EntropyArgs& a, cudaStream_t s, int phase = 0);  // 1: up to the sizes, 2: final placement only
 int launch_stitch_exchange(uint64_t* ctl, int rank, int world, uint64_t epoch, uint64_t base, const uint64_t* d_len, uint64_t* d_off,

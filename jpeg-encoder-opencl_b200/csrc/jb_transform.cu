@@ -458,6 +458,124 @@ __global__ void __launch_bounds__(64) k_transform_edge(const __grid_constant__ T
     }
 }
 
+// ---------------------------------------------------------------- NV12-style input --
+// The image arrives as YCbCr 4:2:0 already (a Y plane and a half-resolution plane of interleaved Cb,Cr pairs, as video
+// decoders and camera pipelines leave it in HBM): no colour conversion, no chroma averaging -- the reference's stages
+// from the mirror padding on (utils.cpp:199-233, 190-196, 314-347, 454-467, 539-558).  Chroma sample (i, j) of an MCU
+// row is the replicated full-resolution plane at the mirrored coordinate of (2i, 2j), exactly as in the RGB path.
+// One thread per 8x8 block, binary32 AAN transform in registers, analytic near-tie band, binary64 replay by k_fixup.
+__device__ __forceinline__ uint32_t nv12_sample(const uint8_t* yp, size_t pitch_y, const uint8_t* uvp, size_t pitch_uv, int W, int H, int x,
+                                                int y, int comp) {  // (x, y): padded full-resolution coordinate
+    const int sx = mirror(x, W), sy = mirror(y, H);
+    return comp == 0 ? __ldg(yp + (size_t)sy * pitch_y + sx) : __ldg(uvp + (size_t)(sy >> 1) * pitch_uv + (size_t)(sx >> 1) * 2 + (comp - 1));
+}
+
+template <int TAB>
+__device__ __forceinline__ void quant_global(const float (&v)[64], const TransformArgs& a, uint4* dst, uint32_t& tie_lo, uint32_t& tie_hi) {
+    uint32_t wd[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int n0 = zz_nat(2 * j), n1 = zz_nat(2 * j + 1);
+        bool t0, t1;
+        uint32_t b0 = quantize_bits(v[n0], a.qc.mul[TAB][n0], a.qc.band[TAB][n0], t0);
+        uint32_t b1 = quantize_bits(v[n1], a.qc.mul[TAB][n1], a.qc.band[TAB][n1], t1);
+        if (j < 16) {
+            if (t0) tie_lo |= 1u << (2 * j);
+            if (t1) tie_lo |= 1u << (2 * j + 1);
+        } else {
+            if (t0) tie_hi |= 1u << (2 * j - 32);
+            if (t1) tie_hi |= 1u << (2 * j - 31);
+        }
+        wd[j] = __byte_perm(b0, b1, 0x5410);
+    }
+    if (a.qc.dc_exact) {
+        wd[0] = __byte_perm(quantize_dc<TAB>(v[0], a), wd[0], 0x7610);
+        tie_lo &= ~1u;
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) dst[p] = make_uint4(wd[4 * p], wd[4 * p + 1], wd[4 * p + 2], wd[4 * p + 3]);
+}
+
+__global__ void __launch_bounds__(128) k_transform_nv12(const __grid_constant__ TransformArgs a) {
+    const uint32_t per_frame = (uint32_t)a.g.n_mcu * 6u, total = per_frame * (uint32_t)a.n_frames;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const uint32_t f = t / per_frame, r = t - f * per_frame, mcu = r / 6u, blk = r - mcu * 6u;
+        const int my = (int)(mcu / (uint32_t)a.g.mcux), mx = (int)(mcu - (uint32_t)my * (uint32_t)a.g.mcux);
+        const uint8_t* yp = a.rgb + (size_t)f * a.frame_stride;
+        const uint8_t* uvp = a.uv + (size_t)f * a.frame_stride_uv;
+        float v[64];
+        if (blk < 4) {
+            const int x0 = mx * 16 + (int)(blk & 1) * 8, y0 = my * 16 + (int)(blk >> 1) * 8;
+            const bool inside = x0 + 8 <= a.g.W;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint8_t* row = yp + (size_t)mirror(y0 + j, a.g.H) * a.pitch;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[j * 8 + i] = (float)((int)__ldg(row + (inside ? x0 + i : mirror(x0 + i, a.g.W))) - 128);
+            }
+        } else {
+            const int comp = (int)blk - 3;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    v[j * 8 + i] = (float)((int)nv12_sample(yp, a.pitch, uvp, a.pitch_uv, a.g.W, a.g.H, 2 * (mx * 8 + i), 2 * (my * 8 + j), comp) - 128);
+        }
+        fdct2d(v);
+        uint32_t tl = 0, th = 0;
+        uint4* dst = reinterpret_cast<uint4*>(a.coef) + (size_t)t * 8;
+        if (blk < 4)
+            quant_global<0>(v, a, dst, tl, th);
+        else
+            quant_global<1>(v, a, dst, tl, th);
+        if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, t, tl, th);
+    }
+}
+
+int launch_transform_nv12(const TransformArgs& a, cudaStream_t s) {
+    const size_t total = (size_t)a.g.n_mcu * 6 * (size_t)a.n_frames;
+    if (!total) return 0;
+    const size_t g = (total + 127) / 128;
+    k_transform_nv12<<<(int)(g > 148 * 64 ? 148 * 64 : g), 128, 0, s>>>(a);
+    return 1;
+}
+
+// RGB8 -> NV12 by the reference's own arithmetic: performCSC (utils.cpp:92-110, exact) and performCDS (utils.cpp:113-141):
+// a complete 2x2 cell carries the truncated mean of its four chroma values, a cell cut by an odd edge the chroma of its
+// top-left pixel.  One thread per cell.
+__global__ void k_rgb_to_nv12(const uint8_t* __restrict__ rgb, int W, int H, size_t pitch, const uint32_t* __restrict__ ydown,
+                              uint8_t* __restrict__ yo, size_t pitch_y, uint8_t* __restrict__ uvo, size_t pitch_uv) {
+    const int cw = (W + 1) / 2, ch = (H + 1) / 2;
+    const size_t n = (size_t)cw * ch;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+        const int cx = (int)(c % cw), cy = (int)(c / cw), x = 2 * cx, y = 2 * cy;
+        const bool whole = x + 1 < W && y + 1 < H;
+        uint32_t scb = 0, scr = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (x + i >= W || y + j >= H) continue;
+                const uint8_t* p = rgb + (size_t)(y + j) * pitch + (size_t)(x + i) * 3;
+                const uint32_t r = p[0], g = p[1], b = p[2];
+                yo[(size_t)(y + j) * pitch_y + x + i] = (uint8_t)csc_y(r, g, b, ydown);
+                if (whole || (i == 0 && j == 0)) {
+                    scb += csc_cb(r, g, b);
+                    scr += csc_cr(r, g, b);
+                }
+            }
+        uvo[(size_t)cy * pitch_uv + 2 * cx] = (uint8_t)(whole ? scb >> 2 : scb);
+        uvo[(size_t)cy * pitch_uv + 2 * cx + 1] = (uint8_t)(whole ? scr >> 2 : scr);
+    }
+}
+
+int launch_rgb_to_nv12(const uint8_t* rgb, size_t W, size_t H, size_t pitch, const uint32_t* ydown, uint8_t* y, size_t pitch_y, uint8_t* uv,
+                       size_t pitch_uv, cudaStream_t s) {
+    const size_t n = ((W + 1) / 2) * ((H + 1) / 2), g = (n + 255) / 256;
+    k_rgb_to_nv12<<<(int)(g > 148 * 32 ? 148 * 32 : g), 256, 0, s>>>(rgb, (int)W, (int)H, pitch, ydown, y, pitch_y, uv, pitch_uv);
+    return 1;
+}
+
 // ================================================================ tensor-core variant ==
 // 4:2:0 only.  The block transform (FDCT + quantiser scale + zigzag) is one 64x64 contraction
 // per block: D[128 blocks][64 coefficients] = A[128 blocks][64 samples] x W^T on the 5th-gen
@@ -1684,7 +1802,7 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
         const uint32_t my_entry = lane < n_here ? a.tie_list[e0 + lane] : 0u;
         // lane L decodes entry L once (block -> frame, MCU, component, first sample, zigzag position); the
         // fields travel to the whole warp by shuffles when the entry's turn comes
-        uint32_t d_x0, d_y0, d_misc, d_flo, d_fhi;  // (two words for the origin: dimensions go up to 2^24 under JB_FLAG_CLAMP_SOF)
+        uint32_t d_x0, d_y0, d_misc, d_f;  // (two words for the origin: dimensions go up to 2^24 under JB_FLAG_CLAMP_SOF)
         int my_comp, my_nat;
         {
             const uint32_t gblock = my_entry >> 6, k = my_entry & 63;
@@ -1714,25 +1832,24 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
             d_x0 = x0;
             d_y0 = y0;
             d_misc = (uint32_t)my_comp | (step << 2) | ((uint32_t)my_nat << 4);
-            const unsigned long long foff = (unsigned long long)f * a.frame_stride;
-            d_flo = (uint32_t)foff;
-            d_fhi = (uint32_t)(foff >> 32);
+            d_f = f;
         }
         uint32_t have_block = 0xFFFFFFFFu;  // consecutive entries of one block (append_ties) share its samples
         for (int j = 0; j < n_here; ++j) {
             const uint32_t misc = __shfl_sync(0xffffffffu, d_misc, j), gblock = __shfl_sync(0xffffffffu, my_entry, j) >> 6;
-            const unsigned long long foff =
-                ((unsigned long long)__shfl_sync(0xffffffffu, d_fhi, j) << 32) | __shfl_sync(0xffffffffu, d_flo, j);
+            const size_t fr = (size_t)__shfl_sync(0xffffffffu, d_f, j);
             const int x0 = (int)__shfl_sync(0xffffffffu, d_x0, j), y0 = (int)__shfl_sync(0xffffffffu, d_y0, j);
             const int comp = (int)(misc & 3u), step = (int)((misc >> 2) & 3u);
             const int nat = (int)(misc >> 4), v = nat >> 3, u = nat & 7;
             if (gblock != have_block) {  // (warp-uniform)
-                Image im{a.rgb + foff, a.pitch, a.g.W, a.g.H, a.ydown};
+                Image im{a.rgb + fr * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
                 __syncwarp();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int i = lane + 32 * h, x = i & 7, y = i >> 3;
-                    const double smp = (double)sample_at(im, x0 + x * step, y0 + y * step, comp, a.g.sub != JB_SUB_444);  // utils.cpp:236
+                    const double smp = a.uv ? (double)nv12_sample(im.base, a.pitch, a.uv + fr * a.frame_stride_uv, a.pitch_uv, a.g.W, a.g.H,
+                                                                   x0 + x * step, y0 + y * step, comp)
+                                            : (double)sample_at(im, x0 + x * step, y0 + y * step, comp, a.g.sub != JB_SUB_444);  // utils.cpp:236
                     s_smp[w][i] = __dsub_rn(smp, 128.0);                                                                  // utils.cpp:190
                 }
                 __syncwarp();

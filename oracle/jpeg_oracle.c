@@ -419,6 +419,26 @@ static void block_to_coef(const uint8_t *smp, size_t stride, size_t step, const 
     }
 }
 
+/* The stages after performCDS for an image that is ALREADY Y,Cb,Cr (AoS bytes, full resolution, unpadded): mirror
+ * padding (utils.cpp:199-233), level shift, DCT, quantisation, zigzag -- orc_transform minus orc_csc / orc_cds.  This is
+ * what an NV12-style input goes through (its chroma replicated to full resolution is exactly the plane performCDS
+ * leaves behind); tests pin it through the identity orc_transform(rgb) == orc_transform_ycc(CSC + CDS of rgb). */
+static int transform_padded(uint8_t *ycc, size_t nW, size_t nH, int sub, const unsigned ql[64], const unsigned qc[64],
+                            int quirks, int16_t *coef);
+int orc_transform_ycc(const uint8_t *ycc_in, size_t W, size_t H, int sub, const unsigned ql[64], const unsigned qc[64],
+                      int quirks, int16_t *coef) {
+    orc_init();
+    size_t nW, nH, m = sub == ORC_SUB_420 ? 16 : 8;
+    orc_padded_size(W, H, m, &nW, &nH);
+    uint8_t *ycc = (uint8_t *)malloc(nW * nH * 3);
+    if (!ycc) return -1;
+    if (orc_pad_mirror(ycc_in, W, H, ycc, nW, nH)) {
+        free(ycc);
+        return -1;
+    }
+    return transform_padded(ycc, nW, nH, sub, ql, qc, quirks, coef);
+}
+
 int orc_transform(const uint8_t *rgb, size_t W, size_t H, int sub, const unsigned ql[64], const unsigned qc[64],
                   int quirks, int16_t *coef) {
     orc_init();
@@ -430,6 +450,13 @@ int orc_transform(const uint8_t *rgb, size_t W, size_t H, int sub, const unsigne
         free(ycc);
         return -1;
     }
+    return transform_padded(ycc, nW, nH, sub, ql, qc, quirks, coef);
+}
+
+/* blocks of the padded Y,Cb,Cr image in scan order; frees ycc */
+static int transform_padded(uint8_t *ycc, size_t nW, size_t nH, int sub, const unsigned ql[64], const unsigned qc[64],
+                            int quirks, int16_t *coef) {
+    size_t m = sub == ORC_SUB_420 ? 16 : 8;
     int inplace = (quirks & ORC_Q1_INPLACE_DCT) != 0;
     size_t mx = nW / m, my = nH / m;
     for (size_t j = 0; j < my; ++j)

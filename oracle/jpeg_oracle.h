@@ -71,6 +71,8 @@ int orc_ycc_padded(const uint8_t *rgb, size_t W, size_t H, int sub, uint8_t *dst
  * quirks: only ORC_Q1_INPLACE_DCT is looked at. */
 int orc_transform(const uint8_t *rgb, size_t W, size_t H, int sub, const unsigned ql[64],
                   const unsigned qc[64], int quirks, int16_t *coef);
+int orc_transform_ycc(const uint8_t *ycc, size_t W, size_t H, int sub, const unsigned ql[64], const unsigned qc[64],
+                      int quirks, int16_t *coef); /* orc_transform for an image that is already Y,Cb,Cr (after utils.cpp:141) */
 size_t orc_num_mcus(size_t W, size_t H, int sub);
 int orc_blocks_per_mcu(int sub);
 /* Entropy-code scan-order coefficients.  restart_interval in MCUs (0 = none).

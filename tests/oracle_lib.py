@@ -62,6 +62,7 @@ def oracle():
     L.orc_quality_tables.argtypes = [C.c_int, u32p, u32p]
     L.orc_ycc_padded.argtypes = [u8p, sz, sz, C.c_int, u8p, C.POINTER(sz), C.POINTER(sz)]
     L.orc_transform.argtypes = [u8p, sz, sz, C.c_int, u32p, u32p, C.c_int, i16p]
+    L.orc_transform_ycc.argtypes = [u8p, sz, sz, C.c_int, u32p, u32p, C.c_int, i16p]
     L.orc_num_mcus.argtypes = [sz, sz, C.c_int]
     L.orc_num_mcus.restype = sz
     L.orc_blocks_per_mcu.argtypes = [C.c_int]
@@ -190,6 +191,42 @@ def transform(rgb, sub, ql, qc, quirks=0):
     rc = L.orc_transform(np.ascontiguousarray(rgb), W, H, sub, ql, qc, quirks, coef)
     assert rc == 0
     return coef
+
+
+def transform_ycc(ycc, sub, ql, qc, quirks=0):
+    """orc_transform for an (H, W, 3) image that is already Y,Cb,Cr (the stages after performCDS)."""
+    H, W, _ = ycc.shape
+    L = oracle()
+    n = L.orc_num_mcus(W, H, sub)
+    coef = np.zeros((n, L.orc_blocks_per_mcu(sub), 64), np.int16)
+    rc = L.orc_transform_ycc(np.ascontiguousarray(ycc), W, H, sub, ql, qc, quirks, coef)
+    assert rc == 0
+    return coef
+
+
+def nv12_from_rgb(rgb):
+    """(Y plane, interleaved CbCr plane) of the reference's CSC + CDS (utils.cpp:92-141): a complete 2x2 cell carries its
+    truncated mean, a cell cut by an odd edge the chroma of its top-left pixel."""
+    H, W, _ = rgb.shape
+    ycc = np.ascontiguousarray(rgb).copy()
+    oracle().orc_csc(ycc.reshape(-1), W * H)
+    if W >= 2 and H >= 2:
+        oracle().orc_cds(ycc.reshape(-1), W, H)
+    return np.ascontiguousarray(ycc[:, :, 0]), np.ascontiguousarray(ycc[0::2, 0::2, 1:3]).reshape((H + 1) // 2, -1)
+
+
+def ycc_from_nv12(y, uv):
+    """Full-resolution Y,Cb,Cr (H, W, 3) with the chroma pairs replicated over their cells."""
+    H, W = y.shape
+    c = uv.reshape(uv.shape[0], -1, 2)
+    full = np.repeat(np.repeat(c, 2, axis=0), 2, axis=1)[:H, :W]
+    return np.ascontiguousarray(np.dstack([y, full[:, :, 0], full[:, :, 1]]))
+
+
+def jfif_from_coef(coef, W, H, sub, ql, qc, restart_interval=0):
+    """header + entropy segment + EOI for coefficients in scan order."""
+    seg, _ = entropy(coef, sub, restart_interval)
+    return bytes(jfif_header(W, H, sub, ql, qc, restart_interval)) + bytes(seg) + b"\xff\xd9"
 
 
 def entropy(coef, sub, restart_interval=0, quirks=0, raw_bits=False, rst_phase=0, final_rst=False):

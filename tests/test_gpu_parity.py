@@ -804,3 +804,91 @@ def test_tma_staged_transform_is_bit_identical(enc, jb, fruit):
     q100 = ol.quality_tables(100)
     pn = jb.make_params(ol.SUB_420, qlum=q100[0], qchrom=q100[1], flags=jb.FLAG_TMA)
     assert np.array_equal(enc.transform(noise, pn), ol.transform(noise, ol.SUB_420, *q100))
+
+
+@pytest.mark.parametrize("sub", SUBS)
+def test_tiles_are_independent_jfif_files_equal_to_the_oracle(enc, jb, sub):
+    """jb_encode_tiles (images beyond SOF0's 16-bit dimensions): every tile is a complete JFIF file equal to the
+    oracle's encode of the cropped tile -- partial last column / row mirror-padded like any image -- and decodes on its own."""
+    import io
+    from PIL import Image
+    ql, qc = ol.quality_tables(75)
+    p = jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=3)
+    img = ol.synth(0x7111, 200, 104)
+    for tw, th in ((64, 48), (208, 112), (96, 16)):
+        tiles = enc.encode_tiles(img, tw, th, p)
+        assert len(tiles) == -(-104 // th) and len(tiles[0]) == -(-200 // tw)
+        for ty, row in enumerate(tiles):
+            for tx, jf in enumerate(row):
+                crop = np.ascontiguousarray(img[ty * th: (ty + 1) * th, tx * tw: (tx + 1) * tw])
+                assert jf == ol.encode_jfif(crop, sub, ql, qc, 3), (tw, th, tx, ty)
+                assert np.array(Image.open(io.BytesIO(jf))).shape == crop.shape
+    m = 16 if sub == ol.SUB_420 else 8
+    with pytest.raises(jb.JbError):
+        enc.encode_tiles(img, 60, 48, p)  # not a multiple of the MCU
+    # wider than 65535 without JB_FLAG_CLAMP_SOF: two tiles, both exact
+    wide = ol.synth(0x7112, 65536 + 4 * m, m)
+    tiles = enc.encode_tiles(wide, 65536 - m, m, p)
+    assert [len(r) for r in tiles] == [2]
+    assert tiles[0][0] == ol.encode_jfif(np.ascontiguousarray(wide[:, : 65536 - m]), sub, ql, qc, 3)
+    assert tiles[0][1] == ol.encode_jfif(np.ascontiguousarray(wide[:, 65536 - m:]), sub, ql, qc, 3)
+    # a buffer that is too small reports the size of the whole grid
+    with pytest.raises(jb.JbError) as e:
+        enc.encode_tiles(img, 64, 48, p, cap=1000)
+    assert e.value.code == jb.E_NOSPACE
+    need = enc.L.jb_required_bytes(enc.h)
+    assert need == sum(len(t) for r in enc.encode_tiles(img, 64, 48, p) for t in r)
+
+
+def test_nv12_device_input(enc, jb):
+    """jb_encode_nv12_device: frames that are YCbCr 4:2:0 already.  (1) jb_rgb8_to_nv12_device == the
+    reference's CSC + CDS; (2) for even sizes NV12 made from RGB encodes to the very file the RGB path produces (the
+    identity that pins the path to the reference); (3) arbitrary NV12 content, odd sizes and pitches, batches ==
+    the oracle's stages from the mirror padding on (orc_transform_ycc)."""
+    import torch
+    ql, qc = ol.quality_tables(75)
+    p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, restart_interval=5)
+    rng = np.random.default_rng(12)
+
+    def encode(y, uv, W, H, N=1, pitch_y=None, pitch_uv=None):
+        pitch_y, pitch_uv = pitch_y or y.shape[-1], pitch_uv or uv.shape[-1]
+        dy, duv = torch.from_numpy(np.ascontiguousarray(y)).cuda(), torch.from_numpy(np.ascontiguousarray(uv)).cuda()
+        cap = N * (W * H * 3 + 4096)
+        out, tab = torch.zeros(cap, dtype=torch.uint8, device="cuda"), torch.zeros(2 * N + 1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        enc.encode_nv12_device(dy.data_ptr(), pitch_y, pitch_y * H, duv.data_ptr(), pitch_uv, pitch_uv * ((H + 1) // 2), N, W, H, p,
+                               out.data_ptr(), cap, tab.data_ptr(), tab.data_ptr() + 8 * N, tab.data_ptr() + 16 * N)
+        enc.sync()
+        t = tab.cpu().numpy()
+        return [bytes(out[int(t[f]): int(t[f] + t[N + f])].cpu().numpy()) for f in range(N)]
+
+    for W, H in ((64, 48), (1920, 1080), (250, 130), (253, 131), (37, 21), (16, 16)):
+        rgb = ol.synth(W + H, W, H)
+        y, uv = ol.nv12_from_rgb(rgb)
+        d_rgb = torch.from_numpy(rgb.copy()).cuda()
+        dy = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+        duv = torch.zeros(((H + 1) // 2, 2 * ((W + 1) // 2)), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        enc.rgb8_to_nv12_device(d_rgb.data_ptr(), W, H, W * 3, dy.data_ptr(), W, duv.data_ptr(), duv.shape[1])
+        enc.sync()
+        assert np.array_equal(dy.cpu().numpy(), y) and np.array_equal(duv.cpu().numpy(), uv), (W, H)
+        got = encode(y, uv, W, H)[0]
+        want = ol.jfif_from_coef(ol.transform_ycc(ol.ycc_from_nv12(y, uv), ol.SUB_420, ql, qc), W, H, ol.SUB_420, ql, qc, 5)
+        assert got == want, (W, H)
+        if W % 2 == 0 and H % 2 == 0:
+            assert got == ol.encode_jfif(rgb, ol.SUB_420, ql, qc, 5) == enc.encode_jfif(rgb, p), (W, H)
+    # arbitrary content (full-range noise: many near ties -> the binary64 replay reads the planes), pitches, a batch
+    W, H, N = 200, 72, 3
+    py, puv = 208, 224
+    y = rng.integers(0, 256, (N, H, py), dtype=np.uint8)
+    uv = rng.integers(0, 256, (N, H // 2, puv), dtype=np.uint8)
+    files = encode(y, uv, W, H, N, py, puv)
+    for f in range(N):
+        ycc = ol.ycc_from_nv12(np.ascontiguousarray(y[f, :, :W]), np.ascontiguousarray(uv[f, :, :W]))
+        assert files[f] == ol.jfif_from_coef(ol.transform_ycc(ycc, ol.SUB_420, ql, qc), W, H, ol.SUB_420, ql, qc, 5), f
+    assert enc.timings()["tie_fixups"] > 0
+    with pytest.raises(jb.JbError) as e:
+        pp = jb.make_params(ol.SUB_444, qlum=ql, qchrom=qc)
+        d = torch.zeros(64 * 64, dtype=torch.uint8, device="cuda")
+        enc.encode_nv12_device(d.data_ptr(), 64, 64 * 64, d.data_ptr(), 64, 64 * 32, 1, 64, 64, pp, d.data_ptr(), 64 * 64, 0, 0, 0)
+    assert e.value.code == jb.E_UNSUPPORTED
