@@ -409,6 +409,60 @@ def run_batch(a, jb, enc, torch, dd, workload, F, steps, warmup, want_e2e, want_
             "dims": (W, H, subname, q, ri)}
 
 
+def run_nv12(a, jb, enc, torch, dd, F=256, steps=3, warmup=3):
+    """the batch frames as NV12-style device input (converted on the device with the reference's CSC + CDS,
+    outside the timing).  Device-resident only: the point of the format is that a GPU producer left the frames in HBM.
+    Parity: for these even-sized frames the files must equal the oracle's encode of the RGB frames."""
+    W, H, _, q, ri, _, seed0 = WORKLOADS["batch1080p"]
+    params = jb.make_params(jb.SUB_420, quality=q, restart_interval=ri)
+    d_rgb = torch.empty(W * H * 3, dtype=torch.uint8, device="cuda")
+    d_y = torch.empty(F * W * H, dtype=torch.uint8, device="cuda")
+    d_uv = torch.empty(F * W * H // 2, dtype=torch.uint8, device="cuda")
+    for f in range(F):
+        enc.synth_device(seed0 + f, W, 0, H, W * 3, d_rgb.data_ptr())
+        enc.rgb8_to_nv12_device(d_rgb.data_ptr(), W, H, W * 3, d_y.data_ptr() + f * W * H, W, d_uv.data_ptr() + f * W * H // 2, W)
+    enc.sync()
+    cap = F * (W * H // 2 + 4096)
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_tab = torch.zeros(2 * F + 1, dtype=torch.int64, device="cuda")
+    ext = torch.cuda.ExternalStream(enc.stream())
+
+    def step():
+        enc.encode_nv12_device(d_y.data_ptr(), W, W * H, d_uv.data_ptr(), W, W * H // 2, F, W, H, params, d_out.data_ptr(), cap,
+                               d_tab.data_ptr(), d_tab.data_ptr() + 8 * F, d_tab.data_ptr() + 16 * F)
+    for _ in range(warmup):
+        step()
+    enc.sync()
+    enc.set_profiling(True)
+    enc.reset_counters()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    for _ in range(steps):
+        step()
+    ev1.record(ext)
+    enc.sync()
+    ms = ev0.elapsed_time(ev1) / steps
+    tm = enc.timings()
+    enc.set_profiling(False)
+    padded = W * (-(-H // 16) * 16)
+    roof = transform_roofline(tm, F * (1.5 * W * H + 3 * padded), steps, "k_transform_nv12 (CUDA cores: no colour conversion to do)")
+    parity = None
+    if not a.no_parity:
+        import oracle_lib as ol
+        tab = d_tab.cpu().numpy()
+        ql, qc = ol.quality_tables(q)
+        fr = [0, F - 1]
+        ok = all(bytes(d_out[int(tab[f]): int(tab[f]) + int(tab[F + f])].cpu().numpy()) ==
+                 ol.encode_jfif(ol.synth(seed0 + f, W, H), ol.SUB_420, ql, qc, ri) for f in fr)
+        parity = {"frames": fr, "equal": bool(ok), "against": "oracle/jpeg_oracle.c encode of the RGB frames (even sizes: NV12 path == RGB path)"}
+    del d_y, d_uv, d_out
+    torch.cuda.empty_cache()
+    return {"workload": f"nv12_1080p: {F} frames of 1920x1080 as NV12-style device input (Y plane + interleaved CbCr plane), 420, q{q}",
+            "value": round(F * W * H / 1e6 / (ms / 1e3), 1), "ms_per_step": round(ms, 4), "e2e": None, "roofline_frac": roof["frac"],
+            "transform_GBps": roof["achieved"], "transform_kernel": "k_transform_nv12", "step_breakdown_us": roof["step_breakdown_us"],
+            "parity_check": parity, "steps": steps}
+
+
 # ----------------------------------------------------------------------------------------
 # config #5: one image as RST strips across the ranks, stitched over NVLink
 # ----------------------------------------------------------------------------------------
@@ -728,6 +782,10 @@ def main():
                     "bits_per_pixel": o["bits_per_pixel"], "parity_check": o["parity_check"], "steps": 3}
             except Exception as e:
                 others[name] = {"error": str(e)[:200]}
+        try:
+            others["nv12_1080p"] = run_nv12(a, jb, enc, torch, dd)
+        except Exception as e:
+            others["nv12_1080p"] = {"error": str(e)[:200]}
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's own code on the host cores ---------------
     cpu = None

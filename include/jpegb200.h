@@ -267,6 +267,28 @@ int jb_ipc_close(jb_ctx *ctx, void *d_ptr);
 /* JFIF header (SOI..SOS) for a W x H image with these parameters (host) */
 int jb_write_header(const jb_params *p, size_t W, size_t H, uint8_t *out, size_t cap, size_t *out_len);
 
+/* ---- decode path -------------------------------------------------------------------------------
+ * Baseline JFIF (3 components, 4:4:4 or 4:2:0, one interleaved scan: what this library writes, and what libjpeg
+ * writes by default) -> quantised coefficients -> RGB8, on the GPU: the PSNR loop of the parity report without a CPU
+ * decoder, and a round-trip check of the byte stream (decoded coefficients == the coefficients that were coded).
+ * The reference has no decoder; the reconstruction repeats libjpeg's default one operation for operation (integer
+ * "islow" IDCT, h2v2 "fancy" upsampling, fixed-point colour conversion), so pixels equal PIL's / OpenCV's exactly. */
+typedef struct {
+    uint32_t W, H;
+    int32_t subsampling;       /* JB_SUB_444 or JB_SUB_420 (the replicated 4:2:0 mode is coded as 4:4:4) */
+    uint32_t restart_interval; /* MCUs, 0 = none */
+    uint64_t scan_offset;      /* first byte of the entropy-coded data */
+} jb_jfif_info;
+int jb_jfif_info_device(jb_ctx *ctx, const uint8_t *d_jfif, size_t len, jb_jfif_info *info);
+/* d_rgb (W*3 <= pitch) and / or d_coef (int16 [n_mcu][blocks_per_mcu][64], zigzag order: the layout jb_transform
+ * produces) may be null; device pointers, synchronous.  One thread decodes one restart interval. */
+int jb_decode_jfif_device(jb_ctx *ctx, const uint8_t *d_jfif, size_t len, uint8_t *d_rgb, size_t pitch, int16_t *d_coef);
+/* host buffers; *W, *H are set even when cap is too small (JB_E_NOSPACE, jb_required_bytes) */
+int jb_decode_jfif(jb_ctx *ctx, const uint8_t *jfif, size_t len, uint8_t *rgb, size_t cap, size_t *W, size_t *H);
+/* PSNR (dB) over the three channels and / or the sum of squared differences of two RGB8 images in HBM */
+int jb_psnr_device(jb_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, size_t W, size_t H,
+                   double *psnr, uint64_t *sq_err);
+
 /* Deterministic synthetic RGB8 image rows [y0, y0+rows) generated on the device */
 int jb_synth_rgb_device(jb_ctx *ctx, uint64_t seed, size_t W, size_t y0, size_t rows, size_t pitch, uint8_t *d_out);
 

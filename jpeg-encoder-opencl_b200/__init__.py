@@ -36,6 +36,7 @@ SYMBOLS = [
     "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32", "jb_optimal_huffman_spec",
     "jb_encode_strip_begin", "jb_encode_strip_finish", "jb_copy_bytes_device", "jb_ipc_export", "jb_ipc_open", "jb_ipc_close",
     "jb_stitch_exchange", "jb_stitch_complete", "jb_encode_tiles", "jb_encode_nv12_device", "jb_rgb8_to_nv12_device",
+    "jb_jfif_info_device", "jb_decode_jfif_device", "jb_decode_jfif", "jb_psnr_device",
     "jb_pad_mirror_planar_u32", "jb_blockify_planar_i32", "jb_f64_to_u8", "jb_remove_red_aos", "jb_value_categories",
 ]
 
@@ -49,6 +50,11 @@ class JbError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("subsampling", C.c_int32), ("restart_interval", C.c_int32), ("flags", C.c_uint32),
                 ("qlum", C.c_uint32 * 64), ("qchrom", C.c_uint32 * 64)]
+
+
+class JfifInfo(C.Structure):
+    _fields_ = [("W", C.c_uint32), ("H", C.c_uint32), ("subsampling", C.c_int32), ("restart_interval", C.c_uint32),
+                ("scan_offset", C.c_uint64)]
 
 
 class Timings(C.Structure):
@@ -132,6 +138,10 @@ def lib():
     L.jb_encode_batch.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp]
     L.jb_encode_nv12_device.argtypes = [vp, vp, sz, sz, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, vp]
     L.jb_rgb8_to_nv12_device.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp, sz]
+    L.jb_jfif_info_device.argtypes = [vp, vp, sz, C.POINTER(JfifInfo)]
+    L.jb_decode_jfif_device.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.jb_decode_jfif.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    L.jb_psnr_device.argtypes = [vp, vp, sz, vp, sz, sz, sz, C.POINTER(C.c_double), C.POINTER(u64)]
     L.jb_encode_tiles.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, C.POINTER(sz)]
     L.jb_encode_batch_device.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, vp]
     L.jb_encode_strip.argtypes = [vp, vp, sz, sz, sz, PP, u64, C.c_int, C.c_int, vp, sz, C.POINTER(sz)]
@@ -438,6 +448,32 @@ class Encoder:
 
     def ipc_close(self, d_ptr):
         self._ck(self.L.jb_ipc_close(self.h, d_ptr))
+
+    # ---- decode path ---------------------------------------------------------------------
+    def decode_jfif(self, data):
+        """JFIF bytes -> (H, W, 3) uint8 RGB, decoded on the GPU (libjpeg-exact reconstruction)."""
+        buf = np.frombuffer(bytes(data), np.uint8)
+        W, H = C.c_size_t(), C.c_size_t()
+        rc = self.L.jb_decode_jfif(self.h, _ptr(buf), buf.size, None, 0, C.byref(W), C.byref(H))
+        if rc != E_NOSPACE:
+            self._ck(rc if rc else E_INTERNAL)
+        out = np.empty((H.value, W.value, 3), np.uint8)
+        self._ck(self.L.jb_decode_jfif(self.h, _ptr(buf), buf.size, _ptr(out), out.size, C.byref(W), C.byref(H)))
+        return out
+
+    def jfif_info_device(self, d_jfif, length):
+        info = JfifInfo()
+        self._ck(self.L.jb_jfif_info_device(self.h, d_jfif, length, C.byref(info)))
+        return info
+
+    def decode_jfif_device(self, d_jfif, length, d_rgb=None, pitch=0, d_coef=None):
+        self._ck(self.L.jb_decode_jfif_device(self.h, d_jfif, length, d_rgb, pitch, d_coef))
+
+    def psnr_device(self, d_a, pitch_a, d_b, pitch_b, W, H):
+        """(PSNR in dB, sum of squared differences) of two RGB8 images in HBM."""
+        ps, se = C.c_double(), C.c_uint64()
+        self._ck(self.L.jb_psnr_device(self.h, d_a, pitch_a, d_b, pitch_b, W, H, C.byref(ps), C.byref(se)))
+        return ps.value, se.value
 
     def write_header(self, params, W, H):
         out = np.empty(1024, np.uint8)

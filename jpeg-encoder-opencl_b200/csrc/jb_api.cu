@@ -1549,6 +1549,126 @@ int jb_rgb8_to_nv12_device(jb_ctx* ctx, const uint8_t* d_rgb, size_t W, size_t H
     return JB_OK;
 }
 
+// ---- decode path: baseline JFIF -> coefficients -> RGB8 on the device, PSNR ------------------------------
+static int fetch_info(jb_ctx* ctx, const uint8_t* d_jfif, size_t len, JfifInfo* info, DecTables* tabs) {
+    // the marker segments are parsed on the host: bring the head of the file over (4 KB, then more while a segment runs past it)
+    std::vector<uint8_t> head;
+    for (size_t n = 4096;; n *= 16) {
+        n = std::min(n, len);
+        head.resize(n);
+        CK(cudaMemcpyAsync(head.data(), d_jfif, n, cudaMemcpyDeviceToHost, ctx->slot[0].st));
+        CK(cudaStreamSynchronize(ctx->slot[0].st));
+        int rc = parse_jfif(head.data(), n, info, tabs);
+        if (rc == JB_E_NOSPACE && n < len) continue;
+        if (rc) return fail(ctx, rc == JB_E_NOSPACE ? JB_E_INVALID : rc, "not a baseline 3-component JFIF file this decoder handles (4:4:4 or 4:2:0, one scan)");
+        return JB_OK;
+    }
+}
+
+int jb_jfif_info_device(jb_ctx* ctx, const uint8_t* d_jfif, size_t len, jb_jfif_info* out) {
+    if (!ctx || !d_jfif || !out || len < 4) return fail(ctx, JB_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    JfifInfo info;
+    DecTables tabs;
+    int rc = fetch_info(ctx, d_jfif, len, &info, &tabs);
+    if (rc) return rc;
+    out->W = info.W;
+    out->H = info.H;
+    out->subsampling = info.sub;
+    out->restart_interval = info.restart_interval;
+    out->scan_offset = info.scan_offset;
+    return JB_OK;
+}
+
+int jb_decode_jfif_device(jb_ctx* ctx, const uint8_t* d_jfif, size_t len, uint8_t* d_rgb, size_t pitch, int16_t* d_coef) {
+    if (!ctx || !d_jfif || len < 4 || (!d_rgb && !d_coef)) return fail(ctx, JB_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    JfifInfo info;
+    DecTables tabs;
+    int rc = fetch_info(ctx, d_jfif, len, &info, &tabs);
+    if (rc) return rc;
+    if (d_rgb && pitch < (size_t)info.W * 3) return fail(ctx, JB_E_INVALID, "pitch smaller than a row");
+    const Geometry g = make_geometry(info.W, info.H, info.sub, (int)info.restart_interval);
+    const size_t n_blocks = (size_t)g.n_mcu * g.bpm, scan_bytes = len - info.scan_offset, chunks = (scan_bytes + 255) / 256;
+    const size_t pitch_y = (size_t)g.mcux * g.mcu_px, rows_y = (size_t)g.mcuy * g.mcu_px;
+    const size_t pitch_c = (size_t)g.mcux * 8, rows_c = (size_t)g.mcuy * 8;
+    const size_t plane_c = info.sub == JB_SUB_420 ? pitch_c * rows_c : pitch_y * rows_y;
+    const size_t need = sizeof(DecTables) + (chunks + chunks / 1024 + 4) * 4 + ((size_t)g.n_int + 2) * 8 + (d_coef ? 0 : n_blocks * 128) +
+                        (d_rgb ? pitch_y * rows_y + 2 * plane_c : 0) + 8 * 256;
+    if ((rc = scratch(ctx, need))) return rc;
+    cudaStream_t st = ctx->slot[0].st;
+    Arena& A = ctx->scratch;
+    DecTables* d_tabs = carve<DecTables>(A, 1);
+    uint32_t* d_cnt = carve<uint32_t>(A, chunks + chunks / 1024 + 4);
+    uint64_t* d_start = carve<uint64_t>(A, (size_t)g.n_int + 2);
+    int16_t* coef = d_coef ? d_coef : carve<int16_t>(A, n_blocks * 64);
+    CK(cudaMemcpyAsync(d_tabs, &tabs, sizeof(tabs), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_start, 0xFF, ((size_t)g.n_int + 1) * 8, st));  // intervals whose marker is missing decode nothing
+    const uint8_t* d_scan = d_jfif + info.scan_offset;
+    {
+        Timed t(ctx, st, 2);
+        ctx->tm.total_launches += launch_rst_index(d_scan, scan_bytes, d_cnt, d_cnt + chunks + 1, d_start, (uint32_t)g.n_int, st);
+        ctx->tm.total_launches += launch_huff_decode(d_scan, scan_bytes, d_start, (uint32_t)g.n_int, (uint32_t)g.ri, (uint32_t)g.n_mcu, g.bpm, d_tabs,
+                                                     info, coef, st);
+    }
+    if (d_rgb) {
+        uint8_t* py = carve<uint8_t>(A, pitch_y * rows_y);
+        uint8_t* pcb = carve<uint8_t>(A, plane_c);
+        uint8_t* pcr = carve<uint8_t>(A, plane_c);
+        Timed t(ctx, st, 0);
+        ctx->tm.total_launches += launch_reconstruct(coef, (uint32_t)g.n_mcu, g.mcux, g.bpm, info, py, pcb, pcr, pitch_y,
+                                                     info.sub == JB_SUB_420 ? pitch_c : pitch_y, d_rgb, pitch, st);
+    }
+    STAGE_END()
+}
+
+int jb_decode_jfif(jb_ctx* ctx, const uint8_t* jfif, size_t len, uint8_t* rgb, size_t cap, size_t* W, size_t* H) {
+    if (!ctx || !jfif || len < 4) return fail(ctx, JB_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    JfifInfo info;
+    DecTables tabs;
+    int rc = parse_jfif(jfif, len, &info, &tabs);
+    if (rc) return fail(ctx, rc == JB_E_NOSPACE ? JB_E_INVALID : rc, "not a baseline 3-component JFIF file this decoder handles");
+    if (W) *W = info.W;
+    if (H) *H = info.H;
+    const size_t out_bytes = (size_t)info.W * info.H * 3;
+    if (!rgb || cap < out_bytes) {
+        ctx->required = out_bytes;
+        return fail(ctx, JB_E_NOSPACE, "output buffer too small: need %zu bytes", out_bytes);
+    }
+    uint8_t *d_in = nullptr, *d_out = nullptr;  // (outside the scratch arena, which the device call carves)
+    if (cudaMalloc(&d_in, len) != cudaSuccess || cudaMalloc(&d_out, out_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(d_in);
+        return fail(ctx, JB_E_NOMEM, "cudaMalloc failed");
+    }
+    cudaStream_t st = ctx->slot[0].st;
+    cudaMemcpyAsync(d_in, jfif, len, cudaMemcpyHostToDevice, st);
+    rc = jb_decode_jfif_device(ctx, d_in, len, d_out, (size_t)info.W * 3, nullptr);
+    if (rc == JB_OK && (cudaMemcpyAsync(rgb, d_out, out_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess))
+        rc = fail(ctx, JB_E_CUDA, "copy back failed");
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+int jb_psnr_device(jb_ctx* ctx, const uint8_t* d_a, size_t pitch_a, const uint8_t* d_b, size_t pitch_b, size_t W, size_t H, double* psnr,
+                   uint64_t* sq_err) {
+    if (!ctx || !d_a || !d_b || W == 0 || H == 0 || pitch_a < W * 3 || pitch_b < W * 3) return fail(ctx, JB_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int rc = scratch(ctx, 256);
+    if (rc) return rc;
+    cudaStream_t st = ctx->slot[0].st;
+    unsigned long long* d_sum = carve<unsigned long long>(ctx->scratch, 1);
+    ctx->tm.total_launches += launch_sq_err(d_a, pitch_a, d_b, pitch_b, W, H, d_sum, st);
+    unsigned long long sum = 0;
+    CK(cudaMemcpyAsync(&sum, d_sum, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (sq_err) *sq_err = sum;
+    if (psnr) *psnr = sum ? 10.0 * log10(255.0 * 255.0 * (double)(W * H * 3) / (double)sum) : INFINITY;
+    return JB_OK;
+}
+
 // ---- multi-GPU strip stitch without a host round trip ------------------------------------------------------------
 // begin: transform + entropy coder up to the sizes, asynchronous; *d_len (device) receives the strip's byte count.
 // finish: the final placement (0xFF00 stuffing, RSTn) writes the strip to d_out + *d_off -- d_off is a device scalar

@@ -159,6 +159,32 @@ struct EntropyArgs {
 #define JB_STATUS_TIE_OVERFLOW 4ull
 #define JB_STATUS_PEER_TIMEOUT 8ull
 
+// ---- decode path (jb_decode.cu) -------------------------------------------------------------------------------------
+struct DecTable {          // one DHT table, T.81 F.2.2.3 decoding arrays + a 9-bit look-ahead
+    uint16_t look[512];    // (code length << 8) | symbol for codes of up to 9 bits, 0 = longer
+    int32_t maxcode[18], mincode[17];
+    uint16_t valptr[17];
+    uint8_t vals[256];
+};
+struct DecTables {
+    DecTable t[4];  // DC 0, DC 1, AC 0, AC 1
+};
+struct JfifInfo {
+    uint32_t W, H;
+    int32_t sub;  // JB_SUB_444 (also what the replicated 4:2:0 mode is coded as) or JB_SUB_420
+    uint32_t restart_interval;
+    uint64_t scan_offset;       // first byte of the entropy-coded data
+    uint32_t dc_tab[3], ac_tab[3];
+    uint32_t q[3][64];          // quantisation table of every component, natural order
+};
+int parse_jfif(const uint8_t* d, size_t n, JfifInfo* o, DecTables* tabs);  // JB_E_NOSPACE: the header continues past n
+int launch_rst_index(const uint8_t* d_scan, size_t n, uint32_t* d_cnt, uint32_t* d_groups, uint64_t* d_start, uint32_t max_int, cudaStream_t s);
+int launch_huff_decode(const uint8_t* d_scan, size_t n, const uint64_t* d_start, uint32_t n_int, uint32_t ri, uint32_t n_mcu, int bpm,
+                       const DecTables* d_tabs, const JfifInfo& info, int16_t* d_coef, cudaStream_t s);
+int launch_reconstruct(const int16_t* d_coef, uint32_t n_mcu, int mcux, int bpm, const JfifInfo& info, uint8_t* py, uint8_t* pcb, uint8_t* pcr,
+                       size_t pitch_y, size_t pitch_c, uint8_t* d_rgb, size_t pitch, cudaStream_t s);
+int launch_sq_err(const uint8_t* a, size_t pitch_a, const uint8_t* b, size_t pitch_b, size_t W, size_t H, unsigned long long* d_sum, cudaStream_t s);
+
 // ---- launchers (each returns the number of kernels it launched) -------------
 int launch_transform(const TransformArgs& a, cudaStream_t s);       // MCUs inside the image (hot kernel)
 int launch_transform_edge(const TransformArgs& a, cudaStream_t s);  // MCUs that need mirror padding
