@@ -368,6 +368,12 @@ def run_batch(a, jb, enc, torch, dd, workload, F, steps, warmup, want_e2e, want_
             equal = equal and got == want
         parity = {"frames": frames, "equal": bool(equal), "against": "oracle/jpeg_oracle.c (whole JFIF files, byte for byte)",
                   "oracle_seconds": round(time.perf_counter() - t_or, 2)}
+        if not ref_exact:  # decoded on the GPU (jb_decode_jfif_device, libjpeg-exact reconstruction) against the source frame
+            d_dec = torch.empty(W * H * 3, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            enc.decode_jfif_device(d_out.data_ptr() + int(tab[0]), int(tab[F]), d_dec.data_ptr(), W * 3, None)
+            parity["psnr_db_frame0_gpu_decoder"] = round(enc.psnr_device(d_dec.data_ptr(), W * 3, d_rgb.data_ptr(), pitch, W, H)[0], 3)
+            del d_dec
 
     # ---- end to end through the public host API: pinned host in, pinned host out ----------------
     e2e = None
@@ -678,7 +684,24 @@ def run_strips(a, jb, enc, torch, dd):
             n1 = int(t1d[2].item())
             single_equal = n1 == total and bool(torch.equal(o1[:n1], buf))
             del whole, o1
-        parity = {"restart_intervals": ks, "rst_markers_in_sequence": bool(markers_ok), "equal": bool(equal),
+        psnr_db = None
+        try:  # the whole stitched file decoded on this GPU (one thread per restart interval) against the regenerated source
+            dw, dh = min(W, 65535), min(H, 65535)  # (what SOF0 declares)
+            src = torch.empty(H * pitch, dtype=torch.uint8, device="cuda")
+            for y in range(0, H, 1024):
+                enc.synth_device(seed, W, y, min(1024, H - y), pitch, src.data_ptr() + y * pitch)
+            dec = torch.empty(dh * dw * 3, dtype=torch.uint8, device="cuda")
+            enc.sync()
+            torch.cuda.synchronize()
+            t_dec = time.perf_counter()
+            enc.decode_jfif_device(buf.data_ptr(), total, dec.data_ptr(), dw * 3, None)
+            t_dec = time.perf_counter() - t_dec
+            psnr_db = {"psnr_db": round(enc.psnr_device(dec.data_ptr(), dw * 3, src.data_ptr(), pitch, dw, dh)[0], 3),
+                       "decoder": "jb_decode_jfif_device on rank 0 (libjpeg-exact reconstruction)", "decode_seconds": round(t_dec, 3)}
+            del src, dec
+        except Exception as e:
+            psnr_db = {"error": str(e)[:200]}
+        parity = {"restart_intervals": ks, "rst_markers_in_sequence": bool(markers_ok), "equal": bool(equal), "decoded": psnr_db,
                   "against": "oracle/jpeg_oracle.c on the same synthetic rows (strip identity: interval k == the oracle's encode of MCU row k), header and EOI",
                   "stitched_equals_single_gpu_file": single_equal}
 

@@ -198,6 +198,7 @@ size_t plan_bytes(const Plan& p) {
     add((p.chunks_cap + 256) * 4);
     add((p.chunks_cap / 256 + 2) * 4);
     add((p.chunks_cap / 256 + 3) * 8);
+    add((p.chunks_cap / 256 + 2) * sizeof(StuffPlan));
     add(p.n_int_total * 4);
     add((p.n_int_total + 1) * 8);
     add(p.out_cap);
@@ -241,6 +242,7 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.w.ff_prefix = carve<uint32_t>(a, p.chunks_cap + 256);
     s.w.ff_tile = carve<uint32_t>(a, p.chunks_cap / 256 + 2);
     s.w.ff_tile_base = carve<uint64_t>(a, p.chunks_cap / 256 + 3);
+    s.w.stuff_plan = carve<StuffPlan>(a, p.chunks_cap / 256 + 2);
     s.w.int_osize = carve<uint32_t>(a, p.n_int_total);
     s.w.int_obase = carve<uint64_t>(a, p.n_int_total + 1);
     s.d_out = carve<uint8_t>(a, p.out_cap);
@@ -1147,7 +1149,7 @@ int jb_transform(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t H, size_t pit
     CK(cudaStreamSynchronize(s.st));
     resolve_events(ctx);
     uint64_t zero[4] = {0, 0, 0, 0};
-    return status_to_rc(ctx, zero, (uint32_t)s.h_res[5], s.tie_cap);
+    return status_to_rc(ctx, zero, s.h_res[5], s.tie_cap);
 }
 
 // Entropy-code coefficients that are already in the slot's d_coef.
@@ -1272,7 +1274,7 @@ int jb_huffman(jb_ctx* ctx, const int32_t* zz, size_t rpc, uint32_t flags, uint8
 static int harvest(jb_ctx* ctx, Slot& s, uint8_t* out, size_t cap, uint64_t* offsets, uint64_t* sizes,
                    uint64_t* running, bool* overflow) {
     CK(cudaEventSynchronize(s.ev_scalars));
-    int rc = status_to_rc(ctx, s.h_res, (uint32_t)s.h_res[5], s.tie_cap);
+    int rc = status_to_rc(ctx, s.h_res, s.h_res[5], s.tie_cap);
     if (rc) return rc;
     uint64_t total = s.h_res[4];
     if (*overflow || *running + total > cap) {
@@ -1485,7 +1487,7 @@ static int encode_strip_once(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t s
     s.h_res[5] = 0;
     CK(cudaMemcpyAsync(s.h_res + 5, s.d_scalars, 4, cudaMemcpyDeviceToHost, s.st));
     CK(cudaStreamSynchronize(s.st));
-    if ((rc = status_to_rc(ctx, s.h_res, (uint32_t)s.h_res[5], s.tie_cap))) return rc;
+    if ((rc = status_to_rc(ctx, s.h_res, s.h_res[5], s.tie_cap))) return rc;
     *out_len = (size_t)s.h_res[4];
     if (!device_io) {
         if (*out_len > cap) {

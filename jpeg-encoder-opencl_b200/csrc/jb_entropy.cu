@@ -616,11 +616,42 @@ __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// interval i with int_ubase[i] <= pos < int_ubase[i+1], searched in [lo, hi)
+__device__ __forceinline__ uint32_t find_interval(const EntropyArgs& a, uint64_t pos, uint32_t lo, uint32_t hi) {
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a.w.int_ubase[mid] <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// One thread per 4 KB tile of the unstuffed buffer: everything k_stuff needs that is uniform over the tile.
+__global__ void __launch_bounds__(256) k_stuff_plan(const __grid_constant__ EntropyArgs a) {
+    const uint64_t total = a.w.int_ubase[a.n_int_total];
+    if (total > a.w.ubuf_cap) return;
+    const uint64_t n_chunks = total >> 4;
+    const uint32_t n_tiles = (uint32_t)((n_chunks + TILE - 1) / TILE);
+    const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= n_tiles) return;
+    const uint64_t c = (uint64_t)tile * TILE, c_last = min(c + TILE - 1, n_chunks - 1);
+    const uint32_t i = find_interval(a, c << 4, 0, a.n_int_total), k = i % (uint32_t)a.g.n_int;
+    const uint64_t ub = a.w.int_ubase[i], off0 = (c << 4) - ub;
+    StuffPlan pl;
+    pl.i0 = i;
+    pl.i1 = find_interval(a, c_last << 4, i, a.n_int_total);
+    pl.k = k;
+    pl.off0 = off0;
+    pl.nb = (a.w.int_bits[i] + 7) >> 3;
+    pl.hdr_first = k == 0 && off0 == 0 && a.fr.hdr_bytes != 0;
+    pl.g0 = a.w.int_obase[i] + (k == 0 && off0 != 0 ? a.fr.hdr_bytes : 0u) + off0 +
+            (a.w.ff_tile_base[tile] - ff_prefix(a, ub >> 4));  // chunk tile * 256 has in-tile prefix 0
+    a.w.stuff_plan[tile] = pl;
+}
+
 __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyArgs a) {
     __shared__ __align__(16) uint8_t win[STUFF_WIN + 32];
-    __shared__ uint64_t s_g0, s_g1, s_off0, s_nb;
-    __shared__ uint32_t s_i0, s_i1, s_k, s_n;
-    __shared__ bool s_hdr_first;
+    __shared__ uint64_t s_g0, s_g1;
+    __shared__ uint32_t s_n;
     uint64_t total = a.w.int_ubase[a.n_int_total];
     // The segment may be placed at a byte offset that is only known on the device (a.out_off): a strip's place in
     // the stitched file follows from the lengths of the strips before it, and a.out may then be another GPU's
@@ -638,37 +669,20 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
     const uint64_t n_chunks = total >> 4;
     const uint32_t n_tiles = (uint32_t)((n_chunks + TILE - 1) / TILE);
     const uint4* p = reinterpret_cast<const uint4*>(a.w.ubuf);
-    // interval i with int_ubase[i] <= pos < int_ubase[i+1], searched in [lo, hi)
-    auto find_interval = [&](uint64_t pos, uint32_t lo, uint32_t hi) {
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (a.w.int_ubase[mid] <= pos) lo = mid; else hi = mid;
-        }
-        return lo;
-    };
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t c = (uint64_t)tile * TILE + threadIdx.x;
         const bool have = c < n_chunks;
-        // the intervals of the tile's first and last chunk bracket every other chunk's search (mostly to nothing:
-        // an interval is usually much longer than a 4 KB tile)
-        if (threadIdx.x == 0) {
-            const uint32_t i = find_interval(c << 4, 0, a.n_int_total), k = i % (uint32_t)a.g.n_int;
-            const uint64_t ub = a.w.int_ubase[i], off0 = (c << 4) - ub;
-            s_i0 = i;
-            // what a tile that lies inside one interval needs from it (the fast path below)
-            s_k = k;
-            s_off0 = off0;
-            s_nb = (a.w.int_bits[i] + 7) >> 3;
-            s_hdr_first = k == 0 && off0 == 0 && a.fr.hdr_bytes != 0;
-            s_g0 = a.w.int_obase[i] + (k == 0 && off0 != 0 ? a.fr.hdr_bytes : 0u) + off0 +
-                   (a.w.ff_tile_base[tile] - ff_prefix(a, ub >> 4));  // chunk tile * 256 has in-tile prefix 0
-        }
-        if (have && (threadIdx.x == TILE - 1 || c + 1 == n_chunks)) s_i1 = find_interval(c << 4, 0, a.n_int_total);
-        __syncthreads();
+        // what is uniform over the tile comes from k_stuff_plan: the restart intervals of the tile's first and last
+        // chunk (they bracket every other chunk's interval search -- mostly to nothing: an interval is usually much
+        // longer than a 4 KB tile), and for a tile that lies inside one interval its place in that interval
+        const StuffPlan pl = a.w.stuff_plan[tile];
+        const uint32_t s_i0 = pl.i0, s_i1 = pl.i1, s_k = pl.k;
+        const uint64_t s_off0 = pl.off0, s_nb = pl.nb;
+        const bool s_hdr_first = pl.hdr_first != 0;
         if (s_i0 == s_i1 && !s_hdr_first) {
             // ---- fast path: the whole tile lies in one interval and starts no frame.  Per thread: its chunk and
             // its in-tile 0xFF prefix; everything else is tile-uniform, offsets are 32 bits relative to the tile.
-            const uint64_t g0 = s_g0, off = s_off0 + 16u * threadIdx.x, nb = s_nb;
+            const uint64_t g0 = pl.g0, off = s_off0 + 16u * threadIdx.x, nb = s_nb;
             uint32_t n_here = 0;
             if (have) {
                 const uint4 q = p[c];
@@ -727,7 +741,7 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
         bool hdr = false;
         if (have) {
             uint64_t pos = c << 4;
-            uint32_t i = find_interval(pos, s_i0, s_i1 + 1), k = i % (uint32_t)a.g.n_int;
+            uint32_t i = find_interval(a, pos, s_i0, s_i1 + 1), k = i % (uint32_t)a.g.n_int;
             uint64_t ub = a.w.int_ubase[i];
             uint64_t off = pos - ub, nb = (a.w.int_bits[i] + 7) >> 3;
             hdr = k == 0 && off == 0 && a.fr.hdr_bytes != 0;
@@ -1005,8 +1019,9 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s, int phase) {
     uint32_t gi = (a.n_int_total + 255) / 256;
     const uint32_t chunk_tiles = (uint32_t)(a.w.ubuf_cap / 16 / TILE + 1);
     if (phase == 2) {
+        k_stuff_plan<<<(chunk_tiles + 255) / 256, 256, 0, s>>>(a);
         k_stuff<<<chunk_tiles < 1184u ? chunk_tiles : 1184u, TILE, 0, s>>>(a);
-        return 1;
+        return 2;
     }
     k_encode<<<n_tiles, TILE, 0, s>>>(a);
     launches += scan_u32(a.w.tile_bits, a.w.tile_base, n_tiles, nullptr, a.w.scan_tmp, s);
@@ -1027,8 +1042,9 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s, int phase) {
     k_finalize<<<gf, 256, 0, s>>>(a);
     launches += 3;
     if (phase == 1) return launches;
+    k_stuff_plan<<<(chunk_tiles + 255) / 256, 256, 0, s>>>(a);
     k_stuff<<<chunk_tiles < 1184u ? chunk_tiles : 1184u, TILE, 0, s>>>(a);
-    return launches + 1;
+    return launches + 2;
 }
 
 }  // namespace jb

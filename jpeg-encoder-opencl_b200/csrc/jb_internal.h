@@ -89,6 +89,7 @@ struct FixupArgs {
     const double* costab;  // [u][x] = cos((2x+1) u pi / 16), from the host's libm
     const double* scale;   // [u][v] = alpha(u) alpha(v) / 4.0
     int inplace_dct;       // Q1: replay the reference's in-place block transform up to the flagged output
+    uint64_t m_bpf, m_mcux;  // ceil(2^52 / blocks per frame), ceil(2^52 / MCUs per row): divisions by multiplication
     const uint8_t* uv;     // NV12-style input: see TransformArgs
     size_t pitch_uv, frame_stride_uv;
     QuantTables qt;
@@ -108,6 +109,17 @@ struct Framing {
     uint32_t final_rst;   // append RSTn after the last interval instead (strips)
     uint32_t rst_phase;   // index of the first interval (strips)
     uint32_t raw_bits;    // reference-style bit string: no padding, no stuffing, no markers
+};
+
+// What the final placement kernel needs to know about one tile of 256 chunks (4 KB of unstuffed bytes), computed by
+// one thread per tile (k_stuff_plan) so that no thread of k_stuff walks dependent loads while 255 others wait.
+struct StuffPlan {
+    uint64_t g0;    // first output byte the tile owns
+    uint64_t off0;  // offset of the tile's first chunk inside its restart interval
+    uint64_t nb;    // data bytes of that interval
+    uint32_t i0, i1;  // restart intervals of the tile's first and last chunk
+    uint32_t k;       // index of interval i0 inside its frame
+    uint32_t hdr_first;  // the tile starts a frame that carries a header
 };
 
 // Device work arrays of the entropy coder (all sized by the context).
@@ -130,6 +142,7 @@ struct EntropyWork {
     uint32_t* n_ff_tiles;   // device scalar
     uint32_t* int_osize;    // [n_int_total]
     uint64_t* int_obase;    // [n_int_total + 1]
+    StuffPlan* stuff_plan;  // [ubuf_cap / 16 / 256 + 2]
     uint64_t* scan_tmp;     // scratch of the multi-CTA scans
     uint64_t* status;       // [0] error bits, [1] required ubuf bytes, [2] required out bytes, [3] total bits
 };

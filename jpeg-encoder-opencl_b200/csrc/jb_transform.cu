@@ -1786,7 +1786,7 @@ int launch_transform_edge(const TransformArgs& a_in, cudaStream_t s) {
 // then utils.cpp:454-467), in binary64 with unfused multiplies and adds: the serial chains of 32
 // entries run side by side instead of one chain occupying a whole warp.
 #ifndef FIX_BATCH
-#define FIX_BATCH 4
+#define FIX_BATCH 8
 #endif
 constexpr int FIX_WARPS = 4;  // the kernel is latency-bound: small batches keep 64 warps per SM resident
 __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant__ FixupArgs a) {
@@ -1806,7 +1806,8 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
         int my_comp, my_nat;
         {
             const uint32_t gblock = my_entry >> 6, k = my_entry & 63;
-            const uint32_t f = gblock / bpf, rb = gblock - f * bpf;
+            // (host magics m = ceil(2^52 / d): exact for x, d < 2^26, as in the entropy coder)
+            const uint32_t f = (uint32_t)__umul64hi((uint64_t)gblock << 12, a.m_bpf), rb = gblock - f * bpf;
             uint32_t mcu, blk;
             if (a.g.bpm == 6) {
                 mcu = rb / 6u;
@@ -1815,7 +1816,7 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
                 mcu = rb / 3u;
                 blk = rb - mcu * 3u;
             }
-            const uint32_t my = mcu / (uint32_t)a.g.mcux, mx = mcu - my * (uint32_t)a.g.mcux;
+            const uint32_t my = (uint32_t)__umul64hi((uint64_t)mcu << 12, a.m_mcux), mx = mcu - my * (uint32_t)a.g.mcux;
             uint32_t x0, y0, step;
             if (a.g.sub == JB_SUB_420) {
                 my_comp = blk < 4 ? 0 : (int)blk - 3;
@@ -1893,7 +1894,10 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
     }
 }
 
-int launch_fixup(const FixupArgs& a, cudaStream_t s) {
+int launch_fixup(const FixupArgs& a_in, cudaStream_t s) {
+    FixupArgs a = a_in;
+    a.m_bpf = ((1ull << 52) + (uint64_t)a.g.n_mcu * a.g.bpm - 1) / ((uint64_t)a.g.n_mcu * a.g.bpm);
+    a.m_mcux = ((1ull << 52) + (uint64_t)a.g.mcux - 1) / (uint64_t)a.g.mcux;
     k_fixup<<<148 * 16, FIX_WARPS * 32, 0, s>>>(a);
     return 1;
 }
