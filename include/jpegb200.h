@@ -279,6 +279,7 @@ typedef struct {
     uint32_t restart_interval; /* MCUs, 0 = none */
     uint64_t scan_offset;      /* first byte of the entropy-coded data */
 } jb_jfif_info;
+int jb_jfif_info_host(const uint8_t *jfif, size_t len, jb_jfif_info *info); /* host buffer, host only (the marker parser) */
 int jb_jfif_info_device(jb_ctx *ctx, const uint8_t *d_jfif, size_t len, jb_jfif_info *info);
 /* d_rgb (W*3 <= pitch) and / or d_coef (int16 [n_mcu][blocks_per_mcu][64], zigzag order: the layout jb_transform
  * produces) may be null; device pointers, synchronous.  One thread decodes one restart interval. */

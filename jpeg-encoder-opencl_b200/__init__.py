@@ -36,7 +36,7 @@ SYMBOLS = [
     "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32", "jb_optimal_huffman_spec",
     "jb_encode_strip_begin", "jb_encode_strip_finish", "jb_copy_bytes_device", "jb_ipc_export", "jb_ipc_open", "jb_ipc_close",
     "jb_stitch_exchange", "jb_stitch_complete", "jb_encode_tiles", "jb_encode_nv12_device", "jb_rgb8_to_nv12_device",
-    "jb_jfif_info_device", "jb_decode_jfif_device", "jb_decode_jfif", "jb_psnr_device",
+    "jb_jfif_info_host", "jb_jfif_info_device", "jb_decode_jfif_device", "jb_decode_jfif", "jb_psnr_device",
     "jb_pad_mirror_planar_u32", "jb_blockify_planar_i32", "jb_f64_to_u8", "jb_remove_red_aos", "jb_value_categories",
 ]
 
@@ -138,6 +138,7 @@ def lib():
     L.jb_encode_batch.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp]
     L.jb_encode_nv12_device.argtypes = [vp, vp, sz, sz, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, vp]
     L.jb_rgb8_to_nv12_device.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp, sz]
+    L.jb_jfif_info_host.argtypes = [vp, sz, C.POINTER(JfifInfo)]
     L.jb_jfif_info_device.argtypes = [vp, vp, sz, C.POINTER(JfifInfo)]
     L.jb_decode_jfif_device.argtypes = [vp, vp, sz, vp, sz, vp]
     L.jb_decode_jfif.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(sz)]
@@ -186,6 +187,16 @@ def optimal_huffman_spec(counts):
     if rc:
         raise JbError(rc, "jb_optimal_huffman_spec")
     return bits, vals[: n.value]
+
+
+def jfif_info(data):
+    """Host-only marker parser: (W, H, subsampling, restart_interval, scan_offset) of a baseline JFIF file."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    info = JfifInfo()
+    rc = lib().jb_jfif_info_host(buf.ctypes.data, buf.size, C.byref(info))
+    if rc:
+        raise JbError(rc, "jb_jfif_info_host: not a baseline 3-component JFIF file the decoder handles")
+    return info
 
 
 def header_bytes(params):

@@ -1567,6 +1567,20 @@ static int fetch_info(jb_ctx* ctx, const uint8_t* d_jfif, size_t len, JfifInfo* 
     }
 }
 
+int jb_jfif_info_host(const uint8_t* jfif, size_t len, jb_jfif_info* out) {  // host only: no device needed
+    if (!jfif || !out || len < 4) return JB_E_INVALID;
+    JfifInfo info;
+    DecTables tabs;
+    int rc = parse_jfif(jfif, len, &info, &tabs);
+    if (rc) return rc == JB_E_NOSPACE ? JB_E_INVALID : rc;
+    out->W = info.W;
+    out->H = info.H;
+    out->subsampling = info.sub;
+    out->restart_interval = info.restart_interval;
+    out->scan_offset = info.scan_offset;
+    return JB_OK;
+}
+
 int jb_jfif_info_device(jb_ctx* ctx, const uint8_t* d_jfif, size_t len, jb_jfif_info* out) {
     if (!ctx || !d_jfif || !out || len < 4) return fail(ctx, JB_E_INVALID, "bad arguments");
     CK(cudaSetDevice(ctx->device));

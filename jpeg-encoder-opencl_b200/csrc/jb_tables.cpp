@@ -466,6 +466,11 @@ void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double step
                 W[k] = wk * JB_TC_W_SCALE;
                 m = fmax(m, fabs(W[k]));
             }
+            if (m == 0.0) {  // an all-zero row (K = 16 cells: the basis functions with u = 4 or v = 4 cancel inside every 2x2
+                             // cell): the matrices stay zero, the accumulator is exactly 0, nothing to replay
+                tband[t][n] = nextafterf(0.5f, 0.0f);
+                continue;
+            }
             int E = 0;
             frexp(m, &E);          // m = f * 2^E with f in [0.5, 1): every |W| is below 2^E
             if (E < -3) E = -3;    // q0 = 2^(E-21) stays a binary16 (subnormal) quantum, 2^-24

@@ -52,14 +52,15 @@ WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
         ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait")]
 
 def kernels():
-    md = ["# ncu --set full summaries (round 1)", "",
+    md = [f"# ncu --set full summaries ({R})", "",
           "Workload: `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline` (512 x 1920x1080, 4:2:0, q75);",
           "`_prof_full`: the same with `--tensor-dct 0` (CUDA-core transform); `_prof_tc3`: `--workload 4k444` (32 x 3840x2160, 4:4:4, q90);",
           "`_prof_tc3r`: `--workload repl1080p` (256 x 1920x1080, replicated 4:2:0, q50: K = 16 chroma contraction).",
+          "`_prof_tma`: the default workload with `--tma` (JB_FLAG_TMA: TMA-staged tiles, `k_transform_tma`).",
           "Captured by `profiles/capture.sh` (each ncu pass after a plain run of the same command that exited 0).",
           "Numbers taken under the profiler are diagnostics only; bench values come from CUDA events.", ""]
     summary = {}
-    for rep in (f"{R}_prof_tc.ncu-rep", f"{R}_prof_full.ncu-rep", f"{R}_prof_tc3.ncu-rep", f"{R}_prof_tc3r.ncu-rep"):
+    for rep in (f"{R}_prof_tc.ncu-rep", f"{R}_prof_tma.ncu-rep", f"{R}_prof_full.ncu-rep", f"{R}_prof_tc3.ncu-rep", f"{R}_prof_tc3r.ncu-rep"):
         if not os.path.exists(os.path.join(OUT, rep)):
             continue
         hdr, units, rows = raw(rep)
@@ -75,6 +76,25 @@ def kernels():
                     rec[label] = (v, u)
             md.append("")
             summary[name] = rec
+    # overview: what bounds each kernel.  All are HBM-bound by construction (byte / integer work); "frac" = DRAM bytes moved /
+    # duration / 6544 GB/s (MEASURED_PEAKS.json); the limiter is read off the issue utilisation and the top stall.
+    def num(rec, label):
+        return float(rec[label][0].replace(",", "")) if label in rec else 0.0
+    over = ["## Overview (one 1.06 Gpx step of the default workload unless noted; durations under ncu)", "",
+            "| kernel | duration | DRAM read + write | GB/s | frac of 6 544 | issue active | warps active | top stall | limiter |",
+            "|---|---:|---:|---:|---:|---:|---:|---|---|"]
+    for name, rec in summary.items():
+        dur = num(rec, "duration")
+        unit = rec["duration"][1]
+        us = dur * {"ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}.get(unit, 1.0)
+        by = to_bytes(*rec["dram read"]) + to_bytes(*rec["dram write"])
+        gbs = by / (us * 1e-6) / 1e9 if us else 0
+        stalls = {k: num(rec, k) for k in rec if k.startswith("stall ")}
+        top = max(stalls, key=stalls.get) if stalls else ""
+        issue = num(rec, "issue active %")
+        lim = "instruction issue" if issue >= 55 else ("latency: " + top.replace("stall ", "") if issue < 50 else "issue + " + top.replace("stall ", ""))
+        over.append(f"| `{name}` | {us:.0f} us | {by/1e9:.2f} GB | {gbs:.0f} | {gbs/6544:.2f} | {issue:.0f} % | {num(rec, 'warps active %'):.0f} % | {top} {stalls.get(top, 0):.1f} | {lim} |")
+    md = md[:9] + over + [""] + md[9:]
     open(os.path.join(ROOT, "profiles", f"{R}_kernels.md"), "w").write("\n".join(md) + "\n")
     return summary
 

@@ -85,6 +85,36 @@ def test_optimal_huffman_spec_matches_oracle(jb):
         assert int(gb.sum()) == n_sym and sum(int(gb[l]) * 2.0 ** -(l + 1) for l in range(16)) < 1.0
 
 
+def test_jfif_marker_parser_host_only(jb):
+    """The decode path's marker parser (host code, no device): the oracle's files in every mode, a file libjpeg wrote (other
+    segment order, optimised tables), and what it must reject (progressive, truncated headers, garbage)."""
+    import io
+    from PIL import Image
+    ql, qc = ol.quality_tables(75)
+    img = ol.synth(3, 200, 120)
+    for sub, ri in ((ol.SUB_444, 0), (ol.SUB_REPL420, 5), (ol.SUB_420, 13)):
+        jf = ol.encode_jfif(img, sub, ql, qc, ri)
+        info = jb.jfif_info(jf)
+        assert (info.W, info.H, info.restart_interval) == (200, 120, ri)
+        assert info.subsampling == (jb.SUB_420 if sub == ol.SUB_420 else jb.SUB_444)
+        assert info.scan_offset == len(ol.jfif_header(200, 120, sub, ql, qc, ri)) == jb.header_bytes(jb.make_params(sub, qlum=ql, qchrom=qc, restart_interval=ri))
+        with pytest.raises(jb.JbError):
+            jb.jfif_info(jf[: info.scan_offset - 20])  # the header is cut short
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, "JPEG", quality=80, subsampling=2, optimize=True)
+    info = jb.jfif_info(buf.getvalue())
+    assert (info.W, info.H, info.subsampling, info.restart_interval) == (200, 120, jb.SUB_420, 0)
+    assert buf.getvalue()[info.scan_offset - 14: info.scan_offset - 12] == b"\xff\xda"  # SOS (12-byte segment) ends at scan_offset
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, "JPEG", progressive=True)
+    with pytest.raises(jb.JbError) as e:
+        jb.jfif_info(buf.getvalue())
+    assert e.value.code == jb.E_UNSUPPORTED
+    for bad in (b"\xff\xd8\xff\xd9", b"hello, world", b"\xff\xd8" + b"\x00" * 64):
+        with pytest.raises(jb.JbError):
+            jb.jfif_info(bad)
+
+
 def test_fails_loudly_without_gpu(jb):
     import torch
     if torch.cuda.is_available():
