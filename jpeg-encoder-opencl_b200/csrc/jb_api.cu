@@ -199,6 +199,7 @@ size_t plan_bytes(const Plan& p) {
     add((p.chunks_cap / 256 + 2) * 4);
     add((p.chunks_cap / 256 + 3) * 8);
     add((p.chunks_cap / 256 + 2) * sizeof(StuffPlan));
+    add((p.n_tiles + 1) * sizeof(PackPlan));
     add(p.n_int_total * 4);
     add((p.n_int_total + 1) * 8);
     add(p.out_cap);
@@ -243,6 +244,7 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.w.ff_tile = carve<uint32_t>(a, p.chunks_cap / 256 + 2);
     s.w.ff_tile_base = carve<uint64_t>(a, p.chunks_cap / 256 + 3);
     s.w.stuff_plan = carve<StuffPlan>(a, p.chunks_cap / 256 + 2);
+    s.w.pack_plan = carve<PackPlan>(a, p.n_tiles + 1);
     s.w.int_osize = carve<uint32_t>(a, p.n_int_total);
     s.w.int_obase = carve<uint64_t>(a, p.n_int_total + 1);
     s.d_out = carve<uint8_t>(a, p.out_cap);

@@ -19,6 +19,7 @@
 //   k_stuff     assemble the final bytes per 4 KB tile in shared memory (0x00 after 0xFF,
 //               markers, JFIF headers) and store them with coalesced 128-bit stores
 // Bit order is MSB first; the unstuffed buffer is addressed as big-endian words.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
 #include "jb_pixels.cuh"  // cat_bits (utils.cpp:623-653)
@@ -45,6 +46,11 @@ struct BitSink {
             atomicOr(wp, __byte_perm((uint32_t)(acc >> n), 0, 0x0123));
             ++wp;
         }
+    }
+    // table-entry form (HuffDev): the code left-aligned in the word, its length in the low five bits
+    __device__ __forceinline__ void put(uint32_t e) {
+        const int len = (int)(e & 31u);
+        if (len) put(e >> (32 - len), len);
     }
     __device__ __forceinline__ void finish() {
         if (n > 0) atomicOr(wp, __byte_perm((uint32_t)(acc << (32 - n)), 0, 0x0123));
@@ -136,131 +142,218 @@ __device__ __forceinline__ uint32_t interleave16(uint32_t x) {
     return e | (o << 1);
 }
 
-// Sink that keeps the first 128 bits of a block's code left-aligned in a 4-word slot (MSB
-// first) and counts all bits.  Blocks longer than 128 bits are re-walked by k_pack.
+// Sink of k_encode: the block's code as ONE right-aligned 128-bit number in four registers (s3 most significant,
+// the first code bit the most significant one of the n bits) plus the bit count.  A symbol is four funnel shifts:
+// no flush branch, no shared-memory traffic inside the walk.  Codes longer than 128 bits lose their first bits here;
+// k_pack_long re-walks those blocks.
 struct SlotSink {
-    uint64_t acc;
-    int n;
-    uint32_t* slot;  // 4 words (shared memory)
-    int wi;          // words completed so far (only the first four are kept)
-    __device__ __forceinline__ void init(uint32_t* s) {
-        slot = s;
-        acc = 0;
-        n = 0;
-        wi = 0;
-        *reinterpret_cast<uint4*>(s) = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t s0, s1, s2, s3, n;
+    __device__ __forceinline__ void init() { s0 = s1 = s2 = s3 = n = 0u; }
+    // e = code left-aligned | length (HuffDev): the funnel shifts take the length from the low five bits of e
+    // themselves, and (s0 : e) << len drops the length field while it moves the code in below s0
+    __device__ __forceinline__ void put(uint32_t e) {
+        s3 = __funnelshift_l(s2, s3, e);
+        s2 = __funnelshift_l(s1, s2, e);
+        s1 = __funnelshift_l(s0, s1, e);
+        s0 = __funnelshift_l(e, s0, e);
+        n += e & 31u;
     }
-    __device__ __forceinline__ void put(uint32_t code, int len) {
-        acc = (acc << len) | code;
-        n += len;
-        if (n >= 32) {
-            n -= 32;
-            if (wi < 4) slot[wi] = (uint32_t)(acc >> n);
-            ++wi;
-        }
-    }
-    __device__ __forceinline__ void finish() {
-        if (n > 0 && wi < 4) slot[wi] = (uint32_t)(acc << (32 - n));
-    }
-    __device__ __forceinline__ uint32_t bits() const { return (uint32_t)(wi * 32 + n); }
 };
 
+// Huffman code t (left-aligned | length hl) followed by the cat value bits of v (utils.cpp:623-653: v for v > 0, the
+// low cat bits of v - 1 for v < 0), as one entry of the same form: hl + cat <= 27 for every table the coder builds.
+template <bool MAY_BE_ZERO>
+__device__ __forceinline__ uint32_t with_value_bits(uint32_t t, int v, int cat) {
+    const uint32_t x = (uint32_t)(v + (v >> 31));
+    uint32_t vbl = x << ((32 - cat) & 31);  // value bits left-aligned (bits above cat fall off)
+    if (MAY_BE_ZERO && cat == 0) vbl = 0u;
+    return (t + (uint32_t)cat) | (vbl >> (t & 31u));
+}
+
 // The block as HuffmanEncoder codes it (utils.cpp:667-694), visiting only the non-zero AC
-// coefficients: mask bit k = coefficient k != 0, value(k) fetches coefficient k.  s_small (may
+// coefficients: bit k of (mlo, mhi) = coefficient k != 0, value(k) fetches coefficient k.  s_small (may
 // be null) maps (run <= 15, |v| <= 15) straight to code + value bits: the common case is one
 // look-up instead of category, value bits and code assembly.
 template <bool SMALL, class Sink, class Fetch>
-__device__ __forceinline__ void encode_sparse(uint64_t mask, Fetch value, int dc_diff, const uint32_t* s_ac,
+__device__ __forceinline__ void encode_sparse(uint32_t mlo, uint32_t mhi, Fetch value, int dc_diff, const uint32_t* s_ac,
                                               const uint32_t* s_dc, const uint32_t* s_small, bool always_eob, Sink& s) {
-    int cat;
-    uint32_t vb;
-    cat_bits(dc_diff, cat, vb);
-    uint32_t e = s_dc[cat];
-    s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
+    {
+        const int cat = 32 - __clz(abs(dc_diff));
+        s.put(with_value_bits<true>(s_dc[cat], dc_diff, cat));
+    }
     int cur = 1;  // next AC position to account for
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {  // positions 1..31, then 32..63: 32-bit mask arithmetic
-        uint32_t m = half ? (uint32_t)(mask >> 32) : ((uint32_t)mask & ~1u);
+        uint32_t m = half ? mhi : (mlo & ~1u);
+        const int base = 32 * half - 1;
         while (m) {
-            int pos = __ffs((int)m) - 1 + 32 * half;
+            const int pos = __ffs((int)m) + base;
             m &= m - 1;
             int run = pos - cur;
             cur = pos + 1;
-            int v = value(pos);
+            const int v = value(pos);
+            uint32_t e;
             if (SMALL && run < 16 && (uint32_t)(v + 15) <= 30u) {
-                // byte offset (run * 32 + (v & 31)) * 4: the two fields do not overlap, one IMAD + one LOP3
+                // byte offset (run * 32 + (v & 31)) * 4: the two fields do not overlap
                 e = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_small) + ((run << 7) | ((v << 2) & 0x7C)));
-                s.put(e >> 5, (int)(e & 31u));
-                continue;
+            } else {
+#pragma unroll 1
+                while (run >= 16) {  // ZRL, utils.cpp:592-597
+                    s.put(s_ac[0xF0]);
+                    run -= 16;
+                }
+                const int cat = 32 - __clz(abs(v));
+                e = with_value_bits<false>(s_ac[(run << 4) | cat], v, cat);
             }
-            while (run >= 16) {  // ZRL, utils.cpp:592-597
-                uint32_t z = s_ac[0xF0];
-                s.put(z >> 5, (int)(z & 31u));
-                run -= 16;
-            }
-            cat_bits(v, cat, vb);
-            e = s_ac[(run << 4) | cat];
-            s.put(((e >> 5) << cat) | vb, (int)(e & 31u) + cat);
+            s.put(e);
         }
     }
-    if (cur < 64 || always_eob) {  // EOB, utils.cpp:607-608 (Q3 when always_eob)
-        e = s_ac[0];
-        s.put(e >> 5, (int)(e & 31u));
+    if (cur < 64 || always_eob) s.put(s_ac[0]);  // EOB, utils.cpp:607-608 (Q3 when always_eob)
+}
+
+// ---- k_encode's walk: the same coding as encode_sparse, on shared-memory addresses ----------------------------
+__device__ __forceinline__ int lds_s16(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// cblk: shared address of the block's 128 bytes (XOR-swizzled by swz = (block & 7) << 4); dc_tab / small_tab: shared
+// addresses of the block's DC and small-value tables (small_tab 128-byte aligned); g_ac: its full AC table (global
+// memory / L1: symbols outside the small-value table, ZRL, EOB).  Positions and runs are kept DOUBLED (byte offsets
+// of int16 coefficients): the doubled position is the coefficient's address, the doubled run times 64 its table row.
+__device__ __forceinline__ void walk_block(uint32_t mlo, uint32_t mhi, uint32_t cblk, uint32_t swz, int dc_diff,
+                                           const uint32_t* __restrict__ g_ac, uint32_t dc_tab, uint32_t small_tab, bool always_eob,
+                                           SlotSink& s) {
+    {
+        const int cat = 32 - __clz(abs(dc_diff));
+        s.put(with_value_bits<true>(lds_u32(dc_tab + 4u * (uint32_t)cat), dc_diff, cat));
     }
+    int cur2 = 2;  // (doubled) next AC position to account for
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {  // positions 1..31, then 32..63: 32-bit mask arithmetic
+        uint32_t m = half ? mhi : (mlo & ~1u);
+        const int base2 = 64 * half - 2;
+        while (m) {
+            const int pos2 = 2 * __ffs((int)m) + base2;
+            m &= m - 1;
+            int run2 = pos2 - cur2;
+            cur2 = pos2 + 2;
+            const int v = lds_s16(cblk | ((uint32_t)pos2 ^ swz));
+            uint32_t e;
+            if (((uint32_t)(v + 15) | ((uint32_t)run2 & ~31u)) <= 30u) {  // |v| <= 15 and run < 16: one look-up
+                e = lds_u32((((uint32_t)v << 2) & 0x7Cu) | (small_tab + (uint32_t)run2 * 64u));
+            } else {
+#pragma unroll 1
+                while (run2 >= 32) {  // ZRL, utils.cpp:592-597
+                    s.put(__ldg(g_ac + 0xF0));
+                    run2 -= 32;
+                }
+                const int cat = 32 - __clz(abs(v));
+                e = with_value_bits<false>(__ldg(g_ac + (((uint32_t)run2 << 3) | (uint32_t)cat)), v, cat);
+            }
+            s.put(e);
+        }
+    }
+    if (cur2 < 128 || always_eob) s.put(__ldg(g_ac));  // EOB, utils.cpp:607-608 (Q3 when always_eob)
 }
 
 #ifndef ENC_CTAS
 #define ENC_CTAS 5
 #endif
-// One thread per block.  The tile's coefficients (256 blocks, 32 KB) are staged in shared
-// memory with coalesced 128-bit loads (XOR swizzle: piece p of block t at t*8 + (p ^ (t&7))).
-// Each thread builds the non-zero mask of its block, walks the non-zero coefficients, keeps
-// the first 128 code bits in a slot and the total length; lengths are scanned per tile.
-__global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant__ EntropyArgs a) {
-    __shared__ uint4 s_coef[TILE * 8];
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One thread per block.  The tile's coefficients (256 blocks, 32 KB, contiguous in global memory) are staged in shared
+// memory with the 128-byte XOR swizzle (piece p of block t at t*8 + (p ^ (t&7)): a thread that reads its own block and
+// its neighbours theirs hit different banks) -- by ONE cp.async.bulk.tensor (TMA = true: a 2-D tensor map over the
+// coefficient array, box = 256 rows x 128 bytes, SWIZZLE_128B produces exactly that layout; completion on an
+// mbarrier) or, for coefficient arrays the tensor map cannot describe, by coalesced 128-bit loads and stores.
+// Each thread builds the non-zero mask of its block; the blocks are counting-sorted by their number of non-zero
+// coefficients; thread t walks the non-zero coefficients of block perm[t]; code lengths are scanned per tile.
+template <bool TMA>
+__global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant__ EntropyArgs a, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(1024) uint4 s_coef[TILE * 8];
     __shared__ __align__(16) uint32_t s_slot[TILE * 4];
-    __shared__ uint64_t s_mask[TILE];
-    __shared__ uint32_t s_dc[2][16], s_warp[8];
-    __shared__ uint32_t s_small[2][512];
+    __shared__ __align__(8) uint2 s_mask[TILE];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(128) uint32_t s_small[2][512];
+    __shared__ __align__(16) uint32_t s_dc[2][16];
+    __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_len[TILE];
     __shared__ uint32_t s_hist[64], s_start[64];
     __shared__ uint16_t s_perm[TILE];
     const uint32_t t = threadIdx.x, b0 = blockIdx.x * TILE, b = b0 + t;
-    const uint4* src = reinterpret_cast<const uint4*>(a.coef) + (size_t)b0 * 8;
-    const uint32_t n_blk = min((uint32_t)TILE, a.n_blocks - b0), n_here = n_blk * 8;
+    const uint32_t n_blk = min((uint32_t)TILE, a.n_blocks - b0);
+    if (TMA) {
+        if (t == 0) {
+            const uint32_t bar = smem_addr(&s_bar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // rows past the end of the array are filled with zeros and count as transferred bytes; the two tables
+            // the walk reads from shared memory travel as plain bulk copies on the same barrier
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(TILE * 128 + 4096 + 128) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                             smem_addr(s_coef)),
+                         "l"(&tmap), "r"(0), "r"((int)b0), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(s_small)),
+                         "l"(&a.huff->small[0][0]), "n"(4096), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(s_dc)),
+                         "l"(&a.huff->dc[0][0]), "n"(128), "r"(bar)
+                         : "memory");
+        }
+    } else {
+        const uint4* src = reinterpret_cast<const uint4*>(a.coef) + (size_t)b0 * 8;
+        const uint32_t n_here = n_blk * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        uint32_t g = i * TILE + t, blk = g >> 3, pc = g & 7;
-        if (g < n_here) s_coef[blk * 8 + (pc ^ (blk & 7))] = __ldg(src + g);
+        for (int i = 0; i < 8; ++i) {
+            uint32_t g = i * TILE + t, blk = g >> 3, pc = g & 7;
+            if (g < n_here) s_coef[blk * 8 + (pc ^ (blk & 7))] = __ldg(src + g);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) (&s_small[0][0])[i * TILE + t] = (&a.huff->small[0][0])[i * TILE + t];
+        if (t < 32) (&s_dc[0][0])[t] = (&a.huff->dc[0][0])[t];
     }
     if (t < 64) s_hist[t] = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) (&s_small[0][0])[i * TILE + t] = (&a.huff->small[0][0])[i * TILE + t];
-    if (t < 32) (&s_dc[0][0])[t] = (&a.huff->dc[0][0])[t];
     __syncthreads();
+    if (TMA) {  // (the barrier above made the mbarrier's initialisation visible to every thread)
+        const uint32_t bar = smem_addr(&s_bar);
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done)
+                         : "r"(bar), "r"(0)
+                         : "memory");
+    }
     // ---- non-zero mask of this thread's block, then a counting sort of the tile's blocks by
     // their number of non-zero AC coefficients: the walk below costs one loop iteration per
     // non-zero, so warps made of similar blocks do not wait for their busiest lane.
     uint32_t cnt = 0;
     if (t < n_blk) {
-        // One half2 "not equal (unordered) to zero" compare flags both int16 halves of a word
-        // (every non-zero coefficient |c| <= 2047 is a non-zero, possibly subnormal or NaN,
-        // binary16 pattern); word j of a 16-word half drops its two flags at bits j and 16+j,
-        // and the even/odd bit planes are interleaved back into zigzag order afterwards.
-        uint32_t eo[2] = {0u, 0u};
+        // One half2 "not equal (unordered) to zero" compare flags both int16 halves of a word (every non-zero
+        // coefficient |c| <= 2047 is a non-zero, possibly subnormal or NaN, binary16 pattern): 0xFFFF per half.  Two
+        // byte permutes line up one flag byte per coefficient of a piece (eight coefficients, zigzag order), two
+        // LOP3 keep bit i of coefficient i, and a multiplication by 0x01010101 adds the four bytes into the top one:
+        // the piece's eight mask bits, inserted into the mask by a third permute.  (The first version of this loop
+        // collected even and odd coefficients in two bit planes and interleaved them afterwards: +50 instructions.)
+        uint32_t m[2] = {0u, 0u};
 #pragma unroll
         for (int pc = 0; pc < 8; ++pc) {
             const uint4 q = s_coef[t * 8 + (pc ^ (t & 7))];
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int j = pc * 4 + i, jj = j & 15;
-                eo[j >> 4] |= nz_flags(w[i]) & ((1u << jj) | (1u << (16 + jj)));
-            }
+            const uint32_t fa = __byte_perm(nz_flags(q.x), nz_flags(q.y), 0x6420);
+            const uint32_t fb = __byte_perm(nz_flags(q.z), nz_flags(q.w), 0x6420);
+            const uint32_t x = (fa & 0x08040201u) | (fb & 0x80402010u);
+            const uint32_t sel = (pc & 3) == 0 ? 0x3217u : (pc & 3) == 1 ? 0x3270u : (pc & 3) == 2 ? 0x3710u : 0x7210u;
+            m[pc >> 2] = __byte_perm(m[pc >> 2], x * 0x01010101u, sel);
         }
-        const uint64_t mask = (uint64_t)interleave16(eo[0]) | ((uint64_t)interleave16(eo[1]) << 32);
-        s_mask[t] = mask;
-        cnt = (uint32_t)__popcll(mask & ~1ull);
+        s_mask[t] = make_uint2(m[0], m[1]);
+        cnt = (uint32_t)(__popc(m[0] & ~1u) + __popc(m[1]));
         atomicAdd(&s_hist[cnt], 1u);
     }
     __syncthreads();
@@ -280,30 +373,47 @@ __global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant
     // ---- encode block s_perm[t] ------------------------------------------------------------
     if (t < n_blk) {
         const uint32_t k = s_perm[t], bk = b0 + k;
-        const short* cf = reinterpret_cast<const short*>(s_coef);
         // coefficient pos of block k: byte k*128 + (((pos >> 3) ^ (k & 7)) << 4) + (pos & 7) * 2 = k*128 | ((2 pos) ^ swz)
-        const char* cblk = reinterpret_cast<const char*>(s_coef) + k * 128;
-        const uint32_t swz = (k & 7) << 4;
-        auto value = [&](int pos) { return (int)*reinterpret_cast<const short*>(cblk + (((uint32_t)pos << 1) ^ swz)); };
-        BlockInfo bi = block_info(a, bk);
-        const int tab = bi.comp ? 1 : 0;
+        const uint32_t cblk = smem_addr(s_coef) + k * 128u, swz = (k & 7u) << 4;
+        // Component, DC predictor and "first MCU of a restart interval" of block bk.  The tile's place in its frame
+        // depends on blockIdx alone (uniform registers); a tile crosses at most one frame boundary unless frames are
+        // smaller than a tile.  mcu % ri == 0 comes from a 32-bit reciprocal whose quotient is at most one too
+        // small: the remainder estimate is then 0 or ri.
+        const uint32_t bpm = (uint32_t)a.g.bpm, bpf = (uint32_t)a.g.n_mcu * bpm, ri = (uint32_t)a.g.ri;
+        uint32_t rb;
+        if (bpf >= (uint32_t)TILE) {
+            rb = (b0 - div_magic(b0, a.m_bpf) * bpf) + k;
+            if (rb >= bpf) rb -= bpf;
+        } else {
+            rb = bk - div_magic(bk, a.m_bpf) * bpf;
+        }
+        const uint32_t mcu = __umulhi(rb, 0xAAAAAAABu) >> (bpm == 3 ? 1 : 2), j = rb - mcu * bpm;  // bpm is 3 or 6
+        const uint32_t r_est = mcu - __umulhi(mcu, a.m32_ri) * ri;
+        const bool first = r_est == 0u || r_est == ri;  // first MCU of its restart interval: predictors are 0
+        // per position j in the MCU, one nibble / bit each: distance to the block whose DC is the predictor
+        // (Y00 <- Y11 of the MCU before, Y01..Y11 <- the block before, Cb / Cr <- one MCU back), and whether that
+        // block lies in the MCU before (no predictor at the start of an interval)
+        const uint32_t dist = ((bpm == 3 ? 0x333u : 0x661113u) >> (4u * j)) & 15u;
+        const bool crosses = ((bpm == 3 ? 0x7u : 0x31u) >> j) & 1u;
+        const uint32_t tab = j >= (bpm == 3 ? 1u : 4u) ? 1u : 0u;
         int pred = 0;  // DC of the previous block of the component (utils.cpp:669-670)
-        if (bi.has_prev) {
-            if (bi.prev >= b0) {
-                uint32_t pt = bi.prev - b0;
-                pred = (int)cf[(pt * 8 + (pt & 7)) * 8];  // piece 0 of block pt sits at pt*8 + (0 ^ (pt&7))
+        if (!(first && crosses)) {
+            const uint32_t prev = bk - dist;
+            if (prev >= b0) {
+                const uint32_t pt = prev - b0;  // coefficient 0 of block pt: piece 0 ^ (pt & 7)
+                pred = lds_s16(smem_addr(s_coef) + pt * 128u + ((pt & 7u) << 4));
             } else {
-                pred = (int)a.coef[(size_t)bi.prev * 64];
+                pred = (int)a.coef[(size_t)prev * 64];
             }
         }
+        const uint2 mk = s_mask[k];
         SlotSink s;
-        s.init(s_slot + k * 4);
-        // the full AC table (symbols outside the small-value table, ZRL, EOB) stays in global memory / L1
-        encode_sparse<true>(s_mask[k], value, value(0) - pred, a.huff->ac[tab], s_dc[tab], s_small[tab], a.always_eob != 0, s);
-        s.finish();
-        const uint32_t nbits = s.bits();
-        s_len[k] = nbits;
-        if (nbits > 128) {  // too long for a slot: k_pack_long re-walks it
+        s.init();
+        walk_block(mk.x, mk.y, cblk, swz, lds_s16(cblk | swz) - pred, a.huff->ac[tab], smem_addr(s_dc[tab]), smem_addr(s_small[tab]),
+                   a.always_eob != 0, s);
+        s_len[k] = s.n;
+        *reinterpret_cast<uint4*>(s_slot + k * 4) = make_uint4(s.s3, s.s2, s.s1, s.s0);  // stream order
+        if (s.n > 128) {  // too long for a slot: k_pack_long re-walks it
             uint32_t idx = atomicAdd(a.w.n_long, 1u);
             a.w.long_list[idx] = bk;
         }
@@ -478,38 +588,64 @@ __global__ void k_zero(const __grid_constant__ EntropyArgs a) {
         p[i] = make_uint4(0, 0, 0, 0);
 }
 
+// One thread per tile of 256 blocks: what k_pack's threads would otherwise each derive again (frame, MCU, restart
+// interval of the block; start of the interval in the unstuffed buffer; two 64-bit bit prefixes): ~200 of k_pack's ~250
+// instructions per block went there.
+__global__ void __launch_bounds__(256) k_pack_plan(const __grid_constant__ EntropyArgs a) {
+    const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x, n_tiles = (a.n_blocks + TILE - 1) / TILE;
+    if (tile >= n_tiles) return;
+    const uint32_t b_first = tile * TILE, b_last = min(b_first + TILE - 1, a.n_blocks - 1);
+    const BlockInfo f = block_info(a, b_first), l = block_info(a, b_last);
+    uint32_t s0, e0;
+    interval_blocks(a, f.interval, s0, e0);
+    PackPlan pl;
+    pl.uniform = f.interval == l.interval ? 1u : 0u;
+    pl.c = a.w.int_ubase[f.interval] * 8 + (a.w.tile_base[tile] - bit_prefix(a, s0));
+    pl.last_b = e0 - 1;
+    a.w.pack_plan[tile] = pl;
+}
+
 // One thread per block: shift the pre-encoded slot to the block's bit offset and OR it into
 // the unstuffed buffer (big-endian words); 1-padding after the last block of an interval.
 // Blocks longer than a slot are left to k_pack_long.
 __global__ void __launch_bounds__(TILE) k_pack(const __grid_constant__ EntropyArgs a) {
     if (a.w.int_ubase[a.n_int_total] > a.w.ubuf_cap) return;
-    uint32_t b = blockIdx.x * TILE + threadIdx.x;
+    const uint32_t b = blockIdx.x * TILE + threadIdx.x;
     if (b >= a.n_blocks) return;
-    BlockInfo bi = block_info(a, b);
-    uint32_t s0, e0;
-    interval_blocks(a, bi.interval, s0, e0);
-    const uint64_t pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
+    const PackPlan pl = a.w.pack_plan[blockIdx.x];
     const uint32_t len = a.w.blk_len[b];
+    uint64_t pos;
+    bool last;
+    if (pl.uniform) {
+        pos = pl.c + a.w.blk_prefix[b];  // (the prefix of a tile's first block is 0)
+        last = b == pl.last_b;
+    } else {
+        const BlockInfo bi = block_info(a, b);
+        uint32_t s0, e0;
+        interval_blocks(a, bi.interval, s0, e0);
+        pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
+        last = bi.last_in_interval;
+    }
     uint32_t* words = reinterpret_cast<uint32_t*>(a.w.ubuf);
     if (len <= 128) {
+        // the slot is a right-aligned 128-bit number: its (all-zero) first bit sits 128 - len bits before pos --
+        // possibly before the buffer; zero words are never written
         const uint4 q = a.w.slots[b];
         const uint32_t w[6] = {0u, q.x, q.y, q.z, q.w, 0u};
-        const uint32_t sh = (uint32_t)(pos & 31);
-        const uint64_t wi = pos >> 5;
-        const uint32_t nw = (sh + len + 31) >> 5;
+        const long long p0 = (long long)pos + (long long)len - 128;
+        const uint32_t sh = (uint32_t)p0 & 31u;
+        uint32_t* dst = words + (p0 >> 5);
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
-            if ((uint32_t)j < nw) {
-                uint32_t o = __funnelshift_r(w[j + 1], w[j], sh);  // bits of (w[j]:w[j+1]) >> sh
-                if (o) atomicOr(words + wi + j, __byte_perm(o, 0, 0x0123));
-            }
+            uint32_t o = __funnelshift_r(w[j + 1], w[j], sh);  // bits of (w[j]:w[j+1]) >> sh
+            if (o) atomicOr(dst + j, __byte_perm(o, 0, 0x0123));
         }
     }
-    if (bi.last_in_interval && !a.fr.raw_bits) {  // pad the interval to a byte boundary with 1s (T.81 F.1.2.3)
-        uint32_t pad = (uint32_t)((8 - (a.w.int_bits[bi.interval] & 7)) & 7);
+    if (last && !a.fr.raw_bits) {  // pad the interval to a byte boundary with 1s (T.81 F.1.2.3)
+        const uint64_t pp = pos + len;  // an interval starts on a byte boundary: its bit count and pp agree modulo 8
+        const uint32_t pad = (8u - ((uint32_t)pp & 7u)) & 7u;
         if (pad) {
-            uint64_t pp = pos + len;
-            uint32_t o = ((1u << pad) - 1u) << (32 - (uint32_t)(pp & 31) - pad);
+            uint32_t o = ((1u << pad) - 1u) << (32 - ((uint32_t)pp & 31) - pad);
             atomicOr(words + (pp >> 5), __byte_perm(o, 0, 0x0123));
         }
     }
@@ -537,7 +673,8 @@ __global__ void __launch_bounds__(TILE) k_pack_long(const __grid_constant__ Entr
         const int tab = bi.comp ? 1 : 0;
         BitSink s;
         s.init(a.w.ubuf, pos);
-        encode_sparse<false>(mask, value, (int)c[0] - pred, s_ac[tab], s_dc[tab], nullptr, a.always_eob != 0, s);
+        encode_sparse<false>((uint32_t)mask, (uint32_t)(mask >> 32), value, (int)c[0] - pred, s_ac[tab], s_dc[tab], nullptr,
+                             a.always_eob != 0, s);
         s.finish();
     }
 }
@@ -547,21 +684,47 @@ __device__ __forceinline__ uint32_t count_ff(uint4 q) {
             __popc(__vcmpeq4(q.z, 0xFFFFFFFFu)) + __popc(__vcmpeq4(q.w, 0xFFFFFFFFu))) >> 3;
 }
 
+// 0xFF bytes per 16-byte chunk of the unstuffed buffer, as exclusive prefixes inside tiles of 256 chunks (the unit
+// k_stuff works on) plus the tile totals.  A CTA takes four tiles per step: a thread counts four consecutive chunks
+// (64 contiguous bytes) and stores their four prefixes as one 128-bit word, a warp covers half a tile, and the halves
+// meet through one shared-memory word per warp -- one barrier per 16 KB (the first version scanned one chunk per
+// thread with two barriers per 4 KB: 63 us per 0.19 GB).
 __global__ void __launch_bounds__(TILE) k_ff_count(const __grid_constant__ EntropyArgs a) {
-    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_warp[2][8];
     uint64_t total = a.w.int_ubase[a.n_int_total];
     if (total > a.w.ubuf_cap) total = 0;
-    uint64_t n_chunks = total >> 4;
-    uint32_t n_tiles = (uint32_t)((n_chunks + TILE - 1) / TILE);
+    const uint64_t n_chunks = total >> 4;
+    const uint32_t n_tiles = (uint32_t)((n_chunks + TILE - 1) / TILE), n_super = (n_tiles + 3) / 4;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.w.n_ff_tiles = n_tiles;
     const uint4* p = reinterpret_cast<const uint4*>(a.w.ubuf);
-    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        uint64_t c = (uint64_t)t * TILE + threadIdx.x;
-        uint32_t cnt = c < n_chunks ? count_ff(p[c]) : 0u;
-        uint32_t tot;
-        uint32_t ex = cta_scan_256(cnt, s_warp, tot);
-        a.w.ff_prefix[c] = ex;
-        if (threadIdx.x == 0) a.w.ff_tile[t] = tot;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t par = 0;
+    for (uint32_t st = blockIdx.x; st < n_super; st += gridDim.x, par ^= 1) {
+        const uint64_t c0 = (uint64_t)st * (4 * TILE) + 4 * threadIdx.x;
+        uint32_t cnt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cnt[j] = c0 + j < n_chunks ? count_ff(p[c0 + j]) : 0u;
+        const uint32_t mine = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        if (lane == 31) s_warp[par][wid] = inc;
+        __syncthreads();  // (the two parities make a second barrier unnecessary)
+        const uint32_t tile = st * 4 + (wid >> 1);
+        if (tile < n_tiles) {
+            const uint32_t lower = s_warp[par][wid & ~1u];  // the tile's first half
+            uint32_t ex = inc - mine + ((wid & 1) ? lower : 0u);
+            uint4 o;
+            o.x = ex;
+            o.y = ex += cnt[0];
+            o.z = ex += cnt[1];
+            o.w = ex += cnt[2];
+            *reinterpret_cast<uint4*>(a.w.ff_prefix + c0) = o;
+            if ((wid & 1) && lane == 31) a.w.ff_tile[tile] = lower + inc;
+        }
     }
 }
 
@@ -934,6 +1097,30 @@ int launch_copy_bytes(uint8_t* dst_base, const uint64_t* d_dst_off, const uint8_
 }
 
 static uint64_t magic52(uint64_t d) { return ((1ull << 52) + d - 1) / d; }
+static uint32_t magic32_floor(uint64_t d) { return d <= 1 ? 0xFFFFFFFFu : (uint32_t)((1ull << 32) / d); }
+
+// k_encode with its tile staged by TMA when a tensor map can describe the coefficient array (16-byte aligned base;
+// the library's own arena always is), otherwise with per-thread loads.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static void launch_encode(const EntropyArgs& a, uint32_t n_tiles, cudaStream_t s) {
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    EncodeTiledFn encode = (EncodeTiledFn)tensor_map_encode_fn();
+    if (encode && (reinterpret_cast<uintptr_t>(a.coef) & 15u) == 0) {
+        const cuuint64_t dims[2] = {32, (cuuint64_t)a.n_blocks};  // uint32 elements: one block = one 128-byte row
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {32, TILE}, estr[2] = {1, 1};
+        if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<int16_t*>(a.coef), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            k_encode<true><<<n_tiles, TILE, 0, s>>>(a, tm);
+            return;
+        }
+    }
+    k_encode<false><<<n_tiles, TILE, 0, s>>>(a, tm);
+}
 
 // ---- symbol histogram for per-call optimal Huffman tables (JB_FLAG_OPTIMIZE_HUFFMAN) ------------------
 // One thread per block, the same symbols k_encode would emit (utils.cpp:572-609, 667-694): DC difference
@@ -1014,6 +1201,7 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s, int phase) {
     EntropyArgs a = a_in;
     a.m_bpf = magic52((uint64_t)a.g.n_mcu * (uint64_t)a.g.bpm);
     a.m_ri = magic52((uint64_t)a.g.ri);
+    a.m32_ri = magic32_floor((uint64_t)a.g.ri);
     int launches = 0;
     uint32_t n_tiles = (a.n_blocks + TILE - 1) / TILE;
     uint32_t gi = (a.n_int_total + 255) / 256;
@@ -1023,17 +1211,18 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s, int phase) {
         k_stuff<<<chunk_tiles < 1184u ? chunk_tiles : 1184u, TILE, 0, s>>>(a);
         return 2;
     }
-    k_encode<<<n_tiles, TILE, 0, s>>>(a);
+    launch_encode(a, n_tiles, s);
     launches += scan_u32(a.w.tile_bits, a.w.tile_base, n_tiles, nullptr, a.w.scan_tmp, s);
     k_intervals<<<gi, 256, 0, s>>>(a);
     launches += scan_u32(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr, a.w.scan_tmp, s);
     // grids of the grid-stride kernels are capped by the work the plan allows: a small image launches few CTAs
     k_zero<<<chunk_tiles < 592u ? chunk_tiles : 592u, 256, 0, s>>>(a);
+    k_pack_plan<<<(n_tiles + 255) / 256, 256, 0, s>>>(a);
     k_pack<<<n_tiles, TILE, 0, s>>>(a);
     k_pack_long<<<n_tiles < 296u ? n_tiles : 296u, TILE, 0, s>>>(a);
-    launches += 5;
+    launches += 6;
     if (a.fr.raw_bits) return launches;
-    k_ff_count<<<chunk_tiles < 1184u ? chunk_tiles : 1184u, TILE, 0, s>>>(a);
+    k_ff_count<<<(chunk_tiles + 3) / 4 < 1184u ? (chunk_tiles + 3) / 4 : 1184u, TILE, 0, s>>>(a);
     launches += scan_u32(a.w.ff_tile, a.w.ff_tile_base, (uint32_t)(a.w.ubuf_cap / 16 / TILE + 1), a.w.n_ff_tiles,
                          a.w.scan_tmp, s);
     k_int_out<<<gi, 256, 0, s>>>(a);

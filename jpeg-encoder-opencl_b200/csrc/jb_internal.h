@@ -97,9 +97,13 @@ struct FixupArgs {
 
 // Huffman tables as the kernels consume them: (code << 5) | length.
 struct HuffDev {
+    // every entry: the code LEFT-ALIGNED in the word (first bit = bit 31), its length in the low five bits, 0 = no
+    // such symbol.  Lengths stay <= 27 (16 + 11 value bits; 17 + 10 with the reference's typo codes), so the two
+    // fields never meet, a funnel shift can take the length from the entry itself, and (x : e) << len moves the
+    // code in below x (jb_entropy.cu: SlotSink).
     uint32_t ac[2][256];  // [luma/chroma][run<<4 | cat]
     uint32_t dc[2][16];   // [luma/chroma][cat]
-    uint32_t small[2][512];  // [luma/chroma][run<<5 | (v & 31)], |v| <= 15: (code + value bits) << 5 | total length
+    uint32_t small[2][512];  // [luma/chroma][run<<5 | (v & 31)], |v| <= 15: code + value bits
 };
 
 // How entropy segments are framed in the output.
@@ -120,6 +124,14 @@ struct StuffPlan {
     uint32_t i0, i1;  // restart intervals of the tile's first and last chunk
     uint32_t k;       // index of interval i0 inside its frame
     uint32_t hdr_first;  // the tile starts a frame that carries a header
+};
+
+// What k_pack needs to know about one tile of 256 blocks (k_pack_plan, one thread per tile): a tile that lies inside one
+// restart interval (the usual case: an interval is much longer than a tile) places block b at bit c + blk_prefix[b].
+struct PackPlan {
+    uint64_t c;        // bit position of the tile's first block in the unstuffed buffer
+    uint32_t last_b;   // last block of that interval (it appends the 1-padding)
+    uint32_t uniform;  // 0: the tile spans several intervals, every block works out its own place
 };
 
 // Device work arrays of the entropy coder (all sized by the context).
@@ -143,6 +155,7 @@ struct EntropyWork {
     uint32_t* int_osize;    // [n_int_total]
     uint64_t* int_obase;    // [n_int_total + 1]
     StuffPlan* stuff_plan;  // [ubuf_cap / 16 / 256 + 2]
+    PackPlan* pack_plan;    // [n_tiles]
     uint64_t* scan_tmp;     // scratch of the multi-CTA scans
     uint64_t* status;       // [0] error bits, [1] required ubuf bytes, [2] required out bytes, [3] total bits
 };
@@ -155,6 +168,7 @@ struct EntropyArgs {
     uint32_t n_int_total;  // n_frames * g.n_int
     const HuffDev* huff;
     uint64_t m_bpf, m_ri;  // ceil(2^52 / blocks per frame), ceil(2^52 / restart interval): see div_magic
+    uint32_t m32_ri;       // floor(2^32 / restart interval), saturated: quotient estimate at most one too small
     uint32_t always_eob;
     Framing fr;
     EntropyWork w;
@@ -205,6 +219,7 @@ int launch_transform_nv12(const TransformArgs& a, cudaStream_t s);  // all MCUs 
 int launch_rgb_to_nv12(const uint8_t* rgb, size_t W, size_t H, size_t pitch, const uint32_t* ydown, uint8_t* y, size_t pitch_y, uint8_t* uv,
                        size_t pitch_uv, cudaStream_t s);
 int launch_fixup(const FixupArgs& a, cudaStream_t s);
+void* tensor_map_encode_fn();  // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint, or null (jb_transform.cu)
 int launch_entropy(const EntropyArgs& a, cudaStream_t s, int phase = 0);  // 1: up to the sizes, 2: final placement only
 int launch_stitch_exchange(uint64_t* ctl, int rank, int world, uint64_t epoch, uint64_t base, const uint64_t* d_len, uint64_t* d_off,
                            cudaStream_t s);

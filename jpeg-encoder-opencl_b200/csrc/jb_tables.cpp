@@ -79,6 +79,17 @@ static void build_small(HuffDev* out) {
             }
 }
 
+// (code << 5) | length, the form the builders above work in, to the device form: code left-aligned | length
+static void left_align(HuffDev* out) {
+    uint32_t* tabs[3] = {&out->ac[0][0], &out->dc[0][0], &out->small[0][0]};
+    const int n[3] = {512, 32, 1024};
+    for (int t = 0; t < 3; ++t)
+        for (int i = 0; i < n[t]; ++i) {
+            const uint32_t e = tabs[t][i], len = e & 31u;
+            tabs[t][i] = len ? ((e >> 5) << (32 - len)) | len : 0u;
+        }
+}
+
 void annex_k_specs(HuffSpecs* sp) {
     memset(sp, 0, sizeof(*sp));
     for (int t = 0; t < 4; ++t) {
@@ -101,6 +112,7 @@ void build_huff_from_specs(const HuffSpecs& sp, HuffDev* out) {
         memcpy(tables[t], full, (t & 1 ? 256 : 16) * sizeof(uint32_t));
     }
     build_small(out);
+    left_align(out);
 }
 
 // Optimal BITS / HUFFVAL for 256 symbol counts: T.81 Annex K.2 (Figures K.1-K.4) in the form libjpeg's
@@ -187,6 +199,7 @@ void build_huff(bool typo, HuffDev* out) {
         }
     }
     build_small(out);
+    left_align(out);
 }
 
 // ---- worst-case error of the binary32 AAN transform -------------------------------

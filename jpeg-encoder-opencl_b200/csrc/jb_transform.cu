@@ -1692,6 +1692,8 @@ static EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 
+void* tensor_map_encode_fn() { return (void*)tensor_map_encoder(); }
+
 static bool launch_tma(const TransformArgs& a_in, int sms, cudaStream_t s) {
     EncodeTiledFn encode = tensor_map_encoder();
     if (!encode) return false;
