@@ -44,7 +44,7 @@ struct Slot {
     uint8_t* d_rgb = nullptr;
     int16_t* d_coef = nullptr;
     uint32_t* d_tie_list = nullptr;
-    uint32_t* d_scalars = nullptr;  // [0] tie_count, [1] n_ff_tiles, [2] n_long, status[4] (u64) at +16 bytes, [12] unit counter
+    uint32_t* d_scalars = nullptr;  // [0] tie_count, [1] n_ff_tiles, [2] n_long, [3] any_slow, status[4] (u64) at +16 bytes, [12] unit counter
     EntropyWork w{};
     uint8_t* d_out = nullptr;
     size_t d_out_cap = 0;
@@ -200,6 +200,7 @@ size_t plan_bytes(const Plan& p) {
     add((p.chunks_cap / 256 + 3) * 8);
     add((p.chunks_cap / 256 + 2) * sizeof(StuffPlan));
     add((p.n_tiles + 1) * sizeof(PackPlan));
+    add((p.n_tiles + 1) * 4);
     add(p.n_int_total * 4);
     add((p.n_int_total + 1) * 8);
     add(p.out_cap);
@@ -245,6 +246,7 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.w.ff_tile_base = carve<uint64_t>(a, p.chunks_cap / 256 + 3);
     s.w.stuff_plan = carve<StuffPlan>(a, p.chunks_cap / 256 + 2);
     s.w.pack_plan = carve<PackPlan>(a, p.n_tiles + 1);
+    s.w.slow_list = carve<uint32_t>(a, p.n_tiles + 1);
     s.w.int_osize = carve<uint32_t>(a, p.n_int_total);
     s.w.int_obase = carve<uint64_t>(a, p.n_int_total + 1);
     s.d_out = carve<uint8_t>(a, p.out_cap);
@@ -257,6 +259,7 @@ int slot_prepare(jb_ctx* ctx, Slot& s, const Plan& p) {
     s.d_huff_opt = carve<HuffDev>(a, 1);
     s.w.n_ff_tiles = s.d_scalars + 1;
     s.w.n_long = s.d_scalars + 2;
+    s.w.any_slow = s.d_scalars + 3;
     s.w.status = reinterpret_cast<uint64_t*>(s.d_scalars + 4);
     // pinned result block: result words, then (last 1 KB) the staging area of the JFIF header
     // ... before it the W matrices (32 KB), the symbol counts (4 KB) and the optimised Huffman tables (8 KB)

@@ -262,8 +262,30 @@ __device__ __forceinline__ void walk_block(uint32_t mlo, uint32_t mhi, uint32_t 
     if (cur2 < 128 || always_eob) s.put(__ldg(g_ac));  // EOB, utils.cpp:607-608 (Q3 when always_eob)
 }
 
+__device__ __forceinline__ void or_slot(uint32_t* words, long long pos, uint32_t len, const uint4 q, bool shared_space) {
+    // the slot is a right-aligned 128-bit number: its (all-zero) first bit sits 128 - len bits before pos --
+    // possibly before the buffer / window; zero words are never written
+    const uint32_t w[6] = {0u, q.x, q.y, q.z, q.w, 0u};
+    const long long p0 = pos + (long long)len - 128;
+    const uint32_t sh = (uint32_t)p0 & 31u;
+    uint32_t* dst = words + (p0 >> 5);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const uint32_t o = __funnelshift_r(w[j + 1], w[j], sh);  // bits of (w[j]:w[j+1]) >> sh
+        if (o) {
+            if (shared_space)
+                atomicOr(dst + j, o);  // (bytes are swapped on the way out)
+            else
+                atomicOr(dst + j, __byte_perm(o, 0, 0x0123));
+        }
+    }
+}
+
 #ifndef ENC_CTAS
 #define ENC_CTAS 5
+#endif
+#ifndef ENC_PREFETCH
+#define ENC_PREFETCH 740  // tiles ahead: 148 SMs x 5 resident CTAs = one CTA lifetime (0: 733 us, 148 - 740: 717 us, 1480: ~790 us)
 #endif
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -286,8 +308,11 @@ __global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant
     __shared__ uint32_t s_len[TILE];
     __shared__ uint32_t s_hist[64], s_start[64];
     __shared__ uint16_t s_perm[TILE];
+    __shared__ uint32_t s_uniform;
     const uint32_t t = threadIdx.x, b0 = blockIdx.x * TILE, b = b0 + t;
     const uint32_t n_blk = min((uint32_t)TILE, a.n_blocks - b0);
+    if (t == 32)  // (k_pack_plan's definition; read after the barriers below)
+        s_uniform = block_info(a, b0).interval == block_info(a, b0 + n_blk - 1).interval ? 1u : 0u;
     if (TMA) {
         if (t == 0) {
             const uint32_t bar = smem_addr(&s_bar);
@@ -307,6 +332,12 @@ __global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(s_dc)),
                          "l"(&a.huff->dc[0][0]), "n"(128), "r"(bar)
                          : "memory");
+#if ENC_PREFETCH
+            // the tile a CTA that starts about one CTA lifetime from now will ask for: into L2 ahead of its TMA
+            const uint32_t b_pf = b0 + ENC_PREFETCH * TILE;
+            if (b_pf + TILE <= a.n_blocks)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.coef + (size_t)b_pf * 64), "n"(TILE * 128) : "memory");
+#endif
         }
     } else {
         const uint4* src = reinterpret_cast<const uint4*>(a.coef) + (size_t)b0 * 8;
@@ -418,17 +449,33 @@ __global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant
             a.w.long_list[idx] = bk;
         }
     }
-    __syncthreads();
+    __syncthreads();  // every walk has ended: the coefficients are dead, s_coef becomes the stream window
     uint32_t bits = 0;
+    uint4 slot = make_uint4(0u, 0u, 0u, 0u);
     if (t < n_blk) {
         bits = s_len[t];
-        a.w.blk_len[b] = bits;
-        a.w.slots[b] = *reinterpret_cast<const uint4*>(s_slot + t * 4);
+        slot = *reinterpret_cast<const uint4*>(s_slot + t * 4);
     }
+    // (the stream window, cleared here: the barriers inside the scan order these stores before the ORs below)
+    uint32_t* win = reinterpret_cast<uint32_t*>(s_coef);
+    reinterpret_cast<uint4*>(win)[t] = make_uint4(0u, 0u, 0u, 0u);
     uint32_t total;
-    uint32_t ex = cta_scan_256(bits, s_warp, total);
+    const uint32_t ex = cta_scan_256(bits, s_warp, total);
     a.w.blk_prefix[b] = ex;  // padded to a whole tile
     if (threadIdx.x == 0) a.w.tile_bits[blockIdx.x] = total;
+    if (s_uniform && total <= STREAM_MAX_BITS) {
+        // Tile stream (PackPlan): the codes of the tile's blocks concatenated at their in-tile bit offsets (blocks
+        // longer than a slot leave a gap of zeros for k_pack_long), assembled with shared-memory atomics and stored
+        // as whole 128-bit words into the tile's 4 KB of the slots array: 1/3 of the bytes that one slot, one
+        // length and one offset per block take, and k_pack places a tile with plain stores.
+        const uint32_t n_vec = (((max(total, 1u) + 31) >> 5) + 3) >> 2;  // (<= 256: one 128-bit word per thread)
+        if (t < n_blk && bits <= 128) or_slot(win, (long long)ex, bits, slot, true);
+        __syncthreads();
+        if (t < n_vec) a.w.slots[(size_t)blockIdx.x * TILE + t] = reinterpret_cast<const uint4*>(win)[t];
+    } else if (t < n_blk) {
+        a.w.blk_len[b] = bits;
+        a.w.slots[b] = slot;
+    }
 }
 
 // Single-CTA exclusive scan: out[i] = sum in[0..i), out[n] = total.
@@ -575,22 +622,36 @@ __global__ void k_intervals(const __grid_constant__ EntropyArgs a) {
     a.w.int_slot[i] = (uint32_t)slot;
 }
 
-__global__ void k_zero(const __grid_constant__ EntropyArgs a) {
+// Clears what the tiles placed with atomics are going to OR into (fast tiles store whole words and need nothing
+// cleared): the listed tiles' ranges when they are few (the usual case: the tiles that straddle two frames), the
+// whole used part of the buffer when they are many (short restart intervals: every tile holds several).
+__global__ void __launch_bounds__(256) k_zero(const __grid_constant__ EntropyArgs a) {
     uint64_t total = a.w.int_ubase[a.n_int_total];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.w.status[1] = total;
         if (total > a.w.ubuf_cap) atomicOr((unsigned long long*)&a.w.status[0], JB_STATUS_UBUF_OVERFLOW);
     }
     if (total > a.w.ubuf_cap) return;
-    uint4* p = reinterpret_cast<uint4*>(a.w.ubuf);
-    uint64_t n = total >> 4;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        p[i] = make_uint4(0, 0, 0, 0);
+    const uint32_t n_slow = *a.w.any_slow, n_tiles = (a.n_blocks + TILE - 1) / TILE;
+    if (n_slow == 0) return;
+    if ((uint64_t)n_slow * 16 > n_tiles) {
+        uint4* p = reinterpret_cast<uint4*>(a.w.ubuf);
+        uint64_t n = total >> 4;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+            p[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    uint32_t* words = reinterpret_cast<uint32_t*>(a.w.ubuf);
+    for (uint32_t i = blockIdx.x; i < n_slow; i += gridDim.x) {
+        const PackPlan pl = a.w.pack_plan[a.w.slow_list[i]];
+        const uint64_t w0 = pl.c >> 5, w1 = min(pl.slot_end_word, total >> 2);
+        for (uint64_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) words[w] = 0u;
+    }
 }
 
 // One thread per tile of 256 blocks: what k_pack's threads would otherwise each derive again (frame, MCU, restart
-// interval of the block; start of the interval in the unstuffed buffer; two 64-bit bit prefixes): ~200 of k_pack's ~250
-// instructions per block went there.
+// interval of the block; start of the interval in the unstuffed buffer; two 64-bit bit prefixes), and what a fast
+// tile has to know about its neighbours (PackPlan).
 __global__ void __launch_bounds__(256) k_pack_plan(const __grid_constant__ EntropyArgs a) {
     const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x, n_tiles = (a.n_blocks + TILE - 1) / TILE;
     if (tile >= n_tiles) return;
@@ -599,54 +660,191 @@ __global__ void __launch_bounds__(256) k_pack_plan(const __grid_constant__ Entro
     uint32_t s0, e0;
     interval_blocks(a, f.interval, s0, e0);
     PackPlan pl;
-    pl.uniform = f.interval == l.interval ? 1u : 0u;
     pl.c = a.w.int_ubase[f.interval] * 8 + (a.w.tile_base[tile] - bit_prefix(a, s0));
+    pl.slot_end_word = a.w.int_ubase[f.interval + 1] >> 2;
     pl.last_b = e0 - 1;
+    pl.tile_bits = a.w.tile_bits[tile];
+    pl.prev_tail = 0;
+    uint32_t fl = 0;
+    if (f.interval == l.interval) {
+        fl |= PACK_UNIFORM;
+        if (pl.tile_bits <= STREAM_MAX_BITS) fl |= PACK_FAST;
+        if (b_first == s0) fl |= PACK_STARTS;
+        if (b_last == e0 - 1) fl |= PACK_ENDS;
+    }
+    if (fl & PACK_FAST) {
+        // the neighbours inside the same interval are uniform when they lie inside it entirely
+        if (!(fl & PACK_STARTS) && b_first - s0 >= (uint32_t)TILE) {
+            const uint32_t tb_prev = a.w.tile_bits[tile - 1], sh = (uint32_t)pl.c & 31u;
+            if (tb_prev <= STREAM_MAX_BITS) {
+                fl |= PACK_PREV_FAST;
+                if (sh) {  // the last sh bits of the previous tile's stream, as the top bits of the shared word
+                    const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.w.slots + (size_t)(tile - 1) * TILE);
+                    const uint32_t start = tb_prev - sh, wi = start >> 5, n_prev = (tb_prev + 31) >> 5;
+                    const uint32_t w0 = sp[wi], w1 = wi + 1 < n_prev ? sp[wi + 1] : 0u;
+                    pl.prev_tail = __funnelshift_l(w1, w0, start & 31u) & ~(0xFFFFFFFFu >> sh);
+                }
+            }
+        }
+        if (!(fl & PACK_ENDS) && min(b_last + TILE, a.n_blocks - 1) <= e0 - 1 && a.w.tile_bits[tile + 1] <= STREAM_MAX_BITS)
+            fl |= PACK_NEXT_FAST;
+    } else {
+        // placed with atomics on cleared memory (k_zero, the next kernel): from the tile's first bit to the end of its
+        // last block, or of that block's interval reservation when it ends the interval
+        a.w.slow_list[atomicAdd(a.w.any_slow, 1u)] = tile;
+        uint32_t s1, e1;
+        interval_blocks(a, l.interval, s1, e1);
+        const uint64_t end_bit = a.w.int_ubase[l.interval] * 8 + (bit_prefix(a, b_last + 1) - bit_prefix(a, s1));
+        pl.slot_end_word = b_last == e1 - 1 ? a.w.int_ubase[l.interval + 1] >> 2 : (end_bit + 31) >> 5;
+    }
+    pl.flags = fl;
     a.w.pack_plan[tile] = pl;
 }
 
-// One thread per block: shift the pre-encoded slot to the block's bit offset and OR it into
-// the unstuffed buffer (big-endian words); 1-padding after the last block of an interval.
-// Blocks longer than a slot are left to k_pack_long.
+// k_pack and k_stuff are bound by the latency of dependent loads (plan -> stream / prefix -> length -> slot; the
+// compiler does not hoist loads over the branches between them, and volatile loads -- LDG.STRONG.SYS -- cost more
+// than they save: 195 -> 315 us).  A CTA takes several tiles and prefetches the next one's lines into L2.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+#ifndef PACK_UNROLL
+#define PACK_UNROLL 2
+#endif
+
+// Places the tiles' codes in the unstuffed buffer (big-endian words); 1-padding after the last block of an interval.
+// Blocks longer than a slot are left to k_pack_long.  ONE WARP PER TILE, several tiles per warp: the work on a tile is
+// a short chain of dependent loads (plan -> stream -> stores), so what counts is how many tiles an SM has in flight
+// (64 with a warp each, 8 with a CTA each: 165 us per 1.06 Gpx whatever the bytes moved), and a warp needs no barrier.
+//   fast tile: output word W0 + k = (S[k-1] : S[k]) >> (c mod 32) of its stream S -- a funnel-shifted copy, a lane
+//     per aligned group of four output words (five stream words, read through L1), stored as whole 128-bit words.
+//     The word it shares with the tile before is completed with that tile's last bits (PackPlan::prev_tail), the word
+//     it shares with the tile after is left to that tile; the tile that ends an interval adds the padding and clears
+//     the rest of the interval's reservation.  No atomics, and nothing has to be cleared beforehand.
+//   any other tile (several intervals in the tile, or more than 4 KB of codes): a lane per block shifts the block's
+//     128-bit slot into place with global atomics on memory k_zero cleared; a fast tile next to one of these ORs its
+//     share of the common word instead of storing it.
 __global__ void __launch_bounds__(TILE) k_pack(const __grid_constant__ EntropyArgs a) {
+    const uint32_t lane = threadIdx.x & 31u, n_tiles = (a.n_blocks + TILE - 1) / TILE;
+    const uint32_t warp = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5), n_warps = gridDim.x * (TILE / 32);
+    auto prefetch_tile = [&](uint32_t tile) {
+        const uint4* sp = a.w.slots + (size_t)tile * TILE;
+        prefetch_l2(sp + 8 * lane);  // (128 bytes per lane: the tile's 4 KB; a stream is usually half of that)
+        if (lane == 0) prefetch_l2(a.w.pack_plan + tile);
+    };
+    if (warp < n_tiles) prefetch_tile(warp);
     if (a.w.int_ubase[a.n_int_total] > a.w.ubuf_cap) return;
-    const uint32_t b = blockIdx.x * TILE + threadIdx.x;
-    if (b >= a.n_blocks) return;
-    const PackPlan pl = a.w.pack_plan[blockIdx.x];
-    const uint32_t len = a.w.blk_len[b];
-    uint64_t pos;
-    bool last;
-    if (pl.uniform) {
-        pos = pl.c + a.w.blk_prefix[b];  // (the prefix of a tile's first block is 0)
-        last = b == pl.last_b;
-    } else {
-        const BlockInfo bi = block_info(a, b);
-        uint32_t s0, e0;
-        interval_blocks(a, bi.interval, s0, e0);
-        pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
-        last = bi.last_in_interval;
-    }
     uint32_t* words = reinterpret_cast<uint32_t*>(a.w.ubuf);
-    if (len <= 128) {
-        // the slot is a right-aligned 128-bit number: its (all-zero) first bit sits 128 - len bits before pos --
-        // possibly before the buffer; zero words are never written
-        const uint4 q = a.w.slots[b];
-        const uint32_t w[6] = {0u, q.x, q.y, q.z, q.w, 0u};
-        const long long p0 = (long long)pos + (long long)len - 128;
-        const uint32_t sh = (uint32_t)p0 & 31u;
-        uint32_t* dst = words + (p0 >> 5);
+    for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
+        if (tile + n_warps < n_tiles) prefetch_tile(tile + n_warps);
+        const PackPlan pl = a.w.pack_plan[tile];
+        if (pl.flags & PACK_FAST) {  // (uniform over the warp)
+            const uint32_t tb = max(pl.tile_bits, 1u), sh = (uint32_t)pl.c & 31u;
+            const uint32_t n_s4 = ((((tb + 31) >> 5) + 3) >> 2) << 2;  // stream words incl. the zero padding of its last 128-bit word
+            const uint64_t W0 = pl.c >> 5;
+            const uint32_t m = (uint32_t)(((pl.c + tb - 1) >> 5) - W0);  // the stream ends in output word W0 + m
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.w.slots + (size_t)tile * TILE);
+            auto S = [&](long long k) { return k >= 0 && k < (long long)n_s4 ? __ldg(sp + k) : 0u; };
+            const bool ends = (pl.flags & PACK_ENDS) != 0, starts = (pl.flags & PACK_STARTS) != 0;
+            const bool shared_prev = !starts && sh != 0, shared_next = !ends && ((pl.c + tb) & 31u) != 0;
+            uint32_t pad_bits = 0;
+            if (ends && !a.fr.raw_bits) {  // pad the interval to a byte boundary with 1s (T.81 F.1.2.3)
+                const uint32_t pp = (uint32_t)(pl.c + tb) & 31u;  // an interval starts on a byte boundary: pp mod 8 = its bits mod 8
+                const uint32_t pad = (8u - (pp & 7u)) & 7u;
+                if (pad) pad_bits = ((1u << pad) - 1u) << (32 - pp - pad);
+            }
+            // the tile writes the words W0 .. last (zeros from W0 + m + 1 on), as aligned groups of four
+            const uint64_t last = ends ? max(W0 + m, pl.slot_end_word - 1) : W0 + m, vec0 = W0 >> 2;
+            const uint32_t n_out = (uint32_t)(last - 4 * vec0) + 1;
+            const long long k_first = (long long)(4 * vec0) - (long long)W0;  // stream index of the first word of group 0
+            // PACK_UNROLL groups per lane at a time: all their stream words are requested before the first is used
+            for (uint32_t vb = lane; 4 * vb < n_out; vb += 32 * PACK_UNROLL) {
+                uint32_t sw[PACK_UNROLL][5];
+                bool inside[PACK_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            uint32_t o = __funnelshift_r(w[j + 1], w[j], sh);  // bits of (w[j]:w[j+1]) >> sh
-            if (o) atomicOr(dst + j, __byte_perm(o, 0, 0x0123));
+                for (int i = 0; i < PACK_UNROLL; ++i) {
+                    const uint32_t v = vb + 32 * i;
+                    const long long k0 = k_first + 4 * (long long)v;
+                    // four words inside the stream: no neighbour, no padding
+                    inside[i] = 4 * v < n_out && k0 >= 1 && k0 + 3 < (long long)m && k0 + 3 < (long long)n_s4;
+                    if (inside[i]) {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) sw[i][j] = __ldg(sp + (k0 - 1) + j);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < PACK_UNROLL; ++i) {
+                    const uint32_t v = vb + 32 * i;
+                    if (4 * v >= n_out) break;
+                    const long long k0 = k_first + 4 * (long long)v;
+                    uint32_t* gw = words + 4 * (vec0 + v);
+                    if (inside[i]) {
+                        *reinterpret_cast<uint4*>(gw) = make_uint4(
+                            __byte_perm(__funnelshift_r(sw[i][1], sw[i][0], sh), 0, 0x0123), __byte_perm(__funnelshift_r(sw[i][2], sw[i][1], sh), 0, 0x0123),
+                            __byte_perm(__funnelshift_r(sw[i][3], sw[i][2], sh), 0, 0x0123), __byte_perm(__funnelshift_r(sw[i][4], sw[i][3], sh), 0, 0x0123));
+                        continue;
+                    }
+                    uint32_t o[4];
+                    uint32_t act = 0;  // per word, two bits: 0 leave, 1 store, 2 atomic OR
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const long long k = k0 + j;
+                        o[j] = 0u;
+                        if (k < 0 || k > (long long)(last - W0)) continue;
+                        uint32_t a_j = 1u;
+                        if (k <= (long long)m) {
+                            o[j] = __funnelshift_r(S(k), S(k - 1), sh);
+                            if (k == 0 && shared_prev) {
+                                if (pl.flags & PACK_PREV_FAST)
+                                    o[j] |= pl.prev_tail;
+                                else
+                                    a_j = 2u;
+                            }
+                            if (k == (long long)m) {
+                                o[j] |= pad_bits;
+                                if (shared_next) a_j = (pl.flags & PACK_NEXT_FAST) ? 0u : 2u;
+                            }
+                        }
+                        o[j] = __byte_perm(o[j], 0, 0x0123);
+                        act |= a_j << (2 * j);
+                    }
+                    if (act == 0x55u) {
+                        *reinterpret_cast<uint4*>(gw) = make_uint4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t a_j = (act >> (2 * j)) & 3u;
+                            if (a_j == 1u)
+                                gw[j] = o[j];
+                            else if (a_j == 2u && o[j])
+                                atomicOr(gw + j, o[j]);
+                        }
+                    }
+                }
+            }
+            continue;
         }
-    }
-    if (last && !a.fr.raw_bits) {  // pad the interval to a byte boundary with 1s (T.81 F.1.2.3)
-        const uint64_t pp = pos + len;  // an interval starts on a byte boundary: its bit count and pp agree modulo 8
-        const uint32_t pad = (8u - ((uint32_t)pp & 7u)) & 7u;
-        if (pad) {
-            uint32_t o = ((1u << pad) - 1u) << (32 - ((uint32_t)pp & 31) - pad);
-            atomicOr(words + (pp >> 5), __byte_perm(o, 0, 0x0123));
+        for (uint32_t b = tile * TILE + lane; b < min((tile + 1) * TILE, a.n_blocks); b += 32) {
+            const uint32_t len = a.w.blk_len[b];
+            uint64_t pos;
+            bool last_blk;
+            if (pl.flags & PACK_UNIFORM) {
+                pos = pl.c + a.w.blk_prefix[b];
+                last_blk = b == pl.last_b;
+            } else {
+                const BlockInfo bi = block_info(a, b);
+                uint32_t s0, e0;
+                interval_blocks(a, bi.interval, s0, e0);
+                pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
+                last_blk = bi.last_in_interval;
+            }
+            if (len <= 128) or_slot(words, (long long)pos, len, a.w.slots[b], false);
+            if (last_blk && !a.fr.raw_bits) {
+                const uint64_t pp = pos + len;
+                const uint32_t pad = (8u - ((uint32_t)pp & 7u)) & 7u;
+                if (pad) {
+                    uint32_t o = ((1u << pad) - 1u) << (32 - ((uint32_t)pp & 31) - pad);
+                    atomicOr(words + (pp >> 5), __byte_perm(o, 0, 0x0123));
+                }
+            }
         }
     }
 }
@@ -839,20 +1037,32 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
         // chunk (they bracket every other chunk's interval search -- mostly to nothing: an interval is usually much
         // longer than a 4 KB tile), and for a tile that lies inside one interval its place in that interval
         const StuffPlan pl = a.w.stuff_plan[tile];
+        const uint4 q_early = have ? p[c] : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t ffp_early = have ? a.w.ff_prefix[c] : 0u;
+        {  // the next tile of this CTA: on its way while this one is assembled
+            const uint64_t cn = c + (uint64_t)gridDim.x * TILE;
+            if (cn < n_chunks) {
+                if ((threadIdx.x & 1u) == 0) prefetch_l2(p + cn);
+                if ((threadIdx.x & 7u) == 0) prefetch_l2(a.w.ff_prefix + cn);
+                if (threadIdx.x == 0) prefetch_l2(a.w.stuff_plan + tile + gridDim.x);
+            }
+        }
         const uint32_t s_i0 = pl.i0, s_i1 = pl.i1, s_k = pl.k;
         const uint64_t s_off0 = pl.off0, s_nb = pl.nb;
         const bool s_hdr_first = pl.hdr_first != 0;
         if (s_i0 == s_i1 && !s_hdr_first) {
             // ---- fast path: the whole tile lies in one interval and starts no frame.  Per thread: its chunk and
             // its in-tile 0xFF prefix; everything else is tile-uniform, offsets are 32 bits relative to the tile.
+            // (Measured and dropped: every warp assembling and storing its 32 chunks on its own, without the two CTA
+            // barriers -- 170 -> 181 us; the kernel is bound by its byte-granular shared-memory stores.)
             const uint64_t g0 = pl.g0, off = s_off0 + 16u * threadIdx.x, nb = s_nb;
             uint32_t n_here = 0;
             if (have) {
-                const uint4 q = p[c];
+                const uint4 q = q_early;
                 const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
                 const int valid = off >= nb ? 0 : (nb - off < 16 ? (int)(nb - off) : 16);
                 const uint32_t marker = off + 16 >= nb ? marker_after(a, s_k) : 0u;  // last chunk of the interval
-                const uint32_t rel = 16u * threadIdx.x + (threadIdx.x ? a.w.ff_prefix[c] : 0u);
+                const uint32_t rel = 16u * threadIdx.x + (threadIdx.x ? ffp_early : 0u);
                 uint32_t d = (uint32_t)__cvta_generic_to_shared(win) + (uint32_t)((reinterpret_cast<uintptr_t>(out) + g0) & 15) + rel;
                 const uint32_t d_begin = d;
 #pragma unroll
@@ -911,7 +1121,7 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
             start = a.w.int_obase[i] + (k == 0 && off != 0 ? a.fr.hdr_bytes : 0u) + off +
                     (ff_prefix(a, c) - ff_prefix(a, ub >> 4));
             dst = start + (hdr ? a.fr.hdr_bytes : 0u);
-            uint4 q = p[c];
+            const uint4 q = q_early;
             wds[0] = q.x; wds[1] = q.y; wds[2] = q.z; wds[3] = q.w;
             valid = off >= nb ? 0 : (nb - off < 16 ? (int)(nb - off) : 16);
             if (off + 16 >= nb) marker = marker_after(a, k);  // last chunk of the interval
@@ -1216,9 +1426,15 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s, int phase) {
     k_intervals<<<gi, 256, 0, s>>>(a);
     launches += scan_u32(a.w.int_slot, a.w.int_ubase, a.n_int_total, nullptr, a.w.scan_tmp, s);
     // grids of the grid-stride kernels are capped by the work the plan allows: a small image launches few CTAs
-    k_zero<<<chunk_tiles < 592u ? chunk_tiles : 592u, 256, 0, s>>>(a);
     k_pack_plan<<<(n_tiles + 255) / 256, 256, 0, s>>>(a);
-    k_pack<<<n_tiles, TILE, 0, s>>>(a);
+    k_zero<<<chunk_tiles < 592u ? chunk_tiles : 592u, 256, 0, s>>>(a);  // (sparse or full: decided on the device)
+    {
+        static int pack_ctas = 0;  // resident CTAs of k_pack per SM: one wave, every warp takes its share of the tiles
+        if (!pack_ctas && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pack_ctas, k_pack, TILE, 0) != cudaSuccess || pack_ctas < 1))
+            pack_ctas = 4;
+        const uint32_t cap = 148u * (uint32_t)pack_ctas;
+        k_pack<<<(n_tiles + 7) / 8 < cap ? (n_tiles + 7) / 8 : cap, TILE, 0, s>>>(a);
+    }
     k_pack_long<<<n_tiles < 296u ? n_tiles : 296u, TILE, 0, s>>>(a);
     launches += 6;
     if (a.fr.raw_bits) return launches;

@@ -126,21 +126,38 @@ struct StuffPlan {
     uint32_t hdr_first;  // the tile starts a frame that carries a header
 };
 
-// What k_pack needs to know about one tile of 256 blocks (k_pack_plan, one thread per tile): a tile that lies inside one
-// restart interval (the usual case: an interval is much longer than a tile) places block b at bit c + blk_prefix[b].
+// What k_pack needs to know about one tile of 256 blocks (k_pack_plan, one thread per tile).  A tile that lies inside
+// one restart interval ("uniform": the usual case, an interval is much longer than a tile) and whose codes fit 4 KB
+// leaves k_encode as a TILE STREAM (its blocks' codes concatenated, in the tile's 4 KB of the slots array) and is
+// placed by plain stores ("fast"); any other tile keeps one 128-bit slot per block and is placed with atomics.
+enum : uint32_t {
+    PACK_UNIFORM = 1u,    // all blocks of the tile belong to one restart interval
+    PACK_FAST = 2u,       // uniform and in stream form
+    PACK_STARTS = 4u,     // the tile's first block starts its interval
+    PACK_ENDS = 8u,       // the tile's last block ends its interval
+    PACK_PREV_FAST = 16u, // the tile before continues the same interval and is fast: its last bits arrive in prev_tail
+    PACK_NEXT_FAST = 32u, // the tile after continues the same interval and is fast: it writes the word the two share
+};
+constexpr uint32_t STREAM_MAX_BITS = 256u * 128u;  // a tile's stream lives in its 256 slots
 struct PackPlan {
-    uint64_t c;        // bit position of the tile's first block in the unstuffed buffer
-    uint32_t last_b;   // last block of that interval (it appends the 1-padding)
-    uint32_t uniform;  // 0: the tile spans several intervals, every block works out its own place
+    uint64_t c;              // bit position of the tile's first block in the unstuffed buffer
+    uint64_t slot_end_word;  // first 32-bit word after the interval's reservation (zero fill up to it when the tile ends the
+                             // interval); for a tile placed with atomics: first word after the range it may touch
+    uint32_t last_b;         // last block of that interval (it appends the 1-padding)
+    uint32_t flags;          // PACK_*
+    uint32_t prev_tail;      // the previous tile's bits of the word the two tiles share, in place (fast after fast)
+    uint32_t tile_bits;
 };
 
 // Device work arrays of the entropy coder (all sized by the context).
 struct EntropyWork {
     uint32_t* blk_prefix;   // [n_blocks] exclusive bit prefix inside its 256-block tile
-    uint32_t* blk_len;      // [n_blocks] code length of every block in bits
-    uint4* slots;           // [n_blocks] first 128 code bits of every block, left aligned, MSB first
+    uint32_t* blk_len;      // [n_blocks] code length of every block in bits (tiles in slot form only)
+    uint4* slots;           // [n_tiles * 256] per tile: its stream, or one right-aligned 128-bit slot per block (PackPlan)
     uint32_t* long_list;    // [n_blocks] blocks whose code does not fit a slot
     uint32_t* n_long;       // device scalar
+    uint32_t* any_slow;     // device scalar: number of tiles placed with atomics (their part of the buffer is cleared first)
+    uint32_t* slow_list;    // [n_tiles] those tiles, in no particular order
     uint32_t* tile_bits;    // [n_tiles]
     uint64_t* tile_base;    // [n_tiles + 1] exclusive scan of tile_bits
     uint32_t* int_slot;     // [n_int_total] bytes reserved in the unstuffed buffer (multiple of 16)
