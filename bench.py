@@ -794,7 +794,7 @@ def main():
     others = None
     if dd.world == 1 and a.workload == "batch1080p" and not a.no_others and not a.optimize_huffman and not a.ref_exact and not a.frames:
         others = {}
-        for name, exact in (("4k444", False), ("8k", False), ("repl1080p", True)):
+        for name, exact in (("4k444", False), ("8k", False), ("repl1080p", False), ("repl1080p", True)):
             try:
                 o = run_batch(a, jb, enc, torch, dd, name, WORKLOADS[name][5], 3, 3, not a.no_e2e, not a.no_parity, ref_exact=exact,
                               sample_clocks=False)
@@ -802,7 +802,8 @@ def main():
                     "workload": workload_name(name), "value": o["value"], "ms_per_step": o["ms_per_step"],
                     "e2e": o["e2e"]["value"] if o["e2e"] else None, "roofline_frac": o["roofline"]["frac"],
                     "transform_GBps": o["roofline"]["achieved"], "transform_kernel": o["transform_kernel"],
-                    "bits_per_pixel": o["bits_per_pixel"], "parity_check": o["parity_check"], "steps": 3}
+                    "bits_per_pixel": o["bits_per_pixel"], "tie_fixups_per_step": o["tie_fixups_per_step"],
+                    "step_breakdown_us": o["roofline"]["step_breakdown_us"], "parity_check": o["parity_check"], "steps": 3}
             except Exception as e:
                 others[name] = {"error": str(e)[:200]}
         try:

@@ -89,6 +89,7 @@ struct FixupArgs {
     const double* costab;  // [u][x] = cos((2x+1) u pi / 16), from the host's libm
     const double* scale;   // [u][v] = alpha(u) alpha(v) / 4.0
     int inplace_dct;       // Q1: replay the reference's in-place block transform up to the flagged output
+    int rgb_align4;        // base, pitch and frame stride are multiples of 4: rows are read as words
     uint64_t m_bpf, m_mcux;  // ceil(2^52 / blocks per frame), ceil(2^52 / MCUs per row): divisions by multiplication
     const uint8_t* uv;     // NV12-style input: see TransformArgs
     size_t pitch_uv, frame_stride_uv;

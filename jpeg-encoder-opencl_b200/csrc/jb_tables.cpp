@@ -505,7 +505,11 @@ void build_tc_matrices(const uint32_t ql[64], const uint32_t qc[64], double step
                 tband[t][n] = -1.0f;
                 continue;
             }
-            const double B = 128.0 * sum_abs, U = ldexp(1.0, ilogb(B) - 23);
+            // (a row whose entries all round to zero -- K = 16 cells: the basis functions with u = 4 or v = 4 cancel inside
+            // every 2x2 cell up to ~1e-16 -- leaves the accumulator exactly 0: no rounding step, only the residual.
+            // ilogb(0) - 23 wrapped around, U became infinite and every such coefficient was replayed: 249 M per
+            // 256 frames in the reference's own mode, 12 ms + 46 ms instead of 1.1 ms + 0.06 ms.)
+            const double B = 128.0 * sum_abs, U = B > 0 ? ldexp(1.0, ilogb(B) - 23) : 0.0;
             const double err = 4.0 * step_ulps * U + 128.0 * resid;
             float band = (float)(0.5 - err / JB_TC_W_SCALE - 1e-6);
             tband[t][n] = nextafterf(band, 0.0f);

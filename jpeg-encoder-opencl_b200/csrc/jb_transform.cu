@@ -1834,16 +1834,47 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
             my_nat = c_zz[k];
             d_x0 = x0;
             d_y0 = y0;
-            d_misc = (uint32_t)my_comp | (step << 2) | ((uint32_t)my_nat << 4);
+            // bit 10: luma block without mirrored columns, RGB input: the row-per-lane path below
+            const uint32_t fast = my_comp == 0 && !a.uv && x0 + 8 <= (uint32_t)a.g.W ? 0x400u : 0u;
+            d_misc = (uint32_t)my_comp | (step << 2) | ((uint32_t)my_nat << 4) | fast;
             d_f = f;
+        }
+        // ---- products.  Luma entries whose block needs no mirrored column (nearly all): a lane per block ROW, eight
+        // lanes per entry, four entries at a time -- one address, 24 contiguous bytes and eight luma values per lane
+        // instead of two pixels with an address (and mirror tests) each.  The others (subsampled chroma: 2x2 cells;
+        // blocks on the right edge; NV12 planes) take the pixel-by-pixel path below, an entry at a time.
+#pragma unroll 1
+        for (int g4 = 0; g4 < FIX_BATCH / 4; ++g4) {
+            const int j = 4 * g4 + (lane >> 3), row = lane & 7;
+            const uint32_t misc = __shfl_sync(0xffffffffu, d_misc, j);
+            const size_t fr = (size_t)__shfl_sync(0xffffffffu, d_f, j);
+            const int x0 = (int)__shfl_sync(0xffffffffu, d_x0, j), y0 = (int)__shfl_sync(0xffffffffu, d_y0, j);
+            const bool fast = j < n_here && (misc & 0x400u) != 0;
+            if (fast) {
+                const int nat = (int)((misc >> 4) & 63u), v = nat >> 3, u = nat & 7;
+                const uint8_t* p = a.rgb + fr * a.frame_stride + (size_t)mirror(y0 + row, a.g.H) * a.pitch + (size_t)x0 * 3;
+                uint32_t px[6];
+                if (a.rgb_align4)
+                    load24<4>(p, px);
+                else
+                    load24<1>(p, px);
+                const double cv = a.costab[v * 8 + row];
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                    const uint32_t y = csc_y(byte24(px, 3 * x), byte24(px, 3 * x + 1), byte24(px, 3 * x + 2), a.ydown);
+                    const double smp = __dsub_rn((double)y, 128.0);                                        // utils.cpp:190
+                    s_term[w][j][row * 8 + x] = a.inplace_dct ? smp : __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), cv);  // utils.cpp:330
+                }
+            }
         }
         uint32_t have_block = 0xFFFFFFFFu;  // consecutive entries of one block (append_ties) share its samples
         for (int j = 0; j < n_here; ++j) {
             const uint32_t misc = __shfl_sync(0xffffffffu, d_misc, j), gblock = __shfl_sync(0xffffffffu, my_entry, j) >> 6;
+            if (misc & 0x400u) continue;  // (warp-uniform) done above
             const size_t fr = (size_t)__shfl_sync(0xffffffffu, d_f, j);
             const int x0 = (int)__shfl_sync(0xffffffffu, d_x0, j), y0 = (int)__shfl_sync(0xffffffffu, d_y0, j);
             const int comp = (int)(misc & 3u), step = (int)((misc >> 2) & 3u);
-            const int nat = (int)(misc >> 4), v = nat >> 3, u = nat & 7;
+            const int nat = (int)((misc >> 4) & 63u), v = nat >> 3, u = nat & 7;
             if (gblock != have_block) {  // (warp-uniform)
                 Image im{a.rgb + fr * a.frame_stride, a.pitch, a.g.W, a.g.H, a.ydown};
                 __syncwarp();
@@ -1900,6 +1931,7 @@ int launch_fixup(const FixupArgs& a_in, cudaStream_t s) {
     FixupArgs a = a_in;
     a.m_bpf = ((1ull << 52) + (uint64_t)a.g.n_mcu * a.g.bpm - 1) / ((uint64_t)a.g.n_mcu * a.g.bpm);
     a.m_mcux = ((1ull << 52) + (uint64_t)a.g.mcux - 1) / (uint64_t)a.g.mcux;
+    a.rgb_align4 = ((reinterpret_cast<uintptr_t>(a.rgb) | a.pitch | a.frame_stride) & 3u) == 0 ? 1 : 0;
     k_fixup<<<148 * 16, FIX_WARPS * 32, 0, s>>>(a);
     return 1;
 }
