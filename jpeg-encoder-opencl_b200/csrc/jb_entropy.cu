@@ -973,8 +973,28 @@ __global__ void k_finalize(const __grid_constant__ EntropyArgs a) {
 // straight to global memory.
 constexpr int STUFF_WIN = 12288;
 
+// k_stuff's window is word-swizzled: 32-bit word i of the window lives at word i ^ ((i >> 5) & 3).  A warp's lanes write
+// at a stride of 16 bytes (a chunk each), i.e. into words 4 apart -- four lanes per bank, every byte store four
+// wavefronts (17.8 M bank conflicts per 0.19 GB); with the swizzle the lanes 8, 16 and 24 apart land in the other three
+// words of the same 16-byte group.  An aligned 16-byte group stays one: the copy-out reads it whole and puts its words
+// back in order.  (The window is 512-byte aligned, so the swizzle can be taken from the shared address itself.)
+__device__ __forceinline__ uint32_t stuff_swz(uint32_t addr) { return addr ^ ((addr >> 5) & 0xCu); }
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(stuff_swz(addr)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stuff_swz(addr)) : "memory");
+    return v;
+}
+// the 16-byte group at the (16-byte aligned) shared address addr, words in logical order
+__device__ __forceinline__ uint4 lds128_unswz(uint32_t addr) {
+    uint4 q;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr) : "memory");
+    const uint32_t k = (addr >> 7) & 3u;
+    if (k & 1u) q = make_uint4(q.y, q.x, q.w, q.z);
+    if (k & 2u) q = make_uint4(q.z, q.w, q.x, q.y);
+    return q;
 }
 
 // interval i with int_ubase[i] <= pos < int_ubase[i+1], searched in [lo, hi)
@@ -1010,7 +1030,7 @@ __global__ void __launch_bounds__(256) k_stuff_plan(const __grid_constant__ Entr
 }
 
 __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyArgs a) {
-    __shared__ __align__(16) uint8_t win[STUFF_WIN + 32];
+    __shared__ __align__(512) uint8_t win[STUFF_WIN + 32];
     __shared__ uint64_t s_g0, s_g1;
     __shared__ uint32_t s_n;
     uint64_t total = a.w.int_ubase[a.n_int_total];
@@ -1057,7 +1077,34 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
             // barriers -- 170 -> 181 us; the kernel is bound by its byte-granular shared-memory stores.)
             const uint64_t g0 = pl.g0, off = s_off0 + 16u * threadIdx.x, nb = s_nb;
             uint32_t n_here = 0;
-            if (have) {
+            if (s_off0 + 16u * TILE < s_nb && (uint64_t)(tile + 1) * TILE <= n_chunks) {
+                // ---- and every chunk of it is 16 data bytes, no marker follows (a tile in the middle of an interval:
+                // nearly all): per word one test for a 0xFF byte, four byte stores
+                const uint32_t wds[4] = {q_early.x, q_early.y, q_early.z, q_early.w};
+                const uint32_t rel = 16u * threadIdx.x + (threadIdx.x ? ffp_early : 0u);
+                uint32_t d = (uint32_t)__cvta_generic_to_shared(win) + (uint32_t)((reinterpret_cast<uintptr_t>(out) + g0) & 15) + rel;
+                const uint32_t d_begin = d;
+#pragma unroll
+                for (int wq = 0; wq < 4; ++wq) {
+                    const uint32_t w = wds[wq];
+                    if ((((~w) - 0x01010101u) & w & 0x80808080u) == 0u) {  // no byte of w is 0xFF
+                        sts8(d, w);
+                        sts8(d + 1, w >> 8);
+                        sts8(d + 2, w >> 16);
+                        sts8(d + 3, w >> 24);
+                        d += 4;
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const uint32_t byte = (w >> (jj * 8)) & 0xFFu;
+                            sts8(d, byte);
+                            if (byte == 0xFFu) sts8(d + 1, 0u);  // T.81 F.1.2.3 byte stuffing
+                            d += byte == 0xFFu ? 2u : 1u;
+                        }
+                    }
+                }
+                if (threadIdx.x == TILE - 1) s_n = rel + (d - d_begin);
+            } else if (have) {
                 const uint4 q = q_early;
                 const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
                 const int valid = off >= nb ? 0 : (nb - off < 16 ? (int)(nb - off) : 16);
@@ -1099,11 +1146,11 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
                 const uint32_t base = (uint32_t)((reinterpret_cast<uintptr_t>(out) + g0) & 15), n = s_n;
                 const uint32_t head = min(n, (16u - base) & 15u);          // bytes before the first 16-byte boundary
                 const uint32_t n16 = (n - head) >> 4, tail = (n - head) & 15u;
-                if (threadIdx.x < head) out[g0 + threadIdx.x] = win[base + threadIdx.x];
+                const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win) + base;
+                if (threadIdx.x < head) out[g0 + threadIdx.x] = (uint8_t)lds8(wbase + threadIdx.x);
                 uint4* gdst = reinterpret_cast<uint4*>(out + g0 + head);
-                const uint4* ssrc = reinterpret_cast<const uint4*>(win + base + head);
-                for (uint32_t j = threadIdx.x; j < n16; j += TILE) gdst[j] = ssrc[j];
-                if (threadIdx.x < tail) out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = win[base + head + 16 * n16 + threadIdx.x];
+                for (uint32_t j = threadIdx.x; j < n16; j += TILE) gdst[j] = lds128_unswz(wbase + head + 16 * j);
+                if (threadIdx.x < tail) out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = (uint8_t)lds8(wbase + head + 16 * n16 + threadIdx.x);
             }
             __syncthreads();
             continue;
@@ -1173,11 +1220,11 @@ __global__ void __launch_bounds__(TILE) k_stuff(const __grid_constant__ EntropyA
             const uint32_t n = (uint32_t)(g1 - g0);
             const uint32_t head = min(n, (16u - base) & 15u);          // bytes before the first 16-byte boundary
             const uint32_t n16 = (n - head) >> 4, tail = (n - head) & 15u;
-            if (threadIdx.x < head) out[g0 + threadIdx.x] = win[base + threadIdx.x];
+            const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(win) + base;
+            if (threadIdx.x < head) out[g0 + threadIdx.x] = (uint8_t)lds8(wbase + threadIdx.x);
             uint4* gdst = reinterpret_cast<uint4*>(out + g0 + head);
-            const uint4* ssrc = reinterpret_cast<const uint4*>(win + base + head);
-            for (uint32_t j = threadIdx.x; j < n16; j += TILE) gdst[j] = ssrc[j];
-            if (threadIdx.x < tail) out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = win[base + head + 16 * n16 + threadIdx.x];
+            for (uint32_t j = threadIdx.x; j < n16; j += TILE) gdst[j] = lds128_unswz(wbase + head + 16 * j);
+            if (threadIdx.x < tail) out[g0 + head + 16 * (uint64_t)n16 + threadIdx.x] = (uint8_t)lds8(wbase + head + 16 * n16 + threadIdx.x);
         }
         __syncthreads();
     }
