@@ -13,12 +13,15 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 240 --csv --log-fil
 # ncu --set full, one complete step of the main kernels (default build: tcgen05 transform, cp.async staging)
 ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tc|k_fixup|k_encode|^k_pack$|k_ff_count|^k_stuff$' \
     --launch-skip 18 --launch-count 6 -f -o gpurun_out/${R}_prof_tc $B > /dev/null 2>&1
+# (gpurun merges at most 64 MiB back: the two variant kernels below are captured only when asked for)
+if [ -n "$CAPTURE_VARIANTS" ]; then
 # the CUDA-core transform kernel (JB_FLAG_FMA_DCT)
 ncu --set full --import-source on --clock-control none -k 'regex:^k_transform$' --launch-skip 3 --launch-count 1 -f \
     -o gpurun_out/${R}_prof_full $B --tensor-dct 0 > /dev/null 2>&1
 # the TMA-staged variant of the 4:2:0 transform (JB_FLAG_TMA)
 ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tma' --launch-skip 3 --launch-count 1 -f \
     -o gpurun_out/${R}_prof_tma $B --tma > /dev/null 2>&1
+fi
 # the 8x8-MCU tcgen05 transform (4K 4:4:4 q90)
 $B --workload 4k444 > gpurun_out/${R}_plain444.json 2>> gpurun_out/${R}_plain.err || exit 1
 ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tc3' --launch-skip 3 --launch-count 1 -f \
