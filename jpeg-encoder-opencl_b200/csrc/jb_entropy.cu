@@ -103,7 +103,9 @@ __device__ __forceinline__ void load_tables(const EntropyArgs& a, uint32_t (&s_a
     __syncthreads();
 }
 
-// exclusive scan of one value per thread over a 256-thread CTA; total in *total
+// exclusive scan of one value per thread over a 256-thread CTA; total in *total.  REUSE: s_warp is written again later
+// (a second barrier keeps this call's readers ahead of that)
+template <bool REUSE = true>
 __device__ __forceinline__ uint32_t cta_scan_256(uint32_t x, uint32_t* s_warp, uint32_t& total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = x;
@@ -121,7 +123,7 @@ __device__ __forceinline__ uint32_t cta_scan_256(uint32_t x, uint32_t* s_warp, u
         if (i < wid) base += t;
         tot += t;
     }
-    __syncthreads();
+    if (REUSE) __syncthreads();
     total = tot;
     return base + inc - x;
 }
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant
     uint32_t* win = reinterpret_cast<uint32_t*>(s_coef);
     reinterpret_cast<uint4*>(win)[t] = make_uint4(0u, 0u, 0u, 0u);
     uint32_t total;
-    const uint32_t ex = cta_scan_256(bits, s_warp, total);
+    const uint32_t ex = cta_scan_256<false>(bits, s_warp, total);  // (the CTA scans once)
     a.w.blk_prefix[b] = ex;  // padded to a whole tile
     if (threadIdx.x == 0) a.w.tile_bits[blockIdx.x] = total;
     if (s_uniform && total <= STREAM_MAX_BITS) {
@@ -725,9 +727,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __global__ void __launch_bounds__(TILE) k_pack(const __grid_constant__ EntropyArgs a) {
     const uint32_t lane = threadIdx.x & 31u, n_tiles = (a.n_blocks + TILE - 1) / TILE;
     const uint32_t warp = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5), n_warps = gridDim.x * (TILE / 32);
+    // (128 bytes per lane, as far as the stream is expected to reach: the size of the tile just placed, plus a margin --
+    // prefetching all 4 KB of every tile read 0.19 GB of unused slots per 1.06 Gpx)
+    uint32_t expect_bytes = 4096;
     auto prefetch_tile = [&](uint32_t tile) {
         const uint4* sp = a.w.slots + (size_t)tile * TILE;
-        prefetch_l2(sp + 8 * lane);  // (128 bytes per lane: the tile's 4 KB; a stream is usually half of that)
+        if (128u * lane < expect_bytes) prefetch_l2(sp + 8 * lane);
         if (lane == 0) prefetch_l2(a.w.pack_plan + tile);
     };
     if (warp < n_tiles) prefetch_tile(warp);
@@ -736,6 +741,7 @@ __global__ void __launch_bounds__(TILE) k_pack(const __grid_constant__ EntropyAr
     for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
         if (tile + n_warps < n_tiles) prefetch_tile(tile + n_warps);
         const PackPlan pl = a.w.pack_plan[tile];
+        expect_bytes = (pl.flags & PACK_FAST) ? min(4096u, (pl.tile_bits >> 3) + 384u) : 4096u;
         if (pl.flags & PACK_FAST) {  // (uniform over the warp)
             const uint32_t tb = max(pl.tile_bits, 1u), sh = (uint32_t)pl.c & 31u;
             const uint32_t n_s4 = ((((tb + 31) >> 5) + 3) >> 2) << 2;  // stream words incl. the zero padding of its last 128-bit word

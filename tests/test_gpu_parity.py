@@ -249,6 +249,37 @@ def test_entropy_stuffing_heavy(enc, jb):
         assert len(got) == len(want) and np.array_equal(got, want), f"ri={ri}"
 
 
+@pytest.mark.parametrize("ri", [0, 1, 100, 256, 700, 7000])
+def test_entropy_tile_streams_and_their_neighbours(enc, jb, ri):
+    """The placement of round 2: tiles of 256 blocks leave k_encode as code streams and are placed with plain
+    stores, completed with their neighbours' bits; tiles that span restart intervals or hold more than 4 KB of codes keep
+    one slot per block and are placed with atomics on ranges k_zero clears (sparsely when such tiles are few: ri = 0, 256,
+    7000 here; wholesale otherwise).  192 tiles of 4:4:4 blocks with every kind next to every other: sparse tiles, a band of
+    dense MCUs (oversize tiles), blocks longer than a slot inside sparse tiles, intervals that end exactly at tile boundaries
+    (ri = 256 MCUs = 3 tiles), inside tiles (100, 700, 7000) and everywhere (1)."""
+    rng = np.random.default_rng(2024 + ri)
+    n_mcu = 16384
+    coef = np.zeros((n_mcu, 3, 64), np.int16)
+    coef[:, :, 0] = rng.integers(-200, 200, (n_mcu, 3))
+    sparse = rng.random((n_mcu, 3, 63)) < 0.08
+    coef[:, :, 1:] = np.where(sparse, rng.integers(-6, 7, (n_mcu, 3, 63)), 0)
+    dense = slice(500, 900)  # ~1300 bits per block: 330 kbit per tile
+    coef[dense, :, 1:] = rng.integers(-1023, 1024, (400, 3, 63))
+    for m in range(20, n_mcu, 97):  # ~200-bit blocks inside sparse tiles (and a few inside the dense band)
+        coef[m, m % 3, 1:13] = rng.integers(300, 1023, 12) * rng.choice([-1, 1], 12)
+    p = jb.make_params(ol.SUB_444, quality=75, restart_interval=ri)
+    want, _ = ol.entropy(coef, ol.SUB_444, ri)
+    got = enc.entropy(coef, p)
+    assert len(got) == len(want) and np.array_equal(got, want), \
+        f"ri={ri}: {len(got)} vs {len(want)} bytes; " + (mismatch_report(got, want) if len(got) == len(want) else "")
+    # and the same blocks as 4:2:0 MCUs (6 blocks each: other tile / interval phases)
+    coef6 = coef[: n_mcu // 2 * 2].reshape(n_mcu // 2, 6, 64)
+    p = jb.make_params(ol.SUB_420, quality=75, restart_interval=ri)
+    want, _ = ol.entropy(coef6, ol.SUB_420, ri)
+    got = enc.entropy(coef6, p)
+    assert len(got) == len(want) and np.array_equal(got, want), f"4:2:0 ri={ri}: {len(got)} vs {len(want)} bytes"
+
+
 @pytest.mark.parametrize("sub", SUBS)
 def test_jfif_fruit_byte_exact_and_decodes(enc, jb, fruit, sub):
     """Config #1: whole file == the oracle's, decodes in PIL and OpenCV with identical PSNR."""
