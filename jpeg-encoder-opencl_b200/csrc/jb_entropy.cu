@@ -144,6 +144,15 @@ __device__ __forceinline__ uint32_t interleave16(uint32_t x) {
     return e | (o << 1);
 }
 
+// eight mask bits (bit i = coefficient 8 pc + i is non-zero) of piece pc of a block, inserted into m[pc >> 2]
+__device__ __forceinline__ void nz_mask_piece(const uint4 q, int pc, uint32_t (&m)[2]) {
+    const uint32_t fa = __byte_perm(nz_flags(q.x), nz_flags(q.y), 0x6420);
+    const uint32_t fb = __byte_perm(nz_flags(q.z), nz_flags(q.w), 0x6420);
+    const uint32_t x = (fa & 0x08040201u) | (fb & 0x80402010u);
+    const uint32_t sel = (pc & 3) == 0 ? 0x3217u : (pc & 3) == 1 ? 0x3270u : (pc & 3) == 2 ? 0x3710u : 0x7210u;
+    m[pc >> 2] = __byte_perm(m[pc >> 2], x * 0x01010101u, sel);
+}
+
 // Sink of k_encode: the block's code as ONE right-aligned 128-bit number in four registers (s3 most significant,
 // the first code bit the most significant one of the n bits) plus the bit count.  A symbol is four funnel shifts:
 // no flush branch, no shared-memory traffic inside the walk.  Codes longer than 128 bits lose their first bits here;
@@ -377,14 +386,7 @@ __global__ void __launch_bounds__(TILE, ENC_CTAS) k_encode(const __grid_constant
         // collected even and odd coefficients in two bit planes and interleaved them afterwards: +50 instructions.)
         uint32_t m[2] = {0u, 0u};
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) {
-            const uint4 q = s_coef[t * 8 + (pc ^ (t & 7))];
-            const uint32_t fa = __byte_perm(nz_flags(q.x), nz_flags(q.y), 0x6420);
-            const uint32_t fb = __byte_perm(nz_flags(q.z), nz_flags(q.w), 0x6420);
-            const uint32_t x = (fa & 0x08040201u) | (fb & 0x80402010u);
-            const uint32_t sel = (pc & 3) == 0 ? 0x3217u : (pc & 3) == 1 ? 0x3270u : (pc & 3) == 2 ? 0x3710u : 0x7210u;
-            m[pc >> 2] = __byte_perm(m[pc >> 2], x * 0x01010101u, sel);
-        }
+        for (int pc = 0; pc < 8; ++pc) nz_mask_piece(s_coef[t * 8 + (pc ^ (t & 7))], pc, m);
         s_mask[t] = make_uint2(m[0], m[1]);
         cnt = (uint32_t)(__popc(m[0] & ~1u) + __popc(m[1]));
         atomicAdd(&s_hist[cnt], 1u);
@@ -869,16 +871,15 @@ __global__ void __launch_bounds__(TILE) k_pack_long(const __grid_constant__ Entr
         interval_blocks(a, bi.interval, s0, e0);
         const uint64_t pos = a.w.int_ubase[bi.interval] * 8 + (bit_prefix(a, b) - bit_prefix(a, s0));
         const short* c = reinterpret_cast<const short*>(a.coef) + (size_t)b * 64;
-        uint64_t mask = 0;
-        for (int k = 0; k < 64; ++k)
-            if (c[k] != 0) mask |= 1ull << k;
-        auto value = [&](int p) { return (int)c[p]; };
+        uint32_t m[2] = {0u, 0u};
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) nz_mask_piece(__ldg(reinterpret_cast<const uint4*>(c) + pc), pc, m);
+        auto value = [&](int p) { return (int)__ldg(c + p); };
         const int pred = bi.has_prev ? (int)a.coef[(size_t)bi.prev * 64] : 0;
         const int tab = bi.comp ? 1 : 0;
         BitSink s;
         s.init(a.w.ubuf, pos);
-        encode_sparse<false>((uint32_t)mask, (uint32_t)(mask >> 32), value, (int)c[0] - pred, s_ac[tab], s_dc[tab], nullptr,
-                             a.always_eob != 0, s);
+        encode_sparse<false>(m[0], m[1], value, value(0) - pred, s_ac[tab], s_dc[tab], nullptr, a.always_eob != 0, s);
         s.finish();
     }
 }
@@ -1488,7 +1489,7 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s, int phase) {
         const uint32_t cap = 148u * (uint32_t)pack_ctas;
         k_pack<<<(n_tiles + 7) / 8 < cap ? (n_tiles + 7) / 8 : cap, TILE, 0, s>>>(a);
     }
-    k_pack_long<<<n_tiles < 296u ? n_tiles : 296u, TILE, 0, s>>>(a);
+    k_pack_long<<<n_tiles < 1184u ? n_tiles : 1184u, TILE, 0, s>>>(a);  // (blocks past the list end leave at once)
     launches += 6;
     if (a.fr.raw_bits) return launches;
     k_ff_count<<<(chunk_tiles + 3) / 4 < 1184u ? (chunk_tiles + 3) / 4 : 1184u, TILE, 0, s>>>(a);
