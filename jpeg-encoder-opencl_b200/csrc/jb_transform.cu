@@ -1834,12 +1834,13 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
             my_nat = c_zz[k];
             d_x0 = x0;
             d_y0 = y0;
-            // bit 10: luma block without mirrored columns, RGB input: the row-per-lane path below
-            const uint32_t fast = my_comp == 0 && !a.uv && x0 + 8 <= (uint32_t)a.g.W ? 0x400u : 0u;
+            // bit 10: full-resolution block (luma, or any component of 4:4:4) without mirrored columns, RGB input: the
+            // row-per-lane path below
+            const uint32_t fast = (my_comp == 0 || a.g.sub == JB_SUB_444) && !a.uv && x0 + 8 <= (uint32_t)a.g.W ? 0x400u : 0u;
             d_misc = (uint32_t)my_comp | (step << 2) | ((uint32_t)my_nat << 4) | fast;
             d_f = f;
         }
-        // ---- products.  Luma entries whose block needs no mirrored column (nearly all): a lane per block ROW, eight
+        // ---- products.  Full-resolution blocks that need no mirrored column (luma; every component of 4:4:4): a lane per block ROW, eight
         // lanes per entry, four entries at a time -- one address, 24 contiguous bytes and eight luma values per lane
         // instead of two pixels with an address (and mirror tests) each.  The others (subsampled chroma: 2x2 cells;
         // blocks on the right edge; NV12 planes) take the pixel-by-pixel path below, an entry at a time.
@@ -1851,7 +1852,7 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
             const int x0 = (int)__shfl_sync(0xffffffffu, d_x0, j), y0 = (int)__shfl_sync(0xffffffffu, d_y0, j);
             const bool fast = j < n_here && (misc & 0x400u) != 0;
             if (fast) {
-                const int nat = (int)((misc >> 4) & 63u), v = nat >> 3, u = nat & 7;
+                const int nat = (int)((misc >> 4) & 63u), v = nat >> 3, u = nat & 7, comp = (int)(misc & 3u);
                 const uint8_t* p = a.rgb + fr * a.frame_stride + (size_t)mirror(y0 + row, a.g.H) * a.pitch + (size_t)x0 * 3;
                 uint32_t px[6];
                 if (a.rgb_align4)
@@ -1861,7 +1862,8 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) k_fixup(const __grid_constant_
                 const double cv = a.costab[v * 8 + row];
 #pragma unroll
                 for (int x = 0; x < 8; ++x) {
-                    const uint32_t y = csc_y(byte24(px, 3 * x), byte24(px, 3 * x + 1), byte24(px, 3 * x + 2), a.ydown);
+                    const uint32_t cr_ = byte24(px, 3 * x), cg_ = byte24(px, 3 * x + 1), cb_ = byte24(px, 3 * x + 2);
+                    const uint32_t y = comp == 0 ? csc_y(cr_, cg_, cb_, a.ydown) : comp == 1 ? csc_cb(cr_, cg_, cb_) : csc_cr(cr_, cg_, cb_);
                     const double smp = __dsub_rn((double)y, 128.0);                                        // utils.cpp:190
                     s_term[w][j][row * 8 + x] = a.inplace_dct ? smp : __dmul_rn(__dmul_rn(smp, a.costab[u * 8 + x]), cv);  // utils.cpp:330
                 }
