@@ -49,7 +49,7 @@ STRIP_WORKLOADS = ("gigapixel", "strips16k")
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="batch1080p", choices=sorted(WORKLOADS))
@@ -175,14 +175,19 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=20):
+        # started BEFORE the warm-up and waited for until it streams: a timed region of a few tens of milliseconds
+        # (10 steps of 2.8 ms) is shorter than nvidia-smi's start-up, and was shorter than the 100 ms period used before
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.perf_counter() + 3.0
+            while not self.rows and time.perf_counter() < t_end:
+                time.sleep(0.005)
         except Exception:
             self.proc = None
 
@@ -193,16 +198,20 @@ class ClockSampler:
     def stop(self, t0, t1):
         if not self.proc:
             return None
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        inside = [r for t, r in self.rows if t0 <= t <= t1]
+        # a region shorter than the sampling period: the nearest samples on both sides (the GPU is under the same load
+        # during the warm-up steps right before t0)
+        near = sorted(self.rows, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))[:3]
+        rows = inside or [r for _, r in near]
         try:
             sm = [float(r[0]) for r in rows]
             mx = max(float(r[1]) for r in rows)
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
             return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
-                    "power_w_max": max(float(r[2]) for r in rows)}
+                    "samples_inside_timed_region": len(inside), "power_w_max": max(float(r[2]) for r in rows)}
         except Exception:
             return None
 
@@ -313,13 +322,13 @@ def run_batch(a, jb, enc, torch, dd, workload, F, steps, warmup, want_e2e, want_
                                 d_tab.data_ptr(), d_tab.data_ptr() + 8 * F, d_tab.data_ptr() + 16 * F)
 
     # ---- device-resident timed region ------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 and sample_clocks else None  # (streaming before the warm-up starts)
     for _ in range(max(warmup, 3)):
         step_device()
     enc.sync()
     enc.set_profiling(True)
     enc.reset_counters()
     dd.barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 and sample_clocks else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record(ext)
