@@ -64,6 +64,9 @@ typedef enum {
                                       * Bit-identical output; needs 16-byte aligned base / pitch / frame stride (else *
                                       * ignored).  Measured 6 % slower than the cp.async kernel on the B200 (DESIGN    *
                                       * 3.1d), hence opt-in                                                           */
+#define JB_FLAG_ENTROPY_LDG 0x200u     /* entropy coder: stage the coefficient tiles with per-thread loads instead of the   *
+                                      * TMA box (the path taken when the driver offers no tensor-map encoder).           *
+                                      * Bit-identical output; exists so that the tests exercise that path                 */
 #define JB_FLAG_OPTIMIZE_HUFFMAN 0x80u /* two passes like libjpeg's optimize_coding: the symbols of the call's   *
                                       * coefficients are counted on the GPU, optimal tables (T.81 K.2) are built  *
                                       * per call (shared by the frames of a batch), written into the DHT          *

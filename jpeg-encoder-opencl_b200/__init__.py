@@ -22,6 +22,7 @@ FLAG_REF_INPLACE_DCT, FLAG_REF_TYPO_TABLES, FLAG_REF_ALWAYS_EOB = 1, 2, 4
 FLAG_CLAMP_SOF, FLAG_NO_TIE_FIXUP, FLAG_TENSOR_DCT, FLAG_FMA_DCT = 8, 16, 32, 64
 FLAG_OPTIMIZE_HUFFMAN = 128
 FLAG_TMA = 256
+FLAG_ENTROPY_LDG = 512
 OK, E_INVALID, E_CUDA, E_NOSPACE, E_NOMEM, E_UNSUPPORTED, E_INTERNAL = range(7)
 
 # every symbol include/jpegb200.h declares (tests check that the library exports them all)

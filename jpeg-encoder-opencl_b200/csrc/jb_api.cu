@@ -542,6 +542,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
     ea.n_int_total = (uint32_t)pl.n_int_total;
     ea.huff = ctx->d_huff[(p->flags & JB_FLAG_REF_TYPO_TABLES) ? 1 : 0];
     ea.always_eob = (p->flags & JB_FLAG_REF_ALWAYS_EOB) ? 1u : 0u;
+    ea.no_tma = (p->flags & JB_FLAG_ENTROPY_LDG) ? 1u : 0u;
     ea.fr = fr;
     ea.w = s.w;
     ea.hdr = s.d_hdr;
@@ -1168,6 +1169,7 @@ static int entropy_from_slot(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_para
     ea.n_int_total = (uint32_t)pl.n_int_total;
     ea.huff = ctx->d_huff[(p->flags & JB_FLAG_REF_TYPO_TABLES) ? 1 : 0];
     ea.always_eob = (p->flags & JB_FLAG_REF_ALWAYS_EOB) ? 1u : 0u;
+    ea.no_tma = (p->flags & JB_FLAG_ENTROPY_LDG) ? 1u : 0u;
     ea.fr = fr;
     ea.w = s.w;
     ea.hdr = s.d_hdr;

@@ -1372,7 +1372,7 @@ static void launch_encode(const EntropyArgs& a, uint32_t n_tiles, cudaStream_t s
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     EncodeTiledFn encode = (EncodeTiledFn)tensor_map_encode_fn();
-    if (encode && (reinterpret_cast<uintptr_t>(a.coef) & 15u) == 0) {
+    if (encode && !a.no_tma && (reinterpret_cast<uintptr_t>(a.coef) & 15u) == 0) {
         const cuuint64_t dims[2] = {32, (cuuint64_t)a.n_blocks};  // uint32 elements: one block = one 128-byte row
         const cuuint64_t strides[1] = {128};
         const cuuint32_t box[2] = {32, TILE}, estr[2] = {1, 1};

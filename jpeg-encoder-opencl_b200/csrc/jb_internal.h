@@ -188,6 +188,7 @@ struct EntropyArgs {
     uint64_t m_bpf, m_ri;  // ceil(2^52 / blocks per frame), ceil(2^52 / restart interval): see div_magic
     uint32_t m32_ri;       // floor(2^32 / restart interval), saturated: quotient estimate at most one too small
     uint32_t always_eob;
+    uint32_t no_tma;       // JB_FLAG_ENTROPY_LDG: k_encode stages its tile with loads (the no-tensor-map fallback)
     Framing fr;
     EntropyWork w;
     const uint8_t* hdr;    // device copy of the JFIF header

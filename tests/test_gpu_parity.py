@@ -280,6 +280,25 @@ def test_entropy_tile_streams_and_their_neighbours(enc, jb, ri):
     assert len(got) == len(want) and np.array_equal(got, want), f"4:2:0 ri={ri}: {len(got)} vs {len(want)} bytes"
 
 
+def test_entropy_tile_staging_without_tma_is_identical(enc, jb, fruit):
+    """JB_FLAG_ENTROPY_LDG: k_encode stages its coefficient tiles with per-thread loads (the path a driver without
+    cuTensorMapEncodeTiled would take) -- same bytes as the TMA box, for files and for the staged entropy call."""
+    rng = np.random.default_rng(5)
+    coef = np.zeros((700, 3, 64), np.int16)
+    coef[:, :, 0] = rng.integers(-300, 300, (700, 3))
+    coef[:, :, 1:] = np.where(rng.random((700, 3, 63)) < 0.15, rng.integers(-40, 41, (700, 3, 63)), 0)
+    for ri in (0, 5):
+        a = enc.entropy(coef, jb.make_params(ol.SUB_444, quality=75, restart_interval=ri))
+        b = enc.entropy(coef, jb.make_params(ol.SUB_444, quality=75, restart_interval=ri, flags=jb.FLAG_ENTROPY_LDG))
+        want, _ = ol.entropy(coef, ol.SUB_444, ri)
+        assert np.array_equal(a, want) and np.array_equal(b, want)
+    for sub in SUBS:
+        for img in (fruit, ol.synth(4, 640, 360)):
+            p0 = jb.make_params(sub, quality=80, restart_interval=7)
+            p1 = jb.make_params(sub, quality=80, restart_interval=7, flags=jb.FLAG_ENTROPY_LDG)
+            assert enc.encode_jfif(img, p0) == enc.encode_jfif(img, p1)
+
+
 @pytest.mark.parametrize("sub", SUBS)
 def test_jfif_fruit_byte_exact_and_decodes(enc, jb, fruit, sub):
     """Config #1: whole file == the oracle's, decodes in PIL and OpenCV with identical PSNR."""
