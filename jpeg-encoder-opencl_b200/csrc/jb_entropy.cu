@@ -2,22 +2,26 @@
 // coder, plus what the reference lacks for a real JPEG stream: byte packing,
 // 1-padding, 0xFF00 stuffing, RSTn/EOI markers.
 //
-//   k_encode    one thread per 8x8 block (tile of 256 blocks staged in shared memory): non-zero
-//               mask, sparse walk of the run/size symbols, first 128 code bits kept in a slot,
-//               code length; exclusive scan of the lengths inside each 256-block tile
+//   k_encode    one thread per 8x8 block; the tile of 256 blocks is staged in shared memory by one TMA box
+//               (cp.async.bulk.tensor, SWIZZLE_128B): non-zero mask, blocks sorted by their number of non-zeros,
+//               sparse walk of the run/size symbols into a 128-bit register sink, code lengths scanned inside the
+//               tile, the tile's codes assembled as ONE stream (a tile inside one restart interval with at most
+//               4 KB of codes) or kept as one 128-bit slot per block
 //   k_scan      exclusive scan of the tile totals (device-wide bit offsets)
 //   k_intervals bits / reserved bytes of every restart interval
 //   k_scan      byte offset of every interval in the unstuffed buffer
-//   k_zero      clear the used part of the unstuffed buffer
-//   k_pack      one thread per block: shift the slot to the block's bit offset and OR it into
-//               the unstuffed buffer (+ 1-padding at interval end; longer blocks are re-walked)
+//   k_pack_plan per tile: its place in the unstuffed buffer, what it shares with its neighbours
+//   k_zero      clear what the tiles in slot form are going to OR into (nothing, a few ranges, or everything)
+//   k_pack      a warp per tile: the stream as a funnel-shifted copy with plain 128-bit stores (tiles in slot
+//               form: a lane per block, atomics; + 1-padding at interval ends)
+//   k_pack_long blocks longer than a slot are re-walked
 //   k_ff_count  0xFF bytes per 16-byte chunk, scan inside 256-chunk tiles
 //   k_scan      device-wide 0xFF prefix
 //   k_int_out   output bytes of every interval (data + stuffing + marker + header)
 //   k_scan      output offset of every interval / frame
 //   k_finalize  capacity check, frame table
-//   k_stuff     assemble the final bytes per 4 KB tile in shared memory (0x00 after 0xFF,
-//               markers, JFIF headers) and store them with coalesced 128-bit stores
+//   k_stuff_plan / k_stuff  assemble the final bytes per 4 KB tile in (word-swizzled) shared memory (0x00 after
+//               0xFF, markers, JFIF headers) and store them with coalesced 128-bit stores
 // Bit order is MSB first; the unstuffed buffer is addressed as big-endian words.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>

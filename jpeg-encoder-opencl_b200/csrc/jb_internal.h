@@ -96,7 +96,7 @@ struct FixupArgs {
     QuantTables qt;
 };
 
-// Huffman tables as the kernels consume them: (code << 5) | length.
+// Huffman tables as the kernels consume them.
 struct HuffDev {
     // every entry: the code LEFT-ALIGNED in the word (first bit = bit 31), its length in the low five bits, 0 = no
     // such symbol.  Lengths stay <= 27 (16 + 11 value bits; 17 + 10 with the reference's typo codes), so the two
