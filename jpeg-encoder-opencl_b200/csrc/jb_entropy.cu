@@ -1490,7 +1490,10 @@ int launch_entropy(const EntropyArgs& a_in, cudaStream_t s, int phase) {
         static int pack_ctas = 0;  // resident CTAs of k_pack per SM: one wave, every warp takes its share of the tiles
         if (!pack_ctas && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pack_ctas, k_pack, TILE, 0) != cudaSuccess || pack_ctas < 1))
             pack_ctas = 4;
-        const uint32_t cap = 148u * (uint32_t)pack_ctas;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const uint32_t cap = (uint32_t)sms * (uint32_t)pack_ctas;
         k_pack<<<(n_tiles + 7) / 8 < cap ? (n_tiles + 7) / 8 : cap, TILE, 0, s>>>(a);
     }
     k_pack_long<<<n_tiles < 1184u ? n_tiles : 1184u, TILE, 0, s>>>(a);  // (blocks past the list end leave at once)
