@@ -459,7 +459,7 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
             tc.tc_valid = false;
         }
         ta.qc = tc.qc;
-        if (!(p->flags & JB_FLAG_FMA_DCT) && !nv) {  // tcgen05 transform, every subsampling mode (launch falls back if unaligned)
+        if (!(p->flags & JB_FLAG_FMA_DCT)) {  // tcgen05 transform, every subsampling mode and NV12-style input (launch falls back if unaligned)
 #ifdef JB_DEBUG_KNOBS  // tests/tools/tc_band_scan.py only (a separate build): the shipped library reads no environment
             const char* e = getenv("JB_TC_STEP_ULPS");
             const double scale = e ? atof(e) : JB_TC_STEP_ULPS;
@@ -494,10 +494,16 @@ int enqueue_encode(jb_ctx* ctx, Slot& s, const Plan& pl, const jb_params* p, con
         for (int t = 0; t < 2; ++t)
             for (int i = 0; i < 64; ++i) ta.qc.band[t][i] = ta.tband[t][i] = 1.0f;  // never flag
     if (nv) {
-        Timed t(ctx, s.st, 0);
-        int n = launch_transform_nv12(ta, s.st);
-        ctx->tm.transform_launches += n;
-        ctx->tm.total_launches += n;
+        {
+            Timed t(ctx, s.st, 0);
+            int n = launch_transform_nv12(ta, s.st);
+            ctx->tm.transform_launches += n;
+            ctx->tm.total_launches += n;
+        }
+        {
+            Timed t(ctx, s.st, 5);
+            ctx->tm.total_launches += launch_transform_nv12_edge(ta, s.st);
+        }
     } else {
         {
             Timed t(ctx, s.st, 0);

@@ -234,7 +234,8 @@ int launch_sq_err(const uint8_t* a, size_t pitch_a, const uint8_t* b, size_t pit
 // ---- launchers (each returns the number of kernels it launched) -------------
 int launch_transform(const TransformArgs& a, cudaStream_t s);       // MCUs inside the image (hot kernel)
 int launch_transform_edge(const TransformArgs& a, cudaStream_t s);  // MCUs that need mirror padding
-int launch_transform_nv12(const TransformArgs& a, cudaStream_t s);  // all MCUs of an NV12-style input
+int launch_transform_nv12(const TransformArgs& a, cudaStream_t s);       // NV12-style input: tcgen05 kernel, or all MCUs on CUDA cores
+int launch_transform_nv12_edge(const TransformArgs& a, cudaStream_t s);  // ... the MCUs the tcgen05 kernel leaves out
 int launch_rgb_to_nv12(const uint8_t* rgb, size_t W, size_t H, size_t pitch, const uint32_t* ydown, uint8_t* y, size_t pitch_y, uint8_t* uv,
                        size_t pitch_uv, cudaStream_t s);
 int launch_fixup(const FixupArgs& a, cudaStream_t s);

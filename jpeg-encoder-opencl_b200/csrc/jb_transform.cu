@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(128) k_transform_nv12(const __grid_constant__ 
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const uint32_t f = t / per_frame, r = t - f * per_frame, mcu = r / 6u, blk = r - mcu * 6u;
         const int my = (int)(mcu / (uint32_t)a.g.mcux), mx = (int)(mcu - (uint32_t)my * (uint32_t)a.g.mcux);
+        if (mx < a.fast_mcux && my < a.fast_mcuy) continue;  // k_transform_tc_nv12's part (fast_* = 0 without it)
         const uint8_t* yp = a.rgb + (size_t)f * a.frame_stride;
         const uint8_t* uvp = a.uv + (size_t)f * a.frame_stride_uv;
         float v[64];
@@ -530,14 +531,6 @@ __global__ void __launch_bounds__(128) k_transform_nv12(const __grid_constant__ 
             quant_global<1>(v, a, dst, tl, th);
         if (tl | th) append_ties(a.tie_list, a.tie_count, a.tie_cap, t, tl, th);
     }
-}
-
-int launch_transform_nv12(const TransformArgs& a, cudaStream_t s) {
-    const size_t total = (size_t)a.g.n_mcu * 6 * (size_t)a.n_frames;
-    if (!total) return 0;
-    const size_t g = (total + 127) / 128;
-    k_transform_nv12<<<(int)(g > 148 * 64 ? 148 * 64 : g), 128, 0, s>>>(a);
-    return 1;
 }
 
 // RGB8 -> NV12 by the reference's own arithmetic: performCSC (utils.cpp:92-110, exact) and performCDS (utils.cpp:113-141):
@@ -1019,6 +1012,250 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc(const __gri
             const uint32_t crow = (uint32_t)it;  // chroma row = K chunk of the chroma tile
             sts64(ac_cb + ((crow ^ sw_cb) << 4), make_uint2(chroma_h2(sb[0], sb[1]), chroma_h2(sb[2], sb[3])));
             sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(chroma_h2(sr[0], sr[1]), chroma_h2(sr[2], sr[3])));
+            if (it == 3) {
+                publish();
+                if (issuer) issue(0, 0, tmem_d0, mbar0);
+            }
+        }
+        publish();
+        if (issuer) issue(0, 0, tmem_d1, mbar1);
+
+        // read this thread's row of the accumulator, round / flag / pack, stage in tileA, store blocks blk, blk+1
+        auto finish = [&](uint32_t tmem_d, int tab, int blk, uint32_t wait_mbar, uint32_t wait_parity) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t t[64];
+            tmem_ld64(tmem_d + lane_off, t);
+            uint4* st = reinterpret_cast<uint4*>(tileA) + wg * 256;  // this warp's 32 rows of the tile
+            uint32_t tl = 0, th = 0;
+            if (tab == 0)
+                tc_quant_stage<0>(t, a, st, lane, tl, th, wait_mbar, wait_parity);
+            else
+                tc_quant_stage<1>(t, a, st, lane, tl, th, wait_mbar, wait_parity);
+            if (valid && (tl | th)) append_ties(a.tie_list, a.tie_count, a.tie_cap, gb0 + blk + half, tl, th);
+            __syncwarp();
+            // coalesced copy-out: 8 x 32 pieces of 16 bytes; piece g belongs to block g >> 3 of the warp, i.e. to
+            // MCU g >> 4, whose index sits in lane pair g >> 4 (32-bit piece indices: n_blocks * 8 < 2^32)
+            const uint32_t piece0 = (uint32_t)(blk + ((lane >> 3) & 1)) * 8u + (uint32_t)(lane & 7);
+#pragma unroll
+            for (int it8 = 0; it8 < 8; ++it8) {
+                const int sb = it8 * 4 + (lane >> 3), pc = lane & 7;
+                const uint32_t m_gm = __shfl_sync(0xffffffffu, gm, 4 * it8 + 2 * (lane >> 4));
+                if (m_gm != 0xFFFFFFFFu) coef4[m_gm * 48u + piece0] = st[sb * 8 + (pc ^ (sb & 7))];
+            }
+            __syncwarp();
+        };
+        phase0 ^= 1;                                  // (rows 0-7: completion already observed at it == 4)
+        finish(tmem_d0, 0, 0, mbar1, phase1);         // Y00 / Y01; staging waits for the MMAs of rows 8-15
+        phase1 ^= 1;
+        publish();                                    // every thread has read accumulator 0: it takes the chroma tile
+        if (issuer) issue(1, 1, tmem_d0, mbar0);
+        finish(tmem_d1, 0, 2, 0, 0);                  // Y10 / Y11
+        mbar_wait(mbar0, phase0);
+        phase0 ^= 1;
+        finish(tmem_d0, 1, 4, 0, 0);                  // Cb / Cr
+        cur = nxt;
+        base = nbase;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(TC_TMEM_COLS));
+}
+
+// ================================================== tensor-core transform for NV12-style input (4:2:0) ==========
+// k_transform_tc with the colour conversion taken out: the frames are a Y plane and a plane of interleaved Cb,Cr
+// pairs already, so a row pair of a unit is 2 x 256 luma bytes + 256 chroma bytes (16 bytes per MCU each), copied
+// warp-cooperatively into the ring (lanes 0-15: luma row 0 and the chroma row, lanes 16-31: luma row 1), and a
+// sample becomes its fp16 operand with one byte permute (0x6400 | byte = 1024 + byte) and half an exact HADD2 (-1152).
+// Everything after the A tiles -- MMA schedule, epilogue, near-tie list -- is k_transform_tc's.  Covers the complete
+// MCU columns (16-byte aligned planes, pitches and frame strides); k_transform_nv12 takes a partial last column.
+struct TcUnitNv {
+    const uint8_t *ptr, *puv;  // first byte of the MCU in luma row 0 / chroma row 0 of the frame
+    int y0;
+    uint32_t gm;
+    bool valid;
+};
+__global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc_nv12(const __grid_constant__ TransformArgs a) {
+    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar[TC_GROUPS][2];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_next[TC_GROUPS];
+    __shared__ uint32_t s_desc[TC_GROUPS + 1][4];  // descriptor low words: [group]{luma tile, chroma tile}, [TC_GROUPS][table * 2 + split]
+    // keep the address arithmetic on the shared-space pointer (1024-byte alignment for the 128B swizzle)
+    uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, wg = gt >> 5, lane = tid & 31;
+    uint8_t* sB = smem;
+    uint8_t* tileA = smem + TC_B_BYTES + g * 2 * TC_TILE_BYTES;  // luma rows 0-7, then 8-15; staging between
+    uint8_t* tileC = tileA + TC_TILE_BYTES;                      // chroma
+    // ring of raw pixels: address of this warp's row `r` (0/1) of slot `sl` (0/1)
+    constexpr uint32_t NV_ROW = 256, NV_ROWS = 4 * NV_ROW, NV_SLOT = 3 * NV_ROWS;  // per group: [slot][luma 0, luma 1, chroma][warp]
+    static_assert(2 * NV_SLOT <= TC_RING_BYTES, "the NV12 ring fits the RGB ring");
+    const uint32_t ring = smem_u32(smem + TC_B_BYTES + TC_GROUPS * 2 * TC_TILE_BYTES + g * TC_RING_BYTES) + wg * NV_ROW;
+    // ---- one-time setup: W matrices, tensor memory, barriers ---------------------------------------
+    for (int i = tid; i < TC_B_BYTES / 16; i += TC_GROUPS * 128)
+        reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.tc_mat) + i);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (gt == 0) {
+        s_desc[g][0] = (uint32_t)umma_desc(smem_u32(tileA));
+        s_desc[g][1] = (uint32_t)umma_desc(smem_u32(tileC));
+        s_desc[TC_GROUPS][g] = (uint32_t)umma_desc(smem_u32(sB + g * 8192));
+    }
+    if (tid < TC_GROUPS * 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[0][0]) + 8 * tid));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d0 = s_tmem + (uint32_t)(g * 128), tmem_d1 = tmem_d0 + 64;  // two accumulators per group
+    const uint32_t lane_off = (uint32_t)(wg * 32) << 16;
+    const uint32_t mbar0 = smem_u32(&s_mbar[g][0]), mbar1 = smem_u32(&s_mbar[g][1]);
+    const uint32_t idesc = (1u << 4) | (8u << 17) | (8u << 24);  // f32 += fp16 x fp16 (formats 0), N=64, M=128
+    uint32_t phase0 = 0, phase1 = 0;
+    uint4* coef4 = reinterpret_cast<uint4*>(a.coef);
+    const int half = lane & 1;
+    const uint32_t stride = gridDim.x * TC_GROUPS * 4;
+    // shared addresses of this thread's A rows: own row (luma), and the rows that take its chroma
+    const uint32_t sw_own = (uint32_t)(gt & 7);
+    const uint32_t a_row = smem_u32(tileA) + gt * 128;
+    const int row_cb = gt & ~1, row_cr = gt | 1;
+    const uint32_t ac_cb = smem_u32(tileC) + row_cb * 128 + half * 8, ac_cr = smem_u32(tileC) + row_cr * 128 + half * 8;
+    const uint32_t sw_cb = (uint32_t)(row_cb & 7), sw_cr = (uint32_t)(row_cr & 7);
+
+    // the 8 MMAs of one tile, issued by one elected lane of the group's first warp; completion arrives on
+    // `mbar`.  Every operand is computed from warp-uniform values (the group index comes out of a shuffle, so
+    // the compiler keeps it in a uniform register): no per-thread descriptor arithmetic, and no
+    // serialisation loop around each tcgen05.mma.
+    const bool issuer = __shfl_sync(0xffffffffu, (uint32_t)wg, 0) == 0;
+    auto issue = [&](int tile_sel, int tab, uint32_t tmem_d, uint32_t mbar) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+            const uint64_t hi = (uint64_t)0x40004040u << 32;
+            const uint64_t da = hi | lds_volatile(smem_u32(&s_desc[g][tile_sel]));
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const uint64_t db = hi | lds_volatile(smem_u32(&s_desc[TC_GROUPS][tab * 2 + s2]));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (s2 | k) ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+        }
+    };
+    // writes of this thread to the tiles become visible to the tensor core, all threads of the group arrive
+    // (a full group barrier: arrive/wait for the non-issuing warps and CTA-wide barriers both measured slower)
+    auto publish = [&]() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    };
+    // n / d and n % d with the host's m = floor(2^32 / d): the estimate is at most one too small
+    auto divmod = [](uint32_t n, uint32_t d, uint32_t m, uint32_t& q, uint32_t& r) {
+        q = __umulhi(n, m);
+        r = n - q * d;
+        if (r >= d) {
+            q += 1;
+            r -= d;
+        }
+    };
+    // every warp of the group runs the same control flow; a warp past the end gets an empty unit
+    auto decode = [&](uint32_t unit_base) {
+        const uint32_t lin = (unit_base + wg) * 16u + (uint32_t)(lane >> 1);  // this lane pair's MCU
+        TcUnitNv u;
+        u.valid = unit_base + wg < a.total_units && lin < a.tc_mcus;
+        const uint32_t l = u.valid ? lin : 0u;
+        uint32_t f, rem, my, mx;
+        divmod(l, a.tc_per_frame, a.tc_magic_frame, f, rem);
+        divmod(rem, a.tc_row_len, a.tc_magic_row, my, mx);
+        u.ptr = a.rgb + (size_t)f * a.frame_stride + (size_t)mx * 16;
+        u.puv = a.uv + (size_t)f * a.frame_stride_uv + (size_t)mx * 16;
+        u.y0 = (int)my * 16;
+        u.gm = f * (uint32_t)a.g.n_mcu + my * (uint32_t)a.g.mcux + mx;
+        return u;
+    };
+    // fetch cursors: chunk c (16 bytes) of a row belongs to MCU c of the unit.  Lane L copies chunk L & 15 of luma row
+    // L >> 4 of the pair, lanes 0-15 also chunk L of the chroma row; the coordinates come from the owning lane pairs.
+    // A cursor is the MCU's column in the frame plus a row counter: rows at or below the image height are mirrored
+    // (utils.cpp:211-233: padded row y reads row 2H - y - 1; a chroma row is the row of the mirrored even luma row).
+    const uint32_t ring_wr = ring + (uint32_t)(lane >> 4) * NV_ROWS + (uint32_t)(lane & 15) * 16u;
+    const uint32_t ring_wr_c = ring + 2 * NV_ROWS + (uint32_t)(lane & 15) * 16u;
+    const uint32_t ring_rd = ring + (uint32_t)lane * 8u;  // this lane's half MCU: 8 bytes of every row
+    const int img_h = a.g.H;
+    const uint8_t *fc_p0 = nullptr, *fc_p1 = nullptr;
+    int fc_y = 0, fc_yc = 0;
+    bool fc_v0 = false, fc_v1 = false;
+    auto shfl_ptr = [&](const uint8_t* p, int src) {
+        unsigned long long v = (unsigned long long)p;
+        uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+        return (const uint8_t*)(((unsigned long long)hi << 32) | lo);
+    };
+    auto aim = [&](const TcUnitNv& u) {
+        const int m = lane & 15, y0 = __shfl_sync(0xffffffffu, u.y0, 2 * m);
+        fc_p0 = shfl_ptr(u.ptr, 2 * m);
+        fc_p1 = shfl_ptr(u.puv, 2 * m);
+        fc_y = y0 + (lane >> 4);
+        fc_yc = y0;  // (the luma row whose chroma row is wanted)
+        fc_v0 = __shfl_sync(0xffffffffu, (int)u.valid, 2 * m) != 0;
+        fc_v1 = fc_v0 && lane < 16;
+    };
+    // start the copy of the next row pair (two luma rows, one chroma row) of every MCU of the unit into ring slot `sl`
+    auto fetch_pair = [&](int sl) {
+        if (fc_v0) cp_async<16>(ring_wr + (uint32_t)sl * NV_SLOT, fc_p0 + (size_t)(uint32_t)mirror(fc_y, img_h) * a.pitch);
+        if (fc_v1) cp_async<16>(ring_wr_c + (uint32_t)sl * NV_SLOT, fc_p1 + (size_t)((uint32_t)mirror(fc_yc, img_h) >> 1) * a.pitch_uv);
+        fc_y += 2;
+        fc_yc += 2;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // Strips are handed out dynamically (the first one statically): groups that meet cheaper content or
+    // emptier edge strips take more of them, so that all SMs finish together.  One thread of the group
+    // draws the next index at the start of a unit; the group reads it after the first barrier of the unit.
+    uint32_t base = (blockIdx.x * TC_GROUPS + g) * 4;
+    TcUnitNv cur = decode(base);
+    if (base < a.total_units) {
+        aim(cur);
+        fetch_pair(0);
+        fetch_pair(1);
+    }
+    while (base < a.total_units) {
+        if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
+        uint32_t nbase = 0;
+        TcUnitNv nxt = cur;
+        const bool valid = cur.valid;
+        const uint32_t gm = valid ? cur.gm : 0xFFFFFFFFu;  // all ones: no such MCU
+        const uint32_t gb0 = cur.gm * 6u;
+
+        // ---- 16 image rows = 8 row pairs: ring -> registers -> colour conversion -> A tiles -----------
+        // The ring holds two pairs; the refill of a slot (the pair after next, possibly of the next unit)
+        // is issued right after the slot has been read, two pairs of work ahead of its use.
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();  // lanes read bytes that other lanes copied
+            const uint32_t src = ring_rd + (uint32_t)(it & 1) * NV_SLOT;
+            const uint2 l0 = lds64(src), l1 = lds64(src + NV_ROWS), cc = lds64(src + 2 * NV_ROWS);
+            __syncwarp();  // every lane has read the slot before anyone refills it
+            if (it == 6) {
+                nbase = s_next[g];  // written before the barrier of it == 3
+                nxt = decode(nbase);  // past the end: an empty unit, nothing is fetched
+                aim(nxt);
+            }
+            fetch_pair(it & 1);
+            if (it == 4) mbar_wait(mbar0, phase0);  // the MMAs of rows 0-7 have consumed the tile: overwrite it
+
+            // bytes -> fp16 operands: 0x6400 | byte is 1024 + byte, minus 1152 is the level-shifted sample (exact)
+            auto h2 = [](uint32_t w, uint32_t sel) {
+                uint32_t bits = __byte_perm(w, 0x64646464u, sel);
+                __half2 h = __hsub2(*reinterpret_cast<__half2*>(&bits), __floats2half2_rn(1152.0f, 1152.0f));
+                return *reinterpret_cast<uint32_t*>(&h);
+            };
+            const uint32_t rp = (uint32_t)(it & 3);
+            sts128(a_row + (((2 * rp) ^ sw_own) << 4), make_uint4(h2(l0.x, 0x4140), h2(l0.x, 0x4342), h2(l0.y, 0x4140), h2(l0.y, 0x4342)));
+            sts128(a_row + (((2 * rp + 1) ^ sw_own) << 4), make_uint4(h2(l1.x, 0x4140), h2(l1.x, 0x4342), h2(l1.y, 0x4140), h2(l1.y, 0x4342)));
+            const uint32_t crow = (uint32_t)it;  // chroma row = K chunk of the chroma tile
+            sts64(ac_cb + ((crow ^ sw_cb) << 4), make_uint2(h2(cc.x, 0x4240), h2(cc.y, 0x4240)));  // Cb of four pairs
+            sts64(ac_cr + ((crow ^ sw_cr) << 4), make_uint2(h2(cc.x, 0x4341), h2(cc.y, 0x4341)));  // Cr
             if (it == 3) {
                 publish();
                 if (issuer) issue(0, 0, tmem_d0, mbar0);
@@ -1718,6 +1955,51 @@ static bool launch_tma(const TransformArgs& a_in, int sms, cudaStream_t s) {
     cudaFuncSetAttribute(k_transform_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     k_transform_tma<<<needg < sms ? needg : sms, TC_GROUPS * 128, TC_SMEM, s>>>(a, tm);
     return true;
+}
+
+// NV12-style input: the MCUs that lie inside the image through the tcgen05 kernel (16-byte aligned planes, pitches and
+// frame strides; JB_FLAG_FMA_DCT off), the rest -- and everything otherwise -- through the CUDA-core kernel.
+static bool nv12_plan_fast(TransformArgs& a) {
+    a.fast_mcux = a.fast_mcuy = 0;
+    const uintptr_t bits = (uintptr_t)a.rgb | (uintptr_t)a.uv | a.pitch | a.pitch_uv | (a.n_frames > 1 ? a.frame_stride | a.frame_stride_uv : 0);
+    if (a.tc_mat == nullptr || (bits & 15u) != 0 || a.g.W < 16 || a.g.H < 16) return false;
+    a.fast_mcux = a.g.W / 16;   // complete MCU columns; rows below the image are mirrored by the kernel itself
+    a.fast_mcuy = a.g.mcuy;
+    return true;
+}
+
+int launch_transform_nv12(const TransformArgs& a_in, cudaStream_t s) {
+    TransformArgs a = a_in;
+    const size_t total = (size_t)a.g.n_mcu * 6 * (size_t)a.n_frames;
+    if (!total) return 0;
+    if (nv12_plan_fast(a)) {
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        a.tc_row_len = (uint32_t)a.fast_mcux;
+        a.tc_per_frame = a.tc_row_len * (uint32_t)a.fast_mcuy;
+        a.tc_mcus = a.tc_per_frame * (uint32_t)a.n_frames;
+        a.total_units = (a.tc_mcus + 15) / 16;
+        a.tc_magic_frame = div_magic32(a.tc_per_frame);
+        a.tc_magic_row = div_magic32(a.tc_row_len);
+        const int needg = (int)((a.total_units + 4 * TC_GROUPS - 1) / (4 * TC_GROUPS));
+        cudaFuncSetAttribute(k_transform_tc_nv12, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        k_transform_tc_nv12<<<needg < sms ? needg : sms, TC_GROUPS * 128, TC_SMEM, s>>>(a);
+        return 1;
+    }
+    const size_t g = (total + 127) / 128;
+    k_transform_nv12<<<(int)(g > 148 * 64 ? 148 * 64 : g), 128, 0, s>>>(a);
+    return 1;
+}
+
+// the MCUs the tcgen05 kernel left out (a partial last MCU row / column)
+int launch_transform_nv12_edge(const TransformArgs& a_in, cudaStream_t s) {
+    TransformArgs a = a_in;
+    const size_t total = (size_t)a.g.n_mcu * 6 * (size_t)a.n_frames;
+    if (!total || !nv12_plan_fast(a) || (size_t)a.fast_mcux * a.fast_mcuy == (size_t)a.g.n_mcu) return 0;
+    const size_t g = (total + 127) / 128;
+    k_transform_nv12<<<(int)(g > 148 * 64 ? 148 * 64 : g), 128, 0, s>>>(a);
+    return 1;
 }
 
 int launch_transform(const TransformArgs& a_in, cudaStream_t s) {

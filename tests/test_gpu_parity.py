@@ -927,7 +927,9 @@ def test_nv12_device_input(enc, jb):
         t = tab.cpu().numpy()
         return [bytes(out[int(t[f]): int(t[f] + t[N + f])].cpu().numpy()) for f in range(N)]
 
-    for W, H in ((64, 48), (1920, 1080), (250, 130), (253, 131), (37, 21), (16, 16)):
+    # (16-byte aligned planes take the tcgen05 kernel -- complete MCU columns, rows below the image mirrored in the kernel,
+    # odd heights included; the others the CUDA-core kernel)
+    for W, H in ((64, 48), (1920, 1080), (250, 130), (253, 131), (37, 21), (16, 16), (64, 37), (208, 75), (48, 1081 // 7)):
         rgb = ol.synth(W + H, W, H)
         y, uv = ol.nv12_from_rgb(rgb)
         d_rgb = torch.from_numpy(rgb.copy()).cuda()
