@@ -1089,7 +1089,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc_nv12(const 
     uint8_t* tileC = tileA + TC_TILE_BYTES;                      // chroma
     // ring of raw pixels: address of this warp's row `r` (0/1) of slot `sl` (0/1)
     constexpr uint32_t NV_ROW = 256, NV_ROWS = 4 * NV_ROW, NV_SLOT = 3 * NV_ROWS;  // per group: [slot][luma 0, luma 1, chroma][warp]
-    static_assert(2 * NV_SLOT <= TC_RING_BYTES, "the NV12 ring fits the RGB ring");
+    static_assert(4 * NV_SLOT <= TC_RING_BYTES, "the NV12 ring (four slots: three row pairs ahead) fits the RGB ring");
     const uint32_t ring = smem_u32(smem + TC_B_BYTES + TC_GROUPS * 2 * TC_TILE_BYTES + g * TC_RING_BYTES) + wg * NV_ROW;
     // ---- one-time setup: W matrices, tensor memory, barriers ---------------------------------------
     for (int i = tid; i < TC_B_BYTES / 16; i += TC_GROUPS * 128)
@@ -1217,6 +1217,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc_nv12(const 
         aim(cur);
         fetch_pair(0);
         fetch_pair(1);
+        fetch_pair(2);
     }
     while (base < a.total_units) {
         if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
@@ -1231,18 +1232,33 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc_nv12(const 
         // is issued right after the slot has been read, two pairs of work ahead of its use.
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
             __syncwarp();  // lanes read bytes that other lanes copied
-            const uint32_t src = ring_rd + (uint32_t)(it & 1) * NV_SLOT;
+            const uint32_t src = ring_rd + (uint32_t)(it & 3) * NV_SLOT;
             const uint2 l0 = lds64(src), l1 = lds64(src + NV_ROWS), cc = lds64(src + 2 * NV_ROWS);
             __syncwarp();  // every lane has read the slot before anyone refills it
-            if (it == 6) {
+            if (it == 5) {  // (the ring runs three pairs ahead: pairs 8, 9, 10 are the next unit's first three)
                 nbase = s_next[g];  // written before the barrier of it == 3
                 nxt = decode(nbase);  // past the end: an empty unit, nothing is fetched
                 aim(nxt);
             }
-            fetch_pair(it & 1);
-            if (it == 4) mbar_wait(mbar0, phase0);  // the MMAs of rows 0-7 have consumed the tile: overwrite it
+            fetch_pair((it + 3) & 3);  // the slot read in the previous iteration
+            if (it == 4) {
+                mbar_wait(mbar0, phase0);  // the MMAs of rows 0-7 have consumed the tile: overwrite it
+                // With no colour conversion between them the two row pairs the ring runs ahead are ~300 cycles of work,
+                // less than a trip to HBM: ask L2 for the rows of the NEXT unit now (its index was drawn at the top of
+                // this one), a lane per row -- 16 luma rows, 8 chroma rows, 256 bytes each when the unit does not wrap.
+                const TcUnitNv pf = decode(s_next[g]);
+                const uint8_t* p0 = shfl_ptr(pf.ptr, 0);
+                const uint8_t* pc = shfl_ptr(pf.puv, 0);
+                const int py = __shfl_sync(0xffffffffu, pf.y0, 0);
+                if (__shfl_sync(0xffffffffu, (int)pf.valid, 0) && lane < 24) {
+                    const uint8_t* r = lane < 16 ? p0 + (size_t)(uint32_t)mirror(py + lane, img_h) * a.pitch
+                                                 : pc + (size_t)((uint32_t)mirror(py + 2 * (lane - 16), img_h) >> 1) * a.pitch_uv;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128));
+                }
+            }
 
             // bytes -> fp16 operands: 0x6400 | byte is 1024 + byte, minus 1152 is the level-shifted sample (exact)
             auto h2 = [](uint32_t w, uint32_t sel) {
