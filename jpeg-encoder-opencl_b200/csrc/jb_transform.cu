@@ -1249,10 +1249,11 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc_nv12(const 
                 // less than a trip to HBM: ask L2 for the rows of the NEXT unit now (its index was drawn at the top of
                 // this one), a lane per row -- 16 luma rows, 8 chroma rows, 256 bytes each when the unit does not wrap.
                 const TcUnitNv pf = decode(s_next[g]);
-                const uint8_t* p0 = shfl_ptr(pf.ptr, 0);
+                const uint8_t *p0 = shfl_ptr(pf.ptr, 0), *p15 = shfl_ptr(pf.ptr, 30);
                 const uint8_t* pc = shfl_ptr(pf.puv, 0);
                 const int py = __shfl_sync(0xffffffffu, pf.y0, 0);
-                if (__shfl_sync(0xffffffffu, (int)pf.valid, 0) && lane < 24) {
+                // (the last MCU of the unit exists and sits 15 MCUs to the right of the first: no wrap, every address is a row's)
+                if (__shfl_sync(0xffffffffu, (int)pf.valid, 30) && p15 == p0 + 15 * 16 && lane < 24) {
                     const uint8_t* r = lane < 16 ? p0 + (size_t)(uint32_t)mirror(py + lane, img_h) * a.pitch
                                                  : pc + (size_t)((uint32_t)mirror(py + 2 * (lane - 16), img_h) >> 1) * a.pitch_uv;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
@@ -1596,7 +1597,7 @@ __global__ void __launch_bounds__(t3_groups(SUB) * 128, 1) k_transform_tc3(const
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar[T3_GROUPS][2];
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_next[T3_GROUPS];
+    __shared__ uint32_t s_next[T3_GROUPS], s_next0[T3_GROUPS];
     __shared__ uint32_t s_desc[T3_GROUPS + 1][4];  // descriptor low words: [group]{Y, Cb, Cr tile}, [T3_GROUPS][table * 2 + split]
     __shared__ uint32_t s_ydown[2048];             // the CSC tie table (jb_math.h), 8 KB
     uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
@@ -1746,9 +1747,9 @@ __global__ void __launch_bounds__(t3_groups(SUB) * 128, 1) k_transform_tc3(const
     // first rows starts at the third, before any barrier of the unit: the index of the next unit is drawn one
     // unit ahead (at the start of a unit, read after the barrier that ends its row loop).
     uint32_t base = (blockIdx.x * T3_GROUPS + g) * 4;
-    if (gt == 0) s_next[g] = stride + atomicAdd(a.unit_counter, 4u);
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-    uint32_t nbase = s_next[g];
+    if (gt == 0) s_next0[g] = stride + atomicAdd(a.unit_counter, 4u);  // (its own word: s_next is rewritten below before the
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");          //  other warps are known to have read this one)
+    uint32_t nbase = s_next0[g];
     TcUnit cur = decode(base);
     if (base < a.total_units) {
         aim(cur);
