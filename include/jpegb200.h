@@ -225,6 +225,12 @@ int jb_encode_batch_device(jb_ctx *ctx, const uint8_t *d_rgb, size_t n_frames, s
 int jb_encode_nv12_device(jb_ctx *ctx, const uint8_t *d_y, size_t pitch_y, size_t frame_stride_y, const uint8_t *d_uv,
                           size_t pitch_uv, size_t frame_stride_uv, size_t n_frames, size_t W, size_t H, const jb_params *p,
                           uint8_t *d_out, size_t cap, uint64_t *d_offsets, uint64_t *d_sizes, uint64_t *d_total);
+/* The same from HOST planes to host JFIF files (the NV12 counterpart of jb_encode_batch: pinned buffers recommended, groups of
+ * frames pipelined over the context's streams).  Half the bytes of RGB8 cross the host link: where jb_encode_batch is bound by
+ * the H2D copy (3 B/px), this path moves 1.5 B/px.  Output layout, JB_E_NOSPACE / jb_required_bytes as jb_encode_batch. */
+int jb_encode_nv12_batch(jb_ctx *ctx, const uint8_t *y, size_t pitch_y, size_t frame_stride_y, const uint8_t *uv, size_t pitch_uv,
+                         size_t frame_stride_uv, size_t n_frames, size_t W, size_t H, const jb_params *p, uint8_t *out, size_t cap,
+                         uint64_t *offsets, uint64_t *sizes);
 /* RGB8 -> NV12 on the device with the reference's own arithmetic: performCSC (utils.cpp:92-110) and performCDS
  * (truncated mean of every complete 2x2 cell; a cell cut by an odd edge keeps its top-left pixel's chroma). */
 int jb_rgb8_to_nv12_device(jb_ctx *ctx, const uint8_t *d_rgb, size_t W, size_t H, size_t pitch, uint8_t *d_y, size_t pitch_y,

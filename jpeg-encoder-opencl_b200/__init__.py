@@ -36,7 +36,7 @@ SYMBOLS = [
     "jb_write_header", "jb_synth_rgb_device", "jb_planar_u32_from_aos", "jb_planar_u32_interleave",
     "jb_planar_u32_to_rgb8_device", "jb_encode_jfif_planar_u32", "jb_optimal_huffman_spec",
     "jb_encode_strip_begin", "jb_encode_strip_finish", "jb_copy_bytes_device", "jb_ipc_export", "jb_ipc_open", "jb_ipc_close",
-    "jb_stitch_exchange", "jb_stitch_complete", "jb_encode_tiles", "jb_encode_nv12_device", "jb_rgb8_to_nv12_device",
+    "jb_stitch_exchange", "jb_stitch_complete", "jb_encode_tiles", "jb_encode_nv12_device", "jb_encode_nv12_batch", "jb_rgb8_to_nv12_device",
     "jb_jfif_info_host", "jb_jfif_info_device", "jb_decode_jfif_device", "jb_decode_jfif", "jb_psnr_device",
     "jb_pad_mirror_planar_u32", "jb_blockify_planar_i32", "jb_f64_to_u8", "jb_remove_red_aos", "jb_value_categories",
 ]
@@ -138,6 +138,7 @@ def lib():
     L.jb_encode_jfif.argtypes = [vp, vp, sz, sz, sz, PP, vp, sz, C.POINTER(sz)]
     L.jb_encode_batch.argtypes = [vp, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp]
     L.jb_encode_nv12_device.argtypes = [vp, vp, sz, sz, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp, vp]
+    L.jb_encode_nv12_batch.argtypes = [vp, vp, sz, sz, vp, sz, sz, sz, sz, sz, PP, vp, sz, vp, vp]
     L.jb_rgb8_to_nv12_device.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp, sz]
     L.jb_jfif_info_host.argtypes = [vp, sz, C.POINTER(JfifInfo)]
     L.jb_jfif_info_device.argtypes = [vp, vp, sz, C.POINTER(JfifInfo)]
@@ -414,6 +415,24 @@ class Encoder:
         """NV12-style frames in HBM (device addresses as ints) -> JFIF files; asynchronous, finish with sync()."""
         self._ck(self.L.jb_encode_nv12_device(self.h, d_y, pitch_y, fs_y, d_uv, pitch_uv, fs_uv, N, W, H, C.byref(params), d_out, cap,
                                               d_offs, d_sizes, d_total))
+
+    def encode_nv12_batch(self, y, uv, W, params, out=None):
+        """NV12-style HOST frames: y (N, H, pitch_y >= W) uint8, uv (N, ceil(H/2), pitch_uv >= 2*ceil(W/2)) uint8 (numpy, ideally
+        pinned) -> (out, offsets, sizes) as encode_batch."""
+        N, H, py = y.shape
+        _, ch, puv = uv.shape
+        assert y.flags.c_contiguous and uv.flags.c_contiguous and uv.shape[0] == N and ch == (H + 1) // 2
+        if out is None:
+            out = np.empty(N * (W * H * 3 + 65536) if N * W * H < (1 << 26) else N * (W * H + 4096), np.uint8)
+        offs = np.zeros(N, np.uint64)
+        sizes = np.zeros(N, np.uint64)
+        self._ck(self.L.jb_encode_nv12_batch(self.h, _ptr(y), py, py * H, _ptr(uv), puv, puv * ch, N, W, H, C.byref(params), _ptr(out),
+                                             out.size, _ptr(offs), _ptr(sizes)))
+        return out, offs, sizes
+
+    def encode_nv12_batch_ptr(self, y_ptr, pitch_y, fs_y, uv_ptr, pitch_uv, fs_uv, N, W, H, params, out_ptr, cap, offs, sizes):
+        self._ck(self.L.jb_encode_nv12_batch(self.h, y_ptr, pitch_y, fs_y, uv_ptr, pitch_uv, fs_uv, N, W, H, C.byref(params), out_ptr, cap,
+                                             _ptr(offs), _ptr(sizes)))
 
     def rgb8_to_nv12_device(self, d_rgb, W, H, pitch, d_y, pitch_y, d_uv, pitch_uv):
         self._ck(self.L.jb_rgb8_to_nv12_device(self.h, d_rgb, W, H, pitch, d_y, pitch_y, d_uv, pitch_uv))

@@ -1313,11 +1313,32 @@ static int harvest(jb_ctx* ctx, Slot& s, uint8_t* out, size_t cap, uint64_t* off
     return JB_OK;
 }
 
+// Host planes of `rows` rows of `width` bytes each, n frames -> device planes: as few copies as the strides allow.
+static int upload_planes(jb_ctx* ctx, cudaStream_t st, uint8_t* d, size_t d_pitch, size_t d_stride, const uint8_t* h, size_t h_pitch,
+                         size_t h_stride, size_t width, size_t rows, size_t n) {
+    if (h_pitch == d_pitch && (h_stride == d_stride || n == 1)) {
+        CK(cudaMemcpyAsync(d, h, d_stride * (n - 1) + d_pitch * (rows - 1) + width, cudaMemcpyHostToDevice, st));
+    } else if (h_stride == h_pitch * rows && d_stride == d_pitch * rows) {
+        CK(cudaMemcpy2DAsync(d, d_pitch, h, h_pitch, width, rows * n, cudaMemcpyHostToDevice, st));
+    } else {
+        for (size_t f = 0; f < n; ++f)
+            CK(cudaMemcpy2DAsync(d + f * d_stride, d_pitch, h + f * h_stride, h_pitch, width, rows, cudaMemcpyHostToDevice, st));
+    }
+    return JB_OK;
+}
+
+// `nvh` set: `rgb` / `pitch` / `frame_stride` describe the Y planes of NV12-style host frames and nvh the CbCr planes.
 static int encode_batch_once(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, size_t W, size_t H, size_t pitch,
                              size_t frame_stride, const jb_params* p, uint8_t* out, size_t cap, uint64_t* offsets,
-                             uint64_t* sizes) {
-    if (!ctx || !rgb || !out) return fail(ctx, JB_E_INVALID, "null argument");
-    if (pitch < W * 3 || (n_frames > 1 && frame_stride < pitch * H)) return fail(ctx, JB_E_INVALID, "bad pitch/stride");
+                             uint64_t* sizes, const Nv12Src* nvh = nullptr) {
+    if (!ctx || !rgb || !out || (nvh && !nvh->uv)) return fail(ctx, JB_E_INVALID, "null argument");
+    const size_t cw = 2 * ((W + 1) / 2), ch = (H + 1) / 2;  // bytes per row / rows of a CbCr plane
+    if (nvh) {
+        if (pitch < W || nvh->pitch_uv < cw || (n_frames > 1 && (frame_stride < pitch * H || nvh->frame_stride_uv < nvh->pitch_uv * ch)))
+            return fail(ctx, JB_E_INVALID, "bad pitch/stride");
+    } else if (pitch < W * 3 || (n_frames > 1 && frame_stride < pitch * H)) {
+        return fail(ctx, JB_E_INVALID, "bad pitch/stride");
+    }
     CK(cudaSetDevice(ctx->device));
     // group size: about 96 MB of RGB per group, at least one frame
     size_t frame_bytes = W * H * 3;
@@ -1350,10 +1371,30 @@ static int encode_batch_once(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, s
             if ((rc = slot_prepare(ctx, s, gp))) goto drain;
             s.first_frame = f0;
             s.n_frames = nf;
-            if ((rc = upload_frames(ctx, s, gp, rgb + f0 * frame_stride, W, H, pitch, frame_stride))) goto drain;
-            if ((rc = enqueue_encode(ctx, s, gp, p, s.d_rgb, gp.d_pitch, gp.d_frame_stride, fr, W, H, s.d_out,
-                                     s.d_out_cap, s.d_frame_off, s.d_frame_size, s.d_total)))
-                goto drain;
+            if (nvh) {
+                // The planes of a group take the place of its RGB frames in the staging buffer (half the bytes): every Y
+                // plane, then every CbCr plane, with 16-byte aligned pitches (what k_transform_tc_nv12 wants) unless the
+                // frames are so narrow that the padding would not fit -- then tight (W H + cw ch <= 3 W H always holds).
+                size_t py = align_up(W, 16), puv = align_up(cw, 16);
+                if (py * H + puv * ch > gp.d_frame_stride) py = W, puv = cw;
+                uint8_t* d_uv = s.d_rgb + py * H * nf;
+                {
+                    Timed t(ctx, s.st, 3);
+                    if ((rc = upload_planes(ctx, s.st, s.d_rgb, py, py * H, rgb + f0 * frame_stride, pitch, frame_stride, W, H, nf))) goto drain;
+                    if ((rc = upload_planes(ctx, s.st, d_uv, puv, puv * ch, nvh->uv + f0 * nvh->frame_stride_uv, nvh->pitch_uv,
+                                            nvh->frame_stride_uv, cw, ch, nf)))
+                        goto drain;
+                }
+                const Nv12Src nv{d_uv, puv, puv * ch};
+                if ((rc = enqueue_encode(ctx, s, gp, p, s.d_rgb, py, py * H, fr, W, H, s.d_out, s.d_out_cap, s.d_frame_off,
+                                         s.d_frame_size, s.d_total, nullptr, nullptr, &nv)))
+                    goto drain;
+            } else {
+                if ((rc = upload_frames(ctx, s, gp, rgb + f0 * frame_stride, W, H, pitch, frame_stride))) goto drain;
+                if ((rc = enqueue_encode(ctx, s, gp, p, s.d_rgb, gp.d_pitch, gp.d_frame_stride, fr, W, H, s.d_out,
+                                         s.d_out_cap, s.d_frame_off, s.d_frame_size, s.d_total)))
+                    goto drain;
+            }
             CK(cudaMemcpyAsync(s.h_res, s.w.status, 32, cudaMemcpyDeviceToHost, s.st));
             CK(cudaMemcpyAsync(s.h_res + 4, s.d_total, 8, cudaMemcpyDeviceToHost, s.st));
             s.h_res[5] = 0;
@@ -1387,6 +1428,13 @@ int jb_encode_batch(jb_ctx* ctx, const uint8_t* rgb, size_t n_frames, size_t W, 
                     size_t frame_stride, const jb_params* p, uint8_t* out, size_t cap, uint64_t* offsets,
                     uint64_t* sizes) {
     return with_workspace_retry(ctx, [&] { return encode_batch_once(ctx, rgb, n_frames, W, H, pitch, frame_stride, p, out, cap, offsets, sizes); });
+}
+
+int jb_encode_nv12_batch(jb_ctx* ctx, const uint8_t* y, size_t pitch_y, size_t frame_stride_y, const uint8_t* uv, size_t pitch_uv,
+                         size_t frame_stride_uv, size_t n_frames, size_t W, size_t H, const jb_params* p, uint8_t* out, size_t cap,
+                         uint64_t* offsets, uint64_t* sizes) {
+    const Nv12Src nvh{uv, pitch_uv, frame_stride_uv};
+    return with_workspace_retry(ctx, [&] { return encode_batch_once(ctx, y, n_frames, W, H, pitch_y, frame_stride_y, p, out, cap, offsets, sizes, &nvh); });
 }
 
 int jb_encode_jfif(jb_ctx* ctx, const uint8_t* rgb, size_t W, size_t H, size_t pitch, const jb_params* p, uint8_t* out,

@@ -1087,7 +1087,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc_nv12(const 
     uint8_t* sB = smem;
     uint8_t* tileA = smem + TC_B_BYTES + g * 2 * TC_TILE_BYTES;  // luma rows 0-7, then 8-15; staging between
     uint8_t* tileC = tileA + TC_TILE_BYTES;                      // chroma
-    // ring of raw pixels: address of this warp's row `r` (0/1) of slot `sl` (0/1)
+    // ring of raw pixels: address of this warp's row `r` (luma 0, luma 1, chroma) of slot `sl` (0-3)
     constexpr uint32_t NV_ROW = 256, NV_ROWS = 4 * NV_ROW, NV_SLOT = 3 * NV_ROWS;  // per group: [slot][luma 0, luma 1, chroma][warp]
     static_assert(4 * NV_SLOT <= TC_RING_BYTES, "the NV12 ring (four slots: three row pairs ahead) fits the RGB ring");
     const uint32_t ring = smem_u32(smem + TC_B_BYTES + TC_GROUPS * 2 * TC_TILE_BYTES + g * TC_RING_BYTES) + wg * NV_ROW;
@@ -1228,8 +1228,8 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_transform_tc_nv12(const 
         const uint32_t gb0 = cur.gm * 6u;
 
         // ---- 16 image rows = 8 row pairs: ring -> registers -> colour conversion -> A tiles -----------
-        // The ring holds two pairs; the refill of a slot (the pair after next, possibly of the next unit)
-        // is issued right after the slot has been read, two pairs of work ahead of its use.
+        // The ring holds four pairs; the refill of a slot (three pairs on, possibly of the next unit) is issued
+        // one iteration after the slot has been read, three pairs of work ahead of its use.
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
             asm volatile("cp.async.wait_group 2;" ::: "memory");

@@ -10,6 +10,7 @@ $B > gpurun_out/${R}_plain.json 2> gpurun_out/${R}_plain.err || exit 1
 # (the 512 k_synth launches that fill the input batch are filtered out by name)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 240 --csv --log-file gpurun_out/${R}_launches.csv \
     -k 'regex:k_transform|k_fixup|k_encode|k_scan|k_intervals|k_zero|k_pack|k_ff_count|k_int_out|k_finalize|k_stuff' $B > /dev/null 2>&1
+if [ -z "$ONLY_NV12" ]; then  # (ONLY_NV12=1: launch list + the NV12 kernel only, the other captures are kept)
 # ncu --set full, one complete step of the main kernels (default build: tcgen05 transform, cp.async staging)
 ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tc|k_fixup|k_encode|^k_pack$|k_ff_count|^k_stuff$' \
     --launch-skip 18 --launch-count 6 -f -o gpurun_out/${R}_prof_tc $B > /dev/null 2>&1
@@ -30,4 +31,10 @@ ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tc3
 $B --workload repl1080p > gpurun_out/${R}_plainrepl.json 2>> gpurun_out/${R}_plain.err || exit 1
 ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tc3' --launch-skip 3 --launch-count 1 -f \
     -o gpurun_out/${R}_prof_tc3r $B --workload repl1080p > /dev/null 2>&1
+fi
+# the NV12-style input kernel: it runs among the default run's other workloads (first timed launch of it)
+B2="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-parity"
+$B2 > gpurun_out/${R}_plain_others.json 2>> gpurun_out/${R}_plain.err || exit 1
+ncu --set full --import-source on --clock-control none -k 'regex:k_transform_tc_nv12' --launch-skip 3 --launch-count 1 -f \
+    -o gpurun_out/${R}_prof_nv12 $B2 > /dev/null 2>&1
 ls -la gpurun_out/${R}_*

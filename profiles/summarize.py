@@ -57,10 +57,11 @@ def kernels():
           "`_prof_full`: the same with `--tensor-dct 0` (CUDA-core transform); `_prof_tc3`: `--workload 4k444` (32 x 3840x2160, 4:4:4, q90);",
           "`_prof_tc3r`: `--workload repl1080p` (256 x 1920x1080, replicated 4:2:0, q50: K = 16 chroma contraction).",
           "`_prof_tma`: the default workload with `--tma` (JB_FLAG_TMA: TMA-staged tiles, `k_transform_tma`).",
+          "`_prof_nv12`: the NV12-style device input of the default run's `other_workloads` (256 x 1920x1080 as Y + CbCr planes, `k_transform_tc_nv12`).",
           "Captured by `profiles/capture.sh` (each ncu pass after a plain run of the same command that exited 0).",
           "Numbers taken under the profiler are diagnostics only; bench values come from CUDA events.", ""]
     summary = {}
-    for rep in (f"{R}_prof_tc.ncu-rep", f"{R}_prof_tma.ncu-rep", f"{R}_prof_full.ncu-rep", f"{R}_prof_tc3.ncu-rep", f"{R}_prof_tc3r.ncu-rep"):
+    for rep in (f"{R}_prof_tc.ncu-rep", f"{R}_prof_tma.ncu-rep", f"{R}_prof_full.ncu-rep", f"{R}_prof_tc3.ncu-rep", f"{R}_prof_tc3r.ncu-rep", f"{R}_prof_nv12.ncu-rep"):
         if not os.path.exists(os.path.join(OUT, rep)):
             continue
         hdr, units, rows = raw(rep)
@@ -94,7 +95,7 @@ def kernels():
         issue = num(rec, "issue active %")
         lim = "instruction issue" if issue >= 55 else ("latency: " + top.replace("stall ", "") if issue < 50 else "issue + " + top.replace("stall ", ""))
         over.append(f"| `{name}` | {us:.0f} us | {by/1e9:.2f} GB | {gbs:.0f} | {gbs/6544:.2f} | {issue:.0f} % | {num(rec, 'warps active %'):.0f} % | {top} {stalls.get(top, 0):.1f} | {lim} |")
-    md = md[:9] + over + [""] + md[9:]
+    md = md[:10] + over + [""] + md[10:]
     open(os.path.join(ROOT, "profiles", f"{R}_kernels.md"), "w").write("\n".join(md) + "\n")
     return summary
 
@@ -109,13 +110,14 @@ if __name__ == "__main__":
     for key, pred in (("k_transform_tc", lambda k: "k_transform_tc<" in k),
                       ("k_transform_tc3", lambda k: "k_transform_tc3<0" in k),
                       ("k_transform_tc3_repl", lambda k: "k_transform_tc3<1" in k),
+                      ("k_transform_tc_nv12", lambda k: "k_transform_tc_nv12" in k),
                       ("k_transform", lambda k: "k_transform<" in k)):
         t = next((v for k, v in summ.items() if pred(k)), None)
         if t:
             ks[key] = {"dram_bytes_per_launch": int(to_bytes(*t["dram read"]) + to_bytes(*t["dram write"])),
                        "dram_read": t["dram read"], "dram_write": t["dram write"], "duration_under_ncu": t["duration"],
-                       "workload": {"k_transform_tc3": "4k444", "k_transform_tc3_repl": "repl1080p"}.get(key, "batch1080p"),
-                       "frames": {"k_transform_tc3": 32, "k_transform_tc3_repl": 256}.get(key, 512)}
+                       "workload": {"k_transform_tc3": "4k444", "k_transform_tc3_repl": "repl1080p", "k_transform_tc_nv12": "nv12_1080p"}.get(key, "batch1080p"),
+                       "frames": {"k_transform_tc3": 32, "k_transform_tc3_repl": 256, "k_transform_tc_nv12": 256}.get(key, 512)}
     traffic = {k: v["dram_bytes_per_launch"] for k, v in ks.items()}
     json.dump({"round": R, "workload": "batch1080p", "frames": 512, "kernels": ks,
                "note": "k_transform_tc3 was captured on the 4k444 workload (32 frames of 3840x2160, 4:4:4, q90)",

@@ -959,3 +959,49 @@ def test_nv12_device_input(enc, jb):
         d = torch.zeros(64 * 64, dtype=torch.uint8, device="cuda")
         enc.encode_nv12_device(d.data_ptr(), 64, 64 * 64, d.data_ptr(), 64, 64 * 32, 1, 64, 64, pp, d.data_ptr(), 64 * 64, 0, 0, 0)
     assert e.value.code == jb.E_UNSUPPORTED
+
+
+def test_nv12_host_batch(enc, jb):
+    """jb_encode_nv12_batch: NV12-style frames in HOST memory -> host JFIF files (the NV12 counterpart of jb_encode_batch).
+    Files == the oracle's stages from the mirror padding on, for the smallest sizes the mirror padding allows, odd sizes, padded host pitches, and across several groups of the host pipeline; for even
+    sizes also == the RGB path's file (NV12 made with the reference's CSC + CDS); too small an output reports what it needs."""
+    ql, qc = ol.quality_tables(75)
+    p = jb.make_params(ol.SUB_420, qlum=ql, qchrom=qc, restart_interval=3)
+    rng = np.random.default_rng(77)
+
+    def want(y, uv, W, H):
+        ycc = ol.ycc_from_nv12(np.ascontiguousarray(y[:, :W]), np.ascontiguousarray(uv[:, :2 * ((W + 1) // 2)]))
+        return ol.jfif_from_coef(ol.transform_ycc(ycc, ol.SUB_420, ql, qc), W, H, ol.SUB_420, ql, qc, 3)
+
+    for W, H, N, pad in ((64, 48, 2, 0), (250, 131, 3, 6), (8, 8, 2, 0), (9, 11, 2, 1), (16, 16, 1, 0), (33, 17, 4, 0), (1920, 1080, 2, 0)):
+        cw, ch = 2 * ((W + 1) // 2), (H + 1) // 2
+        y = rng.integers(0, 256, (N, H, W + pad), dtype=np.uint8)
+        uv = rng.integers(0, 256, (N, ch, cw + pad), dtype=np.uint8)
+        out, offs, sizes = enc.encode_nv12_batch(y, uv, W, p)
+        for f in range(N):
+            assert bytes(out[int(offs[f]): int(offs[f] + sizes[f])]) == want(y[f], uv[f], W, H), (W, H, f)
+    # even sizes: the RGB path's own files
+    W, H = 96, 64
+    rgbs = [ol.synth(40 + f, W, H) for f in range(3)]
+    planes = [ol.nv12_from_rgb(r) for r in rgbs]
+    y, uv = np.stack([a for a, _ in planes]), np.stack([b for _, b in planes])
+    out, offs, sizes = enc.encode_nv12_batch(y, uv, W, p)
+    for f in range(3):
+        assert bytes(out[int(offs[f]): int(offs[f] + sizes[f])]) == enc.encode_jfif(rgbs[f], p) == ol.encode_jfif(rgbs[f], ol.SUB_420, ql, qc, 3)
+    # several groups of the host pipeline (a group is ~96 MB of RGB-equivalent frames): 40 x 1080p = 3 groups
+    W, H, N = 1920, 1080, 40
+    y1, uv1 = ol.nv12_from_rgb(ol.synth(5, W, H))
+    y = np.ascontiguousarray(np.broadcast_to(y1, (N, H, W))).copy()
+    uv = np.ascontiguousarray(np.broadcast_to(uv1, (N, H // 2, W))).copy()
+    y[:, 0, 0] = np.arange(N)  # every frame differs
+    out, offs, sizes = enc.encode_nv12_batch(y, uv, W, p)
+    assert [int(o) for o in offs] == [int(x) for x in np.concatenate(([0], np.cumsum(sizes[:-1])))]
+    for f in (0, 17, 39):
+        assert bytes(out[int(offs[f]): int(offs[f] + sizes[f])]) == want(y[f], uv[f], W, H), f
+    small = np.empty(int(sizes.sum()) - 1, np.uint8)
+    with pytest.raises(jb.JbError) as e:
+        enc.encode_nv12_batch(y, uv, W, p, out=small)
+    assert e.value.code == jb.E_NOSPACE and enc.L.jb_required_bytes(enc.h) == int(sizes.sum())
+    with pytest.raises(jb.JbError) as e:
+        enc.encode_nv12_batch(y[:1], uv[:1], W, jb.make_params(ol.SUB_444, qlum=ql, qchrom=qc))
+    assert e.value.code == jb.E_UNSUPPORTED
