@@ -625,13 +625,15 @@ def run_strips(a, jb, enc, torch, dd):
     step = step_peer if peer_like else step_nccl
     if rows:
         encode_chunks_sync()  # sizes the entropy workspace (sticky growth happens in the synchronous entry point)
+    # (the sampler waits until nvidia-smi streams: started BEFORE the warm-up and the barrier -- started after the barrier
+    # on rank 0 only, the other ranks' timed regions included the wait for rank 0's first exchange)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(a.warmup, 3)):
         step()
     enc.sync()
     enc.set_profiling(True)
     enc.reset_counters()
     dd.barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record(ext)
