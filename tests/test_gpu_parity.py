@@ -1005,3 +1005,18 @@ def test_nv12_host_batch(enc, jb):
     with pytest.raises(jb.JbError) as e:
         enc.encode_nv12_batch(y[:1], uv[:1], W, jb.make_params(ol.SUB_444, qlum=ql, qchrom=qc))
     assert e.value.code == jb.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("sub,q,ri", [(ol.SUB_420, 75, 0), (ol.SUB_444, 90, 0), (ol.SUB_REPL420, 50, 0), (ol.SUB_420, 95, 11)])
+def test_fruit_tiled_stress(enc, jb, fruit, sub, q, ri):
+    """SURVEY 8d's second input distribution: fruit.ppm tiled (a dithered image: very high-frequency, long codes, ZRL, blocks
+    longer than a 128-bit slot, many 0xFF bytes).  Whole files == the oracle, batch == single frames."""
+    H, W = 3 * 254 + 17, 4 * 253 + 5  # odd sizes: mirror padding on both edges, CDS edge rule
+    img = np.tile(fruit, (4, 5, 1))[:H, :W].copy()
+    p, ql, qc = _params(jb, sub, q, ri)
+    got = enc.encode_jfif(img, p)
+    assert got == ol.encode_jfif(img, sub, ql, qc, ri), (len(got),)
+    frames = np.stack([np.roll(img, 7 * i, axis=1) for i in range(3)])
+    out, offs, sizes = enc.encode_batch(frames, p)
+    for i in range(3):
+        assert out[int(offs[i]): int(offs[i] + sizes[i])].tobytes() == ol.encode_jfif(frames[i], sub, ql, qc, ri), i
